@@ -1,0 +1,207 @@
+/*
+ * ppsci_b200.h — C-ABI of the B200-native PINN PDE-residual engine.
+ *
+ * The reference (PaddlePaddle/PaddleScience) has no FFI: its seam for this path is the
+ * Python call  ExpressionSolver.train_forward(...)  followed by  total_loss.backward()
+ *   (ppsci/utils/expression.py:60-131, ppsci/solver/train.py:117-158).
+ * This header is the boundary a maintainer would bind *under* that seam (ctypes stub in
+ * INTEGRATION.md).  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every device buffer is caller-owned
+ *   - all work is enqueued on the caller's stream (cudaStream_t passed as void*)
+ *   - every function returns 0 on success, non-zero on error; ppsci_b200_last_error()
+ *     returns a thread-local human readable message
+ *   - handles are not thread-safe
+ */
+#ifndef PPSCI_B200_H_
+#define PPSCI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPSCI_MAX_IN 8      /* raw input columns (x, y, z, t, ...)                       */
+#define PPSCI_MAX_FEAT 32   /* MLP input features after period embedding                 */
+#define PPSCI_MAX_LAYERS 16 /* linear layers (hidden + last_fc)                          */
+#define PPSCI_MAX_DIR 8     /* univariate Taylor directions                              */
+#define PPSCI_MAX_ORDER 4   /* highest Taylor order per direction                        */
+#define PPSCI_MAX_RES 8     /* residual (equation) outputs per constraint                */
+#define PPSCI_MAX_REG 256   /* register file of the residual program                     */
+
+/* dtype */
+enum { PPSCI_F32 = 0, PPSCI_F64 = 1 };
+
+/* activation of the hidden layers — ppsci/arch/activation.py:139-154 */
+enum {
+  PPSCI_ACT_TANH = 0,
+  PPSCI_ACT_SIN = 1,
+  PPSCI_ACT_COS = 2,
+  PPSCI_ACT_SIGMOID = 3,
+  PPSCI_ACT_SILU = 4, /* x*sigmoid(x): "silu" and "swish"(beta=1) */
+  PPSCI_ACT_IDENTITY = 5,
+  PPSCI_ACT_RELU = 6,
+  PPSCI_ACT_GELU = 7, /* erf form (paddle nn.GELU default approximate=False) */
+};
+
+/* input feature kinds — identity, or PeriodEmbedding (ppsci/arch/mlp.py:95-114) */
+enum { PPSCI_FEAT_ID = 0, PPSCI_FEAT_COS = 1, PPSCI_FEAT_SIN = 2 };
+
+/* residual program opcodes (register machine; see DESIGN.md "residual program") */
+enum {
+  PPSCI_OP_CONST = 0, /* dst = consts[a]            */
+  PPSCI_OP_MOV = 1,   /* dst = r[a]                 */
+  PPSCI_OP_ADD = 2,   /* dst = r[a] + r[b]          */
+  PPSCI_OP_SUB = 3,
+  PPSCI_OP_MUL = 4,
+  PPSCI_OP_DIV = 5,
+  PPSCI_OP_NEG = 6,
+  PPSCI_OP_POWI = 7, /* dst = r[a] ** b (b = small signed int immediate) */
+  PPSCI_OP_POW = 8,  /* dst = pow(r[a], r[b])      */
+  PPSCI_OP_SIN = 9,
+  PPSCI_OP_COS = 10,
+  PPSCI_OP_TANH = 11,
+  PPSCI_OP_EXP = 12,
+  PPSCI_OP_LOG = 13,
+  PPSCI_OP_SQRT = 14,
+  PPSCI_OP_ABS = 15,
+  PPSCI_OP_MAX = 16,
+  PPSCI_OP_MIN = 17,
+  PPSCI_OP_SIGN = 18,
+  PPSCI_OP_FMA = 19, /* dst = r[a] * r[b] + r[dst]  (accumulate form) */
+  PPSCI_OP_SINH = 20,
+  PPSCI_OP_COSH = 21,
+  PPSCI_OP_HEAVISIDE = 22,
+};
+
+/* MSELoss reduction — ppsci/loss/mse.py:82-106 */
+enum { PPSCI_REDUCE_MEAN = 0, PPSCI_REDUCE_SUM = 1 };
+
+/*
+ * One compiled constraint: network + jet layout + residual program + loss.
+ *
+ * Jet layout.  Channel 0 is the value.  Direction d (d < n_dir) is the raw-input-space
+ * vector dir_vec[d][0..n_in) and owns dir_order[d] channels holding the NORMALISED Taylor
+ * coefficients  (1/k!) d^k/dt^k f(x + t v)|_{t=0},  k = 1..dir_order[d].
+ * C = 1 + sum_d dir_order[d].  Channel index of (d, k) = 1 + sum_{e<d} dir_order[e] + (k-1).
+ *
+ * Residual program.  Register file r[0..n_reg).  Before the program runs, the engine loads
+ *   r[c*n_out + j]                 = output-jet channel c of network output j
+ *   r[C*n_out + i]                 = raw input column i          (i < n_in)
+ *   r[C*n_out + n_in + a]          = auxiliary column a          (a < n_aux)
+ * then executes prog (n_ops quads: op, dst, a, b).  Residual k is r[res_reg[k]].
+ * grad_* lists the non-zero partials  d res[grad_res[g]] / d r[grad_in[g]]  (grad_in is an
+ * output-jet register) found in r[grad_reg[g]] — produced by the same program.
+ */
+typedef struct ppsci_plan_spec {
+  int32_t dtype;
+  /* network — replaces ppsci/arch/mlp.py:281-315 (forward_tensor / forward) */
+  int32_t n_in;
+  int32_t n_feat;
+  int32_t feat_src[PPSCI_MAX_FEAT];
+  int32_t feat_kind[PPSCI_MAX_FEAT];
+  double feat_omega[PPSCI_MAX_FEAT];
+  int32_t n_layers;                     /* linear layers, >= 1                      */
+  int32_t widths[PPSCI_MAX_LAYERS + 1]; /* widths[0] = n_feat ... widths[n_layers] = n_out */
+  int32_t act;
+  /* jets — replaces ppsci/autodiff/ad.py:56-160,196-303 (reverse-mode sweeps) */
+  int32_t n_dir;
+  int32_t dir_order[PPSCI_MAX_DIR];
+  double dir_vec[PPSCI_MAX_DIR][PPSCI_MAX_IN];
+  /* residual program — replaces ppsci/utils/symbolic.py:184-504 node execution */
+  int32_t n_aux;
+  int32_t n_reg;
+  int32_t n_ops;
+  const int32_t* prog; /* n_ops * 4 int32 (copied at plan_create) */
+  int32_t n_consts;
+  const double* consts; /* copied at plan_create */
+  int32_t n_res;
+  int32_t res_reg[PPSCI_MAX_RES];
+  int32_t n_grad;
+  const int32_t* grad_res; /* [n_grad] */
+  const int32_t* grad_in;  /* [n_grad] register index < C*n_out */
+  const int32_t* grad_reg; /* [n_grad] */
+  /* loss — replaces ppsci/loss/mse.py:82-106 and ppsci/loss/mtl/sum.py:45-60 */
+  int32_t reduction[PPSCI_MAX_RES];
+  double loss_weight[PPSCI_MAX_RES];
+  /* tuning */
+  int32_t chunk_points; /* points per internal chunk (0 = default) */
+  int32_t backend;      /* 0 = auto, 1 = force SIMT kernels, 2 = force tcgen05 kernels */
+} ppsci_plan_spec;
+
+typedef struct ppsci_plan ppsci_plan;
+
+/* Build a plan.  Validates the spec, copies programs, allocates NO device memory. */
+int ppsci_b200_plan_create(const ppsci_plan_spec* spec, ppsci_plan** out);
+void ppsci_b200_plan_destroy(ppsci_plan* plan);
+
+/* Number of parameters in the flat buffer: for each layer l, W_l [in,out] row-major
+ * (the reference's nn.Linear layout, ppsci/arch/mlp.py:246,274) followed by b_l [out]. */
+int64_t ppsci_b200_plan_param_count(const ppsci_plan* plan);
+int32_t ppsci_b200_plan_channels(const ppsci_plan* plan);
+
+/* Bytes of caller-provided device workspace needed for a call with n_points points. */
+size_t ppsci_b200_plan_workspace_bytes(const ppsci_plan* plan, int64_t n_points);
+
+/*
+ * Forward jets + residuals + MSE + adjoint -> weight gradient.  One call per constraint per
+ * step; replaces  ExpressionSolver.train_forward (ppsci/utils/expression.py:60-131)  +
+ * total_loss.backward() (ppsci/solver/train.py:158)  for that constraint.
+ *
+ *   x_cols[i]      device pointer to raw input column i, n_points contiguous values
+ *   aux_cols[a]    device pointer to auxiliary column a (may be NULL if n_aux == 0)
+ *   label_cols[k]  label column of residual k, or NULL  -> label_const[k]
+ *   weight_cols[k] per-point weight column of residual k, or NULL -> 1
+ *   n_norm         denominator used by "mean" reductions (normally n_points)
+ *   params         flat parameter buffer (see plan_param_count)
+ *   grads          flat gradient buffer, ACCUMULATED in place (supports update_freq > 1,
+ *                  ppsci/solver/train.py:141-164); may be NULL to skip the adjoint
+ *   loss_out       n_res device scalars, OVERWRITTEN with the per-residual loss
+ *   residual_out   optional: n_res device columns receiving the raw residual values
+ */
+int ppsci_b200_residual_loss_fwd_bwd(ppsci_plan* plan, const void* const* x_cols,
+                                     const void* const* aux_cols,
+                                     const void* const* label_cols,
+                                     const double* label_const,
+                                     const void* const* weight_cols, int64_t n_points,
+                                     int64_t n_norm, const void* params, void* grads,
+                                     void* loss_out, void* const* residual_out,
+                                     void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Forward only: network outputs and/or output jets for eval / predict / lambdify parity.
+ * Replaces Arch.forward (ppsci/arch/mlp.py:298-315) and ComposedNode.forward
+ * (ppsci/utils/symbolic.py:498-504) without a loss.
+ *   jets_out   optional device buffer [C][n_points][n_out] receiving NORMALISED Taylor
+ *              coefficients per channel (channel 0 = network outputs)
+ *   residual_out optional n_res device columns
+ */
+int ppsci_b200_residual_fwd(ppsci_plan* plan, const void* const* x_cols,
+                            const void* const* aux_cols, int64_t n_points,
+                            const void* params, void* jets_out, void* const* residual_out,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* Kernel launches enqueued by the most recent call on this plan (for bench accounting). */
+int64_t ppsci_b200_plan_last_launches(const ppsci_plan* plan);
+
+/* 1 if the tcgen05 (tensor-core) kernels serve this plan's hidden layers, else 0. */
+int32_t ppsci_b200_plan_uses_tcgen05(const ppsci_plan* plan);
+
+/* Fused Adam on flat buffers — replaces paddle.optimizer.Adam.step for this path
+ * (ppsci/optimizer/optimizer.py:225-248, ppsci/solver/train.py:175).
+ * grad_scale multiplies grads first (1/world for DP averaging). */
+int ppsci_b200_adam_step(int32_t dtype, void* params, const void* grads, void* exp_avg,
+                         void* exp_avg_sq, int64_t n, double lr, double beta1, double beta2,
+                         double eps, double weight_decay, int64_t step, double grad_scale,
+                         void* stream);
+
+const char* ppsci_b200_last_error(void);
+const char* ppsci_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPSCI_B200_H_ */

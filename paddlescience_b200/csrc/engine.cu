@@ -1,0 +1,615 @@
+// engine.cu — C-ABI implementation (include/ppsci_b200.h): plan validation, workspace carving
+// and the per-chunk launch schedule
+//     forward jets (layer by layer)  ->  residual program + MSE  ->  adjoint (dW, dx per layer).
+// All device memory except the (tiny) residual program is caller-owned workspace.
+#ifdef PPSCI_EMUL
+#include "cuda_emul.h"
+#endif
+
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "kernels_simt.cuh"
+#ifndef PPSCI_EMUL
+#include "kernels_tc.cuh"
+#endif
+
+using namespace ppsci;
+
+static thread_local std::string g_err;
+
+static int fail(const std::string& msg) {
+  g_err = msg;
+  return 1;
+}
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(std::string(#call) + " failed: " + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                  std::to_string(__LINE__) + ")");                                            \
+  } while (0)
+
+struct ppsci_plan {
+  ppsci_plan_spec spec;
+  std::vector<int32_t> prog, grad_res, grad_in, grad_reg;
+  std::vector<double> consts;
+  int C = 1;
+  int kmax = 1;
+  JetLayout J;
+  int64_t w_off[PPSCI_MAX_LAYERS + 1];
+  int64_t b_off[PPSCI_MAX_LAYERS + 1];
+  int ld[PPSCI_MAX_LAYERS + 1];
+  int64_t n_params = 0;
+  int ld_hidden_max = 4;
+  int chunk = 0;
+  int num_sms = 148;
+  bool use_tc = false;
+  // device copies of the residual program
+  int* d_prog = nullptr;
+  double* d_consts = nullptr;
+  int* d_grad_res = nullptr;
+  int* d_grad_in = nullptr;
+  int* d_grad_reg = nullptr;
+  int64_t launches = 0;
+  bool attrs_set = false;
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int round4(int x) { return (x + 3) / 4 * 4; }
+
+struct Carve {
+  size_t z[PPSCI_MAX_LAYERS + 1];  // z[l] for l = 1..n_layers-1 (hidden pre-activations)
+  size_t y, ybar, zbar0, zbar1;
+  size_t wt[PPSCI_MAX_LAYERS + 1];
+  size_t loss_acc;
+  size_t tc;  // scratch of the tcgen05 backend
+  size_t total;
+};
+
+static size_t tc_scratch_bytes(const ppsci_plan* P, int64_t nc);
+
+static void carve(const ppsci_plan* P, int64_t nc, Carve* cv) {
+  const size_t es = P->spec.dtype == PPSCI_F64 ? 8 : 4;
+  const int L = P->spec.n_layers;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return o;
+  };
+  for (int l = 1; l < L; ++l) cv->z[l] = take((size_t)P->C * nc * P->ld[l] * es);
+  cv->y = take((size_t)P->C * nc * P->ld[L] * es);
+  cv->ybar = take((size_t)P->C * nc * P->ld[L] * es);
+  cv->zbar0 = take((size_t)P->C * nc * P->ld_hidden_max * es);
+  cv->zbar1 = take((size_t)P->C * nc * P->ld_hidden_max * es);
+  for (int l = 2; l <= L; ++l) cv->wt[l] = take((size_t)P->spec.widths[l] * P->spec.widths[l - 1] * es);
+  cv->loss_acc = take(PPSCI_MAX_RES * sizeof(double));
+  cv->tc = take(tc_scratch_bytes(P, nc));
+  cv->total = off;
+}
+
+extern "C" const char* ppsci_b200_last_error(void) { return g_err.c_str(); }
+extern "C" const char* ppsci_b200_version(void) {
+#ifdef PPSCI_EMUL
+  return "ppsci_b200 0.1 (CPU emulation build: TEST ONLY)";
+#else
+  return "ppsci_b200 0.1 (sm_100a)";
+#endif
+}
+
+static int op_arity(int op) {
+  switch (op) {
+    case PPSCI_OP_CONST: return 0;
+    case PPSCI_OP_MOV: case PPSCI_OP_NEG: case PPSCI_OP_POWI: case PPSCI_OP_SIN: case PPSCI_OP_COS:
+    case PPSCI_OP_TANH: case PPSCI_OP_EXP: case PPSCI_OP_LOG: case PPSCI_OP_SQRT: case PPSCI_OP_ABS:
+    case PPSCI_OP_SIGN: case PPSCI_OP_SINH: case PPSCI_OP_COSH: case PPSCI_OP_HEAVISIDE:
+      return 1;
+    case PPSCI_OP_ADD: case PPSCI_OP_SUB: case PPSCI_OP_MUL: case PPSCI_OP_DIV: case PPSCI_OP_POW:
+    case PPSCI_OP_MAX: case PPSCI_OP_MIN: case PPSCI_OP_FMA:
+      return 2;
+    default: return -1;
+  }
+}
+
+extern "C" int ppsci_b200_plan_create(const ppsci_plan_spec* s, ppsci_plan** out) {
+  if (!s || !out) return fail("plan_create: null argument");
+  *out = nullptr;
+  if (s->dtype != PPSCI_F32 && s->dtype != PPSCI_F64) return fail("plan_create: dtype must be f32 or f64");
+  if (s->n_in < 1 || s->n_in > PPSCI_MAX_IN) return fail("plan_create: n_in out of range");
+  if (s->n_feat < 1 || s->n_feat > PPSCI_MAX_FEAT) return fail("plan_create: n_feat out of range");
+  if (s->n_layers < 1 || s->n_layers > PPSCI_MAX_LAYERS) return fail("plan_create: n_layers out of range");
+  if (s->widths[0] != s->n_feat) return fail("plan_create: widths[0] must equal n_feat");
+  for (int l = 0; l <= s->n_layers; ++l)
+    if (s->widths[l] < 1 || s->widths[l] > 4096) return fail("plan_create: layer width out of range");
+  if (s->act < 0 || s->act > PPSCI_ACT_GELU) return fail("plan_create: unknown activation");
+  for (int f = 0; f < s->n_feat; ++f) {
+    if (s->feat_src[f] < 0 || s->feat_src[f] >= s->n_in) return fail("plan_create: feat_src out of range");
+    if (s->feat_kind[f] < 0 || s->feat_kind[f] > PPSCI_FEAT_SIN) return fail("plan_create: bad feat_kind");
+  }
+  if (s->n_dir < 0 || s->n_dir > PPSCI_MAX_DIR) return fail("plan_create: n_dir out of range");
+  int C = 1, kmax = 1;
+  for (int d = 0; d < s->n_dir; ++d) {
+    if (s->dir_order[d] < 1 || s->dir_order[d] > PPSCI_MAX_ORDER) return fail("plan_create: dir_order out of range");
+    C += s->dir_order[d];
+    if (s->dir_order[d] > kmax) kmax = s->dir_order[d];
+  }
+  if (C > RC) return fail("plan_create: too many jet channels (max 32)");
+  const int n_out = s->widths[s->n_layers];
+  if (s->n_aux < 0 || s->n_aux > PPSCI_MAX_IN) return fail("plan_create: n_aux out of range");
+  const int n_inreg = C * n_out + s->n_in + s->n_aux;
+  if (s->n_reg < n_inreg || s->n_reg > PPSCI_MAX_REG) return fail("plan_create: n_reg out of range (max 256)");
+  if (s->n_res < 0 || s->n_res > PPSCI_MAX_RES) return fail("plan_create: n_res out of range");
+  if (s->n_ops < 0 || (s->n_ops > 0 && !s->prog)) return fail("plan_create: bad program");
+  for (int i = 0; i < s->n_ops; ++i) {
+    const int op = s->prog[4 * i], dst = s->prog[4 * i + 1], a = s->prog[4 * i + 2], b = s->prog[4 * i + 3];
+    const int ar = op_arity(op);
+    if (ar < 0) return fail("plan_create: unknown opcode at op " + std::to_string(i));
+    if (dst < 0 || dst >= s->n_reg) return fail("plan_create: dst register out of range at op " + std::to_string(i));
+    if (op == PPSCI_OP_CONST) {
+      if (a < 0 || a >= s->n_consts) return fail("plan_create: const index out of range at op " + std::to_string(i));
+    } else {
+      if (a < 0 || a >= s->n_reg) return fail("plan_create: src register out of range at op " + std::to_string(i));
+      if (ar == 2 && (b < 0 || b >= s->n_reg)) return fail("plan_create: src register out of range at op " + std::to_string(i));
+    }
+  }
+  for (int k = 0; k < s->n_res; ++k) {
+    if (s->res_reg[k] < 0 || s->res_reg[k] >= s->n_reg) return fail("plan_create: res_reg out of range");
+    if (s->reduction[k] != PPSCI_REDUCE_MEAN && s->reduction[k] != PPSCI_REDUCE_SUM) return fail("plan_create: bad reduction");
+  }
+  if (s->n_grad < 0) return fail("plan_create: n_grad < 0");
+  for (int g = 0; g < s->n_grad; ++g) {
+    if (s->grad_res[g] < 0 || s->grad_res[g] >= s->n_res) return fail("plan_create: grad_res out of range");
+    if (s->grad_in[g] < 0 || s->grad_in[g] >= C * n_out) return fail("plan_create: grad_in out of range");
+    if (s->grad_reg[g] < 0 || s->grad_reg[g] >= s->n_reg) return fail("plan_create: grad_reg out of range");
+    if (g > 0 && s->grad_in[g] < s->grad_in[g - 1]) return fail("plan_create: grad list must be sorted by grad_in");
+  }
+
+  ppsci_plan* P = new ppsci_plan();
+  P->spec = *s;
+  P->prog.assign(s->prog, s->prog + 4 * (size_t)s->n_ops);
+  P->consts.assign(s->consts, s->consts + (size_t)s->n_consts);
+  P->grad_res.assign(s->grad_res, s->grad_res + (size_t)s->n_grad);
+  P->grad_in.assign(s->grad_in, s->grad_in + (size_t)s->n_grad);
+  P->grad_reg.assign(s->grad_reg, s->grad_reg + (size_t)s->n_grad);
+  P->spec.prog = nullptr; P->spec.consts = nullptr;
+  P->spec.grad_res = P->spec.grad_in = P->spec.grad_reg = nullptr;
+  P->C = C;
+  P->kmax = kmax;
+  P->J.C = C;
+  P->J.n_dir = s->n_dir;
+  int base = 1;
+  for (int d = 0; d < PPSCI_MAX_DIR; ++d) {
+    P->J.dir_order[d] = d < s->n_dir ? s->dir_order[d] : 0;
+    P->J.dir_base[d] = base;
+    if (d < s->n_dir) base += s->dir_order[d];
+  }
+  int64_t off = 0;
+  P->ld[0] = round4(s->widths[0]);
+  for (int l = 1; l <= s->n_layers; ++l) {
+    P->w_off[l] = off;
+    off += (int64_t)s->widths[l - 1] * s->widths[l];
+    P->b_off[l] = off;
+    off += s->widths[l];
+    P->ld[l] = round4(s->widths[l]);
+    if (l < s->n_layers && P->ld[l] > P->ld_hidden_max) P->ld_hidden_max = P->ld[l];
+  }
+  P->n_params = off;
+  P->chunk = s->chunk_points > 0 ? s->chunk_points : (s->dtype == PPSCI_F64 ? 32768 : 65536);
+
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess) {
+    P->num_sms = prop.multiProcessorCount;
+#ifndef PPSCI_EMUL
+    if (prop.major != 10) {
+      delete P;
+      return fail("plan_create: this library is built for sm_100a (B200) only; found compute capability " +
+                  std::to_string(prop.major) + "." + std::to_string(prop.minor));
+    }
+#endif
+  } else {
+    delete P;
+    return fail("plan_create: no CUDA device available (the engine has no CPU fallback)");
+  }
+#ifndef PPSCI_EMUL
+  P->use_tc = tc_plan_supported(P->spec, P->C, P->kmax) && s->backend != 1;
+  if (s->backend == 2 && !P->use_tc) {
+    delete P;
+    return fail("plan_create: backend=2 (tcgen05) requested but the plan is not eligible "
+                "(needs f32, tanh, hidden widths in {128,256}, order<=2)");
+  }
+#else
+  if (s->backend == 2) { delete P; return fail("plan_create: tcgen05 backend is not emulated"); }
+#endif
+
+  auto up = [&](const void* src, size_t bytes, void** dst) -> cudaError_t {
+    cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);
+    if (e != cudaSuccess) return e;
+    if (bytes) return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+    return cudaSuccess;
+  };
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = up(P->prog.data(), P->prog.size() * 4, (void**)&P->d_prog);
+  if (e == cudaSuccess) e = up(P->consts.data(), P->consts.size() * 8, (void**)&P->d_consts);
+  if (e == cudaSuccess) e = up(P->grad_res.data(), P->grad_res.size() * 4, (void**)&P->d_grad_res);
+  if (e == cudaSuccess) e = up(P->grad_in.data(), P->grad_in.size() * 4, (void**)&P->d_grad_in);
+  if (e == cudaSuccess) e = up(P->grad_reg.data(), P->grad_reg.size() * 4, (void**)&P->d_grad_reg);
+  if (e != cudaSuccess) {
+    ppsci_b200_plan_destroy(P);
+    return fail(std::string("plan_create: device upload of the residual program failed: ") + cudaGetErrorString(e));
+  }
+  *out = P;
+  return 0;
+}
+
+extern "C" void ppsci_b200_plan_destroy(ppsci_plan* P) {
+  if (!P) return;
+  cudaFree(P->d_prog);
+  cudaFree(P->d_consts);
+  cudaFree(P->d_grad_res);
+  cudaFree(P->d_grad_in);
+  cudaFree(P->d_grad_reg);
+  delete P;
+}
+
+extern "C" int64_t ppsci_b200_plan_param_count(const ppsci_plan* P) { return P ? P->n_params : -1; }
+extern "C" int32_t ppsci_b200_plan_channels(const ppsci_plan* P) { return P ? P->C : -1; }
+extern "C" int64_t ppsci_b200_plan_last_launches(const ppsci_plan* P) { return P ? P->launches : -1; }
+extern "C" int32_t ppsci_b200_plan_uses_tcgen05(const ppsci_plan* P) { return (P && P->use_tc) ? 1 : 0; }
+
+extern "C" size_t ppsci_b200_plan_workspace_bytes(const ppsci_plan* P, int64_t n_points) {
+  if (!P || n_points <= 0) return 0;
+  const int64_t nc = n_points < P->chunk ? n_points : P->chunk;
+  Carve cv;
+  carve(P, nc, &cv);
+  return cv.total;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+struct Dims {
+  static constexpr int TN = sizeof(T) == 8 ? 64 : 128;
+};
+
+template <typename T, int KMAX>
+static int set_attrs_once(ppsci_plan* P) {
+  constexpr int TN = Dims<T>::TN;
+  auto kf = k_gemm_fwd<T, TN, KMAX>;
+  auto kx = k_gemm_dx<T, TN, KMAX>;
+  auto kw = k_gemm_dw<T, TN, KMAX>;
+  const int smem_f = (KC * TMS + KC * TN) * (int)sizeof(T);
+  const int smem_x = std::max(smem_f, TM * TN * (int)sizeof(T));
+  const int smem_w = (RC * TMS + RC * TN) * (int)sizeof(T);
+  CK(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+  CK(cudaFuncSetAttribute(kx, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_x));
+  CK(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_w));
+  (void)P;
+  return 0;
+}
+
+template <typename T>
+static void fill_seed(const ppsci_plan* P, const void* const* x_cols, int64_t x_off, AOperand<T>* A) {
+  const ppsci_plan_spec& s = P->spec;
+  A->mode = A_SEED;
+  A->act = s.act;
+  A->Z = nullptr;
+  A->ld = 0;
+  A->plane = 0;
+  A->x_off = x_off;
+  SeedSpec& S = A->seed;
+  S.n_in = s.n_in;
+  S.n_feat = s.n_feat;
+  for (int f = 0; f < PPSCI_MAX_FEAT; ++f) {
+    S.feat_src[f] = f < s.n_feat ? s.feat_src[f] : 0;
+    S.feat_kind[f] = f < s.n_feat ? s.feat_kind[f] : 0;
+    S.feat_omega[f] = f < s.n_feat ? s.feat_omega[f] : 0.0;
+  }
+  for (int d = 0; d < PPSCI_MAX_DIR; ++d)
+    for (int i = 0; i < PPSCI_MAX_IN; ++i) S.dir_vec[d][i] = (d < s.n_dir && i < s.n_in) ? s.dir_vec[d][i] : 0.0;
+  for (int i = 0; i < PPSCI_MAX_IN; ++i) S.x_cols[i] = i < s.n_in ? x_cols[i] : nullptr;
+}
+
+template <typename T>
+static void fill_act(const ppsci_plan* P, const T* Z, int ld, int64_t nc, int mode, AOperand<T>* A) {
+  A->mode = mode;
+  A->act = P->spec.act;
+  A->Z = Z;
+  A->ld = ld;
+  A->plane = (long long)nc * ld;
+  A->x_off = 0;
+  memset(&A->seed, 0, sizeof(SeedSpec));
+}
+
+struct CallArgs {
+  const void* const* x_cols;
+  const void* const* aux_cols;
+  const void* const* label_cols;
+  const double* label_const;
+  const void* const* weight_cols;
+  int64_t n_points;
+  int64_t n_norm;
+  const void* params;
+  void* grads;
+  void* loss_out;
+  void* const* residual_out;
+  void* jets_out;
+  void* workspace;
+  size_t workspace_bytes;
+  void* stream;
+  bool want_loss;
+};
+
+template <typename T, int KMAX>
+static int run(ppsci_plan* P, const CallArgs& a) {
+  constexpr int TN = Dims<T>::TN;
+  const ppsci_plan_spec& s = P->spec;
+  const int L = s.n_layers;
+  const int C = P->C;
+  const int n_out = s.widths[L];
+  if (!P->attrs_set) {
+    if (set_attrs_once<T, KMAX>(P)) return 1;
+    P->attrs_set = true;
+  }
+  const int64_t nc_max = a.n_points < P->chunk ? a.n_points : P->chunk;
+  Carve cv;
+  carve(P, nc_max, &cv);
+  if (cv.total > a.workspace_bytes)
+    return fail("workspace too small: need " + std::to_string(cv.total) + " bytes, got " + std::to_string(a.workspace_bytes));
+  if ((reinterpret_cast<uintptr_t>(a.workspace) & 255) != 0) return fail("workspace must be 256-byte aligned");
+  unsigned char* ws = reinterpret_cast<unsigned char*>(a.workspace);
+  cudaStream_t st = (cudaStream_t)a.stream;
+  const T* params = reinterpret_cast<const T*>(a.params);
+  T* grads = reinterpret_cast<T*>(a.grads);
+  double* loss_acc = reinterpret_cast<double*>(ws + cv.loss_acc);
+  P->launches = 0;
+
+  auto kf = k_gemm_fwd<T, TN, KMAX>;
+  auto kx = k_gemm_dx<T, TN, KMAX>;
+  auto kw = k_gemm_dw<T, TN, KMAX>;
+  const int smem_f = (KC * TMS + KC * TN) * (int)sizeof(T);
+  const int smem_x = std::max(smem_f, TM * TN * (int)sizeof(T));
+  const int smem_w = (RC * TMS + RC * TN) * (int)sizeof(T);
+  const int TP = TM / C;
+  const int PT = RC / C;
+
+  if (a.want_loss) CK(cudaMemsetAsync(loss_acc, 0, PPSCI_MAX_RES * sizeof(double), st));
+  const bool do_bwd = a.want_loss && grads != nullptr;
+  if (do_bwd) {
+    for (int l = 2; l <= L; ++l) {
+      const int K = s.widths[l - 1], N = s.widths[l];
+      const long long tot = (long long)K * N;
+      auto kt = k_transpose<T>;
+      PPSCI_LAUNCH(kt, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, params + P->w_off[l],
+                   reinterpret_cast<T*>(ws + cv.wt[l]), K, N);
+      P->launches++;
+    }
+  }
+
+  for (int64_t c0 = 0; c0 < a.n_points; c0 += nc_max) {
+    const int64_t nc = (a.n_points - c0) < nc_max ? (a.n_points - c0) : nc_max;
+    const unsigned ptiles = (unsigned)((nc + TP - 1) / TP);
+    // ---------------- forward ----------------
+#ifndef PPSCI_EMUL
+    bool fwd_done = false;
+    if (P->use_tc) {
+      int rc = tc_forward<KMAX>(P->spec, P->J, P->w_off, P->b_off, P->ld, reinterpret_cast<const float*>(params),
+                                a.x_cols, c0, nc, nc_max, ws, cv.z, cv.y, cv.tc, st, &P->launches, &g_err);
+      if (rc != 0) return 1;
+      fwd_done = true;
+    }
+    if (!fwd_done)
+#endif
+    for (int l = 1; l <= L; ++l) {
+      GemmArgs<T> g;
+      memset(&g, 0, sizeof(g));
+      if (l == 1) fill_seed<T>(P, a.x_cols, c0, &g.A);
+      else fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[l - 1]), P->ld[l - 1], nc_max, A_ACT, &g.A);
+      g.J = P->J;
+      g.B = params + P->w_off[l];
+      g.Kdim = s.widths[l - 1];
+      g.Nout = s.widths[l];
+      g.ldb = s.widths[l];
+      g.bias = params + P->b_off[l];
+      g.Out = reinterpret_cast<T*>(ws + (l < L ? cv.z[l] : cv.y));
+      g.ldo = P->ld[l];
+      g.oplane = (long long)nc_max * P->ld[l];
+      g.Np = nc;
+      g.TP = TP;
+      dim3 grid(ptiles, (unsigned)((g.Nout + TN - 1) / TN));
+      PPSCI_LAUNCH(kf, grid, dim3(NTHREADS), smem_f, st, g);
+      P->launches++;
+    }
+    // ---------------- residual program + loss + output adjoints ----------------
+    if (a.jets_out) {
+      const long long tot = (long long)C * nc * n_out;
+      auto kc = k_copy_jets<T>;
+      PPSCI_LAUNCH(kc, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st,
+                   reinterpret_cast<const T*>(ws + cv.y), P->ld[L], (long long)nc_max * P->ld[L],
+                   reinterpret_cast<T*>(a.jets_out), (long long)a.n_points, (long long)c0, (long long)nc, C, n_out);
+      P->launches++;
+    }
+    if (s.n_res > 0 && (a.want_loss || a.residual_out)) {
+      HeadArgs<T> h;
+      memset(&h, 0, sizeof(h));
+      h.P.prog = P->d_prog;
+      h.P.consts = P->d_consts;
+      h.P.n_ops = s.n_ops;
+      h.P.n_reg = s.n_reg;
+      h.P.n_res = s.n_res;
+      for (int k = 0; k < PPSCI_MAX_RES; ++k) h.P.res_reg[k] = k < s.n_res ? s.res_reg[k] : 0;
+      h.P.n_grad = s.n_grad;
+      h.P.grad_res = P->d_grad_res;
+      h.P.grad_in = P->d_grad_in;
+      h.P.grad_reg = P->d_grad_reg;
+      h.C = C;
+      h.n_out = n_out;
+      h.n_in = s.n_in;
+      h.n_aux = s.n_aux;
+      h.Y = reinterpret_cast<const T*>(ws + cv.y);
+      h.ldy = P->ld[L];
+      h.yplane = (long long)nc_max * P->ld[L];
+      h.Ybar = do_bwd ? reinterpret_cast<T*>(ws + cv.ybar) : nullptr;
+      for (int i = 0; i < s.n_in; ++i) h.x_cols[i] = a.x_cols[i];
+      for (int i = 0; i < s.n_aux; ++i) h.aux_cols[i] = a.aux_cols ? a.aux_cols[i] : nullptr;
+      h.x_off = c0;
+      h.Np = nc;
+      for (int k = 0; k < s.n_res; ++k) {
+        h.label_cols[k] = a.label_cols ? a.label_cols[k] : nullptr;
+        h.label_const[k] = a.label_const ? a.label_const[k] : 0.0;
+        h.weight_cols[k] = a.weight_cols ? a.weight_cols[k] : nullptr;
+        h.coef[k] = s.loss_weight[k] * (s.reduction[k] == PPSCI_REDUCE_MEAN ? 1.0 / (double)a.n_norm : 1.0);
+        h.residual_out[k] = a.residual_out ? a.residual_out[k] : nullptr;
+      }
+      h.loss_acc = a.want_loss ? loss_acc : nullptr;
+      auto kh = k_head<T>;
+      PPSCI_LAUNCH(kh, dim3((unsigned)((nc + HEAD_THREADS - 1) / HEAD_THREADS)), dim3(HEAD_THREADS), 0, st, h);
+      P->launches++;
+    }
+    if (!do_bwd) continue;
+    // ---------------- adjoint ----------------
+    const T* zbar_cur = reinterpret_cast<const T*>(ws + cv.ybar);
+    int zbar_ld = P->ld[L];
+    int flip = 0;
+    for (int l = L; l >= 1; --l) {
+      {  // dW_l, db_l
+        DwArgs<T> g;
+        memset(&g, 0, sizeof(g));
+        if (l == 1) fill_seed<T>(P, a.x_cols, c0, &g.A);
+        else fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[l - 1]), P->ld[l - 1], nc_max, A_ACT, &g.A);
+        g.J = P->J;
+        g.Zbar = zbar_cur;
+        g.ldzb = zbar_ld;
+        g.zbplane = (long long)nc_max * zbar_ld;
+        g.Kdim = s.widths[l - 1];
+        g.Nout = s.widths[l];
+        g.dW = grads + P->w_off[l];
+        g.db = grads + P->b_off[l];
+        g.Np = nc;
+        g.PT = PT;
+        const unsigned kt = (unsigned)((g.Kdim + TM - 1) / TM), nt = (unsigned)((g.Nout + TN - 1) / TN);
+        const long long total_chunks = (nc + PT - 1) / PT;
+        long long want = (4LL * P->num_sms + kt * nt - 1) / (kt * nt);
+        if (want < 1) want = 1;
+        if (want > total_chunks) want = total_chunks;
+        const long long cps = (total_chunks + want - 1) / want;
+        const unsigned splits = (unsigned)((total_chunks + cps - 1) / cps);
+        g.chunks_per_split = (int)cps;
+        PPSCI_LAUNCH(kw, dim3(kt, nt, splits), dim3(NTHREADS), smem_w, st, g);
+        P->launches++;
+      }
+      if (l == 1) break;
+      {  // Zbar_{l-1}
+        GemmArgs<T> g;
+        memset(&g, 0, sizeof(g));
+        fill_act<T>(P, zbar_cur, zbar_ld, nc_max, A_PLAIN, &g.A);
+        g.J = P->J;
+        g.B = reinterpret_cast<const T*>(ws + cv.wt[l]);  // [N_l][K_l]
+        g.Kdim = s.widths[l];
+        g.Nout = s.widths[l - 1];
+        g.ldb = s.widths[l - 1];
+        g.bias = nullptr;
+        T* outp = reinterpret_cast<T*>(ws + (flip ? cv.zbar1 : cv.zbar0));
+        g.Out = outp;
+        g.ldo = P->ld[l - 1];
+        g.oplane = (long long)nc_max * P->ld[l - 1];
+        g.Np = nc;
+        g.TP = TP;
+        g.Zprev = reinterpret_cast<const T*>(ws + cv.z[l - 1]);
+        g.ldz = P->ld[l - 1];
+        g.zplane = (long long)nc_max * P->ld[l - 1];
+        g.act = s.act;
+        dim3 grid(ptiles, (unsigned)((g.Nout + TN - 1) / TN));
+        PPSCI_LAUNCH(kx, grid, dim3(NTHREADS), smem_x, st, g);
+        P->launches++;
+        zbar_cur = outp;
+        zbar_ld = P->ld[l - 1];
+        flip ^= 1;
+      }
+    }
+  }
+  if (a.want_loss && a.loss_out && s.n_res > 0) {
+    auto kfin = k_finalize_loss<T>;
+    PPSCI_LAUNCH(kfin, dim3(1), dim3(32), 0, st, loss_acc, reinterpret_cast<T*>(a.loss_out), s.n_res);
+    P->launches++;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+static int dispatch_k(ppsci_plan* P, const CallArgs& a) {
+  if (P->kmax <= 1) return run<T, 1>(P, a);
+  if (P->kmax == 2) return run<T, 2>(P, a);
+  return run<T, 4>(P, a);
+}
+
+static int dispatch(ppsci_plan* P, const CallArgs& a) {
+  if (!P) return fail("null plan");
+  if (a.n_points <= 0) return fail("n_points must be positive");
+  if (!a.x_cols || !a.params || !a.workspace) return fail("null x_cols / params / workspace");
+  for (int i = 0; i < P->spec.n_in; ++i)
+    if (!a.x_cols[i]) return fail("null input column " + std::to_string(i));
+  if (P->spec.n_aux > 0) {
+    if (!a.aux_cols) return fail("plan needs aux columns but aux_cols is null");
+    for (int i = 0; i < P->spec.n_aux; ++i)
+      if (!a.aux_cols[i]) return fail("null aux column " + std::to_string(i));
+  }
+  if (P->spec.dtype == PPSCI_F64) return dispatch_k<double>(P, a);
+  return dispatch_k<float>(P, a);
+}
+
+extern "C" int ppsci_b200_residual_loss_fwd_bwd(ppsci_plan* plan, const void* const* x_cols,
+                                                const void* const* aux_cols, const void* const* label_cols,
+                                                const double* label_const, const void* const* weight_cols,
+                                                int64_t n_points, int64_t n_norm, const void* params, void* grads,
+                                                void* loss_out, void* const* residual_out, void* workspace,
+                                                size_t workspace_bytes, void* stream) {
+  if (plan && plan->spec.n_res < 1) return fail("residual_loss_fwd_bwd: plan has no residuals");
+  if (!loss_out) return fail("residual_loss_fwd_bwd: loss_out is null");
+  if (n_norm <= 0) return fail("residual_loss_fwd_bwd: n_norm must be positive");
+  CallArgs a{x_cols, aux_cols, label_cols, label_const, weight_cols, n_points, n_norm, params, grads, loss_out,
+             residual_out, nullptr, workspace, workspace_bytes, stream, true};
+  return dispatch(plan, a);
+}
+
+extern "C" int ppsci_b200_residual_fwd(ppsci_plan* plan, const void* const* x_cols, const void* const* aux_cols,
+                                       int64_t n_points, const void* params, void* jets_out,
+                                       void* const* residual_out, void* workspace, size_t workspace_bytes,
+                                       void* stream) {
+  CallArgs a{x_cols, aux_cols, nullptr, nullptr, nullptr, n_points, 1, params, nullptr, nullptr,
+             residual_out, jets_out, workspace, workspace_bytes, stream, false};
+  return dispatch(plan, a);
+}
+
+extern "C" int ppsci_b200_adam_step(int32_t dtype, void* params, const void* grads, void* exp_avg, void* exp_avg_sq,
+                                    int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay,
+                                    int64_t step, double grad_scale, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) return fail("adam_step: bad arguments");
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (dtype == PPSCI_F64) {
+    auto k = k_adam<double>;
+    PPSCI_LAUNCH(k, dim3(blocks), dim3(256), 0, stream, (double*)params, (const double*)grads, (double*)exp_avg,
+                 (double*)exp_avg_sq, (long long)n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale);
+  } else if (dtype == PPSCI_F32) {
+    auto k = k_adam<float>;
+    PPSCI_LAUNCH(k, dim3(blocks), dim3(256), 0, stream, (float*)params, (const float*)grads, (float*)exp_avg,
+                 (float*)exp_avg_sq, (long long)n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale);
+  } else {
+    return fail("adam_step: bad dtype");
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+#ifdef PPSCI_EMUL
+static size_t tc_scratch_bytes(const ppsci_plan*, int64_t) { return 0; }
+#else
+static size_t tc_scratch_bytes(const ppsci_plan* P, int64_t nc) {
+  return P->use_tc ? tc_scratch_bytes_impl(P->spec, P->C, nc) : 0;
+}
+#endif

@@ -1,0 +1,572 @@
+// kernels_simt.cuh — generic (any width / activation / order<=4 / f32|f64) CUDA-core kernels
+// of the jet engine.  They are the correctness anchor and the cross-check for the tcgen05
+// kernels (kernels_tc.cuh) that take over the wide fp32 tanh layers.
+//
+// Data layout (all in the caller's workspace; see DESIGN.md "HBM layout"):
+//   jets of a layer are CHANNEL-MAJOR planes   Z[c][p][h] ,  c < C, p < Np, h < ld
+//   channel 0 = value, channel (d,k) = k-th normalised Taylor coefficient along direction d.
+// Row r of a tile = c*TP + pl  (TP points per tile, pl = point within tile).
+//
+// Reference functions replaced here:
+//   k_gemm_fwd   : nn.Linear + activation per layer, evaluated for all jet channels at once
+//                  (ppsci/arch/mlp.py:281-296) — no reverse sweeps (ppsci/autodiff/ad.py).
+//   k_gemm_dx    : the "dX" half of total_loss.backward() (ppsci/solver/train.py:158)
+//   k_gemm_dw    : the "dW/db" half of the same.
+//   k_head       : ComposedNode.forward residual assembly (ppsci/utils/symbolic.py:498-504),
+//                  MSELoss.forward (ppsci/loss/mse.py:82-106), mtl.Sum (loss/mtl/sum.py:45-60)
+#pragma once
+
+#include "jet_math.h"
+#include "ppsci_b200.h"
+
+#ifndef PPSCI_EMUL
+#include <cuda_runtime.h>
+#define PPSCI_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define PPSCI_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#endif
+
+namespace ppsci {
+
+constexpr int TM = 128;      // tile rows (points x channels)
+constexpr int TMS = TM + 4;  // padded smem row stride of the k-major A tile
+constexpr int KC = 16;       // reduction chunk of the fwd / dx GEMMs
+constexpr int RC = 32;       // reduction (row) chunk of the dW GEMM
+constexpr int NTHREADS = 256;
+
+struct JetLayout {
+  int C;
+  int n_dir;
+  int dir_order[PPSCI_MAX_DIR];
+  int dir_base[PPSCI_MAX_DIR];  // channel index of order-1 coefficient of direction d
+};
+
+struct SeedSpec {
+  int n_in;
+  int n_feat;
+  int feat_src[PPSCI_MAX_FEAT];
+  int feat_kind[PPSCI_MAX_FEAT];
+  double feat_omega[PPSCI_MAX_FEAT];
+  double dir_vec[PPSCI_MAX_DIR][PPSCI_MAX_IN];
+  const void* x_cols[PPSCI_MAX_IN];
+};
+
+enum { A_SEED = 0, A_ACT = 1, A_PLAIN = 2 };
+
+template <typename T>
+struct AOperand {
+  int mode;
+  int act;
+  const T* Z;  // [C][Np][ld]  (A_ACT: pre-activations of the previous layer, A_PLAIN: as is)
+  int ld;
+  long long plane;  // Np * ld
+  SeedSpec seed;  // by value (kernel parameter space), used by A_SEED
+  long long x_off;       // first point of this chunk inside the x columns
+};
+
+// Produce all C channel values of A[(c, p), k] and hand them to st(c, value).
+template <typename T, int KMAX, typename St>
+__device__ __forceinline__ void produce_a(const AOperand<T>& A, const JetLayout& J, long long p,
+                                          int k, bool valid, St st) {
+  if (!valid) {
+    for (int c = 0; c < J.C; ++c) st(c, T(0));
+    return;
+  }
+  if (A.mode == A_PLAIN) {
+    const T* z = A.Z + p * A.ld + k;
+    for (int c = 0; c < J.C; ++c) st(c, z[c * A.plane]);
+    return;
+  }
+  if (A.mode == A_ACT) {
+    const T* z = A.Z + p * A.ld + k;
+    T s[6];
+    T y0;
+    act_coef<T, KMAX>(A.act, z[0], y0, s);
+    st(0, y0);
+    for (int d = 0; d < J.n_dir; ++d) {
+      const int K = J.dir_order[d];
+      const int base = J.dir_base[d];
+      T zz[4], yy[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) zz[q] = (q < KMAX && q < K) ? z[(long long)(base + q) * A.plane] : T(0);
+      jet_fwd_dir<T, KMAX>(s, zz, yy);
+#pragma unroll
+      for (int q = 0; q < KMAX; ++q)
+        if (q < K) st(base + q, yy[q]);
+    }
+    return;
+  }
+  // A_SEED: feature k of the (period-embedded) network input, Taylor-expanded along each direction
+  const SeedSpec& S = A.seed;
+  const int src = S.feat_src[k];
+  const int kind = S.feat_kind[k];
+  const T omega = T(S.feat_omega[k]);
+  const T x = reinterpret_cast<const T*>(S.x_cols[src])[A.x_off + p];
+  T co[5];
+  seed_coef<T, KMAX>(kind, omega, x, T(0), co);
+  st(0, co[0]);
+  for (int d = 0; d < J.n_dir; ++d) {
+    const int K = J.dir_order[d];
+    const int base = J.dir_base[d];
+    seed_coef<T, KMAX>(kind, omega, x, T(S.dir_vec[d][src]), co);
+#pragma unroll
+    for (int q = 0; q < KMAX; ++q)
+      if (q < K) st(base + q, co[q + 1]);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void ld4(const T* p, T* out);
+template <>
+__device__ __forceinline__ void ld4<float>(const float* p, float* out) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+}
+template <>
+__device__ __forceinline__ void ld4<double>(const double* p, double* out) {
+  const double2 v0 = *reinterpret_cast<const double2*>(p);
+  const double2 v1 = *reinterpret_cast<const double2*>(p + 2);
+  out[0] = v0.x; out[1] = v0.y; out[2] = v1.x; out[3] = v1.y;
+}
+
+template <typename T>
+struct GemmArgs {
+  AOperand<T> A;
+  JetLayout J;
+  const T* B;  // row-major [Kdim][ldb]
+  int Kdim;
+  int Nout;
+  int ldb;
+  const T* bias;  // fwd: added to channel-0 rows (may be null)
+  T* Out;         // fwd: Z_l [C][Np][ldo];  dx: Zbar_{l-1} [C][Np][ldo]
+  int ldo;
+  long long oplane;
+  long long Np;  // valid points in this chunk
+  int TP;        // points per tile = TM / C
+  // dx epilogue: pre-activations of the layer whose activation is being back-propagated
+  const T* Zprev;
+  int ldz;
+  long long zplane;
+  int act;
+};
+
+template <int TN>
+struct MicroShape {
+  static constexpr int NJ = TN / 16;  // columns per thread
+  static constexpr int NG = TN / 64;  // groups of 4 columns
+};
+
+// acc[8][NJ] += A_tile[128 x K] * B[K x TN] ; A produced on the fly (k-major smem tile).
+template <typename T, int TN, int KMAX>
+__device__ __forceinline__ void gemm_mainloop(const GemmArgs<T>& g, T* As, T* Bs,
+                                              T (&acc)[8][TN / 16], long long p0, int n0) {
+  constexpr int NJ = TN / 16;
+  constexpr int NG = TN / 64;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int TP = g.TP;
+  const int rows_used = g.J.C * TP;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[i][j] = T(0);
+  for (int idx = tid; idx < KC * TMS; idx += NTHREADS) {
+    const int r = idx % TMS;
+    if (r >= rows_used) As[idx] = T(0);
+  }
+  for (int k0 = 0; k0 < g.Kdim; k0 += KC) {
+    for (int item = tid; item < TP * KC; item += NTHREADS) {
+      const int kk = item % KC, pl = item / KC;
+      const long long p = p0 + pl;
+      const int k = k0 + kk;
+      T* dst = As + kk * TMS + pl;
+      produce_a<T, KMAX>(g.A, g.J, p, k, (p < g.Np) && (k < g.Kdim),
+                         [&](int c, T v) { dst[c * TP] = v; });
+    }
+    for (int idx = tid; idx < KC * TN; idx += NTHREADS) {
+      const int kk = idx / TN, nn = idx % TN;
+      const int k = k0 + kk, n = n0 + nn;
+      Bs[idx] = (k < g.Kdim && n < g.Nout) ? g.B[(long long)k * g.ldb + n] : T(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      T a[8], b[NJ];
+      ld4<T>(As + kk * TMS + ty * 4, a);
+      ld4<T>(As + kk * TMS + 64 + ty * 4, a + 4);
+#pragma unroll
+      for (int gq = 0; gq < NG; ++gq) ld4<T>(Bs + kk * TN + gq * 64 + tx * 4, b + gq * 4);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ int micro_row(int ty, int i) { return (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4); }
+__device__ __forceinline__ int micro_col(int tx, int j) { return (j >> 2) * 64 + tx * 4 + (j & 3); }
+
+// ---- forward layer:  Z_l = A(Z_{l-1}) W_l + b_l ------------------------------------------------
+template <typename T, int TN, int KMAX>
+__global__ void __launch_bounds__(NTHREADS) k_gemm_fwd(GemmArgs<T> g) {
+  PPSCI_DYN_SMEM(smem_raw);
+  T* As = reinterpret_cast<T*>(smem_raw);
+  T* Bs = As + KC * TMS;
+  constexpr int NJ = TN / 16;
+  const long long p0 = (long long)blockIdx.x * g.TP;
+  const int n0 = blockIdx.y * TN;
+  T acc[8][NJ];
+  gemm_mainloop<T, TN, KMAX>(g, As, Bs, acc, p0, n0);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int rows_used = g.J.C * g.TP;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = micro_row(ty, i);
+    if (r >= rows_used) continue;
+    const int c = r / g.TP, pl = r % g.TP;
+    const long long p = p0 + pl;
+    if (p >= g.Np) continue;
+    T* out = g.Out + (long long)c * g.oplane + p * g.ldo;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int n = n0 + micro_col(tx, j);
+      if (n < g.Nout) out[n] = acc[i][j] + ((c == 0 && g.bias) ? g.bias[n] : T(0));
+    }
+  }
+}
+
+// ---- backward dx:  Abar = Zbar_l W_l^T ;  Zbar_{l-1} = act_adjoint(Abar, Z_{l-1}) -----------------
+template <typename T, int TN, int KMAX>
+__global__ void __launch_bounds__(NTHREADS) k_gemm_dx(GemmArgs<T> g) {
+  PPSCI_DYN_SMEM(smem_raw);
+  T* As = reinterpret_cast<T*>(smem_raw);
+  T* Bs = As + KC * TMS;
+  T* Cs = reinterpret_cast<T*>(smem_raw);  // aliases As/Bs after the main loop
+  constexpr int NJ = TN / 16;
+  const long long p0 = (long long)blockIdx.x * g.TP;
+  const int n0 = blockIdx.y * TN;
+  T acc[8][NJ];
+  gemm_mainloop<T, TN, KMAX>(g, As, Bs, acc, p0, n0);  // ends with __syncthreads()
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = micro_row(ty, i);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) Cs[r * TN + micro_col(tx, j)] = acc[i][j];
+  }
+  __syncthreads();
+  const int TP = g.TP;
+  for (int item = threadIdx.x; item < TP * TN; item += NTHREADS) {
+    const int nn = item % TN, pl = item / TN;
+    const long long p = p0 + pl;
+    const int n = n0 + nn;
+    if (p >= g.Np || n >= g.Nout) continue;
+    const T* z = g.Zprev + p * g.ldz + n;
+    T* zb_out = g.Out + p * g.ldo + n;
+    T s[6];
+    T y0;
+    act_coef<T, KMAX + 1>(g.act, z[0], y0, s);
+    const T y0b = Cs[pl * TN + nn];
+    T sb[5] = {T(0), T(0), T(0), T(0), T(0)};
+    for (int d = 0; d < g.J.n_dir; ++d) {
+      const int K = g.J.dir_order[d];
+      const int base = g.J.dir_base[d];
+      T zz[4], yb[4], zb[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const bool on = (q < KMAX && q < K);
+        zz[q] = on ? z[(long long)(base + q) * g.zplane] : T(0);
+        yb[q] = on ? Cs[((base + q) * TP + pl) * TN + nn] : T(0);
+        zb[q] = T(0);
+      }
+      jet_adj_dir<T, KMAX>(s, zz, yb, zb, sb);
+#pragma unroll
+      for (int q = 0; q < KMAX; ++q)
+        if (q < K) zb_out[(long long)(base + q) * g.oplane] = zb[q];
+    }
+    zb_out[0] = jet_adj_z0<T, KMAX>(s, y0b, sb);
+  }
+}
+
+// ---- backward dW:  dW_l += A(Z_{l-1})^T Zbar_l ,  db_l += colsum(Zbar_l[channel 0]) ---------------
+template <typename T>
+struct DwArgs {
+  AOperand<T> A;
+  JetLayout J;
+  const T* Zbar;  // [C][Np][ldzb]
+  int ldzb;
+  long long zbplane;
+  int Kdim;  // rows of dW (= fan-in of the layer)
+  int Nout;  // cols of dW
+  T* dW;     // [Kdim][Nout] (accumulated with atomics)
+  T* db;     // [Nout]
+  long long Np;
+  int PT;  // points per reduction chunk = RC / C
+  int chunks_per_split;
+};
+
+template <typename T, int TN, int KMAX>
+__global__ void __launch_bounds__(NTHREADS) k_gemm_dw(DwArgs<T> g) {
+  PPSCI_DYN_SMEM(smem_raw);
+  T* As = reinterpret_cast<T*>(smem_raw);  // [RC][TMS]   (reduction-row major, k contiguous)
+  T* Bs = As + RC * TMS;                   // [RC][TN]
+  constexpr int NJ = TN / 16;
+  constexpr int NG = TN / 64;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int k0 = blockIdx.x * TM;
+  const int n0 = blockIdx.y * TN;
+  const int PT = g.PT;
+  const int rows_used = g.J.C * PT;
+  const long long total_chunks = (g.Np + PT - 1) / PT;
+  const long long ch_begin = (long long)blockIdx.z * g.chunks_per_split;
+  long long ch_end = ch_begin + g.chunks_per_split;
+  if (ch_end > total_chunks) ch_end = total_chunks;
+  T acc[8][NJ];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[i][j] = T(0);
+  T dbacc = T(0);
+  for (int idx = tid; idx < RC * TMS; idx += NTHREADS) As[idx] = T(0);
+  for (int idx = tid; idx < RC * TN; idx += NTHREADS) Bs[idx] = T(0);
+  __syncthreads();
+  for (long long ch = ch_begin; ch < ch_end; ++ch) {
+    const long long p0 = ch * PT;
+    for (int item = tid; item < PT * TM; item += NTHREADS) {
+      const int kq = item % TM, pl = item / TM;
+      const long long p = p0 + pl;
+      const int k = k0 + kq;
+      T* dst = As + pl * TMS + kq;
+      produce_a<T, KMAX>(g.A, g.J, p, k, (p < g.Np) && (k < g.Kdim),
+                         [&](int c, T v) { dst[c * PT * TMS] = v; });
+    }
+    for (int item = tid; item < rows_used * TN; item += NTHREADS) {
+      const int nn = item % TN, r = item / TN;
+      const int c = r / PT, pl = r % PT;
+      const long long p = p0 + pl;
+      const int n = n0 + nn;
+      Bs[r * TN + nn] = (p < g.Np && n < g.Nout) ? g.Zbar[(long long)c * g.zbplane + p * g.ldzb + n] : T(0);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int rr = 0; rr < RC; ++rr) {
+      T a[8], b[NJ];
+      ld4<T>(As + rr * TMS + ty * 4, a);
+      ld4<T>(As + rr * TMS + 64 + ty * 4, a + 4);
+#pragma unroll
+      for (int gq = 0; gq < NG; ++gq) ld4<T>(Bs + rr * TN + gq * 64 + tx * 4, b + gq * 4);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j] += a[i] * b[j];
+    }
+    if (blockIdx.x == 0 && tid < TN) {
+      for (int pl = 0; pl < PT; ++pl) dbacc += Bs[pl * TN + tid];  // channel-0 rows are rows [0, PT)
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = k0 + micro_row(ty, i);
+    if (k >= g.Kdim) continue;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int n = n0 + micro_col(tx, j);
+      if (n < g.Nout) atomicAdd(g.dW + (long long)k * g.Nout + n, acc[i][j]);
+    }
+  }
+  if (blockIdx.x == 0 && tid < TN && (n0 + tid) < g.Nout && g.db) atomicAdd(g.db + n0 + tid, dbacc);
+}
+
+// ---- small helpers ---------------------------------------------------------------------------
+template <typename T>
+__global__ void k_transpose(const T* W, T* WT, int K, int N) {  // WT[n][k] = W[k][n]
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)K * N) return;
+  const int k = (int)(i / N), n = (int)(i % N);
+  WT[(long long)n * K + k] = W[i];
+}
+
+// ---- residual program + MSE + output-jet adjoints ---------------------------------------------
+struct HeadProgram {  // all pointers are device pointers owned by the plan
+  const int* prog;    // n_ops * 4
+  const double* consts;
+  int n_ops;
+  int n_reg;
+  int n_res;
+  int res_reg[PPSCI_MAX_RES];
+  int n_grad;
+  const int* grad_res;
+  const int* grad_in;
+  const int* grad_reg;
+};
+
+template <typename T>
+struct HeadArgs {
+  HeadProgram P;
+  int C, n_out, n_in, n_aux;
+  const T* Y;  // [C][Np][ldy]
+  int ldy;
+  long long yplane;
+  T* Ybar;  // same layout, may be null
+  const void* x_cols[PPSCI_MAX_IN];
+  const void* aux_cols[PPSCI_MAX_IN];
+  long long x_off;  // chunk offset into the caller's columns
+  long long Np;
+  const void* label_cols[PPSCI_MAX_RES];
+  double label_const[PPSCI_MAX_RES];
+  const void* weight_cols[PPSCI_MAX_RES];
+  double coef[PPSCI_MAX_RES];  // loss_weight * (1/n_norm for mean)
+  void* residual_out[PPSCI_MAX_RES];
+  double* loss_acc;  // [n_res] fp64 accumulators (may be null for fwd-only)
+};
+
+template <typename T>
+__device__ __forceinline__ T vm_powi(T a, int e) {
+  if (e == 0) return T(1);
+  bool neg = e < 0;
+  unsigned u = neg ? (unsigned)(-e) : (unsigned)e;
+  T r = T(1), b = a;
+  while (u) {
+    if (u & 1u) r *= b;
+    b *= b;
+    u >>= 1;
+  }
+  return neg ? T(1) / r : r;
+}
+
+template <typename T>
+__device__ __forceinline__ void vm_run(const HeadProgram& P, T* r) {
+  for (int i = 0; i < P.n_ops; ++i) {
+    const int op = P.prog[4 * i], dst = P.prog[4 * i + 1], a = P.prog[4 * i + 2], b = P.prog[4 * i + 3];
+    T v;
+    switch (op) {
+      case PPSCI_OP_CONST: v = T(P.consts[a]); break;
+      case PPSCI_OP_MOV: v = r[a]; break;
+      case PPSCI_OP_ADD: v = r[a] + r[b]; break;
+      case PPSCI_OP_SUB: v = r[a] - r[b]; break;
+      case PPSCI_OP_MUL: v = r[a] * r[b]; break;
+      case PPSCI_OP_DIV: v = r[a] / r[b]; break;
+      case PPSCI_OP_NEG: v = -r[a]; break;
+      case PPSCI_OP_POWI: v = vm_powi<T>(r[a], b); break;
+      case PPSCI_OP_POW: v = T(pow((double)r[a], (double)r[b])); break;
+      case PPSCI_OP_SIN: v = T(sin((double)r[a])); break;
+      case PPSCI_OP_COS: v = T(cos((double)r[a])); break;
+      case PPSCI_OP_TANH: v = T(tanh((double)r[a])); break;
+      case PPSCI_OP_EXP: v = T(exp((double)r[a])); break;
+      case PPSCI_OP_LOG: v = T(log((double)r[a])); break;
+      case PPSCI_OP_SQRT: v = T(sqrt((double)r[a])); break;
+      case PPSCI_OP_ABS: v = r[a] < T(0) ? -r[a] : r[a]; break;
+      case PPSCI_OP_MAX: v = r[a] > r[b] ? r[a] : r[b]; break;
+      case PPSCI_OP_MIN: v = r[a] < r[b] ? r[a] : r[b]; break;
+      case PPSCI_OP_SIGN: v = r[a] > T(0) ? T(1) : (r[a] < T(0) ? T(-1) : T(0)); break;
+      case PPSCI_OP_FMA: v = r[a] * r[b] + r[dst]; break;
+      case PPSCI_OP_SINH: v = T(sinh((double)r[a])); break;
+      case PPSCI_OP_COSH: v = T(cosh((double)r[a])); break;
+      case PPSCI_OP_HEAVISIDE: v = r[a] > T(0) ? T(1) : (r[a] < T(0) ? T(0) : T(0.5)); break;
+      default: v = T(0); break;
+    }
+    r[dst] = v;
+  }
+}
+
+constexpr int HEAD_THREADS = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(HEAD_THREADS) k_head(HeadArgs<T> h) {
+  __shared__ double red[HEAD_THREADS];
+  const long long p = (long long)blockIdx.x * HEAD_THREADS + threadIdx.x;
+  const bool valid = p < h.Np;
+  T r[PPSCI_MAX_REG];
+  T rb[PPSCI_MAX_RES];
+  double part[PPSCI_MAX_RES];
+  const int nY = h.C * h.n_out;
+  if (valid) {
+    for (int c = 0; c < h.C; ++c)
+      for (int j = 0; j < h.n_out; ++j) r[c * h.n_out + j] = h.Y[(long long)c * h.yplane + p * h.ldy + j];
+    for (int i = 0; i < h.n_in; ++i) r[nY + i] = reinterpret_cast<const T*>(h.x_cols[i])[h.x_off + p];
+    for (int a = 0; a < h.n_aux; ++a)
+      r[nY + h.n_in + a] = reinterpret_cast<const T*>(h.aux_cols[a])[h.x_off + p];
+    vm_run<T>(h.P, r);
+  }
+  for (int k = 0; k < h.P.n_res; ++k) {
+    T res = T(0), e = T(0), w = T(1);
+    if (valid) {
+      res = r[h.P.res_reg[k]];
+      if (h.residual_out[k]) reinterpret_cast<T*>(h.residual_out[k])[h.x_off + p] = res;
+      const T label = h.label_cols[k] ? reinterpret_cast<const T*>(h.label_cols[k])[h.x_off + p]
+                                      : T(h.label_const[k]);
+      w = h.weight_cols[k] ? reinterpret_cast<const T*>(h.weight_cols[k])[h.x_off + p] : T(1);
+      e = res - label;
+    }
+    const T coef = T(h.coef[k]);
+    rb[k] = valid ? T(2) * e * w * coef : T(0);
+    part[k] = valid ? (double)(w * e * e) * h.coef[k] : 0.0;
+  }
+  if (h.loss_acc) {
+    for (int k = 0; k < h.P.n_res; ++k) {
+      red[threadIdx.x] = part[k];
+      __syncthreads();
+      for (int s = HEAD_THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) atomicAdd(h.loss_acc + k, red[0]);
+      __syncthreads();
+    }
+  }
+  if (h.Ybar && valid) {
+    // grad list is sorted by grad_in; every output-jet register gets a value (zero if absent)
+    int gi = 0;
+    for (int idx = 0; idx < nY; ++idx) {
+      T acc = T(0);
+      while (gi < h.P.n_grad && h.P.grad_in[gi] == idx) {
+        acc += rb[h.P.grad_res[gi]] * r[h.P.grad_reg[gi]];
+        ++gi;
+      }
+      const int c = idx / h.n_out, j = idx % h.n_out;
+      h.Ybar[(long long)c * h.yplane + p * h.ldy + j] = acc;
+    }
+  }
+}
+
+template <typename T>
+__global__ void k_finalize_loss(const double* acc, T* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = T(acc[i]);
+}
+
+// jets_out[c][x_off + p][j] (plane = n_total*n_out)  <-  Y[c][p][j]
+template <typename T>
+__global__ void k_copy_jets(const T* Y, int ldy, long long yplane, T* out, long long n_total,
+                            long long x_off, long long Np, int C, int n_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long tot = (long long)C * Np * n_out;
+  if (i >= tot) return;
+  const int j = (int)(i % n_out);
+  const long long p = (i / n_out) % Np;
+  const int c = (int)(i / (n_out * Np));
+  out[((long long)c * n_total + x_off + p) * n_out + j] = Y[(long long)c * yplane + p * ldy + j];
+}
+
+// ---- fused Adam on flat buffers (paddle.optimizer.Adam semantics, no amsgrad) ------------------
+template <typename T>
+__global__ void k_adam(T* p, const T* g, T* m, T* v, long long n, double lr, double b1, double b2,
+                       double eps, double wd, double bc1, double bc2, double gscale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double gi = (double)g[i] * gscale;
+  double pi = (double)p[i];
+  if (wd != 0.0) gi += wd * pi;
+  const double mi = b1 * (double)m[i] + (1.0 - b1) * gi;
+  const double vi = b2 * (double)v[i] + (1.0 - b2) * gi * gi;
+  m[i] = T(mi);
+  v[i] = T(vi);
+  const double denom = sqrt(vi) / sqrt(bc2) + eps;
+  p[i] = T(pi - (lr / bc1) * mi / denom);
+}
+
+}  // namespace ppsci
