@@ -187,6 +187,13 @@ int ppsci_b200_residual_fwd(ppsci_plan* plan, const void* const* x_cols,
 /* Kernel launches enqueued by the most recent call on this plan (for bench accounting). */
 int64_t ppsci_b200_plan_last_launches(const ppsci_plan* plan);
 
+/* Bench instrumentation: when on, every launch of the next calls is bracketed by CUDA events on
+ * the caller's stream (no syncs).  get_profile returns, for the most recent call, the summed
+ * device time [ms] and launch count per kernel class:
+ *   0 forward-jet GEMM, 1 residual head, 2 dW GEMM, 3 dx GEMM (+activation adjoint), 4 misc. */
+int ppsci_b200_plan_set_profile(ppsci_plan* plan, int32_t on);
+int ppsci_b200_plan_get_profile(ppsci_plan* plan, double* ms5, int64_t* count5);
+
 /* 1 if the tcgen05 (tensor-core) kernels serve this plan's hidden layers, else 0. */
 int32_t ppsci_b200_plan_uses_tcgen05(const ppsci_plan* plan);
 

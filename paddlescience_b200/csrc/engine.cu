@@ -56,6 +56,36 @@ struct ppsci_plan {
   int* d_grad_reg = nullptr;
   int64_t launches = 0;
   bool attrs_set = false;
+  // optional per-kernel-class timing (bench only; adds event records, no syncs)
+  bool profile = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::vector<int> ev_cls;  // class of event pair i (events 2i, 2i+1)
+};
+
+enum { CLS_FWD = 0, CLS_HEAD = 1, CLS_DW = 2, CLS_DX = 3, CLS_MISC = 4, CLS_COUNT = 5 };
+
+struct ProfScope {
+  ppsci_plan* P;
+  cudaStream_t st;
+  bool on;
+  ProfScope(ppsci_plan* P_, int cls, cudaStream_t st_) : P(P_), st(st_), on(P_->profile) {
+    if (!on) return;
+    if (P->ev_used + 2 > P->ev_pool.size()) {
+      for (int i = 0; i < 64; ++i) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) { on = false; return; }
+        P->ev_pool.push_back(e);
+      }
+    }
+    P->ev_cls.push_back(cls);
+    cudaEventRecord(P->ev_pool[P->ev_used], st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(P->ev_pool[P->ev_used + 1], st);
+    P->ev_used += 2;
+  }
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -253,12 +283,33 @@ extern "C" void ppsci_b200_plan_destroy(ppsci_plan* P) {
   cudaFree(P->d_grad_res);
   cudaFree(P->d_grad_in);
   cudaFree(P->d_grad_reg);
+  for (cudaEvent_t e : P->ev_pool) cudaEventDestroy(e);
   delete P;
 }
 
 extern "C" int64_t ppsci_b200_plan_param_count(const ppsci_plan* P) { return P ? P->n_params : -1; }
 extern "C" int32_t ppsci_b200_plan_channels(const ppsci_plan* P) { return P ? P->C : -1; }
 extern "C" int64_t ppsci_b200_plan_last_launches(const ppsci_plan* P) { return P ? P->launches : -1; }
+extern "C" int ppsci_b200_plan_set_profile(ppsci_plan* P, int32_t on) {
+  if (!P) return fail("null plan");
+  P->profile = on != 0;
+  return 0;
+}
+// ms[c] / count[c] for c in {fwd GEMM, head, dW GEMM, dx GEMM, misc} of the most recent call.
+extern "C" int ppsci_b200_plan_get_profile(ppsci_plan* P, double* ms, int64_t* count) {
+  if (!P || !ms || !count) return fail("null argument");
+  for (int c = 0; c < CLS_COUNT; ++c) { ms[c] = 0.0; count[c] = 0; }
+#ifndef PPSCI_EMUL
+  for (size_t i = 0; i < P->ev_cls.size(); ++i) {
+    float t = 0.f;
+    CK(cudaEventSynchronize(P->ev_pool[2 * i + 1]));
+    CK(cudaEventElapsedTime(&t, P->ev_pool[2 * i], P->ev_pool[2 * i + 1]));
+    ms[P->ev_cls[i]] += t;
+    count[P->ev_cls[i]] += 1;
+  }
+#endif
+  return 0;
+}
 extern "C" int32_t ppsci_b200_plan_uses_tcgen05(const ppsci_plan* P) { return (P && P->use_tc) ? 1 : 0; }
 
 extern "C" size_t ppsci_b200_plan_workspace_bytes(const ppsci_plan* P, int64_t n_points) {
@@ -366,6 +417,8 @@ static int run(ppsci_plan* P, const CallArgs& a) {
   T* grads = reinterpret_cast<T*>(a.grads);
   double* loss_acc = reinterpret_cast<double*>(ws + cv.loss_acc);
   P->launches = 0;
+  P->ev_used = 0;
+  P->ev_cls.clear();
 
   auto kf = k_gemm_fwd<T, TN, KMAX>;
   auto kx = k_gemm_dx<T, TN, KMAX>;
@@ -383,6 +436,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
       const int K = s.widths[l - 1], N = s.widths[l];
       const long long tot = (long long)K * N;
       auto kt = k_transpose<T>;
+      ProfScope ps_(P, CLS_MISC, st);
       PPSCI_LAUNCH(kt, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, params + P->w_off[l],
                    reinterpret_cast<T*>(ws + cv.wt[l]), K, N);
       P->launches++;
@@ -396,6 +450,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
 #ifndef PPSCI_EMUL
     bool fwd_done = false;
     if (P->use_tc) {
+      ProfScope ps_(P, CLS_FWD, st);
       int rc = tc_forward<KMAX>(P->spec, P->J, P->w_off, P->b_off, P->ld, reinterpret_cast<const float*>(params),
                                 a.x_cols, c0, nc, nc_max, ws, cv.z, cv.y, cv.tc, st, &P->launches, &g_err);
       if (rc != 0) return 1;
@@ -420,6 +475,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
       g.Np = nc;
       g.TP = TP;
       dim3 grid(ptiles, (unsigned)((g.Nout + TN - 1) / TN));
+      ProfScope ps_(P, CLS_FWD, st);
       PPSCI_LAUNCH(kf, grid, dim3(NTHREADS), smem_f, st, g);
       P->launches++;
     }
@@ -427,6 +483,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
     if (a.jets_out) {
       const long long tot = (long long)C * nc * n_out;
       auto kc = k_copy_jets<T>;
+      ProfScope ps_(P, CLS_MISC, st);
       PPSCI_LAUNCH(kc, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st,
                    reinterpret_cast<const T*>(ws + cv.y), P->ld[L], (long long)nc_max * P->ld[L],
                    reinterpret_cast<T*>(a.jets_out), (long long)a.n_points, (long long)c0, (long long)nc, C, n_out);
@@ -466,6 +523,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
       }
       h.loss_acc = a.want_loss ? loss_acc : nullptr;
       auto kh = k_head<T>;
+      ProfScope ps_(P, CLS_HEAD, st);
       PPSCI_LAUNCH(kh, dim3((unsigned)((nc + HEAD_THREADS - 1) / HEAD_THREADS)), dim3(HEAD_THREADS), 0, st, h);
       P->launches++;
     }
@@ -498,6 +556,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         const long long cps = (total_chunks + want - 1) / want;
         const unsigned splits = (unsigned)((total_chunks + cps - 1) / cps);
         g.chunks_per_split = (int)cps;
+        ProfScope ps_(P, CLS_DW, st);
         PPSCI_LAUNCH(kw, dim3(kt, nt, splits), dim3(NTHREADS), smem_w, st, g);
         P->launches++;
       }
@@ -523,6 +582,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         g.zplane = (long long)nc_max * P->ld[l - 1];
         g.act = s.act;
         dim3 grid(ptiles, (unsigned)((g.Nout + TN - 1) / TN));
+        ProfScope ps_(P, CLS_DX, st);
         PPSCI_LAUNCH(kx, grid, dim3(NTHREADS), smem_x, st, g);
         P->launches++;
         zbar_cur = outp;
@@ -533,6 +593,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
   }
   if (a.want_loss && a.loss_out && s.n_res > 0) {
     auto kfin = k_finalize_loss<T>;
+    ProfScope ps_(P, CLS_MISC, st);
     PPSCI_LAUNCH(kfin, dim3(1), dim3(32), 0, st, loss_acc, reinterpret_cast<T*>(a.loss_out), s.n_res);
     P->launches++;
   }

@@ -86,6 +86,8 @@ EXPORTED_SYMBOLS = (
     "ppsci_b200_residual_fwd",
     "ppsci_b200_plan_last_launches",
     "ppsci_b200_plan_uses_tcgen05",
+    "ppsci_b200_plan_set_profile",
+    "ppsci_b200_plan_get_profile",
     "ppsci_b200_adam_step",
     "ppsci_b200_last_error",
     "ppsci_b200_version",
@@ -138,6 +140,10 @@ class Library:
         L.ppsci_b200_plan_last_launches.restype = i64
         L.ppsci_b200_plan_uses_tcgen05.argtypes = [vp]
         L.ppsci_b200_plan_uses_tcgen05.restype = i32
+        L.ppsci_b200_plan_set_profile.argtypes = [vp, i32]
+        L.ppsci_b200_plan_set_profile.restype = C.c_int
+        L.ppsci_b200_plan_get_profile.argtypes = [vp, C.POINTER(dbl), C.POINTER(i64)]
+        L.ppsci_b200_plan_get_profile.restype = C.c_int
         L.ppsci_b200_adam_step.argtypes = [i32, vp, vp, vp, vp, i64, dbl, dbl, dbl, dbl, dbl, i64, dbl, vp]
         L.ppsci_b200_adam_step.restype = C.c_int
         L.ppsci_b200_last_error.argtypes = []

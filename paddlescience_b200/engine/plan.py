@@ -128,6 +128,17 @@ class ResidualPlan:
     def last_launches(self) -> int:
         return int(self.lib.lib.ppsci_b200_plan_last_launches(self.handle))
 
+    PROFILE_CLASSES = ("fwd_gemm", "head", "dw_gemm", "dx_gemm", "misc")
+
+    def set_profile(self, on: bool):
+        self.lib.check(self.lib.lib.ppsci_b200_plan_set_profile(self.handle, 1 if on else 0), "set_profile")
+
+    def get_profile(self):
+        ms = (C.c_double * 5)()
+        cnt = (C.c_int64 * 5)()
+        self.lib.check(self.lib.lib.ppsci_b200_plan_get_profile(self.handle, ms, cnt), "get_profile")
+        return {k: {"ms": ms[i], "launches": int(cnt[i])} for i, k in enumerate(self.PROFILE_CLASSES)}
+
     def _workspace(self, n: int, device) -> torch.Tensor:
         need = int(self.lib.lib.ppsci_b200_plan_workspace_bytes(self.handle, n))
         if self._ws is None or self._ws.numel() < need + 256 or self._ws.device != device:

@@ -1,0 +1,10 @@
+from .base import LossAggregator
+from .sum import Sum
+
+__all__ = ["LossAggregator", "Sum", "build_mtl_aggregator"]
+
+
+def build_mtl_aggregator(cfg):
+    cfg = dict(cfg)
+    name = cfg.pop("name")
+    return globals()[name](**cfg)

@@ -1,0 +1,130 @@
+"""``ExpressionSolver`` — the drop-in seam of the hot path.
+
+Reference: ppsci/utils/expression.py:40-212.  ``train_forward`` keeps the reference signature
+and return value, but each constraint is ONE call into the native library that evaluates the
+network jets, the residual program, the MSE *and* accumulates the weight gradient into
+``model.flat.grad`` (so the reference's separate ``total_loss.backward()``,
+ppsci/solver/train.py:158, has nothing left to do).  Loss values stay on the device: the
+per-key ``.item()`` syncs of expression.py:122 are gone; ``losses_constraint`` holds lazy
+0-dim tensors that the logger converts only when it prints."""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Tuple
+
+import sympy as sp
+import torch
+from torch import nn
+
+from ..engine.compiler import compile_residuals
+from ..engine.plan import ResidualPlan
+from . import symbolic
+
+
+class CompiledConstraint:
+    """Residual plan(s) of one constraint, built lazily per dtype."""
+
+    def __init__(self, model, cst, extra_keys=()):
+        self.model = model
+        self.cst = cst
+        exprs: Dict[str, sp.Basic] = {}
+        out_keys = tuple(model.output_keys)
+        for name, e in cst.output_expr.items():
+            if isinstance(e, symbolic.CompiledExpr):
+                exprs[name] = e.expr
+            elif isinstance(e, sp.Basic):
+                exprs[name] = e
+            elif callable(e):
+                exprs[name] = symbolic.trace_to_sympy(e, model.input_keys, out_keys, extra_keys)
+            else:
+                raise TypeError(f"output_expr['{name}'] must be a sympy expression or a callable, got {type(e)}")
+        # the loss iterates label keys (mse.py:85); keep that order
+        self.names = [k for k in cst.output_keys if k in exprs] if hasattr(cst, "output_keys") else list(exprs)
+        self.exprs = {k: exprs[k] for k in self.names}
+        self.compiled = compile_residuals(model.net_spec(), self.exprs)
+        self._plans: Dict[torch.dtype, ResidualPlan] = {}
+
+    def plan(self, dtype) -> ResidualPlan:
+        if dtype not in self._plans:
+            loss = self.cst.loss
+            red = getattr(loss, "reduction", "mean")
+            lw = [loss.weight_of(k) if hasattr(loss, "weight_of") else 1.0 for k in self.names]
+            if type(loss).__name__ != "MSELoss":
+                raise NotImplementedError(f"{type(loss).__name__} has no fused head kernel; only MSELoss is on the hot path")
+            self._plans[dtype] = ResidualPlan(self.compiled, dtype, [red] * len(self.names), lw)
+        return self._plans[dtype]
+
+
+class ExpressionSolver(nn.Module):
+    """Expression computing helper (same public methods as the reference)."""
+
+    nvtx_flag: bool = False
+
+    def __init__(self):
+        super().__init__()
+        self._compiled: Dict[int, CompiledConstraint] = {}
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("Use train_forward/eval_forward/visu_forward instead of forward.")
+
+    def compiled_for(self, model, cst, input_dict=None) -> CompiledConstraint:
+        key = id(cst)
+        if key not in self._compiled:
+            extra = [k for k in (input_dict or {}) if k not in model.input_keys]
+            self._compiled[key] = CompiledConstraint(model, cst, extra)
+        return self._compiled[key]
+
+    def train_forward(
+        self,
+        expr_dicts: Tuple[Dict[str, Callable], ...],
+        input_dicts: Tuple[Dict[str, torch.Tensor], ...],
+        model,
+        constraint: Dict[str, "object"],
+        label_dicts: Tuple[Dict[str, torch.Tensor], ...],
+        weight_dicts: Tuple[Dict[str, torch.Tensor], ...],
+    ):
+        """Returns (losses_all, losses_constraint) like the reference; additionally the weight
+        gradient of  sum(losses_all)  has been accumulated into ``model.flat.grad``."""
+        losses_all: Dict[str, torch.Tensor] = {}
+        losses_constraint: Dict[str, torch.Tensor] = {}
+        flat = model.flat
+        if flat.grad is None:
+            flat.grad = torch.zeros_like(flat.data)
+        for i, cst_name in enumerate(constraint):
+            cst = constraint[cst_name]
+            use_nvtx = self.nvtx_flag and flat.is_cuda
+            if use_nvtx:
+                torch.cuda.nvtx.range_push(f"Constraint {cst_name}")
+            cc = self.compiled_for(model, cst, input_dicts[i])
+            plan = cc.plan(flat.dtype)
+            weights = weight_dicts[i]
+            if "area" in input_dicts[i]:  # mse.py:92-93 multiplies by the area column when present
+                area = input_dicts[i]["area"]
+                weights = {k: (weights[k] * area if weights and k in weights else area) for k in cc.names}
+            loss_vec = plan.loss_fwd_bwd(input_dicts[i], flat.data, flat.grad, labels=label_dicts[i], weights=weights)
+            loss_vec = loss_vec.clone()
+            losses_constraint[cst_name] = loss_vec.sum()
+            for k, key in enumerate(cc.names):
+                losses_all[key] = losses_all[key] + loss_vec[k] if key in losses_all else loss_vec[k]
+            if use_nvtx:
+                torch.cuda.nvtx.range_pop()
+        return losses_all, losses_constraint
+
+    def eval_forward(self, expr_dict, input_dict, model, validator, label_dict, weight_dict):
+        """Forward for evaluation (expression.py:133-180): outputs + expressions + validator loss."""
+        output_dict = model({k: input_dict[k] for k in model.input_keys})
+        for name, expr in expr_dict.items():
+            if name in output_dict and not isinstance(expr, (sp.Basic, symbolic.CompiledExpr)):
+                continue  # plain "lambda out: out['u']" style pass-through
+            ce = expr if isinstance(expr, symbolic.CompiledExpr) else symbolic.CompiledExpr(
+                expr if isinstance(expr, sp.Basic) else symbolic.trace_to_sympy(
+                    expr, model.input_keys, model.output_keys, [k for k in input_dict if k not in model.input_keys]),
+                model, name)
+            output_dict[name] = ce(input_dict)
+        if "area" in input_dict:
+            output_dict["area"] = input_dict["area"]
+        losses = validator.loss(output_dict, label_dict, weight_dict) if validator is not None else {}
+        return output_dict, losses
+
+    def visu_forward(self, expr_dict, input_dict, model):
+        output_dict, _ = self.eval_forward(expr_dict or {}, input_dict, model, None, None, None)
+        return output_dict

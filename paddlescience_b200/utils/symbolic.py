@@ -1,0 +1,95 @@
+"""``lambdify`` — sympy / callable residual -> executable over the native kernels.
+
+Reference: ppsci/utils/symbolic.py:681-981 builds a ``ComposedNode`` of autograd-backed layers.
+Here the expression is compiled once into Taylor-jet requirements plus a register program
+(engine/compiler.py) and evaluated by the CUDA forward-jet kernels; the returned callable keeps
+the reference's contract ``data_dict -> Tensor[N, 1]``."""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Union
+
+import sympy as sp
+import torch
+
+from ..autodiff.ad import SymTensor
+from ..engine.compiler import compile_residuals, cvt_to_key
+
+__all__ = ["lambdify", "trace_to_sympy", "_cvt_to_key"]
+
+_cvt_to_key = cvt_to_key
+
+
+def trace_to_sympy(fn: Callable, input_keys: Sequence[str], output_keys: Sequence[str],
+                   extra_keys: Sequence[str] = ()) -> sp.Basic:
+    """Call a python equation / output_expr callable ONCE with symbolic proxies and return the
+    sympy expression it computes (see autodiff/ad.py)."""
+    in_syms = [sp.Symbol(k) for k in input_keys]
+    data = {k: SymTensor(s) for k, s in zip(input_keys, in_syms)}
+    for k in output_keys:
+        data[k] = SymTensor(sp.Function(k)(*in_syms))
+    for k in extra_keys:
+        if k not in data:
+            data[k] = SymTensor(sp.Symbol(k))
+    out = fn(data)
+    if isinstance(out, SymTensor):
+        return out.expr
+    if isinstance(out, (int, float)):
+        return sp.sympify(out)
+    if isinstance(out, sp.Basic):
+        return out
+    raise TypeError(
+        f"equation callable returned {type(out).__name__}; it must combine the entries of the dict it "
+        "receives with python / torch / sympy arithmetic so that it can be traced into a residual program")
+
+
+class CompiledExpr:
+    """Callable ``data_dict -> Tensor[N,1]`` bound to a model (stands in for ``ComposedNode``)."""
+
+    def __init__(self, expr: sp.Basic, model, name: str = "expr"):
+        self.expr = expr
+        self.model = model
+        self.name = name
+        self._plans = {}
+
+    def _plan(self, dtype):
+        from ..engine.plan import ResidualPlan
+
+        if dtype not in self._plans:
+            cr = compile_residuals(self.model.net_spec(), {self.name: self.expr}, with_grad=False)
+            self._plans[dtype] = ResidualPlan(cr, dtype, ["mean"], [1.0])
+        return self._plans[dtype]
+
+    def __call__(self, data_dict: Dict[str, torch.Tensor]) -> torch.Tensor:
+        plan = self._plan(self.model.dtype)
+        keys = list(self.model.input_keys) + list(plan.compiled.aux_keys)
+        cols = {k: data_dict[k] for k in keys}
+        _, res = plan.forward(cols, self.model.flat.data, want_jets=False, want_residuals=True)
+        return res[self.name]
+
+    def __repr__(self):
+        return f"CompiledExpr({self.expr})"
+
+
+def lambdify(
+    expr: Union[sp.Basic, List[sp.Basic]],
+    models=None,
+    extra_parameters=None,
+    graph_filename: Optional[str] = None,
+    create_graph: bool = True,
+    retain_graph: Optional[bool] = None,
+    fuse_derivative: bool = False,
+):
+    """Convert sympy expression(s) to callable(s) — same signature as the reference
+    (symbolic.py:681-689).  ``create_graph`` / ``retain_graph`` / ``fuse_derivative`` are accepted
+    for compatibility; they have no meaning without an autograd graph."""
+    if extra_parameters:
+        raise NotImplementedError("learnable equation parameters are not compiled into residual programs yet")
+    if models is None:
+        raise ValueError("lambdify needs the model whose outputs the expression refers to")
+    if isinstance(models, (list, tuple)):
+        if len(models) != 1:
+            raise NotImplementedError("expressions over several models are not supported yet")
+        models = models[0]
+    if isinstance(expr, (list, tuple)):
+        return [CompiledExpr(sp.sympify(e), models, f"expr{i}") for i, e in enumerate(expr)]
+    return CompiledExpr(sp.sympify(expr), models)

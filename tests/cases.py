@@ -1,0 +1,135 @@
+"""Shared parity cases: engine (CUDA library on a B200, or the CPU emulation build of the same
+kernel sources) versus the torch oracle (oracle/ppsci_oracle.py), same seeded inputs."""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import sympy as sp
+import torch
+
+from oracle import ppsci_oracle as O
+from paddlescience_b200.engine.compiler import NetSpec, compile_residuals
+from paddlescience_b200.engine.plan import ResidualPlan
+
+
+def make_net(in_keys, out_keys, hidden, act, periods=None) -> NetSpec:
+    feat_src, feat_kind, feat_omega = [], [], []
+    for i, k in enumerate(in_keys):
+        if periods and k in periods:
+            w = 2 * math.pi / periods[k][0]
+            feat_src += [i, i]
+            feat_kind += [1, 2]
+            feat_omega += [w, w]
+        else:
+            feat_src.append(i)
+            feat_kind.append(0)
+            feat_omega.append(0.0)
+    return NetSpec(tuple(in_keys), tuple(out_keys), feat_src, feat_kind, feat_omega,
+                   [len(feat_src)] + list(hidden) + [len(out_keys)], act)
+
+
+def _ac_exprs():
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")(t, x)
+    return {"allen_cahn": u.diff(t) - 0.01**2 * u.diff(x, 2) + 5 * u**3 - 5 * u}
+
+
+def _biharm_exprs():
+    xs, ys = sp.symbols("x y")
+    q = 2.0 * sp.sin(sp.pi * xs / 2) * sp.sin(sp.pi * ys / 3)
+    return O.biharmonic_expr(2, q, 1.5)
+
+
+def _mixed_exprs():
+    x, y = sp.symbols("x y")
+    u = sp.Function("u")(x, y)
+    v = sp.Function("v")(x, y)
+    return {"mixed": u.diff(x).diff(y) * v + sp.sin(x) * v.diff(y, 2).diff(x) - u * y,
+            "third": u.diff(x, 3) + v.diff(y) * u.diff(y)}
+
+
+CASES = {
+    # name: dict(in_keys, out_keys, hidden, act, exprs, dtype, periods, reduction, weights, labels_rand, oracle_exprs, ranges, chunk)
+    "ns_f32": dict(in_keys=("x", "y"), out_keys=("u", "v", "p"), hidden=[20, 20], act="tanh",
+                   exprs=lambda: O.navier_stokes_expr(0.01, 1.0, 2, False), dtype=torch.float32),
+    "laplace_f32_sum_w": dict(in_keys=("x", "y"), out_keys=("u",), hidden=[20] * 4, act="tanh",
+                              exprs=lambda: O.laplace_expr(2), dtype=torch.float32, reduction="sum",
+                              labels_rand=True, weights=True),
+    "ns_f64_wide": dict(in_keys=("x", "y"), out_keys=("u", "v", "p"), hidden=[150, 140], act="tanh",
+                        exprs=lambda: O.navier_stokes_expr(0.1, 1.0, 2, False), dtype=torch.float64),
+    "ns_f32_wide": dict(in_keys=("x", "y"), out_keys=("u", "v", "p"), hidden=[150, 140], act="tanh",
+                        exprs=lambda: O.navier_stokes_expr(0.1, 1.0, 2, False), dtype=torch.float32),
+    "ns_f64_chunks": dict(in_keys=("x", "y"), out_keys=("u", "v", "p"), hidden=[16, 16], act="tanh",
+                          exprs=lambda: O.navier_stokes_expr(0.1, 1.0, 2, False), dtype=torch.float64,
+                          chunk_div=3, weights=True),
+    "allen_cahn_period_f64": dict(in_keys=("t", "x"), out_keys=("u",), hidden=[16, 16, 16], act="tanh",
+                                  exprs=_ac_exprs, dtype=torch.float64, periods={"x": (2.0, False)},
+                                  oracle_exprs=lambda: O.allen_cahn_callable(0.01), ranges={"x": (-1, 1)}),
+    "allen_cahn_period_f32": dict(in_keys=("t", "x"), out_keys=("u",), hidden=[32, 32], act="tanh",
+                                  exprs=_ac_exprs, dtype=torch.float32, periods={"x": (2.0, False)},
+                                  oracle_exprs=lambda: O.allen_cahn_callable(0.01), ranges={"x": (-1, 1)}),
+    "biharmonic_f64": dict(in_keys=("x", "y"), out_keys=("u",), hidden=[16, 16, 16], act="tanh",
+                           exprs=_biharm_exprs, dtype=torch.float64, ranges={"x": (0, 2), "y": (0, 3)}),
+    "ns3d_time_sin_f64": dict(in_keys=("t", "x", "y", "z"), out_keys=("u", "v", "w", "p"), hidden=[12, 12],
+                              act="sin", exprs=lambda: O.navier_stokes_expr(0.1, 1.0, 3, True), dtype=torch.float64),
+    "laplace3d_silu_f64": dict(in_keys=("x", "y", "z"), out_keys=("u",), hidden=[12, 12], act="silu",
+                               exprs=lambda: O.laplace_expr(3), dtype=torch.float64),
+    "mixed_third_gelu_f64": dict(in_keys=("x", "y"), out_keys=("u", "v"), hidden=[12, 12], act="gelu",
+                                 exprs=_mixed_exprs, dtype=torch.float64),
+    "poisson_sigmoid_f64": dict(in_keys=("x", "y"), out_keys=("p",), hidden=[12, 12], act="sigmoid",
+                                exprs=lambda: O.poisson_expr(2), dtype=torch.float64),
+}
+
+TOL = {  # (loss rel, residual rel-L2, grad rel-L2)
+    torch.float32: (2e-6, 5e-6, 1e-5),
+    torch.float64: (1e-12, 1e-11, 1e-11),
+}
+
+
+def run_case(name: str, n: int, library=None, device="cpu", backend: int = 0, seed: int = 0) -> Dict[str, float]:
+    c = CASES[name]
+    torch.manual_seed(seed)
+    dtype = c["dtype"]
+    exprs = c["exprs"]()
+    periods = c.get("periods")
+    net = make_net(c["in_keys"], c["out_keys"], c["hidden"], c["act"], periods)
+    cr = compile_residuals(net, exprs)
+    nres = len(cr.names)
+    reduction = c.get("reduction", "mean")
+    chunk = (n + c["chunk_div"] - 1) // c["chunk_div"] if c.get("chunk_div") else 0
+    plan = ResidualPlan(cr, dtype, [reduction] * nres, [1.0 + 0.5 * k for k in range(nres)], chunk_points=chunk,
+                        backend=backend, library=library)
+    inputs = {}
+    for k in c["in_keys"]:
+        lo, hi = (c.get("ranges") or {}).get(k, (0, 1))
+        inputs[k] = (torch.rand(n, 1, dtype=torch.float64) * (hi - lo) + lo).to(dtype)
+    om = O.OracleMLP(c["in_keys"], c["out_keys"], c["hidden"], c["act"], periods)
+    params = O.xavier_uniform_params(om.widths, 1, torch.float64)
+    params = (params + 0.1 * torch.randn_like(params)).to(dtype)
+    labels = {k: (torch.randn(n, 1, dtype=torch.float64).to(dtype) if c.get("labels_rand") else torch.zeros(n, 1, dtype=dtype))
+              for k in cr.names}
+    wts = {k: torch.rand(n, 1, dtype=torch.float64).to(dtype) for k in cr.names} if c.get("weights") else None
+    lw = {k: 1.0 + 0.5 * i for i, k in enumerate(cr.names)}
+    oracle_exprs = c["oracle_exprs"]() if c.get("oracle_exprs") else exprs
+    lo_, ro, go = O.train_forward_backward(
+        om, params.double(), oracle_exprs, {k: v.double() for k, v in inputs.items()},
+        {k: v.double() for k, v in labels.items()}, {k: v.double() for k, v in wts.items()} if wts else None,
+        reduction, lw)
+    dev = torch.device(device)
+    d_in = {k: v.to(dev) for k, v in inputs.items()}
+    d_par = params.to(dev)
+    d_grads = torch.zeros_like(d_par)
+    d_lab = {k: v.to(dev) for k, v in labels.items()}
+    d_w = {k: v.to(dev) for k, v in wts.items()} if wts else None
+    d_res = {k: torch.empty(n, 1, dtype=dtype, device=dev) for k in cr.names}
+    loss = plan.loss_fwd_bwd(d_in, d_par, d_grads, labels=d_lab, weights=d_w, residual_out=d_res)
+    loss = loss.cpu()
+    lerr = max(abs(float(loss[i]) - float(lo_[k])) / max(1e-30, abs(float(lo_[k]))) for i, k in enumerate(cr.names))
+    rerr = max(float((d_res[k].cpu().double() - ro[k]).norm() / ro[k].norm().clamp_min(1e-30)) for k in cr.names)
+    gerr = float((d_grads.cpu().double() - go).norm() / go.norm())
+    # forward-only entry point must agree with the fused call
+    _, res2 = plan.forward(d_in, d_par, want_jets=False)
+    ferr = max(float((res2[k] - d_res[k]).abs().max()) for k in cr.names)
+    return dict(loss=lerr, res=rerr, grad=gerr, fwd_vs_fused=ferr, channels=cr.channels, launches=plan.last_launches,
+                tc=plan.uses_tcgen05)

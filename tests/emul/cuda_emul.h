@@ -95,6 +95,13 @@ inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 struct cudaDeviceProp { int multiProcessorCount; int major; int minor; };
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { p->multiProcessorCount = 4; p->major = 10; p->minor = 0; return cudaSuccess; }
 
+typedef void* cudaEvent_t;
+inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = nullptr; return cudaSuccess; }
+inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* t, cudaEvent_t, cudaEvent_t) { *t = 0.f; return cudaSuccess; }
+
 namespace emul {
 // Run `body` once per (block, thread).  Blocks run sequentially; the threads of a block are
 // real OS threads synchronised by a pthread barrier, so __syncthreads() semantics are honest.

@@ -1,0 +1,24 @@
+"""CPU tests of the SIMT kernel SOURCES through the emulation build (tests/emul/cuda_emul.h):
+every CUDA thread is an OS thread, blocks run one at a time.  Same C-ABI, same host code."""
+import pytest
+import torch
+
+from paddlescience_b200.engine import binding as B
+from tests.cases import CASES, TOL, run_case
+from tests.emul.build_emul import build
+
+
+@pytest.fixture(scope="module")
+def emul_lib():
+    return B.Library(build())
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_case_matches_oracle(emul_lib, name):
+    n = 45 if CASES[name]["hidden"][0] > 64 else 70
+    r = run_case(name, n, library=emul_lib, device="cpu")
+    tl, tr, tg = TOL[CASES[name]["dtype"]]
+    assert r["loss"] <= tl, r
+    assert r["res"] <= tr, r
+    assert r["grad"] <= tg, r
+    assert r["fwd_vs_fused"] == 0.0, r
