@@ -187,6 +187,10 @@ int ppsci_b200_residual_fwd(ppsci_plan* plan, const void* const* x_cols,
 /* Kernel launches enqueued by the most recent call on this plan (for bench accounting). */
 int64_t ppsci_b200_plan_last_launches(const ppsci_plan* plan);
 
+/* Test accessor: byte offset inside the (256-aligned) workspace of the jet planes of `layer`
+ * ([C][min(n_points, chunk)][round4(width)]); layer == n_layers addresses the output jets. */
+int64_t ppsci_b200_plan_stash_offset(const ppsci_plan* plan, int64_t n_points, int32_t layer);
+
 /* Bench instrumentation: when on, every launch of the next calls is bracketed by CUDA events on
  * the caller's stream (no syncs).  get_profile returns, for the most recent call, the summed
  * device time [ms] and launch count per kernel class:

@@ -312,6 +312,17 @@ extern "C" int ppsci_b200_plan_get_profile(ppsci_plan* P, double* ms, int64_t* c
 }
 extern "C" int32_t ppsci_b200_plan_uses_tcgen05(const ppsci_plan* P) { return (P && P->use_tc) ? 1 : 0; }
 
+// Debug / test accessor: byte offset (from the 256-aligned workspace base) of the jet planes of
+// `layer` for a call with n_points points: layer in [1, n_layers) -> hidden pre-activations Z_l,
+// layer == n_layers -> output jets Y.  Layout [C][min(n_points, chunk)][ld], ld = round4(width).
+extern "C" int64_t ppsci_b200_plan_stash_offset(const ppsci_plan* P, int64_t n_points, int32_t layer) {
+  if (!P || n_points <= 0 || layer < 1 || layer > P->spec.n_layers) return -1;
+  const int64_t nc = n_points < P->chunk ? n_points : P->chunk;
+  Carve cv;
+  carve(P, nc, &cv);
+  return (int64_t)(layer < P->spec.n_layers ? cv.z[layer] : cv.y);
+}
+
 extern "C" size_t ppsci_b200_plan_workspace_bytes(const ppsci_plan* P, int64_t n_points) {
   if (!P || n_points <= 0) return 0;
   const int64_t nc = n_points < P->chunk ? n_points : P->chunk;
@@ -443,22 +454,55 @@ static int run(ppsci_plan* P, const CallArgs& a) {
     }
   }
 
+#ifndef PPSCI_EMUL
+  if constexpr (sizeof(T) == 4) {
+    if (P->use_tc) {
+      for (int l = 2; l < L; ++l) {
+        if (!tc_layer_ok(s, l)) continue;
+        const int K = s.widths[l - 1], N = s.widths[l];
+        const long long tot = (long long)K * N;
+        ProfScope ps_(P, CLS_MISC, st);
+        tc::k_tc_prep_w<<<dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st>>>(
+            reinterpret_cast<const float*>(params) + P->w_off[l],
+            reinterpret_cast<float*>(ws + cv.tc + tc_img_offset(s, l)), K, N, 0);
+        P->launches++;
+      }
+    }
+  }
+#endif
   for (int64_t c0 = 0; c0 < a.n_points; c0 += nc_max) {
     const int64_t nc = (a.n_points - c0) < nc_max ? (a.n_points - c0) : nc_max;
     const unsigned ptiles = (unsigned)((nc + TP - 1) / TP);
     // ---------------- forward ----------------
-#ifndef PPSCI_EMUL
-    bool fwd_done = false;
-    if (P->use_tc) {
-      ProfScope ps_(P, CLS_FWD, st);
-      int rc = tc_forward<KMAX>(P->spec, P->J, P->w_off, P->b_off, P->ld, reinterpret_cast<const float*>(params),
-                                a.x_cols, c0, nc, nc_max, ws, cv.z, cv.y, cv.tc, st, &P->launches, &g_err);
-      if (rc != 0) return 1;
-      fwd_done = true;
-    }
-    if (!fwd_done)
-#endif
     for (int l = 1; l <= L; ++l) {
+#ifndef PPSCI_EMUL
+      if constexpr (sizeof(T) == 4) {
+        if (P->use_tc && tc_layer_ok(s, l)) {
+          tc::TcFwdArgs t;
+          memset(&t, 0, sizeof(t));
+          fill_act<float>(P, reinterpret_cast<const float*>(ws + cv.z[l - 1]), P->ld[l - 1], nc_max, A_ACT, &t.A);
+          t.J = P->J;
+          t.Wimg = reinterpret_cast<const float*>(ws + cv.tc + tc_img_offset(s, l));
+          t.Kdim = s.widths[l - 1];
+          t.Nout = s.widths[l];
+          t.bias = reinterpret_cast<const float*>(params) + P->b_off[l];
+          t.Out = reinterpret_cast<float*>(ws + cv.z[l]);
+          t.ldo = P->ld[l];
+          t.oplane = (long long)nc_max * P->ld[l];
+          t.Np = nc;
+          t.TP = TP;
+          t.num_tiles = (int)ptiles;
+          const int smem_tc = 2 * tc::tc_stage_bytes(t.Nout) + 1024 + 256;
+          auto ktc = tc::k_tc_fwd<KMAX>;
+          CK(cudaFuncSetAttribute(ktc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc));
+          const unsigned gridx = ptiles < (unsigned)P->num_sms ? ptiles : (unsigned)P->num_sms;
+          ProfScope ps_(P, CLS_FWD, st);
+          ktc<<<dim3(gridx), dim3(tc::THREADS), smem_tc, st>>>(t);
+          P->launches++;
+          continue;
+        }
+      }
+#endif
       GemmArgs<T> g;
       memset(&g, 0, sizeof(g));
       if (l == 1) fill_seed<T>(P, a.x_cols, c0, &g.A);

@@ -86,6 +86,7 @@ EXPORTED_SYMBOLS = (
     "ppsci_b200_residual_fwd",
     "ppsci_b200_plan_last_launches",
     "ppsci_b200_plan_uses_tcgen05",
+    "ppsci_b200_plan_stash_offset",
     "ppsci_b200_plan_set_profile",
     "ppsci_b200_plan_get_profile",
     "ppsci_b200_adam_step",
@@ -140,6 +141,8 @@ class Library:
         L.ppsci_b200_plan_last_launches.restype = i64
         L.ppsci_b200_plan_uses_tcgen05.argtypes = [vp]
         L.ppsci_b200_plan_uses_tcgen05.restype = i32
+        L.ppsci_b200_plan_stash_offset.argtypes = [vp, i64, i32]
+        L.ppsci_b200_plan_stash_offset.restype = i64
         L.ppsci_b200_plan_set_profile.argtypes = [vp, i32]
         L.ppsci_b200_plan_set_profile.restype = C.c_int
         L.ppsci_b200_plan_get_profile.argtypes = [vp, C.POINTER(dbl), C.POINTER(i64)]

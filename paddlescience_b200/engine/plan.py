@@ -7,6 +7,7 @@ network jets, residuals, MSE and (optionally) the weight gradient for one constr
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -99,6 +100,8 @@ class ResidualPlan:
         s.grad_in = C.cast(self._gin, C.POINTER(C.c_int32))
         s.grad_reg = C.cast(self._greg, C.POINTER(C.c_int32))
         s.chunk_points = int(chunk_points)
+        if int(backend) == 0 and os.environ.get("PPSCI_B200_BACKEND"):
+            backend = int(os.environ["PPSCI_B200_BACKEND"])  # 1 = force SIMT kernels, 2 = force tcgen05
         s.backend = int(backend)
         self.spec = s
         handle = C.c_void_p()
