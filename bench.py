@@ -31,6 +31,21 @@ N_PER_GPU = 1 << 20
 NU, RHO = 0.01, 1.0
 
 
+_T0 = time.perf_counter()
+
+
+def log(msg: str):
+    """Progress to stderr and gpurun_out/bench_progress.log (never to stdout: stdout carries the JSON line)."""
+    line = f"[bench +{time.perf_counter() - _T0:7.1f}s] {msg}"
+    print(line, file=sys.stderr, flush=True)
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "bench_progress.log"), "a") as f:
+            f.write(line + "\n")
+    except OSError:
+        pass
+
+
 def flops_per_point(C: int, widths) -> float:
     """F_total = 3*C*F_v, F_v = 2*sum(in*out)."""
     fv = 2.0 * sum(a * b for a, b in zip(widths[:-1], widths[1:]))
@@ -84,14 +99,14 @@ def measured_peaks():
 
 
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_leg(n_sample: int, iters: int, warmup: int):
+def cpu_reference_leg(n_sample: int, iters: int, warmup: int, budget_s: float = 25.0):
     """Time the reference's algorithm (oracle = torch CPU restatement: Paddle is not installable here,
     DESIGN.md) on the host cores for the same workload at a bounded number of points."""
     import torch
 
     from oracle import ppsci_oracle as O
 
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 64)  # all host threads torch's intra-op pool can use productively
     torch.set_num_threads(cores)
     om = O.OracleMLP(("x", "y"), ("u", "v", "p"), HIDDEN, "tanh")
     params = O.xavier_uniform_params(om.widths, 1, torch.float32)
@@ -102,10 +117,14 @@ def cpu_reference_leg(n_sample: int, iters: int, warmup: int):
     for _ in range(warmup):
         O.train_forward_backward(om, params, exprs, x, labels)
     times = []
+    t_begin = time.perf_counter()
     for _ in range(iters):
         t0 = time.perf_counter()
         O.train_forward_backward(om, params, exprs, x, labels)
         times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > budget_s and len(times) >= 2:
+            break
+    iters = len(times)
     sec = sum(times) / len(times)
     return {"value": n_sample / sec, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{iters} timed iterations (after {warmup} warm-up) of forward residuals + MSE + backward to the "
@@ -194,11 +213,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    log(f"setup done: C={C}, tcgen05={plan.uses_tcgen05}")
     # ---------------- device-resident timing ("value") ----------------
     dev_in = {"x": host_x.to(dev), "y": host_y.to(dev)}
     for _ in range(args.warmup):
         step(dev_in)
     sync_all()
+    log("warm-up done")
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -220,6 +241,7 @@ def run_ours(args):
     ms_per_step = float(ms_total) / args.steps
     value = world * N / (ms_per_step * 1e-3)
 
+    log(f"timed region done: {ms_per_step:.2f} ms/step")
     # ---------------- end to end through the public API with host buffers ("e2e") ----------------
     for _ in range(2):
         step({"x": host_x.to(dev, non_blocking=True), "y": host_y.to(dev, non_blocking=True)})
@@ -240,6 +262,7 @@ def run_ours(args):
     e2e_value = world * N / (float(ms_e2e) / args.steps * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
 
+    log(f"e2e done: {float(ms_e2e) / args.steps:.2f} ms/step")
     # ---------------- per-kernel-class shares (separate, untimed pass) ----------------
     plan.set_profile(True)
     prof_acc = None
@@ -274,7 +297,9 @@ def run_ours(args):
         "class_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
         "backend": "tcgen05" if plan.uses_tcgen05 else "simt-fp32",
     }
+    log("profile pass done; timing the CPU baseline")
     cb = cpu_reference_leg(1 << 14, 8, 1)
+    log("cpu baseline done")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
