@@ -7,6 +7,7 @@
 #endif
 
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -48,6 +49,7 @@ struct ppsci_plan {
   int chunk = 0;
   int num_sms = 148;
   bool use_tc = false;
+  int tc_mask = 7;  // bit0 forward, bit1 dx, bit2 dW on the tensor cores (PPSCI_B200_TC_MASK, debugging)
   // device copies of the residual program
   int* d_prog = nullptr;
   double* d_consts = nullptr;
@@ -247,6 +249,7 @@ extern "C" int ppsci_b200_plan_create(const ppsci_plan_spec* s, ppsci_plan** out
   }
 #ifndef PPSCI_EMUL
   P->use_tc = tc_plan_supported(P->spec, P->C, P->kmax) && s->backend != 1;
+  if (const char* m = getenv("PPSCI_B200_TC_MASK")) P->tc_mask = atoi(m);
   if (s->backend == 2 && !P->use_tc) {
     delete P;
     return fail("plan_create: backend=2 (tcgen05) requested but the plan is not eligible "
@@ -467,6 +470,18 @@ static int run(ppsci_plan* P, const CallArgs& a) {
             reinterpret_cast<float*>(ws + cv.tc + tc_img_offset(s, l)), K, N, 0);
         P->launches++;
       }
+      if (do_bwd && (P->tc_mask & 2)) {
+        for (int l = 2; l <= L; ++l) {
+          if (!tc_dx_ok(s, l)) continue;
+          const int K = s.widths[l], N = s.widths[l - 1];  // gemm K = fan-out, gemm N = fan-in
+          const long long tot = (long long)K * N;
+          ProfScope ps_(P, CLS_MISC, st);
+          tc::k_tc_prep_w<<<dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st>>>(
+              reinterpret_cast<const float*>(params) + P->w_off[l],
+              reinterpret_cast<float*>(ws + cv.tc + tc_imgT_offset(s, l)), K, N, 1);
+          P->launches++;
+        }
+      }
     }
   }
 #endif
@@ -477,7 +492,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
     for (int l = 1; l <= L; ++l) {
 #ifndef PPSCI_EMUL
       if constexpr (sizeof(T) == 4) {
-        if (P->use_tc && tc_layer_ok(s, l)) {
+        if (P->use_tc && (P->tc_mask & 1) && tc_layer_ok(s, l)) {
           tc::TcFwdArgs t;
           memset(&t, 0, sizeof(t));
           fill_act<float>(P, reinterpret_cast<const float*>(ws + cv.z[l - 1]), P->ld[l - 1], nc_max, A_ACT, &t.A);
@@ -577,6 +592,52 @@ static int run(ppsci_plan* P, const CallArgs& a) {
     int zbar_ld = P->ld[L];
     int flip = 0;
     for (int l = L; l >= 1; --l) {
+#ifndef PPSCI_EMUL
+      bool dw_done = false;
+      if constexpr (sizeof(T) == 4) {
+        if (P->use_tc && (P->tc_mask & 4) && tc_dw_ok(s, l)) {
+          tc::TcDwArgs t;
+          memset(&t, 0, sizeof(t));
+          fill_act<float>(P, reinterpret_cast<const float*>(ws + cv.z[l - 1]), P->ld[l - 1], nc_max, A_ACT, &t.A);
+          t.J = P->J;
+          t.Zbar = reinterpret_cast<const float*>(zbar_cur);
+          t.ldzb = zbar_ld;
+          t.zbplane = (long long)nc_max * zbar_ld;
+          t.Kdim = s.widths[l - 1];
+          t.Nout = s.widths[l];
+          t.dW = reinterpret_cast<float*>(grads) + P->w_off[l];
+          t.Np = nc;
+          const int PTt = tc::KCH / C;
+          t.PT = PTt;
+          const unsigned kt = (unsigned)(t.Kdim / 128);
+          const long long total_chunks = (nc + PTt - 1) / PTt;
+          long long want = P->num_sms / kt;
+          if (want < 1) want = 1;
+          if (want > total_chunks) want = total_chunks;
+          const long long cps = (total_chunks + want - 1) / want;
+          const unsigned splits = (unsigned)((total_chunks + cps - 1) / cps);
+          t.chunks_per_split = (int)cps;
+          const int smem_tc = 2 * tc::tc_stage_bytes(t.Nout) + 1024 + 256;
+          auto kdw = tc::k_tc_dw<KMAX>;
+          CK(cudaFuncSetAttribute(kdw, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc));
+          {
+            ProfScope ps_(P, CLS_DW, st);
+            kdw<<<dim3(kt, splits), dim3(tc::THREADS), smem_tc, st>>>(t);
+            P->launches++;
+          }
+          {
+            ProfScope ps_(P, CLS_DW, st);
+            const int ppb = 512;
+            tc::k_bias_grad<<<dim3((unsigned)((t.Nout + 127) / 128), (unsigned)((nc + ppb - 1) / ppb)), dim3(128), 0, st>>>(
+                reinterpret_cast<const float*>(zbar_cur), zbar_ld, (long long)nc, t.Nout,
+                reinterpret_cast<float*>(grads) + P->b_off[l], ppb);
+            P->launches++;
+          }
+          dw_done = true;
+        }
+      }
+      if (!dw_done)
+#endif
       {  // dW_l, db_l
         DwArgs<T> g;
         memset(&g, 0, sizeof(g));
@@ -605,6 +666,43 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         P->launches++;
       }
       if (l == 1) break;
+#ifndef PPSCI_EMUL
+      if constexpr (sizeof(T) == 4) {
+        if (P->use_tc && (P->tc_mask & 2) && tc_dx_ok(s, l)) {
+          tc::TcDxArgs t;
+          memset(&t, 0, sizeof(t));
+          fill_act<float>(P, reinterpret_cast<const float*>(zbar_cur), zbar_ld, nc_max, A_PLAIN, &t.A);
+          t.J = P->J;
+          t.Wimg = reinterpret_cast<const float*>(ws + cv.tc + tc_imgT_offset(s, l));
+          t.Kdim = s.widths[l];
+          t.Nout = s.widths[l - 1];
+          t.Zprev = reinterpret_cast<const float*>(ws + cv.z[l - 1]);
+          t.ldz = P->ld[l - 1];
+          t.zplane = (long long)nc_max * P->ld[l - 1];
+          t.act = s.act;
+          float* outp = reinterpret_cast<float*>(ws + (flip ? cv.zbar1 : cv.zbar0));
+          t.Out = outp;
+          t.ldo = P->ld[l - 1];
+          t.oplane = (long long)nc_max * P->ld[l - 1];
+          t.Np = nc;
+          t.TP = TP;
+          t.num_tiles = (int)ptiles;
+          const int smem_tc = 2 * tc::tc_stage_bytes(t.Nout) + 2 * tc::X_TILE_BYTES + 1024 + 256;
+          auto kdx = tc::k_tc_dx<KMAX>;
+          CK(cudaFuncSetAttribute(kdx, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc));
+          const unsigned gridx = ptiles < (unsigned)P->num_sms ? ptiles : (unsigned)P->num_sms;
+          {
+            ProfScope ps_(P, CLS_DX, st);
+            kdx<<<dim3(gridx), dim3(tc::THREADS), smem_tc, st>>>(t);
+            P->launches++;
+          }
+          zbar_cur = reinterpret_cast<const T*>(outp);
+          zbar_ld = P->ld[l - 1];
+          flip ^= 1;
+          continue;
+        }
+      }
+#endif
       {  // Zbar_{l-1}
         GemmArgs<T> g;
         memset(&g, 0, sizeof(g));

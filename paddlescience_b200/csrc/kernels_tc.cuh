@@ -304,6 +304,339 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
   if (warp == 1) tmem_dealloc(tmem_base, ncols);
 }
 
+
+// =====================================================================================================
+// Backward dx on the tensor cores:  Abar = Zbar_l W_l^T  (contraction over the layer's outputs), then the
+// activation adjoint  Zbar_{l-1} = adj(Abar, Z_{l-1})  through a shared-memory exchange tile (the C
+// channels of one point live in different TMEM lanes, the adjoint needs them together).
+// =====================================================================================================
+struct TcDxArgs {
+  AOperand<float> A;   // A_PLAIN over Zbar_l
+  JetLayout J;
+  const float* Wimg;   // transposed image: gemm N = fan-in of the layer, gemm K = fan-out
+  int Kdim;            // gemm K  (= N_l)
+  int Nout;            // gemm N  (= K_l = width of layer l-1)
+  const float* Zprev;  // Z_{l-1} [C][Np][ldz]
+  int ldz;
+  long long zplane;
+  int act;
+  float* Out;          // Zbar_{l-1} [C][Np][ldo]
+  int ldo;
+  long long oplane;
+  long long Np;
+  int TP;
+  int num_tiles;
+};
+
+constexpr int XLD = 33;                          // exchange-tile row pitch (floats): conflict-free both ways
+constexpr int X_TILE_BYTES = 128 * XLD * 4;      // one 128 x 32 block
+
+template <int KMAX>
+__global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
+  const int N = g.Nout;
+  const int stage_bytes = tc_stage_bytes(N);
+  float* xch = reinterpret_cast<float*>(base_ptr + 2 * stage_bytes);  // 2 exchange tiles (one per warp half)
+  const uint32_t bars_off = 2 * stage_bytes + 2 * X_TILE_BYTES;
+  const uint32_t bars = base + bars_off;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 64);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t ncols = tc_tmem_cols(N);
+
+  if (tid == 0) {
+    mbar_init(bars + 0, 1);
+    mbar_init(bars + 8, 1);
+    mbar_init(bars + 16, 1);
+    mbar_init(bars + 24, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) {
+    tmem_alloc(base + bars_off + 64, ncols);
+    tmem_relinquish();
+  }
+  for (int s = 0; s < 2; ++s) {
+    float4* az = reinterpret_cast<float4*>(base_ptr + s * stage_bytes);
+    for (int i = tid; i < 2 * A_TILE_BYTES / 16; i += THREADS) az[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = make_idesc_tf32(128, N);
+  const int nchunks = g.Kdim / KCH;
+  const uint32_t b_bytes = (uint32_t)(2 * N * KCH * 4);
+  const int TP = g.TP;
+
+  uint32_t it = 0;
+  for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+    const long long p0 = (long long)tile * TP;
+    for (int j = 0; j < nchunks; ++j, ++it) {
+      const uint32_t s = it & 1u, u = it >> 1;
+      unsigned char* stage_ptr = base_ptr + s * stage_bytes;
+      const uint32_t stage_addr = base + s * stage_bytes;
+      if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
+      if (tid == 0) {
+        mbar_expect_tx(bars + 8 * s, b_bytes);
+        bulk_g2s(stage_addr + 2 * A_TILE_BYTES, g.Wimg + (long long)j * 2 * N * KCH, b_bytes, bars + 8 * s);
+      }
+      for (int item = tid; item < TP * KCH; item += THREADS) {
+        const int kk = item & (KCH - 1), pl = item / KCH;
+        const long long p = p0 + pl;
+        const int k = j * KCH + kk;
+        produce_a<float, KMAX>(g.A, g.J, p, k, p < g.Np, [&](int c, float v) {
+          const int r = c * TP + pl;
+          const float hi = tf32_rn(v);
+          const uint32_t off = sw128(r, kk);
+          *reinterpret_cast<float*>(stage_ptr + off) = hi;
+          *reinterpret_cast<float*>(stage_ptr + A_TILE_BYTES + off) = v - hi;
+        });
+      }
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+        mbar_wait(bars + 8 * s, u & 1u);
+        tc_fence_after();
+        const uint32_t a_hi = stage_addr, a_lo = stage_addr + A_TILE_BYTES;
+        const uint32_t b_hi = stage_addr + 2 * A_TILE_BYTES, b_lo = b_hi + (uint32_t)(N * KCH * 4);
+#pragma unroll
+        for (int ks = 0; ks < KCH / 8; ++ks) {
+          const uint64_t dah = make_smem_desc(a_hi + ks * 32), dal = make_smem_desc(a_lo + ks * 32);
+          const uint64_t dbh = make_smem_desc(b_hi + ks * 32), dbl = make_smem_desc(b_lo + ks * 32);
+          mma_tf32(tmem_base, dah, dbh, idesc, (j > 0 || ks > 0) ? 1u : 0u);
+          mma_tf32(tmem_base, dal, dbh, idesc, 1u);
+          mma_tf32(tmem_base, dah, dbl, idesc, 1u);
+        }
+        mma_commit(bars + 16 + 8 * s);
+      }
+    }
+    // ---- epilogue: Abar (TMEM) -> exchange tile -> activation adjoint -> Zbar_{l-1} ----
+    {
+      const uint32_t last = it - 1;
+      mbar_wait(bars + 16 + 8 * (last & 1u), (last >> 1) & 1u);
+      tc_fence_after();
+      const int q = warp & 3, half = warp >> 2;
+      float* X = xch + half * (128 * XLD);
+      const int ncb = N / 32;
+      const int tih = tid & 127;  // thread index inside its half
+      for (int cb0 = 0; cb0 < ncb; cb0 += 2) {
+        const int cb = cb0 + half;
+        if (cb < ncb) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), v);
+          tmem_ld_wait();
+          float* xr = X + (q * 32 + lane) * XLD;
+#pragma unroll
+          for (int t = 0; t < 32; ++t) xr[t] = __uint_as_float(v[t]);
+        }
+        __syncthreads();
+        if (cb < ncb) {
+          for (int item = tih; item < TP * 32; item += 128) {
+            const int nn = item & 31, pl = item >> 5;
+            const long long p = p0 + pl;
+            if (p >= g.Np) continue;
+            const int n = cb * 32 + nn;
+            const float* z = g.Zprev + p * g.ldz + n;
+            float* zb_out = g.Out + p * g.ldo + n;
+            float sc[6];
+            float y0;
+            act_coef<float, KMAX + 1>(g.act, z[0], y0, sc);
+            const float y0b = X[pl * XLD + nn];
+            float sb[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+            for (int d = 0; d < g.J.n_dir; ++d) {
+              const int K = g.J.dir_order[d];
+              const int cbase = g.J.dir_base[d];
+              float zz[4], yb[4], zb[4];
+#pragma unroll
+              for (int o = 0; o < 4; ++o) {
+                const bool on = (o < KMAX && o < K);
+                zz[o] = on ? z[(long long)(cbase + o) * g.zplane] : 0.f;
+                yb[o] = on ? X[((cbase + o) * TP + pl) * XLD + nn] : 0.f;
+                zb[o] = 0.f;
+              }
+              jet_adj_dir<float, KMAX>(sc, zz, yb, zb, sb);
+#pragma unroll
+              for (int o = 0; o < KMAX; ++o)
+                if (o < K) zb_out[(long long)(cbase + o) * g.oplane] = zb[o];
+            }
+            zb_out[0] = jet_adj_z0<float, KMAX>(sc, y0b, sb);
+          }
+        }
+        __syncthreads();
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+// =====================================================================================================
+// Backward dW on the tensor cores:  dW_l[k][n] += sum_rows A_{l-1}[row][k] * Zbar_l[row][n].
+// Reduction dimension = jet rows (points x channels).  CTA (kt, split) owns dW rows [128 kt, 128 kt + 128)
+// and a contiguous range of 32-row reduction chunks (PT points each); it accumulates in TMEM across its
+// whole range and flushes once with red.global.add.  Both operands are written transposed into K-major
+// SW128 tiles: warps 0-3 recompute A_{l-1} = act_jets(Z_{l-1}) (thread = dW row k), warps 4-7 split Zbar_l.
+// =====================================================================================================
+struct TcDwArgs {
+  AOperand<float> A;   // A_ACT over Z_{l-1}
+  JetLayout J;
+  const float* Zbar;   // [C][Np][ldzb]
+  int ldzb;
+  long long zbplane;
+  int Kdim;            // fan-in (rows of dW), multiple of 128
+  int Nout;            // fan-out (cols of dW), multiple of 32, <= 256
+  float* dW;           // [Kdim][Nout]
+  long long Np;
+  int PT;              // points per 32-row reduction chunk
+  int chunks_per_split;
+};
+
+template <int KMAX>
+__global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ int row_c[KCH], row_pl[KCH];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
+  const int N = g.Nout;
+  const int stage_bytes = tc_stage_bytes(N);
+  const uint32_t bars_off = 2 * stage_bytes;
+  const uint32_t bars = base + bars_off;  // mma_done[2] at +16, +24 (no TMA here: +0, +8 unused)
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 64);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t ncols = tc_tmem_cols(N);
+  const int PT = g.PT;
+  const int rows_used = g.J.C * PT;
+
+  if (tid == 0) {
+    mbar_init(bars + 16, 1);
+    mbar_init(bars + 24, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (tid < KCH) {
+    row_c[tid] = tid < rows_used ? tid / PT : -1;
+    row_pl[tid] = tid < rows_used ? tid % PT : 0;
+  }
+  if (warp == 1) {
+    tmem_alloc(base + bars_off + 64, ncols);
+    tmem_relinquish();
+  }
+  // clear both stages completely (reduction columns >= rows_used stay zero forever)
+  for (int s = 0; s < 2; ++s) {
+    float4* az = reinterpret_cast<float4*>(base_ptr + s * stage_bytes);
+    for (int i = tid; i < stage_bytes / 16; i += THREADS) az[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t idesc = make_idesc_tf32(128, N);
+  const int k0 = blockIdx.x * 128;
+  const long long total_chunks = (g.Np + PT - 1) / PT;
+  const long long ch_begin = (long long)blockIdx.y * g.chunks_per_split;
+  long long ch_end = ch_begin + g.chunks_per_split;
+  if (ch_end > total_chunks) ch_end = total_chunks;
+
+  uint32_t it = 0;
+  for (long long ch = ch_begin; ch < ch_end; ++ch, ++it) {
+    const uint32_t s = it & 1u, u = it >> 1;
+    unsigned char* stage_ptr = base_ptr + s * stage_bytes;
+    const uint32_t stage_addr = base + s * stage_bytes;
+    if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
+    const long long pbase = ch * PT;
+    if (warp < 4) {
+      // A' tile: row = dW row k (this thread), column rr = c*PT + pl
+      const int k = tid;  // 0..127
+      for (int pl = 0; pl < PT; ++pl) {
+        const long long p = pbase + pl;
+        produce_a<float, KMAX>(g.A, g.J, p, k0 + k, p < g.Np, [&](int c, float v) {
+          const int rr = c * PT + pl;
+          const float hi = tf32_rn(v);
+          const uint32_t off = sw128(k, rr);
+          *reinterpret_cast<float*>(stage_ptr + off) = hi;
+          *reinterpret_cast<float*>(stage_ptr + A_TILE_BYTES + off) = v - hi;
+        });
+      }
+    } else {
+      // B' tile: row = n, 16-byte chunk q holds reduction columns 4q..4q+3
+      unsigned char* b_hi = stage_ptr + 2 * A_TILE_BYTES;
+      unsigned char* b_lo = b_hi + N * KCH * 4;
+      const int nq = (rows_used + 3) / 4;
+      for (int item = tid - 128; item < N * nq; item += 128) {
+        const int n = item % N, q = item / N;
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int rr = 4 * q + e;
+          const int c = row_c[rr];
+          const long long p = pbase + row_pl[rr];
+          const float v = (c >= 0 && p < g.Np) ? g.Zbar[(long long)c * g.zbplane + p * g.ldzb + n] : 0.f;
+          hi[e] = tf32_rn(v);
+          lo[e] = v - hi[e];
+        }
+        const uint32_t off = sw128(n, 4 * q);
+        *reinterpret_cast<float4*>(b_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(b_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a_hi = stage_addr, a_lo = stage_addr + A_TILE_BYTES;
+      const uint32_t b_hi = stage_addr + 2 * A_TILE_BYTES, b_lo = b_hi + (uint32_t)(N * KCH * 4);
+#pragma unroll
+      for (int ks = 0; ks < KCH / 8; ++ks) {
+        const uint64_t dah = make_smem_desc(a_hi + ks * 32), dal = make_smem_desc(a_lo + ks * 32);
+        const uint64_t dbh = make_smem_desc(b_hi + ks * 32), dbl = make_smem_desc(b_lo + ks * 32);
+        mma_tf32(tmem_base, dah, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+        mma_tf32(tmem_base, dal, dbh, idesc, 1u);
+        mma_tf32(tmem_base, dah, dbl, idesc, 1u);
+      }
+      mma_commit(bars + 16 + 8 * s);
+    }
+  }
+  if (it > 0) {
+    const uint32_t last = it - 1;
+    mbar_wait(bars + 16 + 8 * (last & 1u), (last >> 1) & 1u);
+    tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    const int k = k0 + q * 32 + lane;
+    float* dw_row = g.dW + (long long)k * N;
+    const int ncb = N / 32;
+    for (int cb = half; cb < ncb; cb += 2) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), v);
+      tmem_ld_wait();
+      if (k < g.Kdim) {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) atomicAdd(dw_row + cb * 32 + t, __uint_as_float(v[t]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+// db_l[n] += sum over points of Zbar_l[channel 0][p][n]   (tiny, HBM-bound)
+__global__ void k_bias_grad(const float* __restrict__ Zbar0, int ld, long long Np, int N, float* __restrict__ db,
+                            int pts_per_block) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const long long p_begin = (long long)blockIdx.y * pts_per_block;
+  long long p_end = p_begin + pts_per_block;
+  if (p_end > Np) p_end = Np;
+  float acc = 0.f;
+  for (long long p = p_begin; p < p_end; ++p) acc += Zbar0[p * ld + n];
+  atomicAdd(db + n, acc);
+}
+
 }  // namespace tc
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -313,6 +646,21 @@ inline bool tc_layer_ok(const ppsci_plan_spec& s, int l) {
   if (l < 2 || l >= s.n_layers) return false;
   const int K = s.widths[l - 1], N = s.widths[l];
   return (K % tc::KCH == 0) && K >= 32 && K <= 1024 && (N % 32 == 0) && N >= 32 && N <= 256;
+}
+
+// dx through layer l (produces Zbar_{l-1}): gemm K = N_l, gemm N = K_l; the layer below must be hidden
+inline bool tc_dx_ok(const ppsci_plan_spec& s, int l) {
+  if (s.dtype != PPSCI_F32) return false;
+  if (l < 2 || l > s.n_layers) return false;
+  const int K = s.widths[l], N = s.widths[l - 1];
+  return (K % tc::KCH == 0) && K >= 32 && K <= 1024 && (N % 32 == 0) && N >= 32 && N <= 256;
+}
+// dW of layer l: rows = fan-in (multiple of 128), cols = fan-out (multiple of 32, <= 256)
+inline bool tc_dw_ok(const ppsci_plan_spec& s, int l) {
+  if (s.dtype != PPSCI_F32) return false;
+  if (l < 2 || l > s.n_layers) return false;
+  const int K = s.widths[l - 1], N = s.widths[l];
+  return (K % 128 == 0) && K >= 128 && K <= 1024 && (N % 32 == 0) && N >= 32 && N <= 256;
 }
 
 inline bool tc_plan_supported(const ppsci_plan_spec& s, int /*C*/, int /*kmax*/) {
@@ -328,8 +676,14 @@ inline size_t tc_img_offset(const ppsci_plan_spec& s, int layer) {
     if (tc_layer_ok(s, l)) off += (size_t)s.widths[l - 1] * s.widths[l] * 8;
   return off;
 }
+inline size_t tc_imgT_offset(const ppsci_plan_spec& s, int layer) {  // transposed (dx) images follow the forward ones
+  size_t off = tc_img_offset(s, s.n_layers);
+  for (int l = 2; l < layer; ++l)
+    if (tc_dx_ok(s, l)) off += (size_t)s.widths[l - 1] * s.widths[l] * 8;
+  return off;
+}
 inline size_t tc_scratch_bytes_impl(const ppsci_plan_spec& s, int /*C*/, int64_t /*nc*/) {
-  return tc_img_offset(s, s.n_layers) + 1024;
+  return tc_imgT_offset(s, s.n_layers + 1) + 1024;
 }
 
 }  // namespace ppsci

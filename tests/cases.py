@@ -81,6 +81,19 @@ CASES = {
                                 exprs=lambda: O.poisson_expr(2), dtype=torch.float64),
 }
 
+# shapes served by the tcgen05 kernels (hidden widths multiple of 32/128); CPU emulation skips them
+TC_CASES = {
+    "ns_f32_tc_256": dict(in_keys=("x", "y"), out_keys=("u", "v", "p"), hidden=[256, 256, 256], act="tanh",
+                          exprs=lambda: O.navier_stokes_expr(0.01, 1.0, 2, False), dtype=torch.float32),
+    "ns_f32_tc_128_sin": dict(in_keys=("x", "y"), out_keys=("u", "v", "p"), hidden=[128, 128, 128], act="sin",
+                              exprs=lambda: O.navier_stokes_expr(0.01, 1.0, 2, False), dtype=torch.float32),
+    "ac_f32_tc_128": dict(in_keys=("t", "x"), out_keys=("u",), hidden=[128] * 4, act="tanh", exprs=_ac_exprs,
+                          dtype=torch.float32, periods={"x": (2.0, False)},
+                          oracle_exprs=lambda: O.allen_cahn_callable(0.01), ranges={"x": (-1, 1)}),
+    "biharmonic_f32_tc_128": dict(in_keys=("x", "y"), out_keys=("u",), hidden=[128, 128, 128], act="tanh",
+                                  exprs=_biharm_exprs, dtype=torch.float32, ranges={"x": (0, 2), "y": (0, 3)}),
+}
+
 TOL = {  # (loss rel, residual rel-L2, grad rel-L2)
     torch.float32: (2e-6, 5e-6, 1e-5),
     torch.float64: (1e-12, 1e-11, 1e-11),
@@ -88,7 +101,7 @@ TOL = {  # (loss rel, residual rel-L2, grad rel-L2)
 
 
 def run_case(name: str, n: int, library=None, device="cpu", backend: int = 0, seed: int = 0) -> Dict[str, float]:
-    c = CASES[name]
+    c = CASES[name] if name in CASES else TC_CASES[name]
     torch.manual_seed(seed)
     dtype = c["dtype"]
     exprs = c["exprs"]()

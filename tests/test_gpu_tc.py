@@ -1,22 +1,15 @@
-"""GPU tests of the tcgen05 path: parity against the oracle through the C-ABI with backend=2."""
+"""GPU tests of the tcgen05 path: parity against the oracle through the C-ABI with backend=2
+(forward, dx and dW on the tensor cores), tolerance of the 3xTF32 scheme stated here."""
 import pytest
 import torch
 
-from tests.cases import CASES, TOL, run_case
+from tests.cases import TC_CASES, run_case
 
 pytestmark = pytest.mark.gpu
 
-TC_CASES = {
-    "ns_f32_tc_256": dict(in_keys=("x", "y"), out_keys=("u", "v", "p"), hidden=[256, 256, 256], act="tanh",
-                          exprs=CASES["ns_f32"]["exprs"], dtype=torch.float32),
-    "ns_f32_tc_128_sin": dict(in_keys=("x", "y"), out_keys=("u", "v", "p"), hidden=[128, 128, 128], act="sin",
-                              exprs=CASES["ns_f32"]["exprs"], dtype=torch.float32),
-    "ac_f32_tc_128": dict(in_keys=("t", "x"), out_keys=("u",), hidden=[128] * 4, act="tanh",
-                          exprs=CASES["allen_cahn_period_f32"]["exprs"], dtype=torch.float32,
-                          periods={"x": (2.0, False)}, oracle_exprs=CASES["allen_cahn_period_f32"]["oracle_exprs"],
-                          ranges={"x": (-1, 1)}),
-}
-CASES.update(TC_CASES)
+# 3xTF32 + fp32 tensor-core accumulation: residual rel-L2 <= 1e-5 is the north-star bar; the loss
+# (a mean of squares) and the weight gradient inherit the same relative error level.
+TOL_TC = dict(loss=2e-5, res=1e-5, grad=5e-5)
 
 
 @pytest.mark.parametrize("name", sorted(TC_CASES))
@@ -24,7 +17,6 @@ def test_tc_case_matches_oracle(name):
     assert torch.cuda.is_available()
     r = run_case(name, 3000, device="cuda:0", backend=2)
     assert r["tc"], "tcgen05 backend was not selected"
-    tl, tr, tg = TOL[torch.float32]
-    assert r["loss"] <= tl, r
-    assert r["res"] <= tr, r
-    assert r["grad"] <= tg, r
+    assert r["loss"] <= TOL_TC["loss"], r
+    assert r["res"] <= TOL_TC["res"], r
+    assert r["grad"] <= TOL_TC["grad"], r
