@@ -507,7 +507,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           t.Np = nc;
           t.TP = TP;
           t.num_tiles = (int)ptiles;
-          const int smem_tc = 2 * tc::tc_stage_bytes(t.Nout) + 1024 + 256;
+          const int smem_tc = tc::tc_fwd_smem_bytes(t.Nout);
           auto ktc = tc::k_tc_fwd<KMAX>;
           CK(cudaFuncSetAttribute(ktc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc));
           const unsigned gridx = ptiles < (unsigned)P->num_sms ? ptiles : (unsigned)P->num_sms;
@@ -617,7 +617,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           const long long cps = (total_chunks + want - 1) / want;
           const unsigned splits = (unsigned)((total_chunks + cps - 1) / cps);
           t.chunks_per_split = (int)cps;
-          const int smem_tc = 2 * tc::tc_stage_bytes(t.Nout) + 1024 + 256;
+          const int smem_tc = tc::tc_dw_smem_bytes(t.Nout);
           auto kdw = tc::k_tc_dw<KMAX>;
           CK(cudaFuncSetAttribute(kdw, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc));
           {
@@ -687,7 +687,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           t.Np = nc;
           t.TP = TP;
           t.num_tiles = (int)ptiles;
-          const int smem_tc = 2 * tc::tc_stage_bytes(t.Nout) + 2 * tc::X_TILE_BYTES + 1024 + 256;
+          const int smem_tc = tc::tc_fwd_smem_bytes(t.Nout);
           auto kdx = tc::k_tc_dx<KMAX>;
           CK(cudaFuncSetAttribute(kdx, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc));
           const unsigned gridx = ptiles < (unsigned)P->num_sms ? ptiles : (unsigned)P->num_sms;

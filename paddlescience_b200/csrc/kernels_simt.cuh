@@ -115,6 +115,35 @@ __device__ __forceinline__ void produce_a(const AOperand<T>& A, const JetLayout&
   }
 }
 
+// Same arithmetic as produce_a's A_PLAIN / A_ACT branches, but the C channel values of the element
+// come from a caller-supplied loader ld(c) (e.g. a shared-memory staging tile).
+template <typename T, int KMAX, typename Ld, typename St>
+__device__ __forceinline__ void produce_from(int mode, int act, const JetLayout& J, bool valid, Ld ld, St st) {
+  if (!valid) {
+    for (int c = 0; c < J.C; ++c) st(c, T(0));
+    return;
+  }
+  if (mode == A_PLAIN) {
+    for (int c = 0; c < J.C; ++c) st(c, ld(c));
+    return;
+  }
+  T s[6];
+  T y0;
+  act_coef<T, KMAX>(act, ld(0), y0, s);
+  st(0, y0);
+  for (int d = 0; d < J.n_dir; ++d) {
+    const int K = J.dir_order[d];
+    const int base = J.dir_base[d];
+    T zz[4], yy[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) zz[q] = (q < KMAX && q < K) ? ld(base + q) : T(0);
+    jet_fwd_dir<T, KMAX>(s, zz, yy);
+#pragma unroll
+    for (int q = 0; q < KMAX; ++q)
+      if (q < K) st(base + q, yy[q]);
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ void ld4(const T* p, T* out);
 template <>

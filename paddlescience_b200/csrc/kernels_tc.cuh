@@ -151,8 +151,77 @@ __global__ void k_tc_prep_w(const float* __restrict__ W, float* __restrict__ img
   blk[(long long)N * KCH + off] = lo;
 }
 
+// ---- cp.async (LDGSTS) staging of raw fp32 tiles: gives every thread many loads in flight ------------
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 => the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+constexpr int RAW_TILE_BYTES = 128 * KCH * 4;  // 128 rows x 32 fp32, linear (row pitch 128 B)
+
+// Stage rows (c, pl) of the channel-major planes Z[c][p][ld], columns [col0, col0+32), into a linear
+// [row = c*TP + pl][32] tile.  Rows >= rows_used are never touched.
+__device__ __forceinline__ void stage_rows(uint32_t dst, const float* Z, long long plane, int ld, long long p0,
+                                           long long Np, int TP, int rows_used, int col0) {
+  for (int i = threadIdx.x; i < rows_used * 8; i += THREADS) {
+    const int r = i >> 3, q = i & 7;
+    const int c = r / TP, pl = r - c * TP;
+    const long long p = p0 + pl;
+    const bool ok = p < Np;
+    const float* src = ok ? Z + (long long)c * plane + p * ld + col0 + q * 4 : Z;
+    cp_async16(dst + (uint32_t)(r * 128 + q * 16), src, ok);
+  }
+}
+
+__host__ __device__ inline int tc_stage_bytes(int N) { return 2 * A_TILE_BYTES + 2 * N * KCH * 4; }
+__host__ __device__ inline uint32_t tc_pow2_cols(int n) {
+  uint32_t c = 32;
+  while ((int)c < n) c <<= 1;
+  return c;
+}
+
+// 3xTF32 MMAs of one 32-wide K chunk.  Two accumulators: the exact-product "big" term A_hi B_hi
+// alternates between acc0 / acc1 per 8-wide k-step, the small cross terms always go to acc1, so each
+// accumulator sees half as many fp32 round-toward-zero accumulation steps of significant magnitude
+// (tensor cores accumulate with truncation); the epilogue adds acc0 + acc1 with round-to-nearest.
+__device__ __forceinline__ void issue_chunk_mmas(uint32_t acc0, uint32_t acc1, uint32_t stage_addr, int N, uint32_t idesc,
+                                                 bool first_chunk) {
+  const uint32_t a_hi = stage_addr, a_lo = stage_addr + A_TILE_BYTES;
+  const uint32_t b_hi = stage_addr + 2 * A_TILE_BYTES, b_lo = b_hi + (uint32_t)(N * KCH * 4);
+#pragma unroll
+  for (int ks = 0; ks < KCH / 8; ++ks) {  // one MMA consumes K = 8 tf32 = 32 bytes of every row
+    const uint64_t dah = make_smem_desc(a_hi + ks * 32), dal = make_smem_desc(a_lo + ks * 32);
+    const uint64_t dbh = make_smem_desc(b_hi + ks * 32), dbl = make_smem_desc(b_lo + ks * 32);
+    const bool first = first_chunk && ks == 0;
+    if ((ks & 1) == 0) {
+      mma_tf32(acc0, dah, dbh, idesc, first ? 0u : 1u);
+      mma_tf32(acc1, dal, dbh, idesc, first ? 0u : 1u);
+    } else {
+      mma_tf32(acc1, dah, dbh, idesc, 1u);
+      mma_tf32(acc1, dal, dbh, idesc, 1u);
+    }
+    mma_tf32(acc1, dah, dbl, idesc, 1u);
+  }
+}
+
+// acc0 + acc1 for 32 lanes x 32 columns
+__device__ __forceinline__ void load_acc_sum(uint32_t acc0, uint32_t acc1, int q, int col, float (&out)[32]) {
+  uint32_t v0[32], v1[32];
+  const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+  tmem_ld32(acc0 + lane_off + (uint32_t)col, v0);
+  tmem_ld32(acc1 + lane_off + (uint32_t)col, v1);
+  tmem_ld_wait();
+#pragma unroll
+  for (int t = 0; t < 32; ++t) out[t] = __uint_as_float(v0[t]) + __uint_as_float(v1[t]);
+}
+
 struct TcFwdArgs {
-  AOperand<float> A;
+  AOperand<float> A;  // A_ACT over Z_{l-1}
   JetLayout J;
   const float* Wimg;  // [K/32][2][N*32] swizzled hi / lo images
   int Kdim;
@@ -166,12 +235,11 @@ struct TcFwdArgs {
   int num_tiles;
 };
 
-__host__ __device__ inline int tc_stage_bytes(int N) { return 2 * A_TILE_BYTES + 2 * N * KCH * 4; }
-__host__ __device__ inline uint32_t tc_tmem_cols(int N) {
-  uint32_t c = 32;
-  while ((int)c < N) c <<= 1;
-  return c;
-}
+// Shared-memory map of k_tc_fwd / k_tc_dx (offsets from the 1024-aligned base):
+//   [0, 2*stage)                       two operand stages: A_hi | A_lo | B_hi | B_lo
+//   [2*stage, 2*stage + 2*RAW)         raw fp32 staging ring (cp.async), one K chunk ahead
+//   then mbarriers full[2], mma_done[2] and the TMEM base slot
+__host__ __device__ inline int tc_fwd_smem_bytes(int N) { return 2 * tc_stage_bytes(N) + 2 * RAW_TILE_BYTES + 1024 + 256; }
 
 // Forward layer  Z_l = act_jets(Z_{l-1}) W_l + b_l  on the tensor cores.
 // Persistent: CTA t handles tiles t, t+grid, ...; each tile = 128 rows = TP points x C channels.
@@ -182,10 +250,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
   unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
   const int N = g.Nout;
   const int stage_bytes = tc_stage_bytes(N);
-  const uint32_t bars = base + 2 * stage_bytes;  // full[2], mma_done[2]
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 2 * stage_bytes + 64);
+  const uint32_t raw_off = 2 * stage_bytes;
+  const uint32_t bars_off = raw_off + 2 * RAW_TILE_BYTES;
+  const uint32_t bars = base + bars_off;  // full[2] at +0,+8 ; mma_done[2] at +16,+24
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 64);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t ncols = tc_tmem_cols(N);
+  const uint32_t ncols = tc_pow2_cols(2 * N);
 
   if (tid == 0) {
     mbar_init(bars + 0, 1);
@@ -196,7 +266,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
     fence_proxy_async();
   }
   if (warp == 1) {
-    tmem_alloc(base + 2 * stage_bytes + 64, ncols);
+    tmem_alloc(base + bars_off + 64, ncols);
     tmem_relinquish();
   }
   // rows that never receive data (>= C*TP) must read as zero: clear both A tiles once
@@ -207,7 +277,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc0 = *tmem_slot, acc1 = acc0 + (uint32_t)N;
   const uint32_t idesc = make_idesc_tf32(128, N);
   const int nchunks = g.Kdim / KCH;
   const uint32_t b_bytes = (uint32_t)(2 * N * KCH * 4);
@@ -215,45 +285,50 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
   const int rows_used = g.J.C * TP;
 
   uint32_t it = 0;  // running chunk counter (stage = it & 1, use index = it >> 1)
+  if ((int)blockIdx.x < g.num_tiles)
+    stage_rows(base + raw_off, g.A.Z, g.A.plane, g.A.ld, (long long)blockIdx.x * TP, g.Np, TP, rows_used, 0);
+  cp_async_commit();
   for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
     const long long p0 = (long long)tile * TP;
     for (int j = 0; j < nchunks; ++j, ++it) {
       const uint32_t s = it & 1u, u = it >> 1;
       unsigned char* stage_ptr = base_ptr + s * stage_bytes;
       const uint32_t stage_addr = base + s * stage_bytes;
+      // prefetch the next chunk's raw rows (possibly the first chunk of this CTA's next tile)
+      {
+        int ntile = tile, nj = j + 1;
+        if (nj == nchunks) { nj = 0; ntile = tile + gridDim.x; }
+        if (ntile < g.num_tiles)
+          stage_rows(base + raw_off + ((it + 1) & 1u) * RAW_TILE_BYTES, g.A.Z, g.A.plane, g.A.ld, (long long)ntile * TP,
+                     g.Np, TP, rows_used, nj * KCH);
+        cp_async_commit();
+      }
+      cp_async_wait<1>();  // this chunk's raw rows have landed (this thread's pieces) ...
+      __syncthreads();     // ... and everybody else's
       if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);  // MMAs that read this stage have retired
       if (tid == 0) {
         mbar_expect_tx(bars + 8 * s, b_bytes);
         bulk_g2s(stage_addr + 2 * A_TILE_BYTES, g.Wimg + (long long)j * 2 * N * KCH, b_bytes, bars + 8 * s);
       }
-      // produce the A chunk (hi, lo) for k in [32 j, 32 j + 32)
+      const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + (it & 1u) * RAW_TILE_BYTES);
       for (int item = tid; item < TP * KCH; item += THREADS) {
         const int kk = item & (KCH - 1), pl = item / KCH;
-        const long long p = p0 + pl;
-        const int k = j * KCH + kk;
-        produce_a<float, KMAX>(g.A, g.J, p, k, p < g.Np, [&](int c, float v) {
-          const int r = c * TP + pl;
-          const float hi = tf32_rn(v);
-          const uint32_t off = sw128(r, kk);
-          *reinterpret_cast<float*>(stage_ptr + off) = hi;
-          *reinterpret_cast<float*>(stage_ptr + A_TILE_BYTES + off) = v - hi;
-        });
+        produce_from<float, KMAX>(
+            g.A.mode, g.A.act, g.J, (p0 + pl) < g.Np, [&](int c) { return raw[(c * TP + pl) * KCH + kk]; },
+            [&](int c, float v) {
+              const int r = c * TP + pl;
+              const float hi = tf32_rn(v);
+              const uint32_t off = sw128(r, kk);
+              *reinterpret_cast<float*>(stage_ptr + off) = hi;
+              *reinterpret_cast<float*>(stage_ptr + A_TILE_BYTES + off) = v - hi;
+            });
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncthreads();
       if (tid == 0) {
         mbar_wait(bars + 8 * s, u & 1u);  // weight images of this chunk have landed
         tc_fence_after();
-        const uint32_t a_hi = stage_addr, a_lo = stage_addr + A_TILE_BYTES;
-        const uint32_t b_hi = stage_addr + 2 * A_TILE_BYTES, b_lo = b_hi + (uint32_t)(N * KCH * 4);
-#pragma unroll
-        for (int ks = 0; ks < KCH / 8; ++ks) {  // one MMA consumes K = 8 tf32 = 32 bytes of every row
-          const uint64_t dah = make_smem_desc(a_hi + ks * 32), dal = make_smem_desc(a_lo + ks * 32);
-          const uint64_t dbh = make_smem_desc(b_hi + ks * 32), dbl = make_smem_desc(b_lo + ks * 32);
-          mma_tf32(tmem_base, dah, dbh, idesc, (j > 0 || ks > 0) ? 1u : 0u);
-          mma_tf32(tmem_base, dal, dbh, idesc, 1u);
-          mma_tf32(tmem_base, dah, dbl, idesc, 1u);
-        }
+        issue_chunk_mmas(acc0, acc1, stage_addr, N, idesc, j == 0);
         mma_commit(bars + 16 + 8 * s);  // arrives when every MMA issued so far has completed
       }
     }
@@ -269,20 +344,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
       const long long p = p0 + pl;
       const bool st_ok = row_ok && p < g.Np;
       float* out_row = g.Out + (long long)c * g.oplane + p * g.ldo;
-      const int ncb = N / 32;  // 32-column blocks; warps with half=0 take even blocks, half=1 odd blocks
+      const int ncb = N / 32;  // warps with half=0 take even 32-column blocks, half=1 odd blocks
       for (int cb = half; cb < ncb; cb += 2) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), v);
-        tmem_ld_wait();
+        float v[32];
+        load_acc_sum(acc0, acc1, q, cb * 32, v);
         if (st_ok) {
 #pragma unroll
           for (int t = 0; t < 32; t += 4) {
             const int n = cb * 32 + t;
-            float4 o;
-            o.x = __uint_as_float(v[t]);
-            o.y = __uint_as_float(v[t + 1]);
-            o.z = __uint_as_float(v[t + 2]);
-            o.w = __uint_as_float(v[t + 3]);
+            float4 o = make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]);
             if (c == 0 && g.bias) {
               o.x += g.bias[n];
               o.y += g.bias[n + 1];
@@ -293,22 +363,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
           }
         }
       }
-      if (N % 32) {  // N is a multiple of 16: one trailing 16-column block, handled by half 0 via a x32 read is not safe
-        // (not reached: eligibility requires N % 32 == 0)
-      }
       tc_fence_before();
-      __syncthreads();  // accumulator drained before the next tile's first MMA overwrites it
+      __syncthreads();  // accumulators drained before the next tile's first MMA overwrites them
     }
   }
+  cp_async_wait<0>();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+  if (warp == 1) tmem_dealloc(acc0, ncols);
 }
-
 
 // =====================================================================================================
 // Backward dx on the tensor cores:  Abar = Zbar_l W_l^T  (contraction over the layer's outputs), then the
-// activation adjoint  Zbar_{l-1} = adj(Abar, Z_{l-1})  through a shared-memory exchange tile (the C
-// channels of one point live in different TMEM lanes, the adjoint needs them together).
+// activation adjoint  Zbar_{l-1} = adj(Abar, Z_{l-1}).  The C channels of one point live in different TMEM
+// lanes and the adjoint needs them together, so each 32-column block goes through a shared-memory
+// exchange tile; the matching Z_{l-1} block is prefetched with cp.async one block ahead.  During the
+// epilogue all MMAs have retired, so the exchange tile lives in stage 0's A_hi region and the two Z
+// buffers in stage 1's A_hi / A_lo regions (same 128-byte row pitch; pad rows stay zero).
 // =====================================================================================================
 struct TcDxArgs {
   AOperand<float> A;   // A_PLAIN over Zbar_l
@@ -328,9 +398,6 @@ struct TcDxArgs {
   int num_tiles;
 };
 
-constexpr int XLD = 33;                          // exchange-tile row pitch (floats): conflict-free both ways
-constexpr int X_TILE_BYTES = 128 * XLD * 4;      // one 128 x 32 block
-
 template <int KMAX>
 __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
   extern __shared__ unsigned char smem_dyn[];
@@ -338,12 +405,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
   unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
   const int N = g.Nout;
   const int stage_bytes = tc_stage_bytes(N);
-  float* xch = reinterpret_cast<float*>(base_ptr + 2 * stage_bytes);  // 2 exchange tiles (one per warp half)
-  const uint32_t bars_off = 2 * stage_bytes + 2 * X_TILE_BYTES;
+  const uint32_t raw_off = 2 * stage_bytes;
+  const uint32_t bars_off = raw_off + 2 * RAW_TILE_BYTES;
   const uint32_t bars = base + bars_off;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 64);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t ncols = tc_tmem_cols(N);
+  const uint32_t ncols = tc_pow2_cols(2 * N);
 
   if (tid == 0) {
     mbar_init(bars + 0, 1);
@@ -364,51 +431,56 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc0 = *tmem_slot, acc1 = acc0 + (uint32_t)N;
   const uint32_t idesc = make_idesc_tf32(128, N);
   const int nchunks = g.Kdim / KCH;
   const uint32_t b_bytes = (uint32_t)(2 * N * KCH * 4);
   const int TP = g.TP;
+  const int rows_used = g.J.C * TP;
+  float* X = reinterpret_cast<float*>(base_ptr);  // exchange tile: stage 0, A_hi region (16 KB)
+  const uint32_t zbuf_addr = base + stage_bytes;   // two Z blocks: stage 1, A_hi and A_lo regions
+  const float* zbuf_ptr = reinterpret_cast<const float*>(base_ptr + stage_bytes);
 
   uint32_t it = 0;
+  if ((int)blockIdx.x < g.num_tiles)
+    stage_rows(base + raw_off, g.A.Z, g.A.plane, g.A.ld, (long long)blockIdx.x * TP, g.Np, TP, rows_used, 0);
+  cp_async_commit();
   for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
     const long long p0 = (long long)tile * TP;
     for (int j = 0; j < nchunks; ++j, ++it) {
       const uint32_t s = it & 1u, u = it >> 1;
       unsigned char* stage_ptr = base_ptr + s * stage_bytes;
       const uint32_t stage_addr = base + s * stage_bytes;
+      {
+        int ntile = tile, nj = j + 1;
+        if (nj == nchunks) { nj = 0; ntile = tile + gridDim.x; }
+        if (ntile < g.num_tiles)
+          stage_rows(base + raw_off + ((it + 1) & 1u) * RAW_TILE_BYTES, g.A.Z, g.A.plane, g.A.ld, (long long)ntile * TP,
+                     g.Np, TP, rows_used, nj * KCH);
+        cp_async_commit();
+      }
+      cp_async_wait<1>();
+      __syncthreads();
       if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
       if (tid == 0) {
         mbar_expect_tx(bars + 8 * s, b_bytes);
         bulk_g2s(stage_addr + 2 * A_TILE_BYTES, g.Wimg + (long long)j * 2 * N * KCH, b_bytes, bars + 8 * s);
       }
-      for (int item = tid; item < TP * KCH; item += THREADS) {
-        const int kk = item & (KCH - 1), pl = item / KCH;
-        const long long p = p0 + pl;
-        const int k = j * KCH + kk;
-        produce_a<float, KMAX>(g.A, g.J, p, k, p < g.Np, [&](int c, float v) {
-          const int r = c * TP + pl;
-          const float hi = tf32_rn(v);
-          const uint32_t off = sw128(r, kk);
-          *reinterpret_cast<float*>(stage_ptr + off) = hi;
-          *reinterpret_cast<float*>(stage_ptr + A_TILE_BYTES + off) = v - hi;
-        });
+      const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + (it & 1u) * RAW_TILE_BYTES);
+      for (int item = tid; item < rows_used * KCH; item += THREADS) {  // plain split, row by row
+        const int kk = item & (KCH - 1), r = item / KCH;
+        const float v = raw[r * KCH + kk];
+        const float hi = tf32_rn(v);
+        const uint32_t off = sw128(r, kk);
+        *reinterpret_cast<float*>(stage_ptr + off) = hi;
+        *reinterpret_cast<float*>(stage_ptr + A_TILE_BYTES + off) = v - hi;
       }
       fence_proxy_async();
       __syncthreads();
       if (tid == 0) {
         mbar_wait(bars + 8 * s, u & 1u);
         tc_fence_after();
-        const uint32_t a_hi = stage_addr, a_lo = stage_addr + A_TILE_BYTES;
-        const uint32_t b_hi = stage_addr + 2 * A_TILE_BYTES, b_lo = b_hi + (uint32_t)(N * KCH * 4);
-#pragma unroll
-        for (int ks = 0; ks < KCH / 8; ++ks) {
-          const uint64_t dah = make_smem_desc(a_hi + ks * 32), dal = make_smem_desc(a_lo + ks * 32);
-          const uint64_t dbh = make_smem_desc(b_hi + ks * 32), dbl = make_smem_desc(b_lo + ks * 32);
-          mma_tf32(tmem_base, dah, dbh, idesc, (j > 0 || ks > 0) ? 1u : 0u);
-          mma_tf32(tmem_base, dal, dbh, idesc, 1u);
-          mma_tf32(tmem_base, dah, dbl, idesc, 1u);
-        }
+        issue_chunk_mmas(acc0, acc1, stage_addr, N, idesc, j == 0);
         mma_commit(bars + 16 + 8 * s);
       }
     }
@@ -417,62 +489,67 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
       const uint32_t last = it - 1;
       mbar_wait(bars + 16 + 8 * (last & 1u), (last >> 1) & 1u);
       tc_fence_after();
-      const int q = warp & 3, half = warp >> 2;
-      float* X = xch + half * (128 * XLD);
       const int ncb = N / 32;
-      const int tih = tid & 127;  // thread index inside its half
-      for (int cb0 = 0; cb0 < ncb; cb0 += 2) {
-        const int cb = cb0 + half;
-        if (cb < ncb) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), v);
-          tmem_ld_wait();
-          float* xr = X + (q * 32 + lane) * XLD;
+      stage_rows(zbuf_addr, g.Zprev, g.zplane, g.ldz, p0, g.Np, TP, rows_used, 0);
+      cp_async_commit();
+      for (int cb = 0; cb < ncb; ++cb) {
+        if (cb + 1 < ncb)
+          stage_rows(zbuf_addr + ((cb + 1) & 1) * A_TILE_BYTES, g.Zprev, g.zplane, g.ldz, p0, g.Np, TP, rows_used,
+                     (cb + 1) * 32);
+        cp_async_commit();
+        if (warp < 4) {  // 128 lanes x 32 columns of Abar -> X[r][t ^ (r & 31)]  (conflict-free both ways)
+          float v[32];
+          load_acc_sum(acc0, acc1, warp, cb * 32, v);
+          const int r = warp * 32 + lane;
+          float* xr = X + r * KCH;
 #pragma unroll
-          for (int t = 0; t < 32; ++t) xr[t] = __uint_as_float(v[t]);
+          for (int t = 0; t < 32; ++t) xr[t ^ lane] = v[t];
         }
+        cp_async_wait<1>();
         __syncthreads();
-        if (cb < ncb) {
-          for (int item = tih; item < TP * 32; item += 128) {
-            const int nn = item & 31, pl = item >> 5;
-            const long long p = p0 + pl;
-            if (p >= g.Np) continue;
-            const int n = cb * 32 + nn;
-            const float* z = g.Zprev + p * g.ldz + n;
-            float* zb_out = g.Out + p * g.ldo + n;
-            float sc[6];
-            float y0;
-            act_coef<float, KMAX + 1>(g.act, z[0], y0, sc);
-            const float y0b = X[pl * XLD + nn];
-            float sb[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-            for (int d = 0; d < g.J.n_dir; ++d) {
-              const int K = g.J.dir_order[d];
-              const int cbase = g.J.dir_base[d];
-              float zz[4], yb[4], zb[4];
+        const float* zb = zbuf_ptr + (cb & 1) * (A_TILE_BYTES / 4);
+        for (int item = tid; item < TP * 32; item += THREADS) {
+          const int nn = item & 31, pl = item >> 5;
+          const long long p = p0 + pl;
+          if (p >= g.Np) continue;
+          const int n = cb * 32 + nn;
+          float* zb_out = g.Out + p * g.ldo + n;
+          float sc[6];
+          float y0;
+          act_coef<float, KMAX + 1>(g.act, zb[pl * KCH + nn], y0, sc);
+          const float y0b = X[pl * KCH + (nn ^ (pl & 31))];
+          float sb[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int d = 0; d < g.J.n_dir; ++d) {
+            const int K = g.J.dir_order[d];
+            const int cbase = g.J.dir_base[d];
+            float zz[4], yb[4], zbv[4];
 #pragma unroll
-              for (int o = 0; o < 4; ++o) {
-                const bool on = (o < KMAX && o < K);
-                zz[o] = on ? z[(long long)(cbase + o) * g.zplane] : 0.f;
-                yb[o] = on ? X[((cbase + o) * TP + pl) * XLD + nn] : 0.f;
-                zb[o] = 0.f;
-              }
-              jet_adj_dir<float, KMAX>(sc, zz, yb, zb, sb);
-#pragma unroll
-              for (int o = 0; o < KMAX; ++o)
-                if (o < K) zb_out[(long long)(cbase + o) * g.oplane] = zb[o];
+            for (int o = 0; o < 4; ++o) {
+              const bool on = (o < KMAX && o < K);
+              const int rr = (cbase + o) * TP + pl;
+              zz[o] = on ? zb[rr * KCH + nn] : 0.f;
+              yb[o] = on ? X[rr * KCH + (nn ^ (rr & 31))] : 0.f;
+              zbv[o] = 0.f;
             }
-            zb_out[0] = jet_adj_z0<float, KMAX>(sc, y0b, sb);
+            jet_adj_dir<float, KMAX>(sc, zz, yb, zbv, sb);
+#pragma unroll
+            for (int o = 0; o < KMAX; ++o)
+              if (o < K) zb_out[(long long)(cbase + o) * g.oplane] = zbv[o];
           }
+          zb_out[0] = jet_adj_z0<float, KMAX>(sc, y0b, sb);
         }
         __syncthreads();
       }
+      // restore the scratch regions: rows < rows_used get overwritten by the next production anyway, but
+      // they must hold finite data for the pad-row-zero invariant only; X pad rows are exact zeros.
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
     }
   }
+  cp_async_wait<0>();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+  if (warp == 1) tmem_dealloc(acc0, ncols);
 }
 
 // =====================================================================================================
@@ -480,7 +557,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
 // Reduction dimension = jet rows (points x channels).  CTA (kt, split) owns dW rows [128 kt, 128 kt + 128)
 // and a contiguous range of 32-row reduction chunks (PT points each); it accumulates in TMEM across its
 // whole range and flushes once with red.global.add.  Both operands are written transposed into K-major
-// SW128 tiles: warps 0-3 recompute A_{l-1} = act_jets(Z_{l-1}) (thread = dW row k), warps 4-7 split Zbar_l.
+// SW128 tiles: warps 0-3 recompute A_{l-1} = act_jets(Z_{l-1}) from a cp.async-staged raw tile (thread =
+// dW row k), warps 4-7 split Zbar_l, whose values are prefetched into registers one chunk ahead.
 // =====================================================================================================
 struct TcDwArgs {
   AOperand<float> A;   // A_ACT over Z_{l-1}
@@ -496,6 +574,10 @@ struct TcDwArgs {
   int chunks_per_split;
 };
 
+constexpr int DW_RAW_BYTES = KCH * 128 * 4;  // raw Z rows of one chunk: [32 rows][128 k] fp32 = 16 KB
+__host__ __device__ inline int tc_dw_smem_bytes(int N) { return 2 * tc_stage_bytes(N) + 2 * DW_RAW_BYTES + 1024 + 256; }
+constexpr int DW_MAX_ITEMS = 16;  // (N * 8) / 128 B'-items per thread at N = 256
+
 template <int KMAX>
 __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
   extern __shared__ unsigned char smem_dyn[];
@@ -504,11 +586,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
   unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
   const int N = g.Nout;
   const int stage_bytes = tc_stage_bytes(N);
-  const uint32_t bars_off = 2 * stage_bytes;
-  const uint32_t bars = base + bars_off;  // mma_done[2] at +16, +24 (no TMA here: +0, +8 unused)
+  const uint32_t raw_off = 2 * stage_bytes;
+  const uint32_t bars_off = raw_off + 2 * DW_RAW_BYTES;
+  const uint32_t bars = base + bars_off;  // mma_done[2] at +16, +24
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 64);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t ncols = tc_tmem_cols(N);
+  const uint32_t ncols = tc_pow2_cols(2 * N);
   const int PT = g.PT;
   const int rows_used = g.J.C * PT;
 
@@ -534,70 +617,103 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t acc0 = *tmem_slot, acc1 = acc0 + (uint32_t)N;
   const uint32_t idesc = make_idesc_tf32(128, N);
   const int k0 = blockIdx.x * 128;
   const long long total_chunks = (g.Np + PT - 1) / PT;
   const long long ch_begin = (long long)blockIdx.y * g.chunks_per_split;
   long long ch_end = ch_begin + g.chunks_per_split;
   if (ch_end > total_chunks) ch_end = total_chunks;
+  const int nq = (rows_used + 3) / 4;
+  const int n_items = N * nq;  // B' items (n, q) handled by threads 128..255
+
+  // raw Z rows of a chunk: row rr = c*PT + pl, 128 k-columns of this CTA's dW row block
+  auto stage_z = [&](long long ch, uint32_t dst) {
+    const long long pb = ch * PT;
+    for (int i = tid; i < rows_used * 32; i += THREADS) {  // 32 16-byte pieces per 512-byte row
+      const int rr = i >> 5, q = i & 31;
+      const long long p = pb + row_pl[rr];
+      const bool ok = p < g.Np;
+      const float* src = ok ? g.A.Z + (long long)row_c[rr] * g.A.plane + p * g.A.ld + k0 + q * 4 : g.A.Z;
+      cp_async16(dst + (uint32_t)(rr * 512 + q * 16), src, ok);
+    }
+  };
+  float zbreg[DW_MAX_ITEMS][4];  // B' side register prefetch (threads 128..255)
+  auto load_zbar = [&](long long ch) {
+    const long long pb = ch * PT;
+#pragma unroll
+    for (int ii = 0; ii < DW_MAX_ITEMS; ++ii) {
+      const int item = (tid - 128) + ii * 128;
+      const bool on = item < n_items;
+      const int n = on ? item % N : 0, q = on ? item / N : 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int rr = 4 * q + e;
+        const int c = row_c[rr];
+        const long long p = pb + row_pl[rr];
+        zbreg[ii][e] = (on && c >= 0 && p < g.Np) ? g.Zbar[(long long)c * g.zbplane + p * g.ldzb + n] : 0.f;
+      }
+    }
+  };
 
   uint32_t it = 0;
+  if (ch_begin < ch_end) {
+    stage_z(ch_begin, base + raw_off);
+    if (warp >= 4) load_zbar(ch_begin);
+  }
+  cp_async_commit();
   for (long long ch = ch_begin; ch < ch_end; ++ch, ++it) {
     const uint32_t s = it & 1u, u = it >> 1;
     unsigned char* stage_ptr = base_ptr + s * stage_bytes;
     const uint32_t stage_addr = base + s * stage_bytes;
+    if (ch + 1 < ch_end) stage_z(ch + 1, base + raw_off + ((it + 1) & 1u) * DW_RAW_BYTES);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
     if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
     const long long pbase = ch * PT;
     if (warp < 4) {
       // A' tile: row = dW row k (this thread), column rr = c*PT + pl
       const int k = tid;  // 0..127
+      const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + (it & 1u) * DW_RAW_BYTES);
       for (int pl = 0; pl < PT; ++pl) {
-        const long long p = pbase + pl;
-        produce_a<float, KMAX>(g.A, g.J, p, k0 + k, p < g.Np, [&](int c, float v) {
-          const int rr = c * PT + pl;
-          const float hi = tf32_rn(v);
-          const uint32_t off = sw128(k, rr);
-          *reinterpret_cast<float*>(stage_ptr + off) = hi;
-          *reinterpret_cast<float*>(stage_ptr + A_TILE_BYTES + off) = v - hi;
-        });
+        produce_from<float, KMAX>(
+            g.A.mode, g.A.act, g.J, (pbase + pl) < g.Np, [&](int c) { return raw[(c * PT + pl) * 128 + k]; },
+            [&](int c, float v) {
+              const int rr = c * PT + pl;
+              const float hi = tf32_rn(v);
+              const uint32_t off = sw128(k, rr);
+              *reinterpret_cast<float*>(stage_ptr + off) = hi;
+              *reinterpret_cast<float*>(stage_ptr + A_TILE_BYTES + off) = v - hi;
+            });
       }
     } else {
-      // B' tile: row = n, 16-byte chunk q holds reduction columns 4q..4q+3
+      // B' tile: row = n, 16-byte chunk q holds reduction columns 4q..4q+3 (values prefetched in registers)
       unsigned char* b_hi = stage_ptr + 2 * A_TILE_BYTES;
       unsigned char* b_lo = b_hi + N * KCH * 4;
-      const int nq = (rows_used + 3) / 4;
-      for (int item = tid - 128; item < N * nq; item += 128) {
-        const int n = item % N, q = item / N;
-        float hi[4], lo[4];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int rr = 4 * q + e;
-          const int c = row_c[rr];
-          const long long p = pbase + row_pl[rr];
-          const float v = (c >= 0 && p < g.Np) ? g.Zbar[(long long)c * g.zbplane + p * g.ldzb + n] : 0.f;
-          hi[e] = tf32_rn(v);
-          lo[e] = v - hi[e];
+      for (int ii = 0; ii < DW_MAX_ITEMS; ++ii) {
+        const int item = (tid - 128) + ii * 128;
+        if (item < n_items) {
+          const int n = item % N, q = item / N;
+          float hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            hi[e] = tf32_rn(zbreg[ii][e]);
+            lo[e] = zbreg[ii][e] - hi[e];
+          }
+          const uint32_t off = sw128(n, 4 * q);
+          *reinterpret_cast<float4*>(b_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(b_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
-        const uint32_t off = sw128(n, 4 * q);
-        *reinterpret_cast<float4*>(b_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(b_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
       }
+      if (ch + 1 < ch_end) load_zbar(ch + 1);  // in flight while the MMAs of this chunk run
     }
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t a_hi = stage_addr, a_lo = stage_addr + A_TILE_BYTES;
-      const uint32_t b_hi = stage_addr + 2 * A_TILE_BYTES, b_lo = b_hi + (uint32_t)(N * KCH * 4);
-#pragma unroll
-      for (int ks = 0; ks < KCH / 8; ++ks) {
-        const uint64_t dah = make_smem_desc(a_hi + ks * 32), dal = make_smem_desc(a_lo + ks * 32);
-        const uint64_t dbh = make_smem_desc(b_hi + ks * 32), dbl = make_smem_desc(b_lo + ks * 32);
-        mma_tf32(tmem_base, dah, dbh, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-        mma_tf32(tmem_base, dal, dbh, idesc, 1u);
-        mma_tf32(tmem_base, dah, dbl, idesc, 1u);
-      }
+      issue_chunk_mmas(acc0, acc1, stage_addr, N, idesc, it == 0);
       mma_commit(bars + 16 + 8 * s);
     }
   }
@@ -610,18 +726,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
     float* dw_row = g.dW + (long long)k * N;
     const int ncb = N / 32;
     for (int cb = half; cb < ncb; cb += 2) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), v);
-      tmem_ld_wait();
+      float v[32];
+      load_acc_sum(acc0, acc1, q, cb * 32, v);
       if (k < g.Kdim) {
 #pragma unroll
-        for (int t = 0; t < 32; ++t) atomicAdd(dw_row + cb * 32 + t, __uint_as_float(v[t]));
+        for (int t = 0; t < 32; ++t) atomicAdd(dw_row + cb * 32 + t, v[t]);
       }
     }
   }
+  cp_async_wait<0>();
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+  if (warp == 1) tmem_dealloc(acc0, ncols);
 }
 
 // db_l[n] += sum over points of Zbar_l[channel 0][p][n]   (tiny, HBM-bound)

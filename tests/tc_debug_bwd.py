@@ -44,7 +44,7 @@ def run(hidden, n, masks=(1, 2, 4, 7), act="tanh", seed=0, chunk=0):
         torch.cuda.synchronize()
         gerr = float((g - g_ref).norm() / g_ref.norm())
         lerr = float(((l - l_ref).abs() / l_ref.abs()).max())
-        good = gerr < 3e-5 and lerr < 1e-5 and not bool(torch.isnan(g).any())
+        good = gerr < 5e-5 and lerr < 3e-5 and not bool(torch.isnan(g).any())
         print(f"  mask={mask}: launches={plan.last_launches} loss rel {lerr:.2e} grad rel-L2 {gerr:.2e} nan={bool(torch.isnan(g).any())} {'OK' if good else 'BAD'}", flush=True)
         if not good:
             ok = False
