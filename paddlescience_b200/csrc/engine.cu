@@ -442,6 +442,9 @@ static int run(ppsci_plan* P, const CallArgs& a) {
   const int smem_w = (RC * TMS + RC * TN) * (int)sizeof(T);
   const int TP = TM / C;
   const int PT = RC / C;
+  const bool thin_on = getenv("PPSCI_B200_NO_THIN") == nullptr;
+  const bool thin_first = thin_on && L >= 2 && s.widths[0] <= THIN_MAXF;
+  const bool thin_last = thin_on && L >= 2 && n_out <= THIN_MAXM && C * n_out <= THIN_MAXCM;
 
   if (a.want_loss) CK(cudaMemsetAsync(loss_acc, 0, PPSCI_MAX_RES * sizeof(double), st));
   const bool do_bwd = a.want_loss && grads != nullptr;
@@ -490,6 +493,45 @@ static int run(ppsci_plan* P, const CallArgs& a) {
     const unsigned ptiles = (unsigned)((nc + TP - 1) / TP);
     // ---------------- forward ----------------
     for (int l = 1; l <= L; ++l) {
+      if (l == 1 && thin_first) {
+        FirstArgs<T> f;
+        memset(&f, 0, sizeof(f));
+        fill_seed<T>(P, a.x_cols, c0, &f.A);
+        f.J = P->J;
+        f.W = params + P->w_off[1];
+        f.bias = params + P->b_off[1];
+        f.nf = s.widths[0];
+        f.N = s.widths[1];
+        f.Out = reinterpret_cast<T*>(ws + (L > 1 ? cv.z[1] : cv.y));
+        f.ldo = P->ld[1];
+        f.oplane = (long long)nc_max * P->ld[1];
+        f.Np = nc;
+        const long long tot = (long long)nc * f.N;
+        auto k1 = k_first_fwd<T, KMAX>;
+        ProfScope ps_(P, CLS_FWD, st);
+        PPSCI_LAUNCH(k1, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, f);
+        P->launches++;
+        continue;
+      }
+      if (l == L && thin_last) {
+        LastArgs<T> f;
+        memset(&f, 0, sizeof(f));
+        fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[L - 1]), P->ld[L - 1], nc_max, A_ACT, &f.A);
+        f.J = P->J;
+        f.W = params + P->w_off[L];
+        f.bias = params + P->b_off[L];
+        f.K = s.widths[L - 1];
+        f.m = s.widths[L];
+        f.Y = reinterpret_cast<T*>(ws + cv.y);
+        f.ldy = P->ld[L];
+        f.yplane = (long long)nc_max * P->ld[L];
+        f.Np = nc;
+        auto k2 = k_last_fwd<T, KMAX>;
+        ProfScope ps_(P, CLS_FWD, st);
+        PPSCI_LAUNCH(k2, dim3((unsigned)((nc + 7) / 8)), dim3(256), 0, st, f);
+        P->launches++;
+        continue;
+      }
 #ifndef PPSCI_EMUL
       if constexpr (sizeof(T) == 4) {
         if (P->use_tc && (P->tc_mask & 1) && tc_layer_ok(s, l)) {
@@ -508,11 +550,10 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           t.TP = TP;
           t.num_tiles = (int)ptiles;
           const int smem_tc = tc::tc_fwd_smem_bytes(t.Nout);
-          auto ktc = tc::k_tc_fwd<KMAX>;
-          CK(cudaFuncSetAttribute(ktc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc));
           const unsigned gridx = ptiles < (unsigned)P->num_sms ? ptiles : (unsigned)P->num_sms;
           ProfScope ps_(P, CLS_FWD, st);
-          ktc<<<dim3(gridx), dim3(tc::THREADS), smem_tc, st>>>(t);
+          PPSCI_TC_LAUNCH(k_tc_fwd, tc_pick_layout(P->J, s.act), KMAX, dim3(gridx), smem_tc, st, t,
+                          return fail(std::string("cudaFuncSetAttribute(k_tc_fwd): ") + cudaGetErrorString(e_)));
           P->launches++;
           continue;
         }
@@ -592,6 +633,56 @@ static int run(ppsci_plan* P, const CallArgs& a) {
     int zbar_ld = P->ld[L];
     int flip = 0;
     for (int l = L; l >= 1; --l) {
+      if (l == L && thin_last) {  // dW_L, db_L and Zbar_{L-1} in one streaming pass
+        LastArgs<T> f;
+        memset(&f, 0, sizeof(f));
+        fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[L - 1]), P->ld[L - 1], nc_max, A_ACT, &f.A);
+        f.J = P->J;
+        f.W = params + P->w_off[L];
+        f.K = s.widths[L - 1];
+        f.m = s.widths[L];
+        f.Ybar = zbar_cur;
+        f.ldy = P->ld[L];
+        f.yplane = (long long)nc_max * P->ld[L];
+        T* outp = reinterpret_cast<T*>(ws + (flip ? cv.zbar1 : cv.zbar0));
+        f.ZbarOut = outp;
+        f.ldo = P->ld[L - 1];
+        f.oplane = (long long)nc_max * P->ld[L - 1];
+        f.dW = grads + P->w_off[L];
+        f.db = grads + P->b_off[L];
+        f.Np = nc;
+        f.pts_per_block = 128;
+        auto k3 = k_last_bwd<T, KMAX>;
+        {
+          ProfScope ps_(P, CLS_DX, st);
+          PPSCI_LAUNCH(k3, dim3((unsigned)((f.K + 255) / 256), (unsigned)((nc + 127) / 128)), dim3(256), 0, st, f);
+          P->launches++;
+        }
+        zbar_cur = outp;
+        zbar_ld = P->ld[L - 1];
+        flip ^= 1;
+        continue;
+      }
+      if (l == 1 && thin_first) {
+        FirstArgs<T> f;
+        memset(&f, 0, sizeof(f));
+        fill_seed<T>(P, a.x_cols, c0, &f.A);
+        f.J = P->J;
+        f.nf = s.widths[0];
+        f.N = s.widths[1];
+        f.Zbar = zbar_cur;
+        f.ldzb = zbar_ld;
+        f.zbplane = (long long)nc_max * zbar_ld;
+        f.dW = grads + P->w_off[1];
+        f.db = grads + P->b_off[1];
+        f.Np = nc;
+        f.pts_per_block = 256;
+        auto k4 = k_first_dw<T, KMAX>;
+        ProfScope ps_(P, CLS_DW, st);
+        PPSCI_LAUNCH(k4, dim3((unsigned)((f.N + 255) / 256), (unsigned)((nc + 255) / 256)), dim3(256), 0, st, f);
+        P->launches++;
+        break;
+      }
 #ifndef PPSCI_EMUL
       bool dw_done = false;
       if constexpr (sizeof(T) == 4) {
@@ -609,27 +700,30 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           t.Np = nc;
           const int PTt = tc::KCH / C;
           t.PT = PTt;
-          const unsigned kt = (unsigned)(t.Kdim / 128);
+          const int NC = tc_dw_cols_per_cta(s.widths[l]);
+          t.Nout = NC;
+          t.n0_stride = NC;
+          t.ldw = s.widths[l];
+          const unsigned kt = (unsigned)(t.Kdim / 128), nb = (unsigned)(s.widths[l] / NC);
           const long long total_chunks = (nc + PTt - 1) / PTt;
-          long long want = P->num_sms / kt;
+          long long want = P->num_sms / (kt * nb);
           if (want < 1) want = 1;
           if (want > total_chunks) want = total_chunks;
           const long long cps = (total_chunks + want - 1) / want;
           const unsigned splits = (unsigned)((total_chunks + cps - 1) / cps);
           t.chunks_per_split = (int)cps;
-          const int smem_tc = tc::tc_dw_smem_bytes(t.Nout);
-          auto kdw = tc::k_tc_dw<KMAX>;
-          CK(cudaFuncSetAttribute(kdw, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc));
+          const int smem_tc = tc::tc_dw_smem_bytes(NC);
           {
             ProfScope ps_(P, CLS_DW, st);
-            kdw<<<dim3(kt, splits), dim3(tc::THREADS), smem_tc, st>>>(t);
+            PPSCI_TC_LAUNCH(k_tc_dw, tc_pick_layout(P->J, s.act), KMAX, dim3(kt, splits, nb), smem_tc, st, t,
+                            return fail(std::string("cudaFuncSetAttribute(k_tc_dw): ") + cudaGetErrorString(e_)));
             P->launches++;
           }
           {
             ProfScope ps_(P, CLS_DW, st);
             const int ppb = 512;
-            tc::k_bias_grad<<<dim3((unsigned)((t.Nout + 127) / 128), (unsigned)((nc + ppb - 1) / ppb)), dim3(128), 0, st>>>(
-                reinterpret_cast<const float*>(zbar_cur), zbar_ld, (long long)nc, t.Nout,
+            tc::k_bias_grad<<<dim3((unsigned)((s.widths[l] + 127) / 128), (unsigned)((nc + ppb - 1) / ppb)), dim3(128), 0, st>>>(
+                reinterpret_cast<const float*>(zbar_cur), zbar_ld, (long long)nc, s.widths[l],
                 reinterpret_cast<float*>(grads) + P->b_off[l], ppb);
             P->launches++;
           }
@@ -688,12 +782,11 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           t.TP = TP;
           t.num_tiles = (int)ptiles;
           const int smem_tc = tc::tc_fwd_smem_bytes(t.Nout);
-          auto kdx = tc::k_tc_dx<KMAX>;
-          CK(cudaFuncSetAttribute(kdx, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc));
           const unsigned gridx = ptiles < (unsigned)P->num_sms ? ptiles : (unsigned)P->num_sms;
           {
             ProfScope ps_(P, CLS_DX, st);
-            kdx<<<dim3(gridx), dim3(tc::THREADS), smem_tc, st>>>(t);
+            PPSCI_TC_LAUNCH(k_tc_dx, tc_pick_layout(P->J, s.act), KMAX, dim3(gridx), smem_tc, st, t,
+                            return fail(std::string("cudaFuncSetAttribute(k_tc_dx): ") + cudaGetErrorString(e_)));
             P->launches++;
           }
           zbar_cur = reinterpret_cast<const T*>(outp);

@@ -410,6 +410,213 @@ __global__ void __launch_bounds__(NTHREADS) k_gemm_dw(DwArgs<T> g) {
   if (blockIdx.x == 0 && tid < TN && (n0 + tid) < g.Nout && g.db) atomicAdd(g.db + n0 + tid, dbacc);
 }
 
+// =====================================================================================================
+// Thin layers.  The input layer has K = n_feat (2..8) and the output layer N = n_out (1..8): a 128-wide
+// GEMM tile wastes >95 % of its FMAs on them, and they are pure HBM streams (read or write one jet plane
+// set).  Dedicated kernels: one pass over the planes, coalesced along the hidden dimension.
+// =====================================================================================================
+constexpr int THIN_MAXF = 8;    // input features handled by the thin first-layer kernels
+constexpr int THIN_MAXM = 8;    // network outputs handled by the thin last-layer kernels
+constexpr int THIN_MAXCM = 64;  // C * n_out bound of k_last_fwd
+
+template <typename T>
+struct FirstArgs {
+  AOperand<T> A;  // A_SEED
+  JetLayout J;
+  const T* W;     // [nf][N]
+  const T* bias;  // [N]
+  int nf, N;
+  T* Out;         // fwd: Z_1 [C][Np][ldo]
+  int ldo;
+  long long oplane;
+  const T* Zbar;  // dW: Zbar_1 [C][Np][ldzb]
+  int ldzb;
+  long long zbplane;
+  T* dW;          // [nf][N]
+  T* db;          // [N]
+  long long Np;
+  int pts_per_block;
+};
+
+// Z_1[c][p][n] = sum_f seed_c[p][f] W[f][n] (+ b[n] on the value channel)
+template <typename T, int KMAX>
+__global__ void __launch_bounds__(256) k_first_fwd(FirstArgs<T> g) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.Np * g.N) return;
+  const long long p = i / g.N;
+  const int n = (int)(i % g.N);
+  T acc[32];
+  for (int c = 0; c < g.J.C; ++c) acc[c] = T(0);
+  for (int f = 0; f < g.nf; ++f) {
+    const T w = g.W[(long long)f * g.N + n];
+    produce_a<T, KMAX>(g.A, g.J, p, f, true, [&](int c, T v) { acc[c] += v * w; });
+  }
+  T* out = g.Out + p * g.ldo + n;
+  for (int c = 0; c < g.J.C; ++c) out[(long long)c * g.oplane] = acc[c] + (c == 0 ? g.bias[n] : T(0));
+}
+
+// dW_1[f][n] += sum_{c,p} seed_c[p][f] Zbar_1[c][p][n] ;  db_1[n] += sum_p Zbar_1[0][p][n]
+template <typename T, int KMAX>
+__global__ void __launch_bounds__(256) k_first_dw(FirstArgs<T> g) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= g.N) return;
+  const long long p_begin = (long long)blockIdx.y * g.pts_per_block;
+  long long p_end = p_begin + g.pts_per_block;
+  if (p_end > g.Np) p_end = g.Np;
+  T acc[THIN_MAXF];
+#pragma unroll
+  for (int f = 0; f < THIN_MAXF; ++f) acc[f] = T(0);
+  T dbacc = T(0);
+  for (long long p = p_begin; p < p_end; ++p) {
+    const T* zb = g.Zbar + p * g.ldzb + n;
+    dbacc += zb[0];
+#pragma unroll
+    for (int f = 0; f < THIN_MAXF; ++f) {
+      if (f < g.nf) {
+        T a = T(0);
+        produce_a<T, KMAX>(g.A, g.J, p, f, true, [&](int c, T v) { a += v * zb[(long long)c * g.zbplane]; });
+        acc[f] += a;
+      }
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < THIN_MAXF; ++f)
+    if (f < g.nf) atomicAdd(g.dW + (long long)f * g.N + n, acc[f]);
+  atomicAdd(g.db + n, dbacc);
+}
+
+template <typename T>
+struct LastArgs {
+  AOperand<T> A;  // A_ACT over Z_{L-1}  (pre-activations of the last hidden layer)
+  JetLayout J;
+  const T* W;     // [K][m]
+  const T* bias;  // [m]
+  int K, m;
+  T* Y;           // fwd: output jets [C][Np][ldy]
+  const T* Ybar;  // bwd: adjoints of the output jets, same layout
+  int ldy;
+  long long yplane;
+  T* ZbarOut;     // bwd: Zbar_{L-1} [C][Np][ldo]
+  int ldo;
+  long long oplane;
+  T* dW;          // [K][m]
+  T* db;          // [m]
+  long long Np;
+  int pts_per_block;
+};
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Y[c][p][j] = sum_k act_jets(Z_{L-1})[c][p][k] W[k][j] (+ b[j] on the value channel); one warp per point
+template <typename T, int KMAX>
+__global__ void __launch_bounds__(256) k_last_fwd(LastArgs<T> g) {
+  const int lane = threadIdx.x & 31;
+  const long long p = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= g.Np) return;  // whole warp exits together
+  T acc[THIN_MAXCM];
+  const int CM = g.J.C * g.m;
+  for (int i = 0; i < CM; ++i) acc[i] = T(0);
+  for (int k = lane; k < g.K; k += 32) {
+    T w[THIN_MAXM];
+#pragma unroll
+    for (int j = 0; j < THIN_MAXM; ++j) w[j] = j < g.m ? g.W[(long long)k * g.m + j] : T(0);
+    produce_a<T, KMAX>(g.A, g.J, p, k, true, [&](int c, T v) {
+#pragma unroll
+      for (int j = 0; j < THIN_MAXM; ++j)
+        if (j < g.m) acc[c * g.m + j] += v * w[j];
+    });
+  }
+  for (int i = 0; i < CM; ++i) {
+    const T v = warp_sum<T>(acc[i]);
+    if (lane == 0) {
+      const int c = i / g.m, j = i % g.m;
+      g.Y[(long long)c * g.yplane + p * g.ldy + j] = v + (c == 0 ? g.bias[j] : T(0));
+    }
+  }
+}
+
+// Output layer backward, fused: for every (point, hidden unit k)
+//   abar_c = sum_j Ybar[c][p][j] W[k][j];  Zbar_{L-1} = act_adjoint(abar, Z_{L-1});
+//   dW[k][j] += sum_{c,p} a_c[p][k] Ybar[c][p][j];  db[j] += sum_p Ybar[0][p][j]
+template <typename T, int KMAX>
+__global__ void __launch_bounds__(256) k_last_bwd(LastArgs<T> g) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool k_ok = k < g.K;
+  const long long p_begin = (long long)blockIdx.y * g.pts_per_block;
+  long long p_end = p_begin + g.pts_per_block;
+  if (p_end > g.Np) p_end = g.Np;
+  T w[THIN_MAXM], dwacc[THIN_MAXM], dbacc[THIN_MAXM];
+#pragma unroll
+  for (int j = 0; j < THIN_MAXM; ++j) {
+    w[j] = (k_ok && j < g.m) ? g.W[(long long)k * g.m + j] : T(0);
+    dwacc[j] = T(0);
+    dbacc[j] = T(0);
+  }
+  const bool do_db = (blockIdx.x == 0 && threadIdx.x == 0);
+  if (k_ok) {
+    for (long long p = p_begin; p < p_end; ++p) {
+      const T* yb = g.Ybar + p * g.ldy;  // + c*yplane + j   (same address for the whole block: broadcast)
+      const T* z = g.A.Z + p * g.A.ld + k;
+      T* zb_out = g.ZbarOut + p * g.ldo + k;
+      T s[6];
+      T y0;
+      act_coef<T, KMAX + 1>(g.A.act, z[0], y0, s);
+      T y0b = T(0);
+#pragma unroll
+      for (int j = 0; j < THIN_MAXM; ++j)
+        if (j < g.m) {
+          const T ybj = yb[j];
+          y0b += ybj * w[j];
+          dwacc[j] += y0 * ybj;
+          if (do_db) dbacc[j] += ybj;
+        }
+      T sb[5] = {T(0), T(0), T(0), T(0), T(0)};
+      for (int d = 0; d < g.J.n_dir; ++d) {
+        const int Kd = g.J.dir_order[d];
+        const int cb = g.J.dir_base[d];
+        T zz[4], yy[4], ybq[4], zbq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          zz[q] = (q < KMAX && q < Kd) ? z[(long long)(cb + q) * g.A.plane] : T(0);
+          ybq[q] = T(0);
+          zbq[q] = T(0);
+        }
+        jet_fwd_dir<T, KMAX>(s, zz, yy);
+#pragma unroll
+        for (int q = 0; q < KMAX; ++q)
+          if (q < Kd) {
+            const T* ybc = yb + (long long)(cb + q) * g.yplane;
+#pragma unroll
+            for (int j = 0; j < THIN_MAXM; ++j)
+              if (j < g.m) {
+                const T ybj = ybc[j];
+                ybq[q] += ybj * w[j];
+                dwacc[j] += yy[q] * ybj;
+              }
+          }
+        jet_adj_dir<T, KMAX>(s, zz, ybq, zbq, sb);
+#pragma unroll
+        for (int q = 0; q < KMAX; ++q)
+          if (q < Kd) zb_out[(long long)(cb + q) * g.oplane] = zbq[q];
+      }
+      zb_out[0] = jet_adj_z0<T, KMAX>(s, y0b, sb);
+    }
+#pragma unroll
+    for (int j = 0; j < THIN_MAXM; ++j)
+      if (j < g.m) atomicAdd(g.dW + (long long)k * g.m + j, dwacc[j]);
+  }
+  if (do_db) {
+#pragma unroll
+    for (int j = 0; j < THIN_MAXM; ++j)
+      if (j < g.m) atomicAdd(g.db + j, dbacc[j]);
+  }
+}
+
 // ---- small helpers ---------------------------------------------------------------------------
 template <typename T>
 __global__ void k_transpose(const T* W, T* WT, int K, int N) {  // WT[n][k] = W[k][n]

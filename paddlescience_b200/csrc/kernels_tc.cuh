@@ -25,7 +25,7 @@ namespace ppsci {
 namespace tc {
 
 constexpr int KCH = 32;  // K elements per chunk = one 128-byte swizzle row of tf32
-constexpr int THREADS = 256;
+constexpr int THREADS = 512;  // 16 warps: enough issue slots / latency hiding for the operand producers
 constexpr int A_TILE_BYTES = 128 * KCH * 4;  // 16 KB (one of hi / lo)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -151,6 +151,41 @@ __global__ void k_tc_prep_w(const float* __restrict__ W, float* __restrict__ img
   blk[(long long)N * KCH + off] = lo;
 }
 
+// ---- jet layouts ---------------------------------------------------------------------------------
+// The operand producers are instruction-bound, so the channel structure is a compile-time parameter for
+// the common PDE layouts (all index math folds into constants); DLay is the runtime fallback.
+template <int O0, int O1, int O2, int O3>
+struct SLay {
+  static constexpr bool kStatic = true;
+  static constexpr int ND = (O0 > 0) + (O1 > 0) + (O2 > 0) + (O3 > 0);
+  static constexpr int C = 1 + O0 + O1 + O2 + O3;
+  static constexpr int KMAX = (O0 > O1 ? O0 : O1) > (O2 > O3 ? O2 : O3) ? (O0 > O1 ? O0 : O1) : (O2 > O3 ? O2 : O3);
+  static constexpr int KM = KMAX < 1 ? 1 : KMAX;
+  __device__ static __forceinline__ int nd(const JetLayout&) { return ND; }
+  __device__ static __forceinline__ int order(const JetLayout&, int d) { return d == 0 ? O0 : d == 1 ? O1 : d == 2 ? O2 : O3; }
+  __device__ static __forceinline__ int cbase(const JetLayout&, int d) {
+    return 1 + (d > 0 ? O0 : 0) + (d > 1 ? O1 : 0) + (d > 2 ? O2 : 0);
+  }
+  __device__ static __forceinline__ int nchan(const JetLayout&) { return C; }
+  __device__ static __forceinline__ int tp(int) { return 128 / C; }
+  __device__ static __forceinline__ int pt(int) { return KCH / C; }
+};
+template <int KMAX_>
+struct DLay {
+  static constexpr bool kStatic = false;
+  static constexpr int ND = PPSCI_MAX_DIR;
+  static constexpr int KM = KMAX_;
+  __device__ static __forceinline__ int nd(const JetLayout& J) { return J.n_dir; }
+  __device__ static __forceinline__ int order(const JetLayout& J, int d) { return J.dir_order[d]; }
+  __device__ static __forceinline__ int cbase(const JetLayout& J, int d) { return J.dir_base[d]; }
+  __device__ static __forceinline__ int nchan(const JetLayout& J) { return J.C; }
+  __device__ static __forceinline__ int tp(int rt) { return rt; }
+  __device__ static __forceinline__ int pt(int rt) { return rt; }
+};
+// ACT < 0: activation id taken from the arguments at run time
+template <int ACT>
+__device__ __forceinline__ int act_id(int rt) { return ACT >= 0 ? ACT : rt; }
+
 // ---- cp.async (LDGSTS) staging of raw fp32 tiles: gives every thread many loads in flight ------------
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, bool valid) {
   const int sz = valid ? 16 : 0;  // src-size 0 => the 16 destination bytes are zero-filled
@@ -166,6 +201,7 @@ constexpr int RAW_TILE_BYTES = 128 * KCH * 4;  // 128 rows x 32 fp32, linear (ro
 
 // Stage rows (c, pl) of the channel-major planes Z[c][p][ld], columns [col0, col0+32), into a linear
 // [row = c*TP + pl][32] tile.  Rows >= rows_used are never touched.
+template <class L>
 __device__ __forceinline__ void stage_rows(uint32_t dst, const float* Z, long long plane, int ld, long long p0,
                                            long long Np, int TP, int rows_used, int col0) {
   for (int i = threadIdx.x; i < rows_used * 8; i += THREADS) {
@@ -220,6 +256,14 @@ __device__ __forceinline__ void load_acc_sum(uint32_t acc0, uint32_t acc1, int q
   for (int t = 0; t < 32; ++t) out[t] = __uint_as_float(v0[t]) + __uint_as_float(v1[t]);
 }
 
+// store v = hi + lo into the (hi, lo) pair of K-major SW128 tiles at row r, column kk
+__device__ __forceinline__ void store_split(unsigned char* a_hi, int r, int kk, float v) {
+  const float hi = tf32_rn(v);
+  const uint32_t off = sw128(r, kk);
+  *reinterpret_cast<float*>(a_hi + off) = hi;
+  *reinterpret_cast<float*>(a_hi + A_TILE_BYTES + off) = v - hi;
+}
+
 struct TcFwdArgs {
   AOperand<float> A;  // A_ACT over Z_{l-1}
   JetLayout J;
@@ -241,22 +285,11 @@ struct TcFwdArgs {
 //   then mbarriers full[2], mma_done[2] and the TMEM base slot
 __host__ __device__ inline int tc_fwd_smem_bytes(int N) { return 2 * tc_stage_bytes(N) + 2 * RAW_TILE_BYTES + 1024 + 256; }
 
-// Forward layer  Z_l = act_jets(Z_{l-1}) W_l + b_l  on the tensor cores.
-// Persistent: CTA t handles tiles t, t+grid, ...; each tile = 128 rows = TP points x C channels.
-template <int KMAX>
-__global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
-  extern __shared__ unsigned char smem_dyn[];
-  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
-  const int N = g.Nout;
-  const int stage_bytes = tc_stage_bytes(N);
-  const uint32_t raw_off = 2 * stage_bytes;
-  const uint32_t bars_off = raw_off + 2 * RAW_TILE_BYTES;
-  const uint32_t bars = base + bars_off;  // full[2] at +0,+8 ; mma_done[2] at +16,+24
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 64);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t ncols = tc_pow2_cols(2 * N);
-
+// Shared prologue of the three kernels: barriers, TMEM, zeroed operand stages.
+__device__ __forceinline__ void tc_setup(uint32_t base, unsigned char* base_ptr, uint32_t bars_off, int stage_bytes,
+                                         int clear_bytes_per_stage, uint32_t ncols) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t bars = base + bars_off;
   if (tid == 0) {
     mbar_init(bars + 0, 1);
     mbar_init(bars + 8, 1);
@@ -269,67 +302,109 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
     tmem_alloc(base + bars_off + 64, ncols);
     tmem_relinquish();
   }
-  // rows that never receive data (>= C*TP) must read as zero: clear both A tiles once
   for (int s = 0; s < 2; ++s) {
     float4* az = reinterpret_cast<float4*>(base_ptr + s * stage_bytes);
-    for (int i = tid; i < 2 * A_TILE_BYTES / 16; i += THREADS) az[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < clear_bytes_per_stage / 16; i += THREADS) az[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t acc0 = *tmem_slot, acc1 = acc0 + (uint32_t)N;
+}
+
+// Forward layer  Z_l = act_jets(Z_{l-1}) W_l + b_l  on the tensor cores.
+// Persistent: CTA t handles tiles t, t+grid, ...; each tile = 128 rows = TP points x C channels.
+// Pipeline per K chunk `it`:  raw rows of chunk it+1 (cp.async) and weight images of chunk it+1 (TMA) are
+// requested, the A operand of chunk `it` is produced from the raw tile, then its 12 MMAs are issued.
+template <class L, int ACT>
+__global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
+  const int N = g.Nout;
+  const int stage_bytes = tc_stage_bytes(N);
+  const uint32_t raw_off = 2 * stage_bytes;
+  const uint32_t bars_off = raw_off + 2 * RAW_TILE_BYTES;
+  const uint32_t bars = base + bars_off;  // full[2] at +0,+8 ; mma_done[2] at +16,+24
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t ncols = tc_pow2_cols(2 * N);
+  tc_setup(base, base_ptr, bars_off, stage_bytes, 2 * A_TILE_BYTES, ncols);
+  const uint32_t acc0 = *reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 64), acc1 = acc0 + (uint32_t)N;
   const uint32_t idesc = make_idesc_tf32(128, N);
   const int nchunks = g.Kdim / KCH;
   const uint32_t b_bytes = (uint32_t)(2 * N * KCH * 4);
-  const int TP = g.TP;
-  const int rows_used = g.J.C * TP;
+  const int TP = L::tp(g.TP);
+  const int C = L::nchan(g.J);
+  const int rows_used = C * TP;
+  const int act = act_id<ACT>(g.A.act);
+  const int my_tiles = ((int)blockIdx.x < g.num_tiles) ? (g.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const uint32_t total_it = (uint32_t)my_tiles * (uint32_t)nchunks;
 
-  uint32_t it = 0;  // running chunk counter (stage = it & 1, use index = it >> 1)
-  if ((int)blockIdx.x < g.num_tiles)
-    stage_rows(base + raw_off, g.A.Z, g.A.plane, g.A.ld, (long long)blockIdx.x * TP, g.Np, TP, rows_used, 0);
+  auto issue_b = [&](uint32_t itb) {  // weight images of running chunk itb -> stage itb & 1
+    const uint32_t sb = itb & 1u;
+    mbar_expect_tx(bars + 8 * sb, b_bytes);
+    bulk_g2s(base + sb * stage_bytes + 2 * A_TILE_BYTES, g.Wimg + (long long)(itb % nchunks) * 2 * N * KCH, b_bytes,
+             bars + 8 * sb);
+  };
+  if (total_it > 0) {
+    stage_rows<L>(base + raw_off, g.A.Z, g.A.plane, g.A.ld, (long long)blockIdx.x * TP, g.Np, TP, rows_used, 0);
+    if (tid == 0) issue_b(0);
+  }
   cp_async_commit();
+  uint32_t it = 0;  // running chunk counter (stage = it & 1, use index = it >> 1)
   for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
     const long long p0 = (long long)tile * TP;
     for (int j = 0; j < nchunks; ++j, ++it) {
       const uint32_t s = it & 1u, u = it >> 1;
       unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-      const uint32_t stage_addr = base + s * stage_bytes;
-      // prefetch the next chunk's raw rows (possibly the first chunk of this CTA's next tile)
+      // request chunk it+1: raw rows (cp.async) and, once the MMAs of chunk it-1 have left that stage, weights
       {
         int ntile = tile, nj = j + 1;
         if (nj == nchunks) { nj = 0; ntile = tile + gridDim.x; }
         if (ntile < g.num_tiles)
-          stage_rows(base + raw_off + ((it + 1) & 1u) * RAW_TILE_BYTES, g.A.Z, g.A.plane, g.A.ld, (long long)ntile * TP,
-                     g.Np, TP, rows_used, nj * KCH);
+          stage_rows<L>(base + raw_off + ((it + 1) & 1u) * RAW_TILE_BYTES, g.A.Z, g.A.plane, g.A.ld, (long long)ntile * TP,
+                        g.Np, TP, rows_used, nj * KCH);
         cp_async_commit();
       }
       cp_async_wait<1>();  // this chunk's raw rows have landed (this thread's pieces) ...
       __syncthreads();     // ... and everybody else's
       if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);  // MMAs that read this stage have retired
-      if (tid == 0) {
-        mbar_expect_tx(bars + 8 * s, b_bytes);
-        bulk_g2s(stage_addr + 2 * A_TILE_BYTES, g.Wimg + (long long)j * 2 * N * KCH, b_bytes, bars + 8 * s);
-      }
       const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + (it & 1u) * RAW_TILE_BYTES);
-      for (int item = tid; item < TP * KCH; item += THREADS) {
-        const int kk = item & (KCH - 1), pl = item / KCH;
-        produce_from<float, KMAX>(
-            g.A.mode, g.A.act, g.J, (p0 + pl) < g.Np, [&](int c) { return raw[(c * TP + pl) * KCH + kk]; },
-            [&](int c, float v) {
-              const int r = c * TP + pl;
-              const float hi = tf32_rn(v);
-              const uint32_t off = sw128(r, kk);
-              *reinterpret_cast<float*>(stage_ptr + off) = hi;
-              *reinterpret_cast<float*>(stage_ptr + A_TILE_BYTES + off) = v - hi;
-            });
+      // one item = (point pl, column kk = lane): all C channels
+      for (int pl = warp; pl < TP; pl += THREADS / 32) {
+        const int kk = lane;
+        if (p0 + pl < g.Np) {
+          float sc[6];
+          float y0;
+          act_coef<float, L::KM>(act, raw[pl * KCH + kk], y0, sc);
+          store_split(stage_ptr, pl, kk, y0);
+#pragma unroll
+          for (int d = 0; d < L::ND; ++d) {
+            if (d < L::nd(g.J)) {
+              const int K = L::order(g.J, d), cb = L::cbase(g.J, d);
+              float zz[4], yy[4];
+#pragma unroll
+              for (int o = 0; o < 4; ++o) zz[o] = (o < L::KM && o < K) ? raw[((cb + o) * TP + pl) * KCH + kk] : 0.f;
+              jet_fwd_dir<float, L::KM>(sc, zz, yy);
+#pragma unroll
+              for (int o = 0; o < L::KM; ++o)
+                if (o < K) store_split(stage_ptr, (cb + o) * TP + pl, kk, yy[o]);
+            }
+          }
+        } else {
+          for (int c = 0; c < C; ++c) store_split(stage_ptr, c * TP + pl, kk, 0.f);
+        }
       }
       fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncthreads();
       if (tid == 0) {
         mbar_wait(bars + 8 * s, u & 1u);  // weight images of this chunk have landed
         tc_fence_after();
-        issue_chunk_mmas(acc0, acc1, stage_addr, N, idesc, j == 0);
+        issue_chunk_mmas(acc0, acc1, base + s * stage_bytes, N, idesc, j == 0);
         mma_commit(bars + 16 + 8 * s);  // arrives when every MMA issued so far has completed
+        if (it + 1 < total_it) {  // weights of chunk it+1 -> other stage, once chunk it-1's MMAs have left it
+          if (it >= 1) mbar_wait(bars + 16 + 8 * ((it + 1) & 1u), ((it - 1) >> 1) & 1u);
+          issue_b(it + 1);
+        }
       }
     }
     // ---- epilogue: TMEM -> registers -> (+bias) -> Z_l in HBM ----
@@ -337,15 +412,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
       const uint32_t last = it - 1;
       mbar_wait(bars + 16 + 8 * (last & 1u), (last >> 1) & 1u);
       tc_fence_after();
-      const int q = warp & 3, half = warp >> 2;
+      const int q = warp & 3, part = warp >> 2;  // lane quarter, column-block phase (THREADS/128 phases)
       const int r = q * 32 + lane;
       const bool row_ok = r < rows_used;
       const int c = row_ok ? r / TP : 0, pl = row_ok ? r % TP : 0;
       const long long p = p0 + pl;
       const bool st_ok = row_ok && p < g.Np;
       float* out_row = g.Out + (long long)c * g.oplane + p * g.ldo;
-      const int ncb = N / 32;  // warps with half=0 take even 32-column blocks, half=1 odd blocks
-      for (int cb = half; cb < ncb; cb += 2) {
+      const int ncb = N / 32;
+      for (int cb = part; cb < ncb; cb += THREADS / 128) {
         float v[32];
         load_acc_sum(acc0, acc1, q, cb * 32, v);
         if (st_ok) {
@@ -398,7 +473,7 @@ struct TcDxArgs {
   int num_tiles;
 };
 
-template <int KMAX>
+template <class L, int ACT>
 __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -408,80 +483,67 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
   const uint32_t raw_off = 2 * stage_bytes;
   const uint32_t bars_off = raw_off + 2 * RAW_TILE_BYTES;
   const uint32_t bars = base + bars_off;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 64);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ncols = tc_pow2_cols(2 * N);
-
-  if (tid == 0) {
-    mbar_init(bars + 0, 1);
-    mbar_init(bars + 8, 1);
-    mbar_init(bars + 16, 1);
-    mbar_init(bars + 24, 1);
-    fence_barrier_init();
-    fence_proxy_async();
-  }
-  if (warp == 1) {
-    tmem_alloc(base + bars_off + 64, ncols);
-    tmem_relinquish();
-  }
-  for (int s = 0; s < 2; ++s) {
-    float4* az = reinterpret_cast<float4*>(base_ptr + s * stage_bytes);
-    for (int i = tid; i < 2 * A_TILE_BYTES / 16; i += THREADS) az[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t acc0 = *tmem_slot, acc1 = acc0 + (uint32_t)N;
+  tc_setup(base, base_ptr, bars_off, stage_bytes, 2 * A_TILE_BYTES, ncols);
+  const uint32_t acc0 = *reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 64), acc1 = acc0 + (uint32_t)N;
   const uint32_t idesc = make_idesc_tf32(128, N);
   const int nchunks = g.Kdim / KCH;
   const uint32_t b_bytes = (uint32_t)(2 * N * KCH * 4);
-  const int TP = g.TP;
-  const int rows_used = g.J.C * TP;
+  const int TP = L::tp(g.TP);
+  const int C = L::nchan(g.J);
+  const int rows_used = C * TP;
+  const int act = act_id<ACT>(g.act);
   float* X = reinterpret_cast<float*>(base_ptr);  // exchange tile: stage 0, A_hi region (16 KB)
   const uint32_t zbuf_addr = base + stage_bytes;   // two Z blocks: stage 1, A_hi and A_lo regions
   const float* zbuf_ptr = reinterpret_cast<const float*>(base_ptr + stage_bytes);
+  const int my_tiles = ((int)blockIdx.x < g.num_tiles) ? (g.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const uint32_t total_it = (uint32_t)my_tiles * (uint32_t)nchunks;
 
-  uint32_t it = 0;
-  if ((int)blockIdx.x < g.num_tiles)
-    stage_rows(base + raw_off, g.A.Z, g.A.plane, g.A.ld, (long long)blockIdx.x * TP, g.Np, TP, rows_used, 0);
+  auto issue_b = [&](uint32_t itb) {
+    const uint32_t sb = itb & 1u;
+    mbar_expect_tx(bars + 8 * sb, b_bytes);
+    bulk_g2s(base + sb * stage_bytes + 2 * A_TILE_BYTES, g.Wimg + (long long)(itb % nchunks) * 2 * N * KCH, b_bytes,
+             bars + 8 * sb);
+  };
+  if (total_it > 0) {
+    stage_rows<L>(base + raw_off, g.A.Z, g.A.plane, g.A.ld, (long long)blockIdx.x * TP, g.Np, TP, rows_used, 0);
+    if (tid == 0) issue_b(0);
+  }
   cp_async_commit();
+  uint32_t it = 0;
   for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
     const long long p0 = (long long)tile * TP;
     for (int j = 0; j < nchunks; ++j, ++it) {
       const uint32_t s = it & 1u, u = it >> 1;
       unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-      const uint32_t stage_addr = base + s * stage_bytes;
       {
         int ntile = tile, nj = j + 1;
         if (nj == nchunks) { nj = 0; ntile = tile + gridDim.x; }
         if (ntile < g.num_tiles)
-          stage_rows(base + raw_off + ((it + 1) & 1u) * RAW_TILE_BYTES, g.A.Z, g.A.plane, g.A.ld, (long long)ntile * TP,
-                     g.Np, TP, rows_used, nj * KCH);
+          stage_rows<L>(base + raw_off + ((it + 1) & 1u) * RAW_TILE_BYTES, g.A.Z, g.A.plane, g.A.ld, (long long)ntile * TP,
+                        g.Np, TP, rows_used, nj * KCH);
         cp_async_commit();
       }
       cp_async_wait<1>();
       __syncthreads();
       if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
-      if (tid == 0) {
-        mbar_expect_tx(bars + 8 * s, b_bytes);
-        bulk_g2s(stage_addr + 2 * A_TILE_BYTES, g.Wimg + (long long)j * 2 * N * KCH, b_bytes, bars + 8 * s);
-      }
       const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + (it & 1u) * RAW_TILE_BYTES);
-      for (int item = tid; item < rows_used * KCH; item += THREADS) {  // plain split, row by row
-        const int kk = item & (KCH - 1), r = item / KCH;
-        const float v = raw[r * KCH + kk];
-        const float hi = tf32_rn(v);
-        const uint32_t off = sw128(r, kk);
-        *reinterpret_cast<float*>(stage_ptr + off) = hi;
-        *reinterpret_cast<float*>(stage_ptr + A_TILE_BYTES + off) = v - hi;
-      }
+      for (int r = warp; r < rows_used; r += THREADS / 32)  // plain split, one row per warp pass
+        store_split(stage_ptr, r, lane, raw[r * KCH + lane]);
       fence_proxy_async();
       __syncthreads();
       if (tid == 0) {
         mbar_wait(bars + 8 * s, u & 1u);
         tc_fence_after();
-        issue_chunk_mmas(acc0, acc1, stage_addr, N, idesc, j == 0);
+        issue_chunk_mmas(acc0, acc1, base + s * stage_bytes, N, idesc, j == 0);
         mma_commit(bars + 16 + 8 * s);
+        // weights of chunk it+1 go to the other stage; at a tile boundary that stage's A region is used as
+        // epilogue scratch, but its B region is not, so the copy may be in flight across the epilogue
+        if (it + 1 < total_it) {
+          if (it >= 1) mbar_wait(bars + 16 + 8 * ((it + 1) & 1u), ((it - 1) >> 1) & 1u);
+          issue_b(it + 1);
+        }
       }
     }
     // ---- epilogue: Abar (TMEM) -> exchange tile -> activation adjoint -> Zbar_{l-1} ----
@@ -490,58 +552,56 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
       mbar_wait(bars + 16 + 8 * (last & 1u), (last >> 1) & 1u);
       tc_fence_after();
       const int ncb = N / 32;
-      stage_rows(zbuf_addr, g.Zprev, g.zplane, g.ldz, p0, g.Np, TP, rows_used, 0);
+      stage_rows<L>(zbuf_addr, g.Zprev, g.zplane, g.ldz, p0, g.Np, TP, rows_used, 0);
       cp_async_commit();
       for (int cb = 0; cb < ncb; ++cb) {
         if (cb + 1 < ncb)
-          stage_rows(zbuf_addr + ((cb + 1) & 1) * A_TILE_BYTES, g.Zprev, g.zplane, g.ldz, p0, g.Np, TP, rows_used,
-                     (cb + 1) * 32);
+          stage_rows<L>(zbuf_addr + ((cb + 1) & 1) * A_TILE_BYTES, g.Zprev, g.zplane, g.ldz, p0, g.Np, TP, rows_used,
+                        (cb + 1) * 32);
         cp_async_commit();
         if (warp < 4) {  // 128 lanes x 32 columns of Abar -> X[r][t ^ (r & 31)]  (conflict-free both ways)
           float v[32];
           load_acc_sum(acc0, acc1, warp, cb * 32, v);
-          const int r = warp * 32 + lane;
-          float* xr = X + r * KCH;
+          float* xr = X + (warp * 32 + lane) * KCH;
 #pragma unroll
           for (int t = 0; t < 32; ++t) xr[t ^ lane] = v[t];
         }
         cp_async_wait<1>();
         __syncthreads();
         const float* zb = zbuf_ptr + (cb & 1) * (A_TILE_BYTES / 4);
-        for (int item = tid; item < TP * 32; item += THREADS) {
-          const int nn = item & 31, pl = item >> 5;
+        const int nn = lane;
+        for (int pl = warp; pl < TP; pl += THREADS / 32) {
           const long long p = p0 + pl;
           if (p >= g.Np) continue;
-          const int n = cb * 32 + nn;
-          float* zb_out = g.Out + p * g.ldo + n;
+          float* zb_out = g.Out + p * g.ldo + cb * 32 + nn;
           float sc[6];
           float y0;
-          act_coef<float, KMAX + 1>(g.act, zb[pl * KCH + nn], y0, sc);
+          act_coef<float, L::KM + 1>(act, zb[pl * KCH + nn], y0, sc);
           const float y0b = X[pl * KCH + (nn ^ (pl & 31))];
           float sb[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-          for (int d = 0; d < g.J.n_dir; ++d) {
-            const int K = g.J.dir_order[d];
-            const int cbase = g.J.dir_base[d];
-            float zz[4], yb[4], zbv[4];
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-              const bool on = (o < KMAX && o < K);
-              const int rr = (cbase + o) * TP + pl;
-              zz[o] = on ? zb[rr * KCH + nn] : 0.f;
-              yb[o] = on ? X[rr * KCH + (nn ^ (rr & 31))] : 0.f;
-              zbv[o] = 0.f;
+          for (int d = 0; d < L::ND; ++d) {
+            if (d < L::nd(g.J)) {
+              const int K = L::order(g.J, d), cbs = L::cbase(g.J, d);
+              float zz[4], yb[4], zbv[4];
+#pragma unroll
+              for (int o = 0; o < 4; ++o) {
+                const bool on = (o < L::KM && o < K);
+                const int rr = (cbs + o) * TP + pl;
+                zz[o] = on ? zb[rr * KCH + nn] : 0.f;
+                yb[o] = on ? X[rr * KCH + (nn ^ (rr & 31))] : 0.f;
+                zbv[o] = 0.f;
+              }
+              jet_adj_dir<float, L::KM>(sc, zz, yb, zbv, sb);
+#pragma unroll
+              for (int o = 0; o < L::KM; ++o)
+                if (o < K) zb_out[(long long)(cbs + o) * g.oplane] = zbv[o];
             }
-            jet_adj_dir<float, KMAX>(sc, zz, yb, zbv, sb);
-#pragma unroll
-            for (int o = 0; o < KMAX; ++o)
-              if (o < K) zb_out[(long long)(cbase + o) * g.oplane] = zbv[o];
           }
-          zb_out[0] = jet_adj_z0<float, KMAX>(sc, y0b, sb);
+          zb_out[0] = jet_adj_z0<float, L::KM>(sc, y0b, sb);
         }
         __syncthreads();
       }
-      // restore the scratch regions: rows < rows_used get overwritten by the next production anyway, but
-      // they must hold finite data for the pad-row-zero invariant only; X pad rows are exact zeros.
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();
@@ -557,8 +617,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
 // Reduction dimension = jet rows (points x channels).  CTA (kt, split) owns dW rows [128 kt, 128 kt + 128)
 // and a contiguous range of 32-row reduction chunks (PT points each); it accumulates in TMEM across its
 // whole range and flushes once with red.global.add.  Both operands are written transposed into K-major
-// SW128 tiles: warps 0-3 recompute A_{l-1} = act_jets(Z_{l-1}) from a cp.async-staged raw tile (thread =
-// dW row k), warps 4-7 split Zbar_l, whose values are prefetched into registers one chunk ahead.
+// SW128 tiles from cp.async-staged raw tiles:
+//   warps 0-7  : A' = act_jets(Z_{l-1})   (item = (point, dW row k))
+//   warps 8-15 : B' = split(Zbar_l)        (item = (16-byte chunk of 4 reduction rows, column n))
 // =====================================================================================================
 struct TcDwArgs {
   AOperand<float> A;   // A_ACT over Z_{l-1}
@@ -567,153 +628,137 @@ struct TcDwArgs {
   int ldzb;
   long long zbplane;
   int Kdim;            // fan-in (rows of dW), multiple of 128
-  int Nout;            // fan-out (cols of dW), multiple of 32, <= 256
-  float* dW;           // [Kdim][Nout]
+  int Nout;            // fan-out (cols of dW), multiple of 32, <= 128 per CTA column block
+  int n0_stride;       // columns handled per CTA in grid.z (= Nout_cta)
+  float* dW;           // [Kdim][ldw]
+  int ldw;             // full fan-out of the layer (row pitch of dW)
   long long Np;
   int PT;              // points per 32-row reduction chunk
   int chunks_per_split;
 };
 
-constexpr int DW_RAW_BYTES = KCH * 128 * 4;  // raw Z rows of one chunk: [32 rows][128 k] fp32 = 16 KB
-__host__ __device__ inline int tc_dw_smem_bytes(int N) { return 2 * tc_stage_bytes(N) + 2 * DW_RAW_BYTES + 1024 + 256; }
-constexpr int DW_MAX_ITEMS = 16;  // (N * 8) / 128 B'-items per thread at N = 256
+// raw tiles of one reduction chunk: Z rows [32][128 k] (16 KB) and Zbar rows [32][NC n] (NC*128 B)
+__host__ __device__ inline int tc_dw_raw_bytes(int NC) { return KCH * 128 * 4 + KCH * NC * 4; }
+__host__ __device__ inline int tc_dw_smem_bytes(int NC) { return 2 * tc_stage_bytes(NC) + 2 * tc_dw_raw_bytes(NC) + 1024 + 256; }
 
-template <int KMAX>
+template <class L, int ACT>
 __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
   extern __shared__ unsigned char smem_dyn[];
   __shared__ int row_c[KCH], row_pl[KCH];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
-  const int N = g.Nout;
+  const int N = g.Nout;  // columns of this CTA
   const int stage_bytes = tc_stage_bytes(N);
+  const int raw_bytes = tc_dw_raw_bytes(N);
   const uint32_t raw_off = 2 * stage_bytes;
-  const uint32_t bars_off = raw_off + 2 * DW_RAW_BYTES;
+  const uint32_t bars_off = raw_off + 2 * raw_bytes;
   const uint32_t bars = base + bars_off;  // mma_done[2] at +16, +24
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 64);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ncols = tc_pow2_cols(2 * N);
-  const int PT = g.PT;
-  const int rows_used = g.J.C * PT;
-
-  if (tid == 0) {
-    mbar_init(bars + 16, 1);
-    mbar_init(bars + 24, 1);
-    fence_barrier_init();
-    fence_proxy_async();
-  }
+  const int PT = L::pt(g.PT);
+  const int C = L::nchan(g.J);
+  const int rows_used = C * PT;
+  const int act = act_id<ACT>(g.A.act);
   if (tid < KCH) {
     row_c[tid] = tid < rows_used ? tid / PT : -1;
     row_pl[tid] = tid < rows_used ? tid % PT : 0;
   }
-  if (warp == 1) {
-    tmem_alloc(base + bars_off + 64, ncols);
-    tmem_relinquish();
-  }
-  // clear both stages completely (reduction columns >= rows_used stay zero forever)
-  for (int s = 0; s < 2; ++s) {
-    float4* az = reinterpret_cast<float4*>(base_ptr + s * stage_bytes);
-    for (int i = tid; i < stage_bytes / 16; i += THREADS) az[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t acc0 = *tmem_slot, acc1 = acc0 + (uint32_t)N;
+  tc_setup(base, base_ptr, bars_off, stage_bytes, stage_bytes, ncols);  // whole stages cleared (pad columns stay 0)
+  const uint32_t acc0 = *reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 64), acc1 = acc0 + (uint32_t)N;
   const uint32_t idesc = make_idesc_tf32(128, N);
   const int k0 = blockIdx.x * 128;
+  const int n0 = blockIdx.z * g.n0_stride;
   const long long total_chunks = (g.Np + PT - 1) / PT;
   const long long ch_begin = (long long)blockIdx.y * g.chunks_per_split;
   long long ch_end = ch_begin + g.chunks_per_split;
   if (ch_end > total_chunks) ch_end = total_chunks;
-  const int nq = (rows_used + 3) / 4;
-  const int n_items = N * nq;  // B' items (n, q) handled by threads 128..255
+  const int zb_pieces = N / 4;  // 16-byte pieces per Zbar row
 
-  // raw Z rows of a chunk: row rr = c*PT + pl, 128 k-columns of this CTA's dW row block
-  auto stage_z = [&](long long ch, uint32_t dst) {
+  // raw rows of a chunk: row rr = c*PT + pl;  Z: 128 k-columns of this CTA's dW row block;  Zbar: N columns
+  auto stage_chunk = [&](long long ch, uint32_t dst) {
     const long long pb = ch * PT;
-    for (int i = tid; i < rows_used * 32; i += THREADS) {  // 32 16-byte pieces per 512-byte row
+    for (int i = tid; i < rows_used * 32; i += THREADS) {
       const int rr = i >> 5, q = i & 31;
       const long long p = pb + row_pl[rr];
       const bool ok = p < g.Np;
       const float* src = ok ? g.A.Z + (long long)row_c[rr] * g.A.plane + p * g.A.ld + k0 + q * 4 : g.A.Z;
       cp_async16(dst + (uint32_t)(rr * 512 + q * 16), src, ok);
     }
-  };
-  float zbreg[DW_MAX_ITEMS][4];  // B' side register prefetch (threads 128..255)
-  auto load_zbar = [&](long long ch) {
-    const long long pb = ch * PT;
-#pragma unroll
-    for (int ii = 0; ii < DW_MAX_ITEMS; ++ii) {
-      const int item = (tid - 128) + ii * 128;
-      const bool on = item < n_items;
-      const int n = on ? item % N : 0, q = on ? item / N : 0;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int rr = 4 * q + e;
-        const int c = row_c[rr];
-        const long long p = pb + row_pl[rr];
-        zbreg[ii][e] = (on && c >= 0 && p < g.Np) ? g.Zbar[(long long)c * g.zbplane + p * g.ldzb + n] : 0.f;
-      }
+    const uint32_t dzb = dst + KCH * 128 * 4;
+    for (int i = tid; i < rows_used * zb_pieces; i += THREADS) {
+      const int rr = i / zb_pieces, q = i - rr * zb_pieces;
+      const long long p = pb + row_pl[rr];
+      const bool ok = p < g.Np;
+      const float* src = ok ? g.Zbar + (long long)row_c[rr] * g.zbplane + p * g.ldzb + n0 + q * 4 : g.Zbar;
+      cp_async16(dzb + (uint32_t)(rr * N * 4 + q * 16), src, ok);
     }
   };
 
   uint32_t it = 0;
-  if (ch_begin < ch_end) {
-    stage_z(ch_begin, base + raw_off);
-    if (warp >= 4) load_zbar(ch_begin);
-  }
+  if (ch_begin < ch_end) stage_chunk(ch_begin, base + raw_off);
   cp_async_commit();
   for (long long ch = ch_begin; ch < ch_end; ++ch, ++it) {
     const uint32_t s = it & 1u, u = it >> 1;
     unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-    const uint32_t stage_addr = base + s * stage_bytes;
-    if (ch + 1 < ch_end) stage_z(ch + 1, base + raw_off + ((it + 1) & 1u) * DW_RAW_BYTES);
+    if (ch + 1 < ch_end) stage_chunk(ch + 1, base + raw_off + ((it + 1) & 1u) * raw_bytes);
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
     if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
     const long long pbase = ch * PT;
-    if (warp < 4) {
-      // A' tile: row = dW row k (this thread), column rr = c*PT + pl
-      const int k = tid;  // 0..127
-      const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + (it & 1u) * DW_RAW_BYTES);
-      for (int pl = 0; pl < PT; ++pl) {
-        produce_from<float, KMAX>(
-            g.A.mode, g.A.act, g.J, (pbase + pl) < g.Np, [&](int c) { return raw[(c * PT + pl) * 128 + k]; },
-            [&](int c, float v) {
-              const int rr = c * PT + pl;
-              const float hi = tf32_rn(v);
-              const uint32_t off = sw128(k, rr);
-              *reinterpret_cast<float*>(stage_ptr + off) = hi;
-              *reinterpret_cast<float*>(stage_ptr + A_TILE_BYTES + off) = v - hi;
-            });
-      }
-    } else {
-      // B' tile: row = n, 16-byte chunk q holds reduction columns 4q..4q+3 (values prefetched in registers)
-      unsigned char* b_hi = stage_ptr + 2 * A_TILE_BYTES;
-      unsigned char* b_lo = b_hi + N * KCH * 4;
+    const float* rawz = reinterpret_cast<const float*>(base_ptr + raw_off + (it & 1u) * raw_bytes);
+    const float* rawzb = rawz + KCH * 128;
+    if (warp < THREADS / 64) {
+      // A' tile: row = dW row k, column rr = c*PT + pl.  item = (pl, k): 128 k per point
+      for (int item = tid; item < PT * 128; item += THREADS / 2) {
+        const int k = item & 127, pl = item >> 7;
+        if (pbase + pl < g.Np) {
+          float sc[6];
+          float y0;
+          act_coef<float, L::KM>(act, rawz[pl * 128 + k], y0, sc);
+          store_split(stage_ptr, k, pl, y0);
 #pragma unroll
-      for (int ii = 0; ii < DW_MAX_ITEMS; ++ii) {
-        const int item = (tid - 128) + ii * 128;
-        if (item < n_items) {
-          const int n = item % N, q = item / N;
-          float hi[4], lo[4];
+          for (int d = 0; d < L::ND; ++d) {
+            if (d < L::nd(g.J)) {
+              const int K = L::order(g.J, d), cb = L::cbase(g.J, d);
+              float zz[4], yy[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            hi[e] = tf32_rn(zbreg[ii][e]);
-            lo[e] = zbreg[ii][e] - hi[e];
+              for (int o = 0; o < 4; ++o) zz[o] = (o < L::KM && o < K) ? rawz[((cb + o) * PT + pl) * 128 + k] : 0.f;
+              jet_fwd_dir<float, L::KM>(sc, zz, yy);
+#pragma unroll
+              for (int o = 0; o < L::KM; ++o)
+                if (o < K) store_split(stage_ptr, k, (cb + o) * PT + pl, yy[o]);
+            }
           }
-          const uint32_t off = sw128(n, 4 * q);
-          *reinterpret_cast<float4*>(b_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(b_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        } else {
+          for (int c = 0; c < C; ++c) store_split(stage_ptr, k, c * PT + pl, 0.f);
         }
       }
-      if (ch + 1 < ch_end) load_zbar(ch + 1);  // in flight while the MMAs of this chunk run
+    } else {
+      // B' tile: row = n, 16-byte chunk q holds reduction columns 4q..4q+3
+      unsigned char* b_hi = stage_ptr + 2 * A_TILE_BYTES;
+      unsigned char* b_lo = b_hi + N * KCH * 4;
+      const int nq = (rows_used + 3) / 4;
+      for (int item = tid - THREADS / 2; item < N * nq; item += THREADS / 2) {
+        const int n = item % N, q = item / N;
+        float hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int rr = 4 * q + e;
+          const float v = rr < rows_used ? rawzb[rr * N + n] : 0.f;
+          hi[e] = tf32_rn(v);
+          lo[e] = v - hi[e];
+        }
+        const uint32_t off = sw128(n, 4 * q);
+        *reinterpret_cast<float4*>(b_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(b_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
     }
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      issue_chunk_mmas(acc0, acc1, stage_addr, N, idesc, it == 0);
+      issue_chunk_mmas(acc0, acc1, base + s * stage_bytes, N, idesc, it == 0);
       mma_commit(bars + 16 + 8 * s);
     }
   }
@@ -721,11 +766,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
     const uint32_t last = it - 1;
     mbar_wait(bars + 16 + 8 * (last & 1u), (last >> 1) & 1u);
     tc_fence_after();
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, part = warp >> 2;
     const int k = k0 + q * 32 + lane;
-    float* dw_row = g.dW + (long long)k * N;
+    float* dw_row = g.dW + (long long)k * g.ldw + n0;
     const int ncb = N / 32;
-    for (int cb = half; cb < ncb; cb += 2) {
+    for (int cb = part; cb < ncb; cb += THREADS / 128) {
       float v[32];
       load_acc_sum(acc0, acc1, q, cb * 32, v);
       if (k < g.Kdim) {
@@ -772,12 +817,46 @@ inline bool tc_dx_ok(const ppsci_plan_spec& s, int l) {
   return (K % tc::KCH == 0) && K >= 32 && K <= 1024 && (N % 32 == 0) && N >= 32 && N <= 256;
 }
 // dW of layer l: rows = fan-in (multiple of 128), cols = fan-out (multiple of 32, <= 256)
+inline int tc_dw_cols_per_cta(int N) { return N <= 128 ? N : 128; }
 inline bool tc_dw_ok(const ppsci_plan_spec& s, int l) {
   if (s.dtype != PPSCI_F32) return false;
   if (l < 2 || l > s.n_layers) return false;
   const int K = s.widths[l - 1], N = s.widths[l];
-  return (K % 128 == 0) && K >= 128 && K <= 1024 && (N % 32 == 0) && N >= 32 && N <= 256;
+  return (K % 128 == 0) && K >= 128 && K <= 1024 && (N % 32 == 0) && N >= 32 && N <= 1024 &&
+         (N % tc_dw_cols_per_cta(N) == 0);
 }
+
+// ---- kernel selection: static jet layouts for the common PDE structures, runtime layout otherwise ------
+enum { TC_LAY_DYN = 0, TC_LAY_22 = 1, TC_LAY_12 = 2, TC_LAY_222 = 3, TC_LAY_VALUE = 4 };
+inline int tc_pick_layout(const JetLayout& J, int act) {
+  if (act != PPSCI_ACT_TANH) return TC_LAY_DYN;
+  auto is = [&](int n, int a, int b, int c) {
+    return J.n_dir == n && (n < 1 || J.dir_order[0] == a) && (n < 2 || J.dir_order[1] == b) && (n < 3 || J.dir_order[2] == c);
+  };
+  if (is(2, 2, 2, 0)) return TC_LAY_22;
+  if (is(2, 1, 2, 0)) return TC_LAY_12;
+  if (is(3, 2, 2, 2)) return TC_LAY_222;
+  if (is(0, 0, 0, 0)) return TC_LAY_VALUE;
+  return TC_LAY_DYN;
+}
+
+#define PPSCI_TC_LAUNCH(KERNEL, lay, kmax, grid, smem, stream, args, err_expr)                                   \
+  do {                                                                                                            \
+    void (*kfn_)(decltype(args)) = nullptr;                                                                       \
+    switch (lay) {                                                                                                \
+      case TC_LAY_22: kfn_ = tc::KERNEL<tc::SLay<2, 2, 0, 0>, PPSCI_ACT_TANH>; break;                             \
+      case TC_LAY_12: kfn_ = tc::KERNEL<tc::SLay<1, 2, 0, 0>, PPSCI_ACT_TANH>; break;                             \
+      case TC_LAY_222: kfn_ = tc::KERNEL<tc::SLay<2, 2, 2, 0>, PPSCI_ACT_TANH>; break;                            \
+      case TC_LAY_VALUE: kfn_ = tc::KERNEL<tc::SLay<0, 0, 0, 0>, PPSCI_ACT_TANH>; break;                          \
+      default:                                                                                                    \
+        kfn_ = (kmax) <= 1 ? tc::KERNEL<tc::DLay<1>, -1> : (kmax) == 2 ? tc::KERNEL<tc::DLay<2>, -1>              \
+                                                                       : tc::KERNEL<tc::DLay<4>, -1>;             \
+    }                                                                                                             \
+    cudaError_t e_ = cudaFuncSetAttribute(kfn_, cudaFuncAttributeMaxDynamicSharedMemorySize, (smem));             \
+    if (e_ != cudaSuccess) { err_expr; }                                                                          \
+    kfn_<<<(grid), dim3(tc::THREADS), (smem), (stream)>>>(args);                                                  \
+  } while (0)
+
 
 inline bool tc_plan_supported(const ppsci_plan_spec& s, int /*C*/, int /*kmax*/) {
   for (int l = 2; l < s.n_layers; ++l)

@@ -50,6 +50,22 @@ inline pthread_barrier_t g_barrier;
 
 inline void __syncthreads() { pthread_barrier_wait(&emul::g_barrier); }
 
+// warp shuffles: lanes of a warp rendezvous on a per-warp barrier and exchange through scratch
+namespace emul {
+inline pthread_barrier_t g_warp_barrier[64];
+inline double g_warp_scratch[64][32];
+}  // namespace emul
+template <typename T>
+inline T __shfl_xor_sync(unsigned, T v, int lane_mask) {
+  const unsigned t = emul::t_threadIdx.x + emul::g_blockDim.x * (emul::t_threadIdx.y + emul::g_blockDim.y * emul::t_threadIdx.z);
+  const unsigned w = t >> 5, l = t & 31;
+  emul::g_warp_scratch[w][l] = (double)v;
+  pthread_barrier_wait(&emul::g_warp_barrier[w]);
+  const T r = (T)emul::g_warp_scratch[w][l ^ (unsigned)lane_mask];
+  pthread_barrier_wait(&emul::g_warp_barrier[w]);
+  return r;
+}
+
 inline float atomicAdd(float* addr, float v) {
   uint32_t* ia = reinterpret_cast<uint32_t*>(addr);
   uint32_t old = __atomic_load_n(ia, __ATOMIC_RELAXED);
@@ -115,6 +131,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
         pthread_barrier_init(&g_barrier, nullptr, nthr);
+        for (unsigned w = 0; w < (nthr + 31) / 32; ++w) pthread_barrier_init(&g_warp_barrier[w], nullptr, std::min(32u, nthr - 32 * w));
         std::vector<std::thread> th;
         th.reserve(nthr);
         for (unsigned t = 0; t < nthr; ++t) {
@@ -126,6 +143,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function
         }
         for (auto& x : th) x.join();
         pthread_barrier_destroy(&g_barrier);
+        for (unsigned w = 0; w < (nthr + 31) / 32; ++w) pthread_barrier_destroy(&g_warp_barrier[w]);
       }
 }
 }  // namespace emul

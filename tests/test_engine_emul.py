@@ -22,3 +22,12 @@ def test_case_matches_oracle(emul_lib, name):
     assert r["res"] <= tr, r
     assert r["grad"] <= tg, r
     assert r["fwd_vs_fused"] == 0.0, r
+
+
+@pytest.mark.parametrize("name", ["ns_f32", "allen_cahn_period_f64", "biharmonic_f64"])
+def test_tile_gemm_path_for_thin_layers(emul_lib, name, monkeypatch):
+    """The dedicated first/last-layer kernels can be switched off: the generic tile GEMMs must agree."""
+    monkeypatch.setenv("PPSCI_B200_NO_THIN", "1")
+    r = run_case(name, 60, library=emul_lib, device="cpu")
+    tl, tr, tg = TOL[CASES[name]["dtype"]]
+    assert r["loss"] <= tl and r["res"] <= tr and r["grad"] <= tg, r
