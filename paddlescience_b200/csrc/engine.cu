@@ -95,6 +95,7 @@ static inline int round4(int x) { return (x + 3) / 4 * 4; }
 
 struct Carve {
   size_t z[PPSCI_MAX_LAYERS + 1];  // z[l] for l = 1..n_layers-1 (hidden pre-activations)
+  size_t a[PPSCI_MAX_LAYERS + 1];  // a[l] = act_jets(z[l]) stashed by the tcgen05 forward for the dW kernel
   size_t y, ybar, zbar0, zbar1;
   size_t wt[PPSCI_MAX_LAYERS + 1];
   size_t loss_acc;
@@ -103,6 +104,7 @@ struct Carve {
 };
 
 static size_t tc_scratch_bytes(const ppsci_plan* P, int64_t nc);
+static bool tc_astash_needed(const ppsci_plan* P, int l);
 
 static void carve(const ppsci_plan* P, int64_t nc, Carve* cv) {
   const size_t es = P->spec.dtype == PPSCI_F64 ? 8 : 4;
@@ -121,6 +123,7 @@ static void carve(const ppsci_plan* P, int64_t nc, Carve* cv) {
   for (int l = 2; l <= L; ++l) cv->wt[l] = take((size_t)P->spec.widths[l] * P->spec.widths[l - 1] * es);
   cv->loss_acc = take(PPSCI_MAX_RES * sizeof(double));
   cv->tc = take(tc_scratch_bytes(P, nc));
+  for (int l = 1; l < L; ++l) cv->a[l] = take(tc_astash_needed(P, l) ? (size_t)P->C * nc * P->ld[l] * es : 0);
   cv->total = off;
 }
 
@@ -549,6 +552,11 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           t.Np = nc;
           t.TP = TP;
           t.num_tiles = (int)ptiles;
+          if (do_bwd && tc_astash_needed(P, l - 1)) {
+            t.Astash = reinterpret_cast<float*>(ws + cv.a[l - 1]);
+            t.lda = P->ld[l - 1];
+            t.aplane = (long long)nc_max * P->ld[l - 1];
+          }
           const int smem_tc = tc::tc_fwd_smem_bytes(t.Nout);
           const unsigned gridx = ptiles < (unsigned)P->num_sms ? ptiles : (unsigned)P->num_sms;
           ProfScope ps_(P, CLS_FWD, st);
@@ -651,11 +659,11 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         f.dW = grads + P->w_off[L];
         f.db = grads + P->b_off[L];
         f.Np = nc;
-        f.pts_per_block = 128;
+        f.pts_per_block = 64;
         auto k3 = k_last_bwd<T, KMAX>;
         {
           ProfScope ps_(P, CLS_DX, st);
-          PPSCI_LAUNCH(k3, dim3((unsigned)((f.K + 255) / 256), (unsigned)((nc + 127) / 128)), dim3(256), 0, st, f);
+          PPSCI_LAUNCH(k3, dim3((unsigned)((f.K + 255) / 256), (unsigned)((nc + 63) / 64)), dim3(256), 0, st, f);
           P->launches++;
         }
         zbar_cur = outp;
@@ -676,20 +684,22 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         f.dW = grads + P->w_off[1];
         f.db = grads + P->b_off[1];
         f.Np = nc;
-        f.pts_per_block = 256;
+        f.pts_per_block = 32;
         auto k4 = k_first_dw<T, KMAX>;
         ProfScope ps_(P, CLS_DW, st);
-        PPSCI_LAUNCH(k4, dim3((unsigned)((f.N + 255) / 256), (unsigned)((nc + 255) / 256)), dim3(256), 0, st, f);
+        PPSCI_LAUNCH(k4, dim3((unsigned)((f.N + 255) / 256), (unsigned)((nc + 31) / 32)), dim3(256), 0, st, f);
         P->launches++;
         break;
       }
 #ifndef PPSCI_EMUL
       bool dw_done = false;
       if constexpr (sizeof(T) == 4) {
-        if (P->use_tc && (P->tc_mask & 4) && tc_dw_ok(s, l)) {
+        if (tc_astash_needed(P, l - 1)) {
           tc::TcDwArgs t;
           memset(&t, 0, sizeof(t));
-          fill_act<float>(P, reinterpret_cast<const float*>(ws + cv.z[l - 1]), P->ld[l - 1], nc_max, A_ACT, &t.A);
+          t.Aact = reinterpret_cast<const float*>(ws + cv.a[l - 1]);
+          t.lda = P->ld[l - 1];
+          t.aplane = (long long)nc_max * P->ld[l - 1];
           t.J = P->J;
           t.Zbar = reinterpret_cast<const float*>(zbar_cur);
           t.ldzb = zbar_ld;
@@ -715,7 +725,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           const int smem_tc = tc::tc_dw_smem_bytes(NC);
           {
             ProfScope ps_(P, CLS_DW, st);
-            PPSCI_TC_LAUNCH(k_tc_dw, tc_pick_layout(P->J, s.act), KMAX, dim3(kt, splits, nb), smem_tc, st, t,
+            PPSCI_TC_LAUNCH_L(k_tc_dw, tc_pick_layout(P->J, PPSCI_ACT_TANH), KMAX, dim3(kt, splits, nb), smem_tc, st, t,
                             return fail(std::string("cudaFuncSetAttribute(k_tc_dw): ") + cudaGetErrorString(e_)));
             P->launches++;
           }
@@ -904,7 +914,14 @@ extern "C" int ppsci_b200_adam_step(int32_t dtype, void* params, const void* gra
 
 #ifdef PPSCI_EMUL
 static size_t tc_scratch_bytes(const ppsci_plan*, int64_t) { return 0; }
+static bool tc_astash_needed(const ppsci_plan*, int) { return false; }
 #else
+// a_l is stashed by the tensor-core forward of layer l+1 and consumed by the tensor-core dW of layer l+1
+static bool tc_astash_needed(const ppsci_plan* P, int l) {
+  const int lay = l + 1;
+  return P->use_tc && (P->tc_mask & 1) && (P->tc_mask & 4) && lay < P->spec.n_layers && tc_layer_ok(P->spec, lay) &&
+         tc_dw_ok(P->spec, lay);
+}
 static size_t tc_scratch_bytes(const ppsci_plan* P, int64_t nc) {
   return P->use_tc ? tc_scratch_bytes_impl(P->spec, P->C, nc) : 0;
 }

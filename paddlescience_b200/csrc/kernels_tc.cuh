@@ -186,31 +186,22 @@ struct DLay {
 template <int ACT>
 __device__ __forceinline__ int act_id(int rt) { return ACT >= 0 ? ACT : rt; }
 
-// ---- cp.async (LDGSTS) staging of raw fp32 tiles: gives every thread many loads in flight ------------
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, bool valid) {
-  const int sz = valid ? 16 : 0;  // src-size 0 => the 16 destination bytes are zero-filled
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
+// ---- raw-tile staging by TMA bulk row copies ------------------------------------------------------------
+// Every row (channel c, point p) of a jet plane is contiguous, so one cp.async.bulk per row lands a
+// [rows x 32] (or wider) fp32 tile in shared memory; one warp issues them (<= 4 rows per lane) and the copies
+// complete on an mbarrier.  Invalid rows (points past the end) are simply not copied: consumers test validity.
 constexpr int RAW_TILE_BYTES = 128 * KCH * 4;  // 128 rows x 32 fp32, linear (row pitch 128 B)
 
-// Stage rows (c, pl) of the channel-major planes Z[c][p][ld], columns [col0, col0+32), into a linear
-// [row = c*TP + pl][32] tile.  Rows >= rows_used are never touched.
-template <class L>
-__device__ __forceinline__ void stage_rows(uint32_t dst, const float* Z, long long plane, int ld, long long p0,
-                                           long long Np, int TP, int rows_used, int col0) {
-  for (int i = threadIdx.x; i < rows_used * 8; i += THREADS) {
-    const int r = i >> 3, q = i & 7;
+// rows r = c*TP + pl, pl < valid_pts;  src row = Z[c][p0 + pl][col0 .. col0 + 32)
+__device__ __forceinline__ void bulk_stage_rows(uint32_t dst, uint32_t bar, const float* Z, long long plane, int ld,
+                                                long long p0, int valid_pts, int TP, int C, int col0) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) mbar_expect_tx(bar, (uint32_t)(C * valid_pts * 128));
+  __syncwarp();
+  const int rows = C * TP;
+  for (int r = lane; r < rows; r += 32) {
     const int c = r / TP, pl = r - c * TP;
-    const long long p = p0 + pl;
-    const bool ok = p < Np;
-    const float* src = ok ? Z + (long long)c * plane + p * ld + col0 + q * 4 : Z;
-    cp_async16(dst + (uint32_t)(r * 128 + q * 16), src, ok);
+    if (pl < valid_pts) bulk_g2s(dst + (uint32_t)(r * 128), Z + (long long)c * plane + (p0 + pl) * ld + col0, 128u, bar);
   }
 }
 
@@ -256,12 +247,15 @@ __device__ __forceinline__ void load_acc_sum(uint32_t acc0, uint32_t acc1, int q
   for (int t = 0; t < 32; ++t) out[t] = __uint_as_float(v0[t]) + __uint_as_float(v1[t]);
 }
 
-// store v = hi + lo into the (hi, lo) pair of K-major SW128 tiles at row r, column kk
-__device__ __forceinline__ void store_split(unsigned char* a_hi, int r, int kk, float v) {
+// store v = hi + lo into the (hi, lo) pair of K-major SW128 tiles; `off` = sw128(row, col)
+__device__ __forceinline__ void store_split_at(unsigned char* a_hi, uint32_t off, float v) {
   const float hi = tf32_rn(v);
-  const uint32_t off = sw128(r, kk);
   *reinterpret_cast<float*>(a_hi + off) = hi;
   *reinterpret_cast<float*>(a_hi + A_TILE_BYTES + off) = v - hi;
+}
+// column kk = lane: the swizzled in-row offset only depends on (row & 7)
+__device__ __forceinline__ uint32_t sw128_lane(int row, int lane) {
+  return (uint32_t)(row * 128 + ((((lane >> 2) ^ row) & 7) << 4) + ((lane & 3) << 2));
 }
 
 struct TcFwdArgs {
@@ -274,6 +268,9 @@ struct TcFwdArgs {
   float* Out;
   int ldo;
   long long oplane;
+  float* Astash;      // optional: post-activation jets a_{l-1} [C][Np][lda] for the dW kernel
+  int lda;
+  long long aplane;
   long long Np;
   int TP;
   int num_tiles;
@@ -281,8 +278,8 @@ struct TcFwdArgs {
 
 // Shared-memory map of k_tc_fwd / k_tc_dx (offsets from the 1024-aligned base):
 //   [0, 2*stage)                       two operand stages: A_hi | A_lo | B_hi | B_lo
-//   [2*stage, 2*stage + 2*RAW)         raw fp32 staging ring (cp.async), one K chunk ahead
-//   then mbarriers full[2], mma_done[2] and the TMEM base slot
+//   [2*stage, 2*stage + 2*RAW)         raw fp32 staging ring (TMA row copies), one K chunk ahead
+//   then mbarriers b_full[2] (+0,+8), mma_done[2] (+16,+24), raw_full[2] (+32,+40) and the TMEM base slot (+64)
 __host__ __device__ inline int tc_fwd_smem_bytes(int N) { return 2 * tc_stage_bytes(N) + 2 * RAW_TILE_BYTES + 1024 + 256; }
 
 // Shared prologue of the three kernels: barriers, TMEM, zeroed operand stages.
@@ -291,10 +288,7 @@ __device__ __forceinline__ void tc_setup(uint32_t base, unsigned char* base_ptr,
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bars = base + bars_off;
   if (tid == 0) {
-    mbar_init(bars + 0, 1);
-    mbar_init(bars + 8, 1);
-    mbar_init(bars + 16, 1);
-    mbar_init(bars + 24, 1);
+    for (int i = 0; i < 6; ++i) mbar_init(bars + 8 * i, 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -313,8 +307,9 @@ __device__ __forceinline__ void tc_setup(uint32_t base, unsigned char* base_ptr,
 
 // Forward layer  Z_l = act_jets(Z_{l-1}) W_l + b_l  on the tensor cores.
 // Persistent: CTA t handles tiles t, t+grid, ...; each tile = 128 rows = TP points x C channels.
-// Pipeline per K chunk `it`:  raw rows of chunk it+1 (cp.async) and weight images of chunk it+1 (TMA) are
-// requested, the A operand of chunk `it` is produced from the raw tile, then its 12 MMAs are issued.
+// Pipeline per K chunk `it`:  raw rows of chunk it+1 (TMA row copies, warp 0) and weight images of chunk it+1
+// (one TMA bulk copy) are requested, the A operand of chunk `it` is produced from the raw tile by all warps
+// (item = point x lane-column: all C channels), then thread 0 issues its 12 MMAs.
 template <class L, int ACT>
 __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
   extern __shared__ unsigned char smem_dyn[];
@@ -324,7 +319,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
   const int stage_bytes = tc_stage_bytes(N);
   const uint32_t raw_off = 2 * stage_bytes;
   const uint32_t bars_off = raw_off + 2 * RAW_TILE_BYTES;
-  const uint32_t bars = base + bars_off;  // full[2] at +0,+8 ; mma_done[2] at +16,+24
+  const uint32_t bars = base + bars_off;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ncols = tc_pow2_cols(2 * N);
   tc_setup(base, base_ptr, bars_off, stage_bytes, 2 * A_TILE_BYTES, ncols);
@@ -345,56 +340,62 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
     bulk_g2s(base + sb * stage_bytes + 2 * A_TILE_BYTES, g.Wimg + (long long)(itb % nchunks) * 2 * N * KCH, b_bytes,
              bars + 8 * sb);
   };
+  auto issue_raw = [&](uint32_t itr, int tile_r, int jr) {  // warp 0: raw rows of running chunk itr
+    const long long p0r = (long long)tile_r * TP;
+    long long vp = g.Np - p0r;
+    const int valid = vp >= TP ? TP : (vp > 0 ? (int)vp : 0);
+    bulk_stage_rows(base + raw_off + (itr & 1u) * RAW_TILE_BYTES, bars + 32 + 8 * (itr & 1u), g.A.Z, g.A.plane, g.A.ld, p0r,
+                    valid, TP, C, jr * KCH);
+  };
   if (total_it > 0) {
-    stage_rows<L>(base + raw_off, g.A.Z, g.A.plane, g.A.ld, (long long)blockIdx.x * TP, g.Np, TP, rows_used, 0);
+    if (warp == 0) issue_raw(0, blockIdx.x, 0);
     if (tid == 0) issue_b(0);
   }
-  cp_async_commit();
   uint32_t it = 0;  // running chunk counter (stage = it & 1, use index = it >> 1)
   for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
     const long long p0 = (long long)tile * TP;
     for (int j = 0; j < nchunks; ++j, ++it) {
       const uint32_t s = it & 1u, u = it >> 1;
       unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-      // request chunk it+1: raw rows (cp.async) and, once the MMAs of chunk it-1 have left that stage, weights
-      {
+      if (warp == 0 && it + 1 < total_it) {  // raw rows of chunk it+1 (buffer last read in iteration it-1)
         int ntile = tile, nj = j + 1;
         if (nj == nchunks) { nj = 0; ntile = tile + gridDim.x; }
-        if (ntile < g.num_tiles)
-          stage_rows<L>(base + raw_off + ((it + 1) & 1u) * RAW_TILE_BYTES, g.A.Z, g.A.plane, g.A.ld, (long long)ntile * TP,
-                        g.Np, TP, rows_used, nj * KCH);
-        cp_async_commit();
+        issue_raw(it + 1, ntile, nj);
       }
-      cp_async_wait<1>();  // this chunk's raw rows have landed (this thread's pieces) ...
-      __syncthreads();     // ... and everybody else's
+      mbar_wait(bars + 32 + 8 * s, u & 1u);                    // raw rows of this chunk have landed
       if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);  // MMAs that read this stage have retired
-      const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + (it & 1u) * RAW_TILE_BYTES);
-      // one item = (point pl, column kk = lane): all C channels
+      const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + s * RAW_TILE_BYTES);
+      const int k = j * KCH + lane;
       for (int pl = warp; pl < TP; pl += THREADS / 32) {
-        const int kk = lane;
-        if (p0 + pl < g.Np) {
+        const long long p = p0 + pl;
+        if (p < g.Np) {
           float sc[6];
           float y0;
-          act_coef<float, L::KM>(act, raw[pl * KCH + kk], y0, sc);
-          store_split(stage_ptr, pl, kk, y0);
+          act_coef<float, L::KM>(act, raw[pl * KCH + lane], y0, sc);
+          store_split_at(stage_ptr, sw128_lane(pl, lane), y0);
+          float* ast = g.Astash ? g.Astash + p * g.lda + k : nullptr;
+          if (ast) ast[0] = y0;
 #pragma unroll
           for (int d = 0; d < L::ND; ++d) {
             if (d < L::nd(g.J)) {
               const int K = L::order(g.J, d), cb = L::cbase(g.J, d);
               float zz[4], yy[4];
 #pragma unroll
-              for (int o = 0; o < 4; ++o) zz[o] = (o < L::KM && o < K) ? raw[((cb + o) * TP + pl) * KCH + kk] : 0.f;
+              for (int o = 0; o < 4; ++o) zz[o] = (o < L::KM && o < K) ? raw[((cb + o) * TP + pl) * KCH + lane] : 0.f;
               jet_fwd_dir<float, L::KM>(sc, zz, yy);
 #pragma unroll
               for (int o = 0; o < L::KM; ++o)
-                if (o < K) store_split(stage_ptr, (cb + o) * TP + pl, kk, yy[o]);
+                if (o < K) {
+                  store_split_at(stage_ptr, sw128_lane((cb + o) * TP + pl, lane), yy[o]);
+                  if (ast) ast[(long long)(cb + o) * g.aplane] = yy[o];
+                }
             }
           }
         } else {
-          for (int c = 0; c < C; ++c) store_split(stage_ptr, c * TP + pl, kk, 0.f);
+          for (int c = 0; c < C; ++c) store_split_at(stage_ptr, sw128_lane(c * TP + pl, lane), 0.f);
         }
       }
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      fence_proxy_async();  // generic-proxy smem accesses ordered before the async-proxy ones that follow
       __syncthreads();
       if (tid == 0) {
         mbar_wait(bars + 8 * s, u & 1u);  // weight images of this chunk have landed
@@ -442,7 +443,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
       __syncthreads();  // accumulators drained before the next tile's first MMA overwrites them
     }
   }
-  cp_async_wait<0>();
   __syncthreads();
   if (warp == 1) tmem_dealloc(acc0, ncols);
 }
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
 // Backward dx on the tensor cores:  Abar = Zbar_l W_l^T  (contraction over the layer's outputs), then the
 // activation adjoint  Zbar_{l-1} = adj(Abar, Z_{l-1}).  The C channels of one point live in different TMEM
 // lanes and the adjoint needs them together, so each 32-column block goes through a shared-memory
-// exchange tile; the matching Z_{l-1} block is prefetched with cp.async one block ahead.  During the
+// exchange tile; the matching Z_{l-1} block is prefetched by TMA row copies one block ahead.  During the
 // epilogue all MMAs have retired, so the exchange tile lives in stage 0's A_hi region and the two Z
 // buffers in stage 1's A_hi / A_lo regions (same 128-byte row pitch; pad rows stay zero).
 // =====================================================================================================
@@ -476,6 +476,7 @@ struct TcDxArgs {
 template <class L, int ACT>
 __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
   extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) unsigned long long zbar_bars[2];  // epilogue Z-block barriers
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
   const int N = g.Nout;
@@ -485,6 +486,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
   const uint32_t bars = base + bars_off;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ncols = tc_pow2_cols(2 * N);
+  const uint32_t zbars = smem_u32(zbar_bars);
+  if (tid == 0) {
+    mbar_init(zbars, 1);
+    mbar_init(zbars + 8, 1);
+  }
   tc_setup(base, base_ptr, bars_off, stage_bytes, 2 * A_TILE_BYTES, ncols);
   const uint32_t acc0 = *reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 64), acc1 = acc0 + (uint32_t)N;
   const uint32_t idesc = make_idesc_tf32(128, N);
@@ -499,6 +505,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
   const float* zbuf_ptr = reinterpret_cast<const float*>(base_ptr + stage_bytes);
   const int my_tiles = ((int)blockIdx.x < g.num_tiles) ? (g.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const uint32_t total_it = (uint32_t)my_tiles * (uint32_t)nchunks;
+  uint32_t zuse = 0;  // running count of epilogue Z blocks (barrier zuse & 1, phase (zuse >> 1) & 1)
 
   auto issue_b = [&](uint32_t itb) {
     const uint32_t sb = itb & 1u;
@@ -506,31 +513,38 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
     bulk_g2s(base + sb * stage_bytes + 2 * A_TILE_BYTES, g.Wimg + (long long)(itb % nchunks) * 2 * N * KCH, b_bytes,
              bars + 8 * sb);
   };
+  auto valid_pts = [&](long long p0r) {
+    const long long vp = g.Np - p0r;
+    return vp >= TP ? TP : (vp > 0 ? (int)vp : 0);
+  };
+  auto issue_raw = [&](uint32_t itr, int tile_r, int jr) {
+    const long long p0r = (long long)tile_r * TP;
+    bulk_stage_rows(base + raw_off + (itr & 1u) * RAW_TILE_BYTES, bars + 32 + 8 * (itr & 1u), g.A.Z, g.A.plane, g.A.ld, p0r,
+                    valid_pts(p0r), TP, C, jr * KCH);
+  };
   if (total_it > 0) {
-    stage_rows<L>(base + raw_off, g.A.Z, g.A.plane, g.A.ld, (long long)blockIdx.x * TP, g.Np, TP, rows_used, 0);
+    if (warp == 0) issue_raw(0, blockIdx.x, 0);
     if (tid == 0) issue_b(0);
   }
-  cp_async_commit();
   uint32_t it = 0;
   for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
     const long long p0 = (long long)tile * TP;
+    const int vpts = valid_pts(p0);
     for (int j = 0; j < nchunks; ++j, ++it) {
       const uint32_t s = it & 1u, u = it >> 1;
       unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-      {
+      if (warp == 0 && it + 1 < total_it) {
         int ntile = tile, nj = j + 1;
         if (nj == nchunks) { nj = 0; ntile = tile + gridDim.x; }
-        if (ntile < g.num_tiles)
-          stage_rows<L>(base + raw_off + ((it + 1) & 1u) * RAW_TILE_BYTES, g.A.Z, g.A.plane, g.A.ld, (long long)ntile * TP,
-                        g.Np, TP, rows_used, nj * KCH);
-        cp_async_commit();
+        issue_raw(it + 1, ntile, nj);
       }
-      cp_async_wait<1>();
-      __syncthreads();
+      mbar_wait(bars + 32 + 8 * s, u & 1u);
       if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
-      const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + (it & 1u) * RAW_TILE_BYTES);
-      for (int r = warp; r < rows_used; r += THREADS / 32)  // plain split, one row per warp pass
-        store_split(stage_ptr, r, lane, raw[r * KCH + lane]);
+      const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + s * RAW_TILE_BYTES);
+      for (int r = warp; r < rows_used; r += THREADS / 32) {  // plain split, one row per warp pass
+        const int c = r / TP, pl = r - c * TP;
+        store_split_at(stage_ptr, sw128_lane(r, lane), pl < vpts ? raw[r * KCH + lane] : 0.f);
+      }
       fence_proxy_async();
       __syncthreads();
       if (tid == 0) {
@@ -552,13 +566,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
       mbar_wait(bars + 16 + 8 * (last & 1u), (last >> 1) & 1u);
       tc_fence_after();
       const int ncb = N / 32;
-      stage_rows<L>(zbuf_addr, g.Zprev, g.zplane, g.ldz, p0, g.Np, TP, rows_used, 0);
-      cp_async_commit();
-      for (int cb = 0; cb < ncb; ++cb) {
-        if (cb + 1 < ncb)
-          stage_rows<L>(zbuf_addr + ((cb + 1) & 1) * A_TILE_BYTES, g.Zprev, g.zplane, g.ldz, p0, g.Np, TP, rows_used,
-                        (cb + 1) * 32);
-        cp_async_commit();
+      if (warp == 0)
+        bulk_stage_rows(zbuf_addr + (zuse & 1u) * A_TILE_BYTES, zbars + 8 * (zuse & 1u), g.Zprev, g.zplane, g.ldz, p0, vpts, TP, C, 0);
+      for (int cb = 0; cb < ncb; ++cb, ++zuse) {
+        if (warp == 0 && cb + 1 < ncb)
+          bulk_stage_rows(zbuf_addr + ((zuse + 1) & 1u) * A_TILE_BYTES, zbars + 8 * ((zuse + 1) & 1u), g.Zprev, g.zplane, g.ldz,
+                          p0, vpts, TP, C, (cb + 1) * 32);
         if (warp < 4) {  // 128 lanes x 32 columns of Abar -> X[r][t ^ (r & 31)]  (conflict-free both ways)
           float v[32];
           load_acc_sum(acc0, acc1, warp, cb * 32, v);
@@ -566,14 +579,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
 #pragma unroll
           for (int t = 0; t < 32; ++t) xr[t ^ lane] = v[t];
         }
-        cp_async_wait<1>();
+        mbar_wait(zbars + 8 * (zuse & 1u), (zuse >> 1) & 1u);
         __syncthreads();
-        const float* zb = zbuf_ptr + (cb & 1) * (A_TILE_BYTES / 4);
+        const float* zb = zbuf_ptr + (zuse & 1u) * (A_TILE_BYTES / 4);
         const int nn = lane;
-        for (int pl = warp; pl < TP; pl += THREADS / 32) {
-          const long long p = p0 + pl;
-          if (p >= g.Np) continue;
-          float* zb_out = g.Out + p * g.ldo + cb * 32 + nn;
+        for (int pl = warp; pl < vpts; pl += THREADS / 32) {
+          float* zb_out = g.Out + (p0 + pl) * g.ldo + cb * 32 + nn;
           float sc[6];
           float y0;
           act_coef<float, L::KM + 1>(act, zb[pl * KCH + nn], y0, sc);
@@ -600,36 +611,36 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
           }
           zb_out[0] = jet_adj_z0<float, L::KM>(sc, y0b, sb);
         }
+        fence_proxy_async();
         __syncthreads();
       }
-      fence_proxy_async();
       tc_fence_before();
       __syncthreads();
     }
   }
-  cp_async_wait<0>();
   __syncthreads();
   if (warp == 1) tmem_dealloc(acc0, ncols);
 }
 
 // =====================================================================================================
 // Backward dW on the tensor cores:  dW_l[k][n] += sum_rows A_{l-1}[row][k] * Zbar_l[row][n].
-// Reduction dimension = jet rows (points x channels).  CTA (kt, split) owns dW rows [128 kt, 128 kt + 128)
-// and a contiguous range of 32-row reduction chunks (PT points each); it accumulates in TMEM across its
-// whole range and flushes once with red.global.add.  Both operands are written transposed into K-major
-// SW128 tiles from cp.async-staged raw tiles:
-//   warps 0-7  : A' = act_jets(Z_{l-1})   (item = (point, dW row k))
-//   warps 8-15 : B' = split(Zbar_l)        (item = (16-byte chunk of 4 reduction rows, column n))
+// Reduction dimension = jet rows (points x channels).  CTA (kt, split, nb) owns dW rows [128 kt, +128),
+// columns [NC nb, +NC) and a contiguous range of 32-row reduction chunks (PT points each); it accumulates in
+// TMEM across its whole range and flushes once with red.global.add.  A_{l-1} (post-activation jets) was
+// stashed by the forward kernel, so both operands are plain copies: raw rows arrive by TMA row copies
+// (one row per lane of warp 0) and all warps split + transpose them into K-major SW128 tiles.
 // =====================================================================================================
 struct TcDwArgs {
-  AOperand<float> A;   // A_ACT over Z_{l-1}
+  const float* Aact;   // a_{l-1} [C][Np][lda]
+  int lda;
+  long long aplane;
   JetLayout J;
   const float* Zbar;   // [C][Np][ldzb]
   int ldzb;
   long long zbplane;
   int Kdim;            // fan-in (rows of dW), multiple of 128
-  int Nout;            // fan-out (cols of dW), multiple of 32, <= 128 per CTA column block
-  int n0_stride;       // columns handled per CTA in grid.z (= Nout_cta)
+  int Nout;            // columns per CTA (NC), multiple of 32, <= 128
+  int n0_stride;
   float* dW;           // [Kdim][ldw]
   int ldw;             // full fan-out of the layer (row pitch of dW)
   long long Np;
@@ -637,14 +648,13 @@ struct TcDwArgs {
   int chunks_per_split;
 };
 
-// raw tiles of one reduction chunk: Z rows [32][128 k] (16 KB) and Zbar rows [32][NC n] (NC*128 B)
+// raw tiles of one reduction chunk: A rows [32][128 k] (16 KB) and Zbar rows [32][NC n] (NC*128 B)
 __host__ __device__ inline int tc_dw_raw_bytes(int NC) { return KCH * 128 * 4 + KCH * NC * 4; }
 __host__ __device__ inline int tc_dw_smem_bytes(int NC) { return 2 * tc_stage_bytes(NC) + 2 * tc_dw_raw_bytes(NC) + 1024 + 256; }
 
-template <class L, int ACT>
+template <class L>
 __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
   extern __shared__ unsigned char smem_dyn[];
-  __shared__ int row_c[KCH], row_pl[KCH];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
   const int N = g.Nout;  // columns of this CTA
@@ -652,17 +662,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
   const int raw_bytes = tc_dw_raw_bytes(N);
   const uint32_t raw_off = 2 * stage_bytes;
   const uint32_t bars_off = raw_off + 2 * raw_bytes;
-  const uint32_t bars = base + bars_off;  // mma_done[2] at +16, +24
+  const uint32_t bars = base + bars_off;  // mma_done[2] at +16,+24 ; raw_full[2] at +32,+40
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ncols = tc_pow2_cols(2 * N);
   const int PT = L::pt(g.PT);
   const int C = L::nchan(g.J);
   const int rows_used = C * PT;
-  const int act = act_id<ACT>(g.A.act);
-  if (tid < KCH) {
-    row_c[tid] = tid < rows_used ? tid / PT : -1;
-    row_pl[tid] = tid < rows_used ? tid % PT : 0;
-  }
   tc_setup(base, base_ptr, bars_off, stage_bytes, stage_bytes, ncols);  // whole stages cleared (pad columns stay 0)
   const uint32_t acc0 = *reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 64), acc1 = acc0 + (uint32_t)N;
   const uint32_t idesc = make_idesc_tf32(128, N);
@@ -672,87 +677,64 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
   const long long ch_begin = (long long)blockIdx.y * g.chunks_per_split;
   long long ch_end = ch_begin + g.chunks_per_split;
   if (ch_end > total_chunks) ch_end = total_chunks;
-  const int zb_pieces = N / 4;  // 16-byte pieces per Zbar row
 
-  // raw rows of a chunk: row rr = c*PT + pl;  Z: 128 k-columns of this CTA's dW row block;  Zbar: N columns
-  auto stage_chunk = [&](long long ch, uint32_t dst) {
-    const long long pb = ch * PT;
-    for (int i = tid; i < rows_used * 32; i += THREADS) {
-      const int rr = i >> 5, q = i & 31;
-      const long long p = pb + row_pl[rr];
-      const bool ok = p < g.Np;
-      const float* src = ok ? g.A.Z + (long long)row_c[rr] * g.A.plane + p * g.A.ld + k0 + q * 4 : g.A.Z;
-      cp_async16(dst + (uint32_t)(rr * 512 + q * 16), src, ok);
-    }
-    const uint32_t dzb = dst + KCH * 128 * 4;
-    for (int i = tid; i < rows_used * zb_pieces; i += THREADS) {
-      const int rr = i / zb_pieces, q = i - rr * zb_pieces;
-      const long long p = pb + row_pl[rr];
-      const bool ok = p < g.Np;
-      const float* src = ok ? g.Zbar + (long long)row_c[rr] * g.zbplane + p * g.ldzb + n0 + q * 4 : g.Zbar;
-      cp_async16(dzb + (uint32_t)(rr * N * 4 + q * 16), src, ok);
+  auto valid_pts = [&](long long ch) {
+    const long long vp = g.Np - ch * PT;
+    return vp >= PT ? PT : (vp > 0 ? (int)vp : 0);
+  };
+  // warp 0, lane = reduction row rr = c*PT + pl: one A row (128 k, 512 B) and one Zbar row (N cols)
+  auto issue_raw = [&](long long ch, uint32_t itr) {
+    const int vp = valid_pts(ch);
+    const uint32_t bar = bars + 32 + 8 * (itr & 1u);
+    const uint32_t dst = base + raw_off + (itr & 1u) * raw_bytes;
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(C * vp * (512 + N * 4)));
+    __syncwarp();
+    if (lane < rows_used) {
+      const int c = lane / PT, pl = lane - c * PT;
+      if (pl < vp) {
+        const long long p = ch * PT + pl;
+        bulk_g2s(dst + (uint32_t)(lane * 512), g.Aact + (long long)c * g.aplane + p * g.lda + k0, 512u, bar);
+        bulk_g2s(dst + (uint32_t)(KCH * 512 + lane * N * 4), g.Zbar + (long long)c * g.zbplane + p * g.ldzb + n0,
+                 (uint32_t)(N * 4), bar);
+      }
     }
   };
 
   uint32_t it = 0;
-  if (ch_begin < ch_end) stage_chunk(ch_begin, base + raw_off);
-  cp_async_commit();
+  if (warp == 0 && ch_begin < ch_end) issue_raw(ch_begin, 0);
+  const int nq = (rows_used + 3) / 4;  // 16-byte chunks of 4 reduction rows
   for (long long ch = ch_begin; ch < ch_end; ++ch, ++it) {
     const uint32_t s = it & 1u, u = it >> 1;
     unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-    if (ch + 1 < ch_end) stage_chunk(ch + 1, base + raw_off + ((it + 1) & 1u) * raw_bytes);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
+    if (warp == 0 && ch + 1 < ch_end) issue_raw(ch + 1, it + 1);
+    mbar_wait(bars + 32 + 8 * s, u & 1u);
     if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
-    const long long pbase = ch * PT;
-    const float* rawz = reinterpret_cast<const float*>(base_ptr + raw_off + (it & 1u) * raw_bytes);
-    const float* rawzb = rawz + KCH * 128;
-    if (warp < THREADS / 64) {
-      // A' tile: row = dW row k, column rr = c*PT + pl.  item = (pl, k): 128 k per point
-      for (int item = tid; item < PT * 128; item += THREADS / 2) {
-        const int k = item & 127, pl = item >> 7;
-        if (pbase + pl < g.Np) {
-          float sc[6];
-          float y0;
-          act_coef<float, L::KM>(act, rawz[pl * 128 + k], y0, sc);
-          store_split(stage_ptr, k, pl, y0);
+    const int vp = valid_pts(ch);
+    const float* rawa = reinterpret_cast<const float*>(base_ptr + raw_off + s * raw_bytes);
+    const float* rawzb = rawa + KCH * 128;
+    unsigned char* b_hi = stage_ptr + 2 * A_TILE_BYTES;
+    // items [0, 128 nq): A'(row k, chunk q) ; items [128 nq, 128 nq + N nq): B'(row n, chunk q)
+    const int itemsA = 128 * nq, items = itemsA + N * nq;
+    for (int item = tid; item < items; item += THREADS) {
+      const bool isA = item < itemsA;
+      const int local = isA ? item : item - itemsA;
+      const int width = isA ? 128 : N;
+      const int row = local % width, q = local / width;
+      const float* src = isA ? rawa : rawzb;
+      float hi[4], lo[4];
 #pragma unroll
-          for (int d = 0; d < L::ND; ++d) {
-            if (d < L::nd(g.J)) {
-              const int K = L::order(g.J, d), cb = L::cbase(g.J, d);
-              float zz[4], yy[4];
-#pragma unroll
-              for (int o = 0; o < 4; ++o) zz[o] = (o < L::KM && o < K) ? rawz[((cb + o) * PT + pl) * 128 + k] : 0.f;
-              jet_fwd_dir<float, L::KM>(sc, zz, yy);
-#pragma unroll
-              for (int o = 0; o < L::KM; ++o)
-                if (o < K) store_split(stage_ptr, k, (cb + o) * PT + pl, yy[o]);
-            }
-          }
-        } else {
-          for (int c = 0; c < C; ++c) store_split(stage_ptr, k, c * PT + pl, 0.f);
-        }
+      for (int e = 0; e < 4; ++e) {
+        const int rr = 4 * q + e;
+        const int c = rr / PT, pl = rr - c * PT;
+        const float v = (rr < rows_used && pl < vp) ? src[rr * width + row] : 0.f;
+        hi[e] = tf32_rn(v);
+        lo[e] = v - hi[e];
       }
-    } else {
-      // B' tile: row = n, 16-byte chunk q holds reduction columns 4q..4q+3
-      unsigned char* b_hi = stage_ptr + 2 * A_TILE_BYTES;
-      unsigned char* b_lo = b_hi + N * KCH * 4;
-      const int nq = (rows_used + 3) / 4;
-      for (int item = tid - THREADS / 2; item < N * nq; item += THREADS / 2) {
-        const int n = item % N, q = item / N;
-        float hi[4], lo[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int rr = 4 * q + e;
-          const float v = rr < rows_used ? rawzb[rr * N + n] : 0.f;
-          hi[e] = tf32_rn(v);
-          lo[e] = v - hi[e];
-        }
-        const uint32_t off = sw128(n, 4 * q);
-        *reinterpret_cast<float4*>(b_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(b_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-      }
+      const uint32_t off = sw128(row, 4 * q);
+      unsigned char* t_hi = isA ? stage_ptr : b_hi;
+      const int lo_off = isA ? A_TILE_BYTES : N * KCH * 4;
+      *reinterpret_cast<float4*>(t_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(t_hi + lo_off + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
     }
     fence_proxy_async();
     __syncthreads();
@@ -779,7 +761,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
       }
     }
   }
-  cp_async_wait<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(acc0, ncols);
@@ -839,6 +820,21 @@ inline int tc_pick_layout(const JetLayout& J, int act) {
   if (is(0, 0, 0, 0)) return TC_LAY_VALUE;
   return TC_LAY_DYN;
 }
+
+#define PPSCI_TC_LAUNCH_L(KERNEL, lay, kmax, grid, smem, stream, args, err_expr)                                 \
+  do {                                                                                                            \
+    void (*kfn_)(decltype(args)) = nullptr;                                                                       \
+    switch (lay) {                                                                                                \
+      case TC_LAY_22: kfn_ = tc::KERNEL<tc::SLay<2, 2, 0, 0>>; break;                                             \
+      case TC_LAY_12: kfn_ = tc::KERNEL<tc::SLay<1, 2, 0, 0>>; break;                                             \
+      case TC_LAY_222: kfn_ = tc::KERNEL<tc::SLay<2, 2, 2, 0>>; break;                                            \
+      case TC_LAY_VALUE: kfn_ = tc::KERNEL<tc::SLay<0, 0, 0, 0>>; break;                                          \
+      default: kfn_ = tc::KERNEL<tc::DLay<4>>;                                                                    \
+    }                                                                                                             \
+    cudaError_t e_ = cudaFuncSetAttribute(kfn_, cudaFuncAttributeMaxDynamicSharedMemorySize, (smem));             \
+    if (e_ != cudaSuccess) { err_expr; }                                                                          \
+    kfn_<<<(grid), dim3(tc::THREADS), (smem), (stream)>>>(args);                                                  \
+  } while (0)
 
 #define PPSCI_TC_LAUNCH(KERNEL, lay, kmax, grid, smem, stream, args, err_expr)                                   \
   do {                                                                                                            \

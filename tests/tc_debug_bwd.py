@@ -23,7 +23,7 @@ def layer_slices(widths):
     return out
 
 
-def run(hidden, n, masks=(1, 2, 4, 7), act="tanh", seed=0, chunk=0):
+def run(hidden, n, masks=(1, 2, 5, 7), act="tanh", seed=0, chunk=0):
     dev = torch.device("cuda:0")
     torch.manual_seed(seed)
     net = make_net(("x", "y"), ("u", "v", "p"), hidden, act)
