@@ -186,24 +186,49 @@ struct DLay {
 template <int ACT>
 __device__ __forceinline__ int act_id(int rt) { return ACT >= 0 ? ACT : rt; }
 
-// ---- raw-tile staging by TMA bulk row copies ------------------------------------------------------------
-// Every row (channel c, point p) of a jet plane is contiguous, so one cp.async.bulk per row lands a
-// [rows x 32] (or wider) fp32 tile in shared memory; one warp issues them (<= 4 rows per lane) and the copies
-// complete on an mbarrier.  Invalid rows (points past the end) are simply not copied: consumers test validity.
-constexpr int RAW_TILE_BYTES = 128 * KCH * 4;  // 128 rows x 32 fp32, linear (row pitch 128 B)
-
-// rows r = c*TP + pl, pl < valid_pts;  src row = Z[c][p0 + pl][col0 .. col0 + 32)
-__device__ __forceinline__ void bulk_stage_rows(uint32_t dst, uint32_t bar, const float* Z, long long plane, int ld,
-                                                long long p0, int valid_pts, int TP, int C, int col0) {
-  const int lane = threadIdx.x & 31;
-  if (lane == 0) mbar_expect_tx(bar, (uint32_t)(C * valid_pts * 128));
-  __syncwarp();
-  const int rows = C * TP;
-  for (int r = lane; r < rows; r += 32) {
-    const int c = r / TP, pl = r - c * TP;
-    if (pl < valid_pts) bulk_g2s(dst + (uint32_t)(r * 128), Z + (long long)c * plane + (p0 + pl) * ld + col0, 128u, bar);
-  }
+// ---- raw-tile staging with cp.async (LDGSTS) ----------------------------------------------------------
+// (Measured: one cp.async.bulk per 128-byte row costs ~100 issue cycles each and serialises; 16-byte
+// cp.async pieces spread over all threads are 2x faster here.)  The piece -> (row, 16-byte column) mapping
+// does not change from chunk to chunk, so each thread precomputes its pieces once.
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 => the 16 destination bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+constexpr int RAW_TILE_BYTES = 128 * KCH * 4;  // 128 rows x 32 fp32, linear (row pitch 128 B)
+constexpr int ROW_PIECES = (128 * 8) / THREADS;  // 16-byte pieces of a [128 x 32] tile per thread
+
+// pieces of a [rows_used x 32] tile whose row r = c*TP + pl comes from plane c, point p0 + pl
+struct RowPieces {
+  long long src[ROW_PIECES];  // c*plane + pl*ld + 4q  (element offset; add p0*ld + col0)
+  uint32_t dst[ROW_PIECES];   // r*128 + 16 q
+  int pl[ROW_PIECES];         // -1: no piece
+  __device__ __forceinline__ void init(int TP, int rows_used, long long plane, int ld) {
+#pragma unroll
+    for (int j = 0; j < ROW_PIECES; ++j) {
+      const int i = threadIdx.x + j * THREADS;
+      const int r = i >> 3, q = i & 7;
+      const int c = r / TP, pl_ = r - c * TP;
+      pl[j] = r < rows_used ? pl_ : -1;
+      src[j] = (long long)c * plane + (long long)pl_ * ld + q * 4;
+      dst[j] = (uint32_t)(r * 128 + q * 16);
+    }
+  }
+  __device__ __forceinline__ void issue(uint32_t dst_base, const float* Z, long long p0_ld_col0, int valid_pts) const {
+#pragma unroll
+    for (int j = 0; j < ROW_PIECES; ++j) {
+      if (pl[j] >= 0) {
+        const bool ok = pl[j] < valid_pts;
+        cp_async16(dst_base + dst[j], ok ? Z + src[j] + p0_ld_col0 : Z, ok);
+      }
+    }
+  }
+};
 
 __host__ __device__ inline int tc_stage_bytes(int N) { return 2 * A_TILE_BYTES + 2 * N * KCH * 4; }
 __host__ __device__ inline uint32_t tc_pow2_cols(int n) {
@@ -340,29 +365,33 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
     bulk_g2s(base + sb * stage_bytes + 2 * A_TILE_BYTES, g.Wimg + (long long)(itb % nchunks) * 2 * N * KCH, b_bytes,
              bars + 8 * sb);
   };
-  auto issue_raw = [&](uint32_t itr, int tile_r, int jr) {  // warp 0: raw rows of running chunk itr
+  RowPieces pcs;
+  pcs.init(TP, rows_used, g.A.plane, g.A.ld);
+  auto issue_raw = [&](uint32_t itr, int tile_r, int jr) {  // raw rows of running chunk itr (all threads)
     const long long p0r = (long long)tile_r * TP;
-    long long vp = g.Np - p0r;
+    const long long vp = g.Np - p0r;
     const int valid = vp >= TP ? TP : (vp > 0 ? (int)vp : 0);
-    bulk_stage_rows(base + raw_off + (itr & 1u) * RAW_TILE_BYTES, bars + 32 + 8 * (itr & 1u), g.A.Z, g.A.plane, g.A.ld, p0r,
-                    valid, TP, C, jr * KCH);
+    pcs.issue(base + raw_off + (itr & 1u) * RAW_TILE_BYTES, g.A.Z, p0r * g.A.ld + jr * KCH, valid);
   };
   if (total_it > 0) {
-    if (warp == 0) issue_raw(0, blockIdx.x, 0);
+    issue_raw(0, blockIdx.x, 0);
     if (tid == 0) issue_b(0);
   }
+  cp_async_commit();
   uint32_t it = 0;  // running chunk counter (stage = it & 1, use index = it >> 1)
   for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
     const long long p0 = (long long)tile * TP;
     for (int j = 0; j < nchunks; ++j, ++it) {
       const uint32_t s = it & 1u, u = it >> 1;
       unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-      if (warp == 0 && it + 1 < total_it) {  // raw rows of chunk it+1 (buffer last read in iteration it-1)
+      if (it + 1 < total_it) {  // raw rows of chunk it+1 (buffer last read in iteration it-1)
         int ntile = tile, nj = j + 1;
         if (nj == nchunks) { nj = 0; ntile = tile + gridDim.x; }
         issue_raw(it + 1, ntile, nj);
       }
-      mbar_wait(bars + 32 + 8 * s, u & 1u);                    // raw rows of this chunk have landed
+      cp_async_commit();
+      cp_async_wait<1>();  // this chunk's raw rows have landed (this thread's pieces) ...
+      __syncthreads();     // ... and everybody else's
       if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);  // MMAs that read this stage have retired
       const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + s * RAW_TILE_BYTES);
       const int k = j * KCH + lane;
@@ -443,6 +472,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
       __syncthreads();  // accumulators drained before the next tile's first MMA overwrites them
     }
   }
+  cp_async_wait<0>();
   __syncthreads();
   if (warp == 1) tmem_dealloc(acc0, ncols);
 }
@@ -476,7 +506,6 @@ struct TcDxArgs {
 template <class L, int ACT>
 __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
   extern __shared__ unsigned char smem_dyn[];
-  __shared__ __align__(8) unsigned long long zbar_bars[2];  // epilogue Z-block barriers
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
   const int N = g.Nout;
@@ -486,11 +515,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
   const uint32_t bars = base + bars_off;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ncols = tc_pow2_cols(2 * N);
-  const uint32_t zbars = smem_u32(zbar_bars);
-  if (tid == 0) {
-    mbar_init(zbars, 1);
-    mbar_init(zbars + 8, 1);
-  }
   tc_setup(base, base_ptr, bars_off, stage_bytes, 2 * A_TILE_BYTES, ncols);
   const uint32_t acc0 = *reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 64), acc1 = acc0 + (uint32_t)N;
   const uint32_t idesc = make_idesc_tf32(128, N);
@@ -505,7 +529,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
   const float* zbuf_ptr = reinterpret_cast<const float*>(base_ptr + stage_bytes);
   const int my_tiles = ((int)blockIdx.x < g.num_tiles) ? (g.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const uint32_t total_it = (uint32_t)my_tiles * (uint32_t)nchunks;
-  uint32_t zuse = 0;  // running count of epilogue Z blocks (barrier zuse & 1, phase (zuse >> 1) & 1)
 
   auto issue_b = [&](uint32_t itb) {
     const uint32_t sb = itb & 1u;
@@ -517,15 +540,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
     const long long vp = g.Np - p0r;
     return vp >= TP ? TP : (vp > 0 ? (int)vp : 0);
   };
+  RowPieces pcs, zpcs;
+  pcs.init(TP, rows_used, g.A.plane, g.A.ld);
+  zpcs.init(TP, rows_used, g.zplane, g.ldz);
   auto issue_raw = [&](uint32_t itr, int tile_r, int jr) {
     const long long p0r = (long long)tile_r * TP;
-    bulk_stage_rows(base + raw_off + (itr & 1u) * RAW_TILE_BYTES, bars + 32 + 8 * (itr & 1u), g.A.Z, g.A.plane, g.A.ld, p0r,
-                    valid_pts(p0r), TP, C, jr * KCH);
+    pcs.issue(base + raw_off + (itr & 1u) * RAW_TILE_BYTES, g.A.Z, p0r * g.A.ld + jr * KCH, valid_pts(p0r));
   };
   if (total_it > 0) {
-    if (warp == 0) issue_raw(0, blockIdx.x, 0);
+    issue_raw(0, blockIdx.x, 0);
     if (tid == 0) issue_b(0);
   }
+  cp_async_commit();
   uint32_t it = 0;
   for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
     const long long p0 = (long long)tile * TP;
@@ -533,12 +559,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
     for (int j = 0; j < nchunks; ++j, ++it) {
       const uint32_t s = it & 1u, u = it >> 1;
       unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-      if (warp == 0 && it + 1 < total_it) {
+      if (it + 1 < total_it) {
         int ntile = tile, nj = j + 1;
         if (nj == nchunks) { nj = 0; ntile = tile + gridDim.x; }
         issue_raw(it + 1, ntile, nj);
       }
-      mbar_wait(bars + 32 + 8 * s, u & 1u);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncthreads();
       if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
       const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + s * RAW_TILE_BYTES);
       for (int r = warp; r < rows_used; r += THREADS / 32) {  // plain split, one row per warp pass
@@ -566,12 +594,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
       mbar_wait(bars + 16 + 8 * (last & 1u), (last >> 1) & 1u);
       tc_fence_after();
       const int ncb = N / 32;
-      if (warp == 0)
-        bulk_stage_rows(zbuf_addr + (zuse & 1u) * A_TILE_BYTES, zbars + 8 * (zuse & 1u), g.Zprev, g.zplane, g.ldz, p0, vpts, TP, C, 0);
-      for (int cb = 0; cb < ncb; ++cb, ++zuse) {
-        if (warp == 0 && cb + 1 < ncb)
-          bulk_stage_rows(zbuf_addr + ((zuse + 1) & 1u) * A_TILE_BYTES, zbars + 8 * ((zuse + 1) & 1u), g.Zprev, g.zplane, g.ldz,
-                          p0, vpts, TP, C, (cb + 1) * 32);
+      zpcs.issue(zbuf_addr, g.Zprev, p0 * g.ldz, vpts);
+      cp_async_commit();
+      for (int cb = 0; cb < ncb; ++cb) {
+        if (cb + 1 < ncb) zpcs.issue(zbuf_addr + ((cb + 1) & 1) * A_TILE_BYTES, g.Zprev, p0 * g.ldz + (cb + 1) * 32, vpts);
+        cp_async_commit();
         if (warp < 4) {  // 128 lanes x 32 columns of Abar -> X[r][t ^ (r & 31)]  (conflict-free both ways)
           float v[32];
           load_acc_sum(acc0, acc1, warp, cb * 32, v);
@@ -579,9 +606,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
 #pragma unroll
           for (int t = 0; t < 32; ++t) xr[t ^ lane] = v[t];
         }
-        mbar_wait(zbars + 8 * (zuse & 1u), (zuse >> 1) & 1u);
+        cp_async_wait<1>();
         __syncthreads();
-        const float* zb = zbuf_ptr + (zuse & 1u) * (A_TILE_BYTES / 4);
+        const float* zb = zbuf_ptr + (cb & 1) * (A_TILE_BYTES / 4);
         const int nn = lane;
         for (int pl = warp; pl < vpts; pl += THREADS / 32) {
           float* zb_out = g.Out + (p0 + pl) * g.ldo + cb * 32 + nn;
@@ -618,6 +645,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
       __syncthreads();
     }
   }
+  cp_async_wait<0>();
   __syncthreads();
   if (warp == 1) tmem_dealloc(acc0, ncols);
 }
@@ -682,32 +710,62 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
     const long long vp = g.Np - ch * PT;
     return vp >= PT ? PT : (vp > 0 ? (int)vp : 0);
   };
-  // warp 0, lane = reduction row rr = c*PT + pl: one A row (128 k, 512 B) and one Zbar row (N cols)
+  // cp.async pieces of one chunk: A rows (32 pieces of 16 B per 512-byte row) then Zbar rows (N/4 pieces per row);
+  // the piece -> (row, column) mapping is chunk-invariant and precomputed.
+  constexpr int DW_PIECES = (KCH * 32 + KCH * 32) / THREADS;  // N <= 128
+  const int zb_pieces = N / 4;
+  long long psrc[DW_PIECES];
+  uint32_t pdst[DW_PIECES];
+  int ppl[DW_PIECES];  // -1 none; bit 8 set => Zbar piece
+#pragma unroll
+  for (int jj = 0; jj < DW_PIECES; ++jj) {
+    const int i = tid + jj * THREADS;
+    ppl[jj] = -1;
+    psrc[jj] = 0;
+    pdst[jj] = 0;
+    if (i < rows_used * 32) {
+      const int rr = i >> 5, q = i & 31;
+      const int c = rr / PT, pl = rr - c * PT;
+      ppl[jj] = pl;
+      psrc[jj] = (long long)c * g.aplane + (long long)pl * g.lda + k0 + q * 4;
+      pdst[jj] = (uint32_t)(rr * 512 + q * 16);
+    } else {
+      const int i2 = i - rows_used * 32;
+      if (i2 < rows_used * zb_pieces) {
+        const int rr = i2 / zb_pieces, q = i2 - rr * zb_pieces;
+        const int c = rr / PT, pl = rr - c * PT;
+        ppl[jj] = pl | 256;
+        psrc[jj] = (long long)c * g.zbplane + (long long)pl * g.ldzb + n0 + q * 4;
+        pdst[jj] = (uint32_t)(KCH * 512 + rr * N * 4 + q * 16);
+      }
+    }
+  }
   auto issue_raw = [&](long long ch, uint32_t itr) {
     const int vp = valid_pts(ch);
-    const uint32_t bar = bars + 32 + 8 * (itr & 1u);
     const uint32_t dst = base + raw_off + (itr & 1u) * raw_bytes;
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(C * vp * (512 + N * 4)));
-    __syncwarp();
-    if (lane < rows_used) {
-      const int c = lane / PT, pl = lane - c * PT;
-      if (pl < vp) {
-        const long long p = ch * PT + pl;
-        bulk_g2s(dst + (uint32_t)(lane * 512), g.Aact + (long long)c * g.aplane + p * g.lda + k0, 512u, bar);
-        bulk_g2s(dst + (uint32_t)(KCH * 512 + lane * N * 4), g.Zbar + (long long)c * g.zbplane + p * g.ldzb + n0,
-                 (uint32_t)(N * 4), bar);
+    const long long pb = ch * PT;
+#pragma unroll
+    for (int jj = 0; jj < DW_PIECES; ++jj) {
+      if (ppl[jj] >= 0) {
+        const bool isz = (ppl[jj] & 256) != 0;
+        const bool ok = (ppl[jj] & 255) < vp;
+        const float* bp = isz ? g.Zbar : g.Aact;
+        cp_async16(dst + pdst[jj], ok ? bp + psrc[jj] + pb * (isz ? g.ldzb : g.lda) : bp, ok);
       }
     }
   };
 
   uint32_t it = 0;
-  if (warp == 0 && ch_begin < ch_end) issue_raw(ch_begin, 0);
+  if (ch_begin < ch_end) issue_raw(ch_begin, 0);
+  cp_async_commit();
   const int nq = (rows_used + 3) / 4;  // 16-byte chunks of 4 reduction rows
   for (long long ch = ch_begin; ch < ch_end; ++ch, ++it) {
     const uint32_t s = it & 1u, u = it >> 1;
     unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-    if (warp == 0 && ch + 1 < ch_end) issue_raw(ch + 1, it + 1);
-    mbar_wait(bars + 32 + 8 * s, u & 1u);
+    if (ch + 1 < ch_end) issue_raw(ch + 1, it + 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
     if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
     const int vp = valid_pts(ch);
     const float* rawa = reinterpret_cast<const float*>(base_ptr + raw_off + s * raw_bytes);
@@ -761,6 +819,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
       }
     }
   }
+  cp_async_wait<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(acc0, ncols);
