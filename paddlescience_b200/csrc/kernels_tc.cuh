@@ -25,7 +25,10 @@ namespace ppsci {
 namespace tc {
 
 constexpr int KCH = 32;  // K elements per chunk = one 128-byte swizzle row of tf32
-constexpr int THREADS = 512;  // 16 warps: enough issue slots / latency hiding for the operand producers
+constexpr int THREADS = 512;  // 16 warps: 15 operand-producer warps + 1 MMA/TMA-issue warp
+constexpr int NPROD = THREADS - 32;  // producer threads (warps 0..14)
+constexpr int NPW = NPROD / 32;      // producer warps
+constexpr int MMA_WARP = THREADS / 32 - 1;
 constexpr int A_TILE_BYTES = 128 * KCH * 4;  // 16 KB (one of hi / lo)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -201,7 +204,10 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 constexpr int RAW_TILE_BYTES = 128 * KCH * 4;  // 128 rows x 32 fp32, linear (row pitch 128 B)
-constexpr int ROW_PIECES = (128 * 8) / THREADS;  // 16-byte pieces of a [128 x 32] tile per thread
+constexpr int ROW_PIECES = (128 * 8 + NPROD - 1) / NPROD;  // 16-byte pieces of a [128 x 32] tile per producer thread
+
+// barrier among the producer warps only (the MMA warp never joins it)
+__device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory"); }
 
 // pieces of a [rows_used x 32] tile whose row r = c*TP + pl comes from plane c, point p0 + pl
 struct RowPieces {
@@ -211,10 +217,10 @@ struct RowPieces {
   __device__ __forceinline__ void init(int TP, int rows_used, long long plane, int ld) {
 #pragma unroll
     for (int j = 0; j < ROW_PIECES; ++j) {
-      const int i = threadIdx.x + j * THREADS;
+      const int i = threadIdx.x + j * NPROD;
       const int r = i >> 3, q = i & 7;
       const int c = r / TP, pl_ = r - c * TP;
-      pl[j] = r < rows_used ? pl_ : -1;
+      pl[j] = (threadIdx.x < NPROD && r < rows_used) ? pl_ : -1;
       src[j] = (long long)c * plane + (long long)pl_ * ld + q * 4;
       dst[j] = (uint32_t)(r * 128 + q * 16);
     }
@@ -373,9 +379,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
     const int valid = vp >= TP ? TP : (vp > 0 ? (int)vp : 0);
     pcs.issue(base + raw_off + (itr & 1u) * RAW_TILE_BYTES, g.A.Z, p0r * g.A.ld + jr * KCH, valid);
   };
+  const bool is_mma = (warp == MMA_WARP);
   if (total_it > 0) {
-    issue_raw(0, blockIdx.x, 0);
-    if (tid == 0) issue_b(0);
+    issue_raw(0, blockIdx.x, 0);  // (the MMA warp owns no pieces)
+    if (is_mma && lane == 0) issue_b(0);
   }
   cp_async_commit();
   uint32_t it = 0;  // running chunk counter (stage = it & 1, use index = it >> 1)
@@ -383,58 +390,63 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
     const long long p0 = (long long)tile * TP;
     for (int j = 0; j < nchunks; ++j, ++it) {
       const uint32_t s = it & 1u, u = it >> 1;
-      unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-      if (it + 1 < total_it) {  // raw rows of chunk it+1 (buffer last read in iteration it-1)
-        int ntile = tile, nj = j + 1;
-        if (nj == nchunks) { nj = 0; ntile = tile + gridDim.x; }
-        issue_raw(it + 1, ntile, nj);
-      }
-      cp_async_commit();
-      cp_async_wait<1>();  // this chunk's raw rows have landed (this thread's pieces) ...
-      __syncthreads();     // ... and everybody else's
-      if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);  // MMAs that read this stage have retired
-      const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + s * RAW_TILE_BYTES);
-      const int k = j * KCH + lane;
-      for (int pl = warp; pl < TP; pl += THREADS / 32) {
-        const long long p = p0 + pl;
-        if (p < g.Np) {
-          float sc[6];
-          float y0;
-          act_coef<float, L::KM>(act, raw[pl * KCH + lane], y0, sc);
-          store_split_at(stage_ptr, sw128_lane(pl, lane), y0);
-          float* ast = g.Astash ? g.Astash + p * g.lda + k : nullptr;
-          if (ast) ast[0] = y0;
+      if (!is_mma) {
+        unsigned char* stage_ptr = base_ptr + s * stage_bytes;
+        if (it + 1 < total_it) {  // raw rows of chunk it+1 (buffer last read in iteration it-1)
+          int ntile = tile, nj = j + 1;
+          if (nj == nchunks) { nj = 0; ntile = tile + gridDim.x; }
+          issue_raw(it + 1, ntile, nj);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();  // this chunk's raw rows have landed (this thread's pieces) ...
+        producer_sync();     // ... and every other producer's
+        if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);  // MMAs that read this stage have retired
+        const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + s * RAW_TILE_BYTES);
+        const int k = j * KCH + lane;
+        for (int pl = warp; pl < TP; pl += NPW) {
+          const long long p = p0 + pl;
+          if (p < g.Np) {
+            float sc[6];
+            float y0;
+            act_coef<float, L::KM>(act, raw[pl * KCH + lane], y0, sc);
+            store_split_at(stage_ptr, sw128_lane(pl, lane), y0);
+            float* ast = g.Astash ? g.Astash + p * g.lda + k : nullptr;
+            if (ast) ast[0] = y0;
 #pragma unroll
-          for (int d = 0; d < L::ND; ++d) {
-            if (d < L::nd(g.J)) {
-              const int K = L::order(g.J, d), cb = L::cbase(g.J, d);
-              float zz[4], yy[4];
+            for (int d = 0; d < L::ND; ++d) {
+              if (d < L::nd(g.J)) {
+                const int K = L::order(g.J, d), cb = L::cbase(g.J, d);
+                float zz[4], yy[4];
 #pragma unroll
-              for (int o = 0; o < 4; ++o) zz[o] = (o < L::KM && o < K) ? raw[((cb + o) * TP + pl) * KCH + lane] : 0.f;
-              jet_fwd_dir<float, L::KM>(sc, zz, yy);
+                for (int o = 0; o < 4; ++o) zz[o] = (o < L::KM && o < K) ? raw[((cb + o) * TP + pl) * KCH + lane] : 0.f;
+                jet_fwd_dir<float, L::KM>(sc, zz, yy);
 #pragma unroll
-              for (int o = 0; o < L::KM; ++o)
-                if (o < K) {
-                  store_split_at(stage_ptr, sw128_lane((cb + o) * TP + pl, lane), yy[o]);
-                  if (ast) ast[(long long)(cb + o) * g.aplane] = yy[o];
-                }
+                for (int o = 0; o < L::KM; ++o)
+                  if (o < K) {
+                    store_split_at(stage_ptr, sw128_lane((cb + o) * TP + pl, lane), yy[o]);
+                    if (ast) ast[(long long)(cb + o) * g.aplane] = yy[o];
+                  }
+              }
             }
+          } else {
+            for (int c = 0; c < C; ++c) store_split_at(stage_ptr, sw128_lane(c * TP + pl, lane), 0.f);
           }
-        } else {
-          for (int c = 0; c < C; ++c) store_split_at(stage_ptr, sw128_lane(c * TP + pl, lane), 0.f);
         }
+        fence_proxy_async();  // generic-proxy smem accesses ordered before the async-proxy ones that follow
       }
-      fence_proxy_async();  // generic-proxy smem accesses ordered before the async-proxy ones that follow
-      __syncthreads();
-      if (tid == 0) {
-        mbar_wait(bars + 8 * s, u & 1u);  // weight images of this chunk have landed
-        tc_fence_after();
-        issue_chunk_mmas(acc0, acc1, base + s * stage_bytes, N, idesc, j == 0);
-        mma_commit(bars + 16 + 8 * s);  // arrives when every MMA issued so far has completed
-        if (it + 1 < total_it) {  // weights of chunk it+1 -> other stage, once chunk it-1's MMAs have left it
-          if (it >= 1) mbar_wait(bars + 16 + 8 * ((it + 1) & 1u), ((it - 1) >> 1) & 1u);
-          issue_b(it + 1);
+      __syncthreads();  // A operand of this chunk complete (producers) -> MMA warp may issue
+      if (is_mma) {
+        if (lane == 0) {
+          mbar_wait(bars + 8 * s, u & 1u);  // weight images of this chunk have landed
+          tc_fence_after();
+          issue_chunk_mmas(acc0, acc1, base + s * stage_bytes, N, idesc, j == 0);
+          mma_commit(bars + 16 + 8 * s);  // arrives when every MMA issued so far has completed
+          if (it + 1 < total_it) {  // weights of chunk it+1 -> other stage, once chunk it-1's MMAs have left it
+            if (it >= 1) mbar_wait(bars + 16 + 8 * ((it + 1) & 1u), ((it - 1) >> 1) & 1u);
+            issue_b(it + 1);
+          }
         }
+        __syncwarp();
       }
     }
     // ---- epilogue: TMEM -> registers -> (+bias) -> Z_l in HBM ----
@@ -547,9 +559,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
     const long long p0r = (long long)tile_r * TP;
     pcs.issue(base + raw_off + (itr & 1u) * RAW_TILE_BYTES, g.A.Z, p0r * g.A.ld + jr * KCH, valid_pts(p0r));
   };
+  const bool is_mma = (warp == MMA_WARP);
   if (total_it > 0) {
     issue_raw(0, blockIdx.x, 0);
-    if (tid == 0) issue_b(0);
+    if (is_mma && lane == 0) issue_b(0);
   }
   cp_async_commit();
   uint32_t it = 0;
@@ -558,34 +571,39 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
     const int vpts = valid_pts(p0);
     for (int j = 0; j < nchunks; ++j, ++it) {
       const uint32_t s = it & 1u, u = it >> 1;
-      unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-      if (it + 1 < total_it) {
-        int ntile = tile, nj = j + 1;
-        if (nj == nchunks) { nj = 0; ntile = tile + gridDim.x; }
-        issue_raw(it + 1, ntile, nj);
-      }
-      cp_async_commit();
-      cp_async_wait<1>();
-      __syncthreads();
-      if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
-      const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + s * RAW_TILE_BYTES);
-      for (int r = warp; r < rows_used; r += THREADS / 32) {  // plain split, one row per warp pass
-        const int c = r / TP, pl = r - c * TP;
-        store_split_at(stage_ptr, sw128_lane(r, lane), pl < vpts ? raw[r * KCH + lane] : 0.f);
-      }
-      fence_proxy_async();
-      __syncthreads();
-      if (tid == 0) {
-        mbar_wait(bars + 8 * s, u & 1u);
-        tc_fence_after();
-        issue_chunk_mmas(acc0, acc1, base + s * stage_bytes, N, idesc, j == 0);
-        mma_commit(bars + 16 + 8 * s);
-        // weights of chunk it+1 go to the other stage; at a tile boundary that stage's A region is used as
-        // epilogue scratch, but its B region is not, so the copy may be in flight across the epilogue
+      if (!is_mma) {
+        unsigned char* stage_ptr = base_ptr + s * stage_bytes;
         if (it + 1 < total_it) {
-          if (it >= 1) mbar_wait(bars + 16 + 8 * ((it + 1) & 1u), ((it - 1) >> 1) & 1u);
-          issue_b(it + 1);
+          int ntile = tile, nj = j + 1;
+          if (nj == nchunks) { nj = 0; ntile = tile + gridDim.x; }
+          issue_raw(it + 1, ntile, nj);
         }
+        cp_async_commit();
+        cp_async_wait<1>();
+        producer_sync();
+        if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
+        const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + s * RAW_TILE_BYTES);
+        for (int r = warp; r < rows_used; r += NPW) {  // plain split, one row per warp pass
+          const int c = r / TP, pl = r - c * TP;
+          store_split_at(stage_ptr, sw128_lane(r, lane), pl < vpts ? raw[r * KCH + lane] : 0.f);
+        }
+        fence_proxy_async();
+      }
+      __syncthreads();
+      if (is_mma) {
+        if (lane == 0) {
+          mbar_wait(bars + 8 * s, u & 1u);
+          tc_fence_after();
+          issue_chunk_mmas(acc0, acc1, base + s * stage_bytes, N, idesc, j == 0);
+          mma_commit(bars + 16 + 8 * s);
+          // weights of chunk it+1 go to the other stage; at a tile boundary that stage's A region is used as
+          // epilogue scratch, but its B region is not, so the copy may be in flight across the epilogue
+          if (it + 1 < total_it) {
+            if (it >= 1) mbar_wait(bars + 16 + 8 * ((it + 1) & 1u), ((it - 1) >> 1) & 1u);
+            issue_b(it + 1);
+          }
+        }
+        __syncwarp();
       }
     }
     // ---- epilogue: Abar (TMEM) -> exchange tile -> activation adjoint -> Zbar_{l-1} ----
@@ -712,18 +730,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
   };
   // cp.async pieces of one chunk: A rows (32 pieces of 16 B per 512-byte row) then Zbar rows (N/4 pieces per row);
   // the piece -> (row, column) mapping is chunk-invariant and precomputed.
-  constexpr int DW_PIECES = (KCH * 32 + KCH * 32) / THREADS;  // N <= 128
+  constexpr int DW_PIECES = (KCH * 32 + KCH * 32 + NPROD - 1) / NPROD;  // N <= 128
   const int zb_pieces = N / 4;
   long long psrc[DW_PIECES];
   uint32_t pdst[DW_PIECES];
   int ppl[DW_PIECES];  // -1 none; bit 8 set => Zbar piece
 #pragma unroll
   for (int jj = 0; jj < DW_PIECES; ++jj) {
-    const int i = tid + jj * THREADS;
+    const int i = tid + jj * NPROD;
     ppl[jj] = -1;
     psrc[jj] = 0;
     pdst[jj] = 0;
-    if (i < rows_used * 32) {
+    if (tid >= NPROD) {
+    } else if (i < rows_used * 32) {
       const int rr = i >> 5, q = i & 31;
       const int c = rr / PT, pl = rr - c * PT;
       ppl[jj] = pl;
@@ -759,47 +778,53 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
   if (ch_begin < ch_end) issue_raw(ch_begin, 0);
   cp_async_commit();
   const int nq = (rows_used + 3) / 4;  // 16-byte chunks of 4 reduction rows
+  const bool is_mma = (warp == MMA_WARP);
   for (long long ch = ch_begin; ch < ch_end; ++ch, ++it) {
     const uint32_t s = it & 1u, u = it >> 1;
-    unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-    if (ch + 1 < ch_end) issue_raw(ch + 1, it + 1);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
-    const int vp = valid_pts(ch);
-    const float* rawa = reinterpret_cast<const float*>(base_ptr + raw_off + s * raw_bytes);
-    const float* rawzb = rawa + KCH * 128;
-    unsigned char* b_hi = stage_ptr + 2 * A_TILE_BYTES;
-    // items [0, 128 nq): A'(row k, chunk q) ; items [128 nq, 128 nq + N nq): B'(row n, chunk q)
-    const int itemsA = 128 * nq, items = itemsA + N * nq;
-    for (int item = tid; item < items; item += THREADS) {
-      const bool isA = item < itemsA;
-      const int local = isA ? item : item - itemsA;
-      const int width = isA ? 128 : N;
-      const int row = local % width, q = local / width;
-      const float* src = isA ? rawa : rawzb;
-      float hi[4], lo[4];
+    if (!is_mma) {
+      unsigned char* stage_ptr = base_ptr + s * stage_bytes;
+      if (ch + 1 < ch_end) issue_raw(ch + 1, it + 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+      producer_sync();
+      if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
+      const int vp = valid_pts(ch);
+      const float* rawa = reinterpret_cast<const float*>(base_ptr + raw_off + s * raw_bytes);
+      const float* rawzb = rawa + KCH * 128;
+      unsigned char* b_hi = stage_ptr + 2 * A_TILE_BYTES;
+      // items [0, 128 nq): A'(row k, chunk q) ; items [128 nq, 128 nq + N nq): B'(row n, chunk q)
+      const int itemsA = 128 * nq, items = itemsA + N * nq;
+      for (int item = tid; item < items; item += NPROD) {
+        const bool isA = item < itemsA;
+        const int local = isA ? item : item - itemsA;
+        const int width = isA ? 128 : N;
+        const int row = local % width, q = local / width;
+        const float* src = isA ? rawa : rawzb;
+        float hi[4], lo[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int rr = 4 * q + e;
-        const int c = rr / PT, pl = rr - c * PT;
-        const float v = (rr < rows_used && pl < vp) ? src[rr * width + row] : 0.f;
-        hi[e] = tf32_rn(v);
-        lo[e] = v - hi[e];
+        for (int e = 0; e < 4; ++e) {
+          const int rr = 4 * q + e;
+          const int c = rr / PT, pl = rr - c * PT;
+          const float v = (rr < rows_used && pl < vp) ? src[rr * width + row] : 0.f;
+          hi[e] = tf32_rn(v);
+          lo[e] = v - hi[e];
+        }
+        const uint32_t off = sw128(row, 4 * q);
+        unsigned char* t_hi = isA ? stage_ptr : b_hi;
+        const int lo_off = isA ? A_TILE_BYTES : N * KCH * 4;
+        *reinterpret_cast<float4*>(t_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(t_hi + lo_off + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
       }
-      const uint32_t off = sw128(row, 4 * q);
-      unsigned char* t_hi = isA ? stage_ptr : b_hi;
-      const int lo_off = isA ? A_TILE_BYTES : N * KCH * 4;
-      *reinterpret_cast<float4*>(t_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<float4*>(t_hi + lo_off + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      fence_proxy_async();
     }
-    fence_proxy_async();
     __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_chunk_mmas(acc0, acc1, base + s * stage_bytes, N, idesc, it == 0);
-      mma_commit(bars + 16 + 8 * s);
+    if (is_mma) {
+      if (lane == 0) {
+        tc_fence_after();
+        issue_chunk_mmas(acc0, acc1, base + s * stage_bytes, N, idesc, it == 0);
+        mma_commit(bars + 16 + 8 * s);
+      }
+      __syncwarp();
     }
   }
   if (it > 0) {
