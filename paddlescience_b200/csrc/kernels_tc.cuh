@@ -774,10 +774,36 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
     }
   };
 
+  // split/transpose items: [0, 128 nq) -> A'(row k, 16-byte chunk q) ; [128 nq, 128 nq + N nq) -> B'(row n, chunk q)
+  const int nq = (rows_used + 3) / 4;  // 16-byte chunks of 4 reduction rows
+  constexpr int DW_ITEMS = (128 * 8 + 128 * 8 + NPROD - 1) / NPROD;
+  int i_src[DW_ITEMS], i_stride[DW_ITEMS], i_ne[DW_ITEMS], i_lo[DW_ITEMS];
+  uint32_t i_dst[DW_ITEMS];
+#pragma unroll
+  for (int jj = 0; jj < DW_ITEMS; ++jj) {
+    const int item = tid + jj * NPROD;
+    const int itemsA = 128 * nq;
+    i_ne[jj] = 0;
+    i_src[jj] = 0;
+    i_stride[jj] = 0;
+    i_lo[jj] = 0;
+    i_dst[jj] = 0;
+    if (tid < NPROD && item < itemsA + N * nq) {
+      const bool isA = item < itemsA;
+      const int local = isA ? item : item - itemsA;
+      const int width = isA ? 128 : N;
+      const int row = local % width, q = local / width;
+      const int left = rows_used - 4 * q;
+      i_ne[jj] = left >= 4 ? 4 : left;
+      i_stride[jj] = width;
+      i_src[jj] = (isA ? 0 : KCH * 128) + 4 * q * width + row;
+      i_dst[jj] = sw128(row, 4 * q) + (isA ? 0u : (uint32_t)(2 * A_TILE_BYTES));
+      i_lo[jj] = isA ? A_TILE_BYTES : N * KCH * 4;
+    }
+  }
   uint32_t it = 0;
   if (ch_begin < ch_end) issue_raw(ch_begin, 0);
   cp_async_commit();
-  const int nq = (rows_used + 3) / 4;  // 16-byte chunks of 4 reduction rows
   const bool is_mma = (warp == MMA_WARP);
   for (long long ch = ch_begin; ch < ch_end; ++ch, ++it) {
     const uint32_t s = it & 1u, u = it >> 1;
@@ -788,32 +814,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
       cp_async_wait<1>();
       producer_sync();
       if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
-      const int vp = valid_pts(ch);
-      const float* rawa = reinterpret_cast<const float*>(base_ptr + raw_off + s * raw_bytes);
-      const float* rawzb = rawa + KCH * 128;
-      unsigned char* b_hi = stage_ptr + 2 * A_TILE_BYTES;
-      // items [0, 128 nq): A'(row k, chunk q) ; items [128 nq, 128 nq + N nq): B'(row n, chunk q)
-      const int itemsA = 128 * nq, items = itemsA + N * nq;
-      for (int item = tid; item < items; item += NPROD) {
-        const bool isA = item < itemsA;
-        const int local = isA ? item : item - itemsA;
-        const int width = isA ? 128 : N;
-        const int row = local % width, q = local / width;
-        const float* src = isA ? rawa : rawzb;
-        float hi[4], lo[4];
+      // split + transpose: item descriptors were precomputed (chunk-invariant); invalid tail rows were zero-filled
+      // by cp.async, rows >= rows_used are masked by the per-item element count
+      const float* rawf = reinterpret_cast<const float*>(base_ptr + raw_off + s * raw_bytes);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int rr = 4 * q + e;
-          const int c = rr / PT, pl = rr - c * PT;
-          const float v = (rr < rows_used && pl < vp) ? src[rr * width + row] : 0.f;
-          hi[e] = tf32_rn(v);
-          lo[e] = v - hi[e];
+      for (int jj = 0; jj < DW_ITEMS; ++jj) {
+        if (i_ne[jj] > 0) {
+          const float* src = rawf + i_src[jj];
+          float hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float v = e < i_ne[jj] ? src[e * i_stride[jj]] : 0.f;
+            hi[e] = tf32_rn(v);
+            lo[e] = v - hi[e];
+          }
+          unsigned char* t_hi = stage_ptr + i_dst[jj];
+          *reinterpret_cast<float4*>(t_hi) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(t_hi + i_lo[jj]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
-        const uint32_t off = sw128(row, 4 * q);
-        unsigned char* t_hi = isA ? stage_ptr : b_hi;
-        const int lo_off = isA ? A_TILE_BYTES : N * KCH * 4;
-        *reinterpret_cast<float4*>(t_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<float4*>(t_hi + lo_off + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
       }
       fence_proxy_async();
     }
