@@ -449,39 +449,48 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
         __syncwarp();
       }
     }
-    // ---- epilogue: TMEM -> registers -> (+bias) -> Z_l in HBM ----
+    // ---- epilogue: TMEM -> shared exchange tiles -> (+bias) -> Z_l in HBM, fully coalesced ----
+    // A thread owns one accumulator ROW after tcgen05.ld; storing it directly would emit 32 scattered 16-byte
+    // writes per warp instruction.  Four 128x32 blocks at a time are transposed through the (now idle)
+    // A regions of both stages — X[b][r][t ^ (r & 31)] — and written back row-wise (128 B per warp store).
     {
       const uint32_t last = it - 1;
       mbar_wait(bars + 16 + 8 * (last & 1u), (last >> 1) & 1u);
       tc_fence_after();
-      const int q = warp & 3, part = warp >> 2;  // lane quarter, column-block phase (THREADS/128 phases)
-      const int r = q * 32 + lane;
-      const bool row_ok = r < rows_used;
-      const int c = row_ok ? r / TP : 0, pl = row_ok ? r % TP : 0;
-      const long long p = p0 + pl;
-      const bool st_ok = row_ok && p < g.Np;
-      float* out_row = g.Out + (long long)c * g.oplane + p * g.ldo;
+      const int q = warp & 3, part = warp >> 2;
       const int ncb = N / 32;
-      for (int cb = part; cb < ncb; cb += THREADS / 128) {
-        float v[32];
-        load_acc_sum(acc0, acc1, q, cb * 32, v);
-        if (st_ok) {
+      for (int cb0 = 0; cb0 < ncb; cb0 += 4) {
+        const int cb = cb0 + part;
+        float* Xb = reinterpret_cast<float*>(base_ptr + (part >> 1) * stage_bytes + (part & 1) * A_TILE_BYTES);
+        if (cb < ncb) {
+          float v[32];
+          load_acc_sum(acc0, acc1, q, cb * 32, v);
+          float* xr = Xb + (q * 32 + lane) * KCH;
 #pragma unroll
-          for (int t = 0; t < 32; t += 4) {
-            const int n = cb * 32 + t;
-            float4 o = make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]);
-            if (c == 0 && g.bias) {
-              o.x += g.bias[n];
-              o.y += g.bias[n + 1];
-              o.z += g.bias[n + 2];
-              o.w += g.bias[n + 3];
+          for (int t = 0; t < 32; ++t) xr[t ^ lane] = v[t];
+        }
+        __syncthreads();
+        for (int r = warp; r < rows_used; r += THREADS / 32) {
+          const int c = r / TP, pl = r - c * TP;
+          const long long p = p0 + pl;
+          if (p < g.Np) {
+            float* out_row = g.Out + (long long)c * g.oplane + p * g.ldo + cb0 * 32 + lane;
+#pragma unroll
+            for (int b4 = 0; b4 < 4; ++b4) {
+              if (cb0 + b4 < ncb) {
+                const float* Xr = reinterpret_cast<const float*>(base_ptr + (b4 >> 1) * stage_bytes + (b4 & 1) * A_TILE_BYTES);
+                float val = Xr[r * KCH + (lane ^ (r & 31))];
+                if (c == 0 && g.bias) val += g.bias[(cb0 + b4) * 32 + lane];
+                out_row[b4 * 32] = val;
+              }
             }
-            *reinterpret_cast<float4*>(out_row + n) = o;
           }
         }
+        __syncthreads();
       }
+      fence_proxy_async();
       tc_fence_before();
-      __syncthreads();  // accumulators drained before the next tile's first MMA overwrites them
+      __syncthreads();  // accumulators drained / scratch released before the next tile starts
     }
   }
   cp_async_wait<0>();
@@ -696,7 +705,10 @@ struct TcDwArgs {
 
 // raw tiles of one reduction chunk: A rows [32][128 k] (16 KB) and Zbar rows [32][NC n] (NC*128 B)
 __host__ __device__ inline int tc_dw_raw_bytes(int NC) { return KCH * 128 * 4 + KCH * NC * 4; }
-__host__ __device__ inline int tc_dw_smem_bytes(int NC) { return 2 * tc_stage_bytes(NC) + 2 * tc_dw_raw_bytes(NC) + 1024 + 256; }
+constexpr int DW_RAW_STAGES = 3;  // raw-tile ring: two chunks of prefetch distance (a loaded HBM round trip is ~1.4 us)
+__host__ __device__ inline int tc_dw_smem_bytes(int NC) {
+  return 2 * tc_stage_bytes(NC) + DW_RAW_STAGES * tc_dw_raw_bytes(NC) + 1024 + 256;
+}
 
 template <class L>
 __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
@@ -707,8 +719,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
   const int stage_bytes = tc_stage_bytes(N);
   const int raw_bytes = tc_dw_raw_bytes(N);
   const uint32_t raw_off = 2 * stage_bytes;
-  const uint32_t bars_off = raw_off + 2 * raw_bytes;
-  const uint32_t bars = base + bars_off;  // mma_done[2] at +16,+24 ; raw_full[2] at +32,+40
+  const uint32_t bars_off = raw_off + DW_RAW_STAGES * raw_bytes;
+  const uint32_t bars = base + bars_off;  // mma_done[2] at +16,+24
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ncols = tc_pow2_cols(2 * N);
   const int PT = L::pt(g.PT);
@@ -761,7 +773,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
   }
   auto issue_raw = [&](long long ch, uint32_t itr) {
     const int vp = valid_pts(ch);
-    const uint32_t dst = base + raw_off + (itr & 1u) * raw_bytes;
+    const uint32_t dst = base + raw_off + (itr % DW_RAW_STAGES) * raw_bytes;
     const long long pb = ch * PT;
 #pragma unroll
     for (int jj = 0; jj < DW_PIECES; ++jj) {
@@ -804,19 +816,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
   uint32_t it = 0;
   if (ch_begin < ch_end) issue_raw(ch_begin, 0);
   cp_async_commit();
+  if (ch_begin + 1 < ch_end) issue_raw(ch_begin + 1, 1);
+  cp_async_commit();
   const bool is_mma = (warp == MMA_WARP);
   for (long long ch = ch_begin; ch < ch_end; ++ch, ++it) {
     const uint32_t s = it & 1u, u = it >> 1;
     if (!is_mma) {
       unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-      if (ch + 1 < ch_end) issue_raw(ch + 1, it + 1);
+      if (ch + 2 < ch_end) issue_raw(ch + 2, it + 2);  // buffer (it+2)%3 was last read in iteration it-1
       cp_async_commit();
-      cp_async_wait<1>();
+      cp_async_wait<2>();
       producer_sync();
       if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
       // split + transpose: item descriptors were precomputed (chunk-invariant); invalid tail rows were zero-filled
       // by cp.async, rows >= rows_used are masked by the per-item element count
-      const float* rawf = reinterpret_cast<const float*>(base_ptr + raw_off + s * raw_bytes);
+      const float* rawf = reinterpret_cast<const float*>(base_ptr + raw_off + (it % DW_RAW_STAGES) * raw_bytes);
 #pragma unroll
       for (int jj = 0; jj < DW_ITEMS; ++jj) {
         if (i_ne[jj] > 0) {
