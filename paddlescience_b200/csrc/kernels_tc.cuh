@@ -247,14 +247,26 @@ __host__ __device__ inline uint32_t tc_pow2_cols(int n) {
 // alternates between acc0 / acc1 per 8-wide k-step, the small cross terms always go to acc1, so each
 // accumulator sees half as many fp32 round-toward-zero accumulation steps of significant magnitude
 // (tensor cores accumulate with truncation); the epilogue adds acc0 + acc1 with round-to-nearest.
-__device__ __forceinline__ void issue_chunk_mmas(uint32_t acc0, uint32_t acc1, uint32_t stage_addr, int N, uint32_t idesc,
-                                                 bool first_chunk) {
-  const uint32_t a_hi = stage_addr, a_lo = stage_addr + A_TILE_BYTES;
-  const uint32_t b_hi = stage_addr + 2 * A_TILE_BYTES, b_lo = b_hi + (uint32_t)(N * KCH * 4);
+// The issuing lane is the kernel's critical serial path: descriptors are a precomputed base (stage 0,
+// k-step 0) plus increments of the 14-bit start-address field (units of 16 bytes).
+struct ChunkDescs {
+  uint64_t a_hi, a_lo, b_hi, b_lo;  // stage 0, k-step 0
+  uint64_t stage_inc;               // stage_bytes >> 4
+  __device__ __forceinline__ void init(uint32_t base_addr, int stage_bytes, int N) {
+    a_hi = make_smem_desc(base_addr);
+    a_lo = make_smem_desc(base_addr + A_TILE_BYTES);
+    b_hi = make_smem_desc(base_addr + 2 * A_TILE_BYTES);
+    b_lo = make_smem_desc(base_addr + 2 * A_TILE_BYTES + (uint32_t)(N * KCH * 4));
+    stage_inc = (uint64_t)(stage_bytes >> 4);
+  }
+};
+__device__ __forceinline__ void issue_chunk_mmas(uint32_t acc0, uint32_t acc1, const ChunkDescs& D, uint32_t stage,
+                                                 uint32_t idesc, bool first_chunk) {
+  const uint64_t so = stage ? D.stage_inc : 0;
 #pragma unroll
-  for (int ks = 0; ks < KCH / 8; ++ks) {  // one MMA consumes K = 8 tf32 = 32 bytes of every row
-    const uint64_t dah = make_smem_desc(a_hi + ks * 32), dal = make_smem_desc(a_lo + ks * 32);
-    const uint64_t dbh = make_smem_desc(b_hi + ks * 32), dbl = make_smem_desc(b_lo + ks * 32);
+  for (int ks = 0; ks < KCH / 8; ++ks) {  // one MMA consumes K = 8 tf32 = 32 bytes (2 x 16 B) of every row
+    const uint64_t inc = so + (uint64_t)(2 * ks);
+    const uint64_t dah = D.a_hi + inc, dal = D.a_lo + inc, dbh = D.b_hi + inc, dbl = D.b_lo + inc;
     const bool first = first_chunk && ks == 0;
     if ((ks & 1) == 0) {
       mma_tf32(acc0, dah, dbh, idesc, first ? 0u : 1u);
@@ -264,6 +276,21 @@ __device__ __forceinline__ void issue_chunk_mmas(uint32_t acc0, uint32_t acc1, u
       mma_tf32(acc1, dal, dbh, idesc, 1u);
     }
     mma_tf32(acc1, dah, dbl, idesc, 1u);
+  }
+}
+// dW variant (N <= 128): B_hi and B_lo are adjacent 128-byte-row tiles, i.e. one K-major tile with 2N rows, so
+//   accX[128 x 2N] += A_hi [B_hi ; B_lo]^T     (one MMA gives A_hi B_hi | A_hi B_lo)
+//   accY[128 x  N] += A_lo  B_hi^T
+// 8 MMAs per chunk instead of 12; the epilogue adds accX[:, :N] + accX[:, N:] + accY.
+__device__ __forceinline__ void issue_chunk_mmas_cat(uint32_t accX, uint32_t accY, const ChunkDescs& D, uint32_t stage,
+                                                     uint32_t idesc_2n, uint32_t idesc_n, bool first_chunk) {
+  const uint64_t so = stage ? D.stage_inc : 0;
+#pragma unroll
+  for (int ks = 0; ks < KCH / 8; ++ks) {
+    const uint64_t inc = so + (uint64_t)(2 * ks);
+    const bool first = first_chunk && ks == 0;
+    mma_tf32(accX, D.a_hi + inc, D.b_hi + inc, idesc_2n, first ? 0u : 1u);
+    mma_tf32(accY, D.a_lo + inc, D.b_hi + inc, idesc_n, first ? 0u : 1u);
   }
 }
 
@@ -356,6 +383,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
   tc_setup(base, base_ptr, bars_off, stage_bytes, 2 * A_TILE_BYTES, ncols);
   const uint32_t acc0 = *reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 64), acc1 = acc0 + (uint32_t)N;
   const uint32_t idesc = make_idesc_tf32(128, N);
+  ChunkDescs descs;
+  descs.init(base, stage_bytes, N);
   const int nchunks = g.Kdim / KCH;
   const uint32_t b_bytes = (uint32_t)(2 * N * KCH * 4);
   const int TP = L::tp(g.TP);
@@ -439,7 +468,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
         if (lane == 0) {
           mbar_wait(bars + 8 * s, u & 1u);  // weight images of this chunk have landed
           tc_fence_after();
-          issue_chunk_mmas(acc0, acc1, base + s * stage_bytes, N, idesc, j == 0);
+          issue_chunk_mmas(acc0, acc1, descs, s, idesc, j == 0);
           mma_commit(bars + 16 + 8 * s);  // arrives when every MMA issued so far has completed
           if (it + 1 < total_it) {  // weights of chunk it+1 -> other stage, once chunk it-1's MMAs have left it
             if (it >= 1) mbar_wait(bars + 16 + 8 * ((it + 1) & 1u), ((it - 1) >> 1) & 1u);
@@ -539,6 +568,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
   tc_setup(base, base_ptr, bars_off, stage_bytes, 2 * A_TILE_BYTES, ncols);
   const uint32_t acc0 = *reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 64), acc1 = acc0 + (uint32_t)N;
   const uint32_t idesc = make_idesc_tf32(128, N);
+  ChunkDescs descs;
+  descs.init(base, stage_bytes, N);
   const int nchunks = g.Kdim / KCH;
   const uint32_t b_bytes = (uint32_t)(2 * N * KCH * 4);
   const int TP = L::tp(g.TP);
@@ -603,7 +634,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
         if (lane == 0) {
           mbar_wait(bars + 8 * s, u & 1u);
           tc_fence_after();
-          issue_chunk_mmas(acc0, acc1, base + s * stage_bytes, N, idesc, j == 0);
+          issue_chunk_mmas(acc0, acc1, descs, s, idesc, j == 0);
           mma_commit(bars + 16 + 8 * s);
           // weights of chunk it+1 go to the other stage; at a tile boundary that stage's A region is used as
           // epilogue scratch, but its B region is not, so the copy may be in flight across the epilogue
@@ -722,13 +753,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
   const uint32_t bars_off = raw_off + DW_RAW_STAGES * raw_bytes;
   const uint32_t bars = base + bars_off;  // mma_done[2] at +16,+24
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t ncols = tc_pow2_cols(2 * N);
+  const uint32_t ncols = tc_pow2_cols(3 * N);
   const int PT = L::pt(g.PT);
   const int C = L::nchan(g.J);
   const int rows_used = C * PT;
   tc_setup(base, base_ptr, bars_off, stage_bytes, stage_bytes, ncols);  // whole stages cleared (pad columns stay 0)
-  const uint32_t acc0 = *reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 64), acc1 = acc0 + (uint32_t)N;
-  const uint32_t idesc = make_idesc_tf32(128, N);
+  // accX: 2N columns (A_hi B_hi | A_hi B_lo), accY: N columns (A_lo B_hi)
+  const uint32_t accX = *reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 64), accY = accX + (uint32_t)(2 * N);
+  const uint32_t idesc_2n = make_idesc_tf32(128, 2 * N), idesc_n = make_idesc_tf32(128, N);
+  ChunkDescs descs;
+  descs.init(base, stage_bytes, N);
   const int k0 = blockIdx.x * 128;
   const int n0 = blockIdx.z * g.n0_stride;
   const long long total_chunks = (g.Np + PT - 1) / PT;
@@ -853,7 +887,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
     if (is_mma) {
       if (lane == 0) {
         tc_fence_after();
-        issue_chunk_mmas(acc0, acc1, base + s * stage_bytes, N, idesc, it == 0);
+        issue_chunk_mmas_cat(accX, accY, descs, s, idesc_2n, idesc_n, it == 0);
         mma_commit(bars + 16 + 8 * s);
       }
       __syncwarp();
@@ -868,8 +902,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
     float* dw_row = g.dW + (long long)k * g.ldw + n0;
     const int ncb = N / 32;
     for (int cb = part; cb < ncb; cb += THREADS / 128) {
-      float v[32];
-      load_acc_sum(acc0, acc1, q, cb * 32, v);
+      float v[32], w[32];
+      load_acc_sum(accX, accX + (uint32_t)N, q, cb * 32, v);
+      {
+        uint32_t y[32];
+        tmem_ld32(accY + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), y);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) w[t] = __uint_as_float(y[t]);
+      }
+#pragma unroll
+      for (int t = 0; t < 32; ++t) v[t] += w[t];
       if (k < g.Kdim) {
 #pragma unroll
         for (int t = 0; t < 32; ++t) atomicAdd(dw_row + cb * 32 + t, v[t]);
@@ -879,7 +922,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
   cp_async_wait<0>();
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(acc0, ncols);
+  if (warp == 1) tmem_dealloc(accX, ncols);
 }
 
 // db_l[n] += sum over points of Zbar_l[channel 0][p][n]   (tiny, HBM-bound)
