@@ -51,6 +51,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -346,7 +349,9 @@ __device__ __forceinline__ void tc_setup(uint32_t base, unsigned char* base_ptr,
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bars = base + bars_off;
   if (tid == 0) {
-    for (int i = 0; i < 6; ++i) mbar_init(bars + 8 * i, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(bars + 8 * i, 1);
+    mbar_init(bars + 32, NPW);  // a_ready[2]: one arrival per producer warp
+    mbar_init(bars + 40, NPW);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -421,14 +426,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
       const uint32_t s = it & 1u, u = it >> 1;
       if (!is_mma) {
         unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-        if (it + 1 < total_it) {  // raw rows of chunk it+1 (buffer last read in iteration it-1)
+        cp_async_wait<0>();  // this chunk's raw rows have landed (this thread's pieces) ...
+        producer_sync();     // ... and every other producer's; all producers are also done reading chunk it-1
+        if (it + 1 < total_it) {  // raw rows of chunk it+1 -> the buffer chunk it-1 occupied
           int ntile = tile, nj = j + 1;
           if (nj == nchunks) { nj = 0; ntile = tile + gridDim.x; }
           issue_raw(it + 1, ntile, nj);
         }
         cp_async_commit();
-        cp_async_wait<1>();  // this chunk's raw rows have landed (this thread's pieces) ...
-        producer_sync();     // ... and every other producer's
         if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);  // MMAs that read this stage have retired
         const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + s * RAW_TILE_BYTES);
         const int k = j * KCH + lane;
@@ -462,10 +467,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
           }
         }
         fence_proxy_async();  // generic-proxy smem accesses ordered before the async-proxy ones that follow
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 32 + 8 * s);  // this warp's share of the A operand is in place
       }
-      __syncthreads();  // A operand of this chunk complete (producers) -> MMA warp may issue
       if (is_mma) {
         if (lane == 0) {
+          mbar_wait(bars + 32 + 8 * s, u & 1u);  // every producer warp has delivered its rows of this chunk
           mbar_wait(bars + 8 * s, u & 1u);  // weight images of this chunk have landed
           tc_fence_after();
           issue_chunk_mmas(acc0, acc1, descs, s, idesc, j == 0);
@@ -613,14 +620,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
       const uint32_t s = it & 1u, u = it >> 1;
       if (!is_mma) {
         unsigned char* stage_ptr = base_ptr + s * stage_bytes;
+        cp_async_wait<0>();
+        producer_sync();
         if (it + 1 < total_it) {
           int ntile = tile, nj = j + 1;
           if (nj == nchunks) { nj = 0; ntile = tile + gridDim.x; }
           issue_raw(it + 1, ntile, nj);
         }
         cp_async_commit();
-        cp_async_wait<1>();
-        producer_sync();
         if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
         const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + s * RAW_TILE_BYTES);
         for (int r = warp; r < rows_used; r += NPW) {  // plain split, one row per warp pass
@@ -628,10 +635,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
           store_split_at(stage_ptr, sw128_lane(r, lane), pl < vpts ? raw[r * KCH + lane] : 0.f);
         }
         fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + 32 + 8 * s);
       }
-      __syncthreads();
       if (is_mma) {
         if (lane == 0) {
+          mbar_wait(bars + 32 + 8 * s, u & 1u);
           mbar_wait(bars + 8 * s, u & 1u);
           tc_fence_after();
           issue_chunk_mmas(acc0, acc1, descs, s, idesc, j == 0);
@@ -857,10 +866,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
     const uint32_t s = it & 1u, u = it >> 1;
     if (!is_mma) {
       unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-      if (ch + 2 < ch_end) issue_raw(ch + 2, it + 2);  // buffer (it+2)%3 was last read in iteration it-1
+      cp_async_wait<1>();  // chunk `it` has landed (chunk it+1 may still be in flight)
+      producer_sync();     // visible to all producers, and everybody is done reading chunk it-1
+      if (ch + 2 < ch_end) issue_raw(ch + 2, it + 2);  // -> buffer (it+2)%3 == (it-1)%3
       cp_async_commit();
-      cp_async_wait<2>();
-      producer_sync();
       if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
       // split + transpose: item descriptors were precomputed (chunk-invariant); invalid tail rows were zero-filled
       // by cp.async, rows >= rows_used are masked by the per-item element count
@@ -882,10 +891,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
         }
       }
       fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 32 + 8 * s);
     }
-    __syncthreads();
     if (is_mma) {
       if (lane == 0) {
+        mbar_wait(bars + 32 + 8 * s, u & 1u);
         tc_fence_after();
         issue_chunk_mmas_cat(accX, accY, descs, s, idesc_2n, idesc_n, it == 0);
         mma_commit(bars + 16 + 8 * s);
