@@ -15,6 +15,7 @@
 #include "kernels_simt.cuh"
 #ifndef PPSCI_EMUL
 #include "kernels_tc.cuh"
+#include "kernels_tc2.cuh"
 #endif
 
 using namespace ppsci;
@@ -49,7 +50,7 @@ struct ppsci_plan {
   int chunk = 0;
   int num_sms = 148;
   bool use_tc = false;
-  int tc_mask = 7;  // bit0 forward, bit1 dx, bit2 dW on the tensor cores (PPSCI_B200_TC_MASK, debugging)
+  int tc_mask = 31;  // bit0 forward, bit1 dx, bit2 dW on the tensor cores; bit3 / bit4: CTA-pair forward / dx kernels (PPSCI_B200_TC_MASK, debugging)
   // device copies of the residual program
   int* d_prog = nullptr;
   double* d_consts = nullptr;
@@ -343,6 +344,15 @@ struct Dims {
   static constexpr int TN = sizeof(T) == 8 ? 64 : 128;
 };
 
+// bring-up instrumentation: PPSCI_B200_DEBUG_TIMELINE=<device pointer> PPSCI_B200_DEBUG_KERNEL=<0 dW | 1 fwd | 2 dx>
+static long long* debug_timeline_ptr(int which) {
+  const char* dp = getenv("PPSCI_B200_DEBUG_TIMELINE");
+  if (!dp) return nullptr;
+  const char* dk = getenv("PPSCI_B200_DEBUG_KERNEL");
+  if ((dk ? atoi(dk) : 0) != which) return nullptr;
+  return reinterpret_cast<long long*>(strtoull(dp, nullptr, 0));
+}
+
 template <typename T, int KMAX>
 static int set_attrs_once(ppsci_plan* P) {
   constexpr int TN = Dims<T>::TN;
@@ -552,10 +562,22 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           t.Np = nc;
           t.TP = TP;
           t.num_tiles = (int)ptiles;
+          t.dbg = debug_timeline_ptr(1);
           if (do_bwd && tc_astash_needed(P, l - 1)) {
             t.Astash = reinterpret_cast<float*>(ws + cv.a[l - 1]);
             t.lda = P->ld[l - 1];
             t.aplane = (long long)nc_max * P->ld[l - 1];
+          }
+          const int lay_f = tc_pick_layout(P->J, s.act);
+          if ((P->tc_mask & 8) && lay_f != TC_LAY_DYN && P->num_sms >= 2) {  // CTA pairs (cta_group::2)
+            const int smem2 = tc::tc2_smem_bytes(t.Nout);
+            const unsigned tile_pairs = (ptiles + 1) / 2, sm_pairs = (unsigned)P->num_sms / 2;
+            const unsigned gridx2 = 2 * (tile_pairs < sm_pairs ? tile_pairs : sm_pairs);
+            ProfScope ps_(P, CLS_FWD, st);
+            PPSCI_TC2_LAUNCH(k_tc2_fwd, lay_f, dim3(gridx2), smem2, st, t,
+                             return fail(std::string("cudaFuncSetAttribute(k_tc2_fwd): ") + cudaGetErrorString(e_)));
+            P->launches++;
+            continue;
           }
           const int smem_tc = tc::tc_fwd_smem_bytes(t.Nout);
           const unsigned gridx = ptiles < (unsigned)P->num_sms ? ptiles : (unsigned)P->num_sms;
@@ -722,6 +744,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           const long long cps = (total_chunks + want - 1) / want;
           const unsigned splits = (unsigned)((total_chunks + cps - 1) / cps);
           t.chunks_per_split = (int)cps;
+          t.dbg = debug_timeline_ptr(0);
           const int smem_tc = tc::tc_dw_smem_bytes(NC);
           {
             ProfScope ps_(P, CLS_DW, st);
@@ -791,6 +814,17 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           t.Np = nc;
           t.TP = TP;
           t.num_tiles = (int)ptiles;
+          t.dbg = debug_timeline_ptr(2);
+          const int lay_x = tc_pick_layout(P->J, s.act);
+          if ((P->tc_mask & 16) && lay_x != TC_LAY_DYN && P->num_sms >= 2) {  // CTA pairs (cta_group::2)
+            const int smem2 = tc::tc2_smem_bytes(t.Nout);
+            const unsigned tile_pairs = (ptiles + 1) / 2, sm_pairs = (unsigned)P->num_sms / 2;
+            const unsigned gridx2 = 2 * (tile_pairs < sm_pairs ? tile_pairs : sm_pairs);
+            ProfScope ps_(P, CLS_DX, st);
+            PPSCI_TC2_LAUNCH(k_tc2_dx, lay_x, dim3(gridx2), smem2, st, t,
+                             return fail(std::string("cudaFuncSetAttribute(k_tc2_dx): ") + cudaGetErrorString(e_)));
+            P->launches++;
+          } else {
           const int smem_tc = tc::tc_fwd_smem_bytes(t.Nout);
           const unsigned gridx = ptiles < (unsigned)P->num_sms ? ptiles : (unsigned)P->num_sms;
           {
@@ -798,6 +832,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
             PPSCI_TC_LAUNCH(k_tc_dx, tc_pick_layout(P->J, s.act), KMAX, dim3(gridx), smem_tc, st, t,
                             return fail(std::string("cudaFuncSetAttribute(k_tc_dx): ") + cudaGetErrorString(e_)));
             P->launches++;
+          }
           }
           zbar_cur = reinterpret_cast<const T*>(outp);
           zbar_ld = P->ld[l - 1];

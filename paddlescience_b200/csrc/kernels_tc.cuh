@@ -54,6 +54,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {  // non-suspending probe
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -71,6 +82,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 24)) __trap();
   }
+}
+// One lane polls the mbarrier, the rest of the warp waits at __syncwarp: 32x fewer pollers on the barrier word.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -165,6 +181,7 @@ struct SLay {
   static constexpr bool kStatic = true;
   static constexpr int ND = (O0 > 0) + (O1 > 0) + (O2 > 0) + (O3 > 0);
   static constexpr int C = 1 + O0 + O1 + O2 + O3;
+  static constexpr int CS = C;  // compile-time channel count
   static constexpr int KMAX = (O0 > O1 ? O0 : O1) > (O2 > O3 ? O2 : O3) ? (O0 > O1 ? O0 : O1) : (O2 > O3 ? O2 : O3);
   static constexpr int KM = KMAX < 1 ? 1 : KMAX;
   __device__ static __forceinline__ int nd(const JetLayout&) { return ND; }
@@ -180,6 +197,7 @@ template <int KMAX_>
 struct DLay {
   static constexpr bool kStatic = false;
   static constexpr int ND = PPSCI_MAX_DIR;
+  static constexpr int CS = 1;  // (channel count only known at run time)
   static constexpr int KM = KMAX_;
   __device__ static __forceinline__ int nd(const JetLayout& J) { return J.n_dir; }
   __device__ static __forceinline__ int order(const JetLayout& J, int d) { return J.dir_order[d]; }
@@ -314,6 +332,15 @@ __device__ __forceinline__ void store_split_at(unsigned char* a_hi, uint32_t off
   *reinterpret_cast<float*>(a_hi + off) = hi;
   *reinterpret_cast<float*>(a_hi + A_TILE_BYTES + off) = v - hi;
 }
+// 128-bit variant: four consecutive k (one 16-byte chunk of the row); `off` = sw128_q(row, kq)
+__device__ __forceinline__ void store_split4_at(unsigned char* a_hi, uint32_t off, const float (&v)[4]) {
+  float4 h, l;
+  h.x = tf32_rn(v[0]); h.y = tf32_rn(v[1]); h.z = tf32_rn(v[2]); h.w = tf32_rn(v[3]);
+  l.x = v[0] - h.x; l.y = v[1] - h.y; l.z = v[2] - h.z; l.w = v[3] - h.w;
+  *reinterpret_cast<float4*>(a_hi + off) = h;
+  *reinterpret_cast<float4*>(a_hi + A_TILE_BYTES + off) = l;
+}
+__device__ __forceinline__ uint32_t sw128_q(int row, int kq) { return (uint32_t)(row * 128 + (((kq ^ row) & 7) << 4)); }
 // column kk = lane: the swizzled in-row offset only depends on (row & 7)
 __device__ __forceinline__ uint32_t sw128_lane(int row, int lane) {
   return (uint32_t)(row * 128 + ((((lane >> 2) ^ row) & 7) << 4) + ((lane & 3) << 2));
@@ -335,23 +362,24 @@ struct TcFwdArgs {
   long long Np;
   int TP;
   int num_tiles;
+  long long* dbg;     // optional timeline buffer (bring-up instrumentation; null in production)
 };
 
 // Shared-memory map of k_tc_fwd / k_tc_dx (offsets from the 1024-aligned base):
 //   [0, 2*stage)                       two operand stages: A_hi | A_lo | B_hi | B_lo
 //   [2*stage, 2*stage + 2*RAW)         raw fp32 staging ring (TMA row copies), one K chunk ahead
 //   then mbarriers b_full[2] (+0,+8), mma_done[2] (+16,+24), raw_full[2] (+32,+40) and the TMEM base slot (+64)
-__host__ __device__ inline int tc_fwd_smem_bytes(int N) { return 2 * tc_stage_bytes(N) + 2 * RAW_TILE_BYTES + 1024 + 256; }
+__host__ __device__ inline int tc_fwd_smem_bytes(int N) { return 2 * tc_stage_bytes(N) + 1024 + 256; }
 
 // Shared prologue of the three kernels: barriers, TMEM, zeroed operand stages.
 __device__ __forceinline__ void tc_setup(uint32_t base, unsigned char* base_ptr, uint32_t bars_off, int stage_bytes,
-                                         int clear_bytes_per_stage, uint32_t ncols) {
+                                         int clear_bytes_per_stage, uint32_t ncols, int npw = NPW) {
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bars = base + bars_off;
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(bars + 8 * i, 1);
-    mbar_init(bars + 32, NPW);  // a_ready[2]: one arrival per producer warp
-    mbar_init(bars + 40, NPW);
+    mbar_init(bars + 32, npw);  // a_ready[2]: one arrival per producer warp
+    mbar_init(bars + 40, npw);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -361,7 +389,7 @@ __device__ __forceinline__ void tc_setup(uint32_t base, unsigned char* base_ptr,
   }
   for (int s = 0; s < 2; ++s) {
     float4* az = reinterpret_cast<float4*>(base_ptr + s * stage_bytes);
-    for (int i = tid; i < clear_bytes_per_stage / 16; i += THREADS) az[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < clear_bytes_per_stage / 16; i += (int)blockDim.x) az[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   tc_fence_before();
   __syncthreads();
@@ -380,8 +408,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
   unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
   const int N = g.Nout;
   const int stage_bytes = tc_stage_bytes(N);
-  const uint32_t raw_off = 2 * stage_bytes;
-  const uint32_t bars_off = raw_off + 2 * RAW_TILE_BYTES;
+  const uint32_t bars_off = 2 * stage_bytes;
   const uint32_t bars = base + bars_off;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ncols = tc_pow2_cols(2 * N);
@@ -405,78 +432,150 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
     bulk_g2s(base + sb * stage_bytes + 2 * A_TILE_BYTES, g.Wimg + (long long)(itb % nchunks) * 2 * N * KCH, b_bytes,
              bars + 8 * sb);
   };
-  RowPieces pcs;
-  pcs.init(TP, rows_used, g.A.plane, g.A.ld);
-  auto issue_raw = [&](uint32_t itr, int tile_r, int jr) {  // raw rows of running chunk itr (all threads)
-    const long long p0r = (long long)tile_r * TP;
-    const long long vp = g.Np - p0r;
-    const int valid = vp >= TP ? TP : (vp > 0 ? (int)vp : 0);
-    pcs.issue(base + raw_off + (itr & 1u) * RAW_TILE_BYTES, g.A.Z, p0r * g.A.ld + jr * KCH, valid);
-  };
+  // Operand rows are fetched straight from HBM/L2 into REGISTERS one chunk ahead, and every LSU instruction of the
+  // producers is 128 bits wide.  Measured on the timeline of these kernels: the LSU instruction rate (global loads,
+  // shared stores), not bytes, bounds the producers -- cp.async staging cost ~900 cycles of issue per chunk plus a
+  // second LDS pass, and 32-bit loads/stores cost 4x the instructions.  An item = (point, 4 consecutive k): per
+  // channel one LDG.128, one STG.128 (a-stash) and two STS.128 (hi / lo; 4 consecutive k = one 16-byte chunk of a
+  // K-major SW128 row).  Lanes: kq = lane & 7 (k quad of the 32-wide chunk), point = 4 warp + (lane >> 3): a
+  // quarter warp writes the 8 chunks of one row (bank-conflict free) and reads 128 contiguous bytes.
+  constexpr int CS = L::CS;
+  constexpr int PPR = NPW * 4;  // points per pass of the producer warps
+  constexpr int MAXI = L::kStatic ? (128 / CS + PPR - 1) / PPR : (128 + NPW - 1) / NPW;
+  float4 zreg[L::kStatic ? MAXI : 1][CS];
   const bool is_mma = (warp == MMA_WARP);
+  const int kq = lane & 7, psub = lane >> 3;
+  auto prefetch = [&](int tile_r, int jr) {
+    if constexpr (L::kStatic) {
+      const long long p0r = (long long)tile_r * TP;
+      const int col = jr * KCH + 4 * kq;
+#pragma unroll
+      for (int i = 0; i < MAXI; ++i) {
+        const int pl = warp * 4 + psub + i * PPR;
+        const long long p = p0r + pl;
+        const bool ok = pl < TP && p < g.Np;
+        const float* src = g.A.Z + p * g.A.ld + col;
+#pragma unroll
+        for (int c = 0; c < CS; ++c)
+          zreg[i][c] = ok ? __ldg(reinterpret_cast<const float4*>(src + (long long)c * g.A.plane)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  };
   if (total_it > 0) {
-    issue_raw(0, blockIdx.x, 0);  // (the MMA warp owns no pieces)
+    if (!is_mma) prefetch(blockIdx.x, 0);
     if (is_mma && lane == 0) issue_b(0);
   }
-  cp_async_commit();
+  const bool dbgp = g.dbg && blockIdx.x == 0 && tid == 0;
+  const bool dbgm = g.dbg && blockIdx.x == 0 && is_mma && lane == 0;
+#define DBG_STAMP(cond, slot) do { if ((cond) && it < 48) g.dbg[it * 16 + (slot)] = clock64(); } while (0)
   uint32_t it = 0;  // running chunk counter (stage = it & 1, use index = it >> 1)
   for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
     const long long p0 = (long long)tile * TP;
     for (int j = 0; j < nchunks; ++j, ++it) {
       const uint32_t s = it & 1u, u = it >> 1;
       if (!is_mma) {
+        DBG_STAMP(dbgp, 0);
         unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-        cp_async_wait<0>();  // this chunk's raw rows have landed (this thread's pieces) ...
-        producer_sync();     // ... and every other producer's; all producers are also done reading chunk it-1
-        if (it + 1 < total_it) {  // raw rows of chunk it+1 -> the buffer chunk it-1 occupied
-          int ntile = tile, nj = j + 1;
-          if (nj == nchunks) { nj = 0; ntile = tile + gridDim.x; }
-          issue_raw(it + 1, ntile, nj);
-        }
-        cp_async_commit();
-        if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);  // MMAs that read this stage have retired
-        const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + s * RAW_TILE_BYTES);
-        const int k = j * KCH + lane;
-        for (int pl = warp; pl < TP; pl += NPW) {
-          const long long p = p0 + pl;
-          if (p < g.Np) {
-            float sc[6];
-            float y0;
-            act_coef<float, L::KM>(act, raw[pl * KCH + lane], y0, sc);
-            store_split_at(stage_ptr, sw128_lane(pl, lane), y0);
-            float* ast = g.Astash ? g.Astash + p * g.lda + k : nullptr;
-            if (ast) ast[0] = y0;
+        if constexpr (L::kStatic) {
+          float4 zcur[MAXI][CS];
 #pragma unroll
-            for (int d = 0; d < L::ND; ++d) {
-              if (d < L::nd(g.J)) {
+          for (int i = 0; i < MAXI; ++i)
+#pragma unroll
+            for (int c = 0; c < CS; ++c) zcur[i][c] = zreg[i][c];
+          if (it + 1 < total_it) {  // next chunk's rows start flying now and land while this chunk is produced
+            int ntile = tile, nj = j + 1;
+            if (nj == nchunks) { nj = 0; ntile = tile + gridDim.x; }
+            prefetch(ntile, nj);
+          }
+          DBG_STAMP(dbgp, 1);
+          if (u >= 1) mbar_wait_warp(bars + 16 + 8 * s, (u - 1) & 1u);  // MMAs that read this stage have retired
+          DBG_STAMP(dbgp, 3);
+#pragma unroll
+          for (int i = 0; i < MAXI; ++i) {
+            const int pl = warp * 4 + psub + i * PPR;
+            if (pl >= TP) continue;
+            const long long p = p0 + pl;
+            const bool valid = p < g.Np;
+            float yout[CS][4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              auto comp = [&](const float4& v) { return t == 0 ? v.x : t == 1 ? v.y : t == 2 ? v.z : v.w; };
+              float sc[6];
+              float y0;
+              act_coef<float, L::KM>(act, comp(zcur[i][0]), y0, sc);
+              yout[0][t] = valid ? y0 : 0.f;
+#pragma unroll
+              for (int d = 0; d < L::ND; ++d) {
                 const int K = L::order(g.J, d), cb = L::cbase(g.J, d);
                 float zz[4], yy[4];
 #pragma unroll
-                for (int o = 0; o < 4; ++o) zz[o] = (o < L::KM && o < K) ? raw[((cb + o) * TP + pl) * KCH + lane] : 0.f;
+                for (int o = 0; o < 4; ++o) zz[o] = (o < L::KM && o < K) ? comp(zcur[i][(cb + o) < CS ? (cb + o) : 0]) : 0.f;
                 jet_fwd_dir<float, L::KM>(sc, zz, yy);
 #pragma unroll
                 for (int o = 0; o < L::KM; ++o)
-                  if (o < K) {
-                    store_split_at(stage_ptr, sw128_lane((cb + o) * TP + pl, lane), yy[o]);
-                    if (ast) ast[(long long)(cb + o) * g.aplane] = yy[o];
-                  }
+                  if (o < K && cb + o < CS) yout[cb + o][t] = valid ? yy[o] : 0.f;
               }
             }
-          } else {
-            for (int c = 0; c < C; ++c) store_split_at(stage_ptr, sw128_lane(c * TP + pl, lane), 0.f);
+            float* ast = (g.Astash && valid) ? g.Astash + p * g.lda + j * KCH + 4 * kq : nullptr;
+#pragma unroll
+            for (int c = 0; c < CS; ++c) {
+              store_split4_at(stage_ptr, sw128_q(c * TP + pl, kq), yout[c]);
+              if (ast)
+                *reinterpret_cast<float4*>(ast + (long long)c * g.aplane) = make_float4(yout[c][0], yout[c][1], yout[c][2], yout[c][3]);
+            }
+          }
+        } else {
+          // runtime-layout fallback: item = (point, lane column), scalar and unprefetched
+          if (u >= 1) mbar_wait_warp(bars + 16 + 8 * s, (u - 1) & 1u);
+          const int k = j * KCH + lane;
+          for (int pl = warp; pl < TP; pl += NPW) {
+            const long long p = p0 + pl;
+            if (p < g.Np) {
+              const float* zsrc = g.A.Z + p * g.A.ld + k;
+              float sc[6];
+              float y0;
+              act_coef<float, L::KM>(act, zsrc[0], y0, sc);
+              store_split_at(stage_ptr, sw128_lane(pl, lane), y0);
+              float* ast = g.Astash ? g.Astash + p * g.lda + k : nullptr;
+              if (ast) ast[0] = y0;
+#pragma unroll
+              for (int d = 0; d < L::ND; ++d) {
+                if (d < L::nd(g.J)) {
+                  const int K = L::order(g.J, d), cb = L::cbase(g.J, d);
+                  float zz[4], yy[4];
+#pragma unroll
+                  for (int o = 0; o < 4; ++o) zz[o] = (o < L::KM && o < K) ? zsrc[(long long)(cb + o) * g.A.plane] : 0.f;
+                  jet_fwd_dir<float, L::KM>(sc, zz, yy);
+#pragma unroll
+                  for (int o = 0; o < L::KM; ++o)
+                    if (o < K) {
+                      store_split_at(stage_ptr, sw128_lane((cb + o) * TP + pl, lane), yy[o]);
+                      if (ast) ast[(long long)(cb + o) * g.aplane] = yy[o];
+                    }
+                }
+              }
+            } else {
+              for (int c = 0; c < C; ++c) store_split_at(stage_ptr, sw128_lane(c * TP + pl, lane), 0.f);
+            }
           }
         }
+        DBG_STAMP(dbgp, 4);
         fence_proxy_async();  // generic-proxy smem accesses ordered before the async-proxy ones that follow
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + 32 + 8 * s);  // this warp's share of the A operand is in place
+        DBG_STAMP(dbgp, 5);
       }
       if (is_mma) {
         if (lane == 0) {
+          DBG_STAMP(dbgm, 8);
           mbar_wait(bars + 32 + 8 * s, u & 1u);  // every producer warp has delivered its rows of this chunk
+          DBG_STAMP(dbgm, 9);
           mbar_wait(bars + 8 * s, u & 1u);  // weight images of this chunk have landed
+          DBG_STAMP(dbgm, 12);
           tc_fence_after();
           issue_chunk_mmas(acc0, acc1, descs, s, idesc, j == 0);
           mma_commit(bars + 16 + 8 * s);  // arrives when every MMA issued so far has completed
+          DBG_STAMP(dbgm, 10);
           if (it + 1 < total_it) {  // weights of chunk it+1 -> other stage, once chunk it-1's MMAs have left it
             if (it >= 1) mbar_wait(bars + 16 + 8 * ((it + 1) & 1u), ((it - 1) >> 1) & 1u);
             issue_b(it + 1);
@@ -485,51 +584,59 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
         __syncwarp();
       }
     }
-    // ---- epilogue: TMEM -> shared exchange tiles -> (+bias) -> Z_l in HBM, fully coalesced ----
-    // A thread owns one accumulator ROW after tcgen05.ld; storing it directly would emit 32 scattered 16-byte
-    // writes per warp instruction.  Four 128x32 blocks at a time are transposed through the (now idle)
-    // A regions of both stages — X[b][r][t ^ (r & 31)] — and written back row-wise (128 B per warp store).
+    // ---- epilogue: TMEM -> shared exchange tiles -> (+bias) -> Z_l in HBM, 128-bit and coalesced ----
+    // A thread owns one accumulator ROW after tcgen05.ld.  Four 128x32 blocks at a time are exchanged through the
+    // (now idle) A regions of both stages -- X[b][row][chunk ^ (row & 7)], 16-byte chunks, conflict-free both
+    // ways -- and written back as (row, k quad) items: 8 lanes cover 128 contiguous bytes of one output row.
     {
       const uint32_t last = it - 1;
-      mbar_wait(bars + 16 + 8 * (last & 1u), (last >> 1) & 1u);
+      mbar_wait_warp(bars + 16 + 8 * (last & 1u), (last >> 1) & 1u);
       tc_fence_after();
+      if (dbgp && last < 48) g.dbg[last * 16 + 13] = clock64();
       const int q = warp & 3, part = warp >> 2;
       const int ncb = N / 32;
       for (int cb0 = 0; cb0 < ncb; cb0 += 4) {
         const int cb = cb0 + part;
-        float* Xb = reinterpret_cast<float*>(base_ptr + (part >> 1) * stage_bytes + (part & 1) * A_TILE_BYTES);
+        unsigned char* Xb = base_ptr + (part >> 1) * stage_bytes + (part & 1) * A_TILE_BYTES;
         if (cb < ncb) {
           float v[32];
           load_acc_sum(acc0, acc1, q, cb * 32, v);
-          float* xr = Xb + (q * 32 + lane) * KCH;
+          const int row = q * 32 + lane;
 #pragma unroll
-          for (int t = 0; t < 32; ++t) xr[t ^ lane] = v[t];
+          for (int t4 = 0; t4 < 8; ++t4)
+            *reinterpret_cast<float4*>(Xb + sw128_q(row, t4)) = make_float4(v[4 * t4], v[4 * t4 + 1], v[4 * t4 + 2], v[4 * t4 + 3]);
         }
         __syncthreads();
-        for (int r = warp; r < rows_used; r += THREADS / 32) {
+        for (int r = warp * 4 + psub; r < rows_used; r += (THREADS / 32) * 4) {
           const int c = r / TP, pl = r - c * TP;
           const long long p = p0 + pl;
           if (p < g.Np) {
-            float* out_row = g.Out + (long long)c * g.oplane + p * g.ldo + cb0 * 32 + lane;
+            float* out_row = g.Out + (long long)c * g.oplane + p * g.ldo + cb0 * 32 + 4 * kq;
 #pragma unroll
             for (int b4 = 0; b4 < 4; ++b4) {
               if (cb0 + b4 < ncb) {
-                const float* Xr = reinterpret_cast<const float*>(base_ptr + (b4 >> 1) * stage_bytes + (b4 & 1) * A_TILE_BYTES);
-                float val = Xr[r * KCH + (lane ^ (r & 31))];
-                if (c == 0 && g.bias) val += g.bias[(cb0 + b4) * 32 + lane];
-                out_row[b4 * 32] = val;
+                const unsigned char* Xr = base_ptr + (b4 >> 1) * stage_bytes + (b4 & 1) * A_TILE_BYTES;
+                float4 val = *reinterpret_cast<const float4*>(Xr + sw128_q(r, kq));
+                if (c == 0 && g.bias) {  // (the flat parameter vector does not guarantee 16-byte aligned biases)
+                  const float* bp = g.bias + (cb0 + b4) * 32 + 4 * kq;
+                  val.x += __ldg(bp); val.y += __ldg(bp + 1); val.z += __ldg(bp + 2); val.w += __ldg(bp + 3);
+                }
+                *reinterpret_cast<float4*>(out_row + b4 * 32) = val;
               }
             }
           }
         }
         __syncthreads();
       }
+      // (rows >= rows_used of the exchange tiles hold accumulators of all-zero operand rows, i.e. zeros: the
+      //  A regions' pad rows stay valid zero operands)
+      if (dbgp && last < 48) g.dbg[last * 16 + 14] = clock64();
       fence_proxy_async();
       tc_fence_before();
       __syncthreads();  // accumulators drained / scratch released before the next tile starts
     }
   }
-  cp_async_wait<0>();
+#undef DBG_STAMP
   __syncthreads();
   if (warp == 1) tmem_dealloc(acc0, ncols);
 }
@@ -558,6 +665,7 @@ struct TcDxArgs {
   long long Np;
   int TP;
   int num_tiles;
+  long long* dbg;      // optional timeline buffer (bring-up instrumentation; null in production)
 };
 
 template <class L, int ACT>
@@ -567,8 +675,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
   unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
   const int N = g.Nout;
   const int stage_bytes = tc_stage_bytes(N);
-  const uint32_t raw_off = 2 * stage_bytes;
-  const uint32_t bars_off = raw_off + 2 * RAW_TILE_BYTES;
+  const uint32_t bars_off = 2 * stage_bytes;
   const uint32_t bars = base + bars_off;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ncols = tc_pow2_cols(2 * N);
@@ -583,7 +690,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
   const int C = L::nchan(g.J);
   const int rows_used = C * TP;
   const int act = act_id<ACT>(g.act);
-  float* X = reinterpret_cast<float*>(base_ptr);  // exchange tile: stage 0, A_hi region (16 KB)
   const uint32_t zbuf_addr = base + stage_bytes;   // two Z blocks: stage 1, A_hi and A_lo regions
   const float* zbuf_ptr = reinterpret_cast<const float*>(base_ptr + stage_bytes);
   const int my_tiles = ((int)blockIdx.x < g.num_tiles) ? (g.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -599,19 +705,34 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
     const long long vp = g.Np - p0r;
     return vp >= TP ? TP : (vp > 0 ? (int)vp : 0);
   };
-  RowPieces pcs, zpcs;
-  pcs.init(TP, rows_used, g.A.plane, g.A.ld);
+  RowPieces zpcs;
   zpcs.init(TP, rows_used, g.zplane, g.ldz);
-  auto issue_raw = [&](uint32_t itr, int tile_r, int jr) {
-    const long long p0r = (long long)tile_r * TP;
-    pcs.issue(base + raw_off + (itr & 1u) * RAW_TILE_BYTES, g.A.Z, p0r * g.A.ld + jr * KCH, valid_pts(p0r));
-  };
+  // Zbar rows of the next chunk are prefetched into registers; items = (row, 4 consecutive k), 128-bit loads and
+  // shared stores (see k_tc_fwd for why)
+  constexpr int RPP = NPW * 4;  // rows per pass of the producer warps
+  constexpr int MAXR = (128 + RPP - 1) / RPP;
+  float4 zreg[MAXR];
   const bool is_mma = (warp == MMA_WARP);
+  const int kq = lane & 7, psub = lane >> 3;
+  auto prefetch = [&](int tile_r, int jr) {
+    const long long p0r = (long long)tile_r * TP;
+    const int col = jr * KCH + 4 * kq;
+#pragma unroll
+    for (int i = 0; i < MAXR; ++i) {
+      const int r = warp * 4 + psub + i * RPP;
+      const int c = r / TP, pl = r - c * TP;
+      const bool ok = r < rows_used && p0r + pl < g.Np;
+      zreg[i] = ok ? __ldg(reinterpret_cast<const float4*>(g.A.Z + (long long)c * g.A.plane + (p0r + pl) * g.A.ld + col))
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
   if (total_it > 0) {
-    issue_raw(0, blockIdx.x, 0);
+    if (!is_mma) prefetch(blockIdx.x, 0);
     if (is_mma && lane == 0) issue_b(0);
   }
-  cp_async_commit();
+  const bool dbgp = g.dbg && blockIdx.x == 0 && tid == 0;
+  const bool dbgm = g.dbg && blockIdx.x == 0 && is_mma && lane == 0;
+#define DBG_STAMP(cond, slot) do { if ((cond) && it < 48) g.dbg[it * 16 + (slot)] = clock64(); } while (0)
   uint32_t it = 0;
   for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
     const long long p0 = (long long)tile * TP;
@@ -619,32 +740,44 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
     for (int j = 0; j < nchunks; ++j, ++it) {
       const uint32_t s = it & 1u, u = it >> 1;
       if (!is_mma) {
+        DBG_STAMP(dbgp, 0);
         unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-        cp_async_wait<0>();
-        producer_sync();
+        float4 zcur[MAXR];
+#pragma unroll
+        for (int i = 0; i < MAXR; ++i) zcur[i] = zreg[i];
         if (it + 1 < total_it) {
           int ntile = tile, nj = j + 1;
           if (nj == nchunks) { nj = 0; ntile = tile + gridDim.x; }
-          issue_raw(it + 1, ntile, nj);
+          prefetch(ntile, nj);
         }
-        cp_async_commit();
-        if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
-        const float* raw = reinterpret_cast<const float*>(base_ptr + raw_off + s * RAW_TILE_BYTES);
-        for (int r = warp; r < rows_used; r += NPW) {  // plain split, one row per warp pass
-          const int c = r / TP, pl = r - c * TP;
-          store_split_at(stage_ptr, sw128_lane(r, lane), pl < vpts ? raw[r * KCH + lane] : 0.f);
+        DBG_STAMP(dbgp, 1);
+        if (u >= 1) mbar_wait_warp(bars + 16 + 8 * s, (u - 1) & 1u);
+        DBG_STAMP(dbgp, 3);
+#pragma unroll
+        for (int i = 0; i < MAXR; ++i) {  // plain split
+          const int r = warp * 4 + psub + i * RPP;
+          if (r < rows_used) {
+            const float v[4] = {zcur[i].x, zcur[i].y, zcur[i].z, zcur[i].w};
+            store_split4_at(stage_ptr, sw128_q(r, kq), v);
+          }
         }
+        DBG_STAMP(dbgp, 4);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(bars + 32 + 8 * s);
+        DBG_STAMP(dbgp, 5);
       }
       if (is_mma) {
         if (lane == 0) {
+          DBG_STAMP(dbgm, 8);
           mbar_wait(bars + 32 + 8 * s, u & 1u);
+          DBG_STAMP(dbgm, 9);
           mbar_wait(bars + 8 * s, u & 1u);
+          DBG_STAMP(dbgm, 12);
           tc_fence_after();
           issue_chunk_mmas(acc0, acc1, descs, s, idesc, j == 0);
           mma_commit(bars + 16 + 8 * s);
+          DBG_STAMP(dbgm, 10);
           // weights of chunk it+1 go to the other stage; at a tile boundary that stage's A region is used as
           // epilogue scratch, but its B region is not, so the copy may be in flight across the epilogue
           if (it + 1 < total_it) {
@@ -658,60 +791,109 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
     // ---- epilogue: Abar (TMEM) -> exchange tile -> activation adjoint -> Zbar_{l-1} ----
     {
       const uint32_t last = it - 1;
-      mbar_wait(bars + 16 + 8 * (last & 1u), (last >> 1) & 1u);
+      mbar_wait_warp(bars + 16 + 8 * (last & 1u), (last >> 1) & 1u);
       tc_fence_after();
+      if (dbgp && last < 48) g.dbg[last * 16 + 13] = clock64();
       const int ncb = N / 32;
+      unsigned char* Xb = base_ptr;  // exchange tile: stage 0, A_hi region; X[row][chunk ^ (row & 7)]
       zpcs.issue(zbuf_addr, g.Zprev, p0 * g.ldz, vpts);
       cp_async_commit();
       for (int cb = 0; cb < ncb; ++cb) {
         if (cb + 1 < ncb) zpcs.issue(zbuf_addr + ((cb + 1) & 1) * A_TILE_BYTES, g.Zprev, p0 * g.ldz + (cb + 1) * 32, vpts);
         cp_async_commit();
-        if (warp < 4) {  // 128 lanes x 32 columns of Abar -> X[r][t ^ (r & 31)]  (conflict-free both ways)
+        if (warp < 4) {  // 128 lanes x 32 columns of Abar
           float v[32];
           load_acc_sum(acc0, acc1, warp, cb * 32, v);
-          float* xr = X + (warp * 32 + lane) * KCH;
+          const int row = warp * 32 + lane;
 #pragma unroll
-          for (int t = 0; t < 32; ++t) xr[t ^ lane] = v[t];
+          for (int t4 = 0; t4 < 8; ++t4)
+            *reinterpret_cast<float4*>(Xb + sw128_q(row, t4)) = make_float4(v[4 * t4], v[4 * t4 + 1], v[4 * t4 + 2], v[4 * t4 + 3]);
         }
         cp_async_wait<1>();
         __syncthreads();
-        const float* zb = zbuf_ptr + (cb & 1) * (A_TILE_BYTES / 4);
-        const int nn = lane;
-        for (int pl = warp; pl < vpts; pl += THREADS / 32) {
-          float* zb_out = g.Out + (p0 + pl) * g.ldo + cb * 32 + nn;
-          float sc[6];
-          float y0;
-          act_coef<float, L::KM + 1>(act, zb[pl * KCH + nn], y0, sc);
-          const float y0b = X[pl * KCH + (nn ^ (pl & 31))];
-          float sb[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+        const unsigned char* zb = reinterpret_cast<const unsigned char*>(zbuf_ptr) + (cb & 1) * A_TILE_BYTES;  // [row][32] linear
+        if constexpr (L::kStatic) {
+          constexpr int CS = L::CS;
+          for (int pl = warp * 4 + psub; pl < vpts; pl += (THREADS / 32) * 4) {  // item = (point, k quad)
+            float4 zc[CS], xc[CS];
 #pragma unroll
-          for (int d = 0; d < L::ND; ++d) {
-            if (d < L::nd(g.J)) {
-              const int K = L::order(g.J, d), cbs = L::cbase(g.J, d);
-              float zz[4], yb[4], zbv[4];
-#pragma unroll
-              for (int o = 0; o < 4; ++o) {
-                const bool on = (o < L::KM && o < K);
-                const int rr = (cbs + o) * TP + pl;
-                zz[o] = on ? zb[rr * KCH + nn] : 0.f;
-                yb[o] = on ? X[rr * KCH + (nn ^ (rr & 31))] : 0.f;
-                zbv[o] = 0.f;
-              }
-              jet_adj_dir<float, L::KM>(sc, zz, yb, zbv, sb);
-#pragma unroll
-              for (int o = 0; o < L::KM; ++o)
-                if (o < K) zb_out[(long long)(cbs + o) * g.oplane] = zbv[o];
+            for (int c = 0; c < CS; ++c) {
+              const int rr = c * TP + pl;
+              zc[c] = *reinterpret_cast<const float4*>(zb + rr * 128 + kq * 16);
+              xc[c] = *reinterpret_cast<const float4*>(Xb + sw128_q(rr, kq));
             }
+            float ob[CS][4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              auto comp = [&](const float4& v) { return t == 0 ? v.x : t == 1 ? v.y : t == 2 ? v.z : v.w; };
+              float sc[6];
+              float y0;
+              act_coef<float, L::KM + 1>(act, comp(zc[0]), y0, sc);
+              float sb[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int d = 0; d < L::ND; ++d) {
+                const int K = L::order(g.J, d), cbs = L::cbase(g.J, d);
+                float zz[4], yb[4], zbv[4];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                  const bool on = (o < L::KM && o < K && cbs + o < CS);
+                  zz[o] = on ? comp(zc[on ? cbs + o : 0]) : 0.f;
+                  yb[o] = on ? comp(xc[on ? cbs + o : 0]) : 0.f;
+                  zbv[o] = 0.f;
+                }
+                jet_adj_dir<float, L::KM>(sc, zz, yb, zbv, sb);
+#pragma unroll
+                for (int o = 0; o < L::KM; ++o)
+                  if (o < K && cbs + o < CS) ob[cbs + o][t] = zbv[o];
+              }
+              ob[0][t] = jet_adj_z0<float, L::KM>(sc, comp(xc[0]), sb);
+            }
+            float* out = g.Out + (p0 + pl) * g.ldo + cb * 32 + 4 * kq;
+#pragma unroll
+            for (int c = 0; c < CS; ++c)
+              *reinterpret_cast<float4*>(out + (long long)c * g.oplane) = make_float4(ob[c][0], ob[c][1], ob[c][2], ob[c][3]);
           }
-          zb_out[0] = jet_adj_z0<float, L::KM>(sc, y0b, sb);
+        } else {
+          const int nn = lane;  // runtime-layout fallback: item = (point, lane column), scalar
+          const uint32_t nsw = (uint32_t)((nn & 3) << 2);
+          for (int pl = warp; pl < vpts; pl += THREADS / 32) {
+            float* zb_out = g.Out + (p0 + pl) * g.ldo + cb * 32 + nn;
+            float sc[6];
+            float y0;
+            act_coef<float, L::KM + 1>(act, *reinterpret_cast<const float*>(zb + pl * 128 + nn * 4), y0, sc);
+            const float y0b = *reinterpret_cast<const float*>(Xb + sw128_q(pl, nn >> 2) + nsw);
+            float sb[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int d = 0; d < L::ND; ++d) {
+              if (d < L::nd(g.J)) {
+                const int K = L::order(g.J, d), cbs = L::cbase(g.J, d);
+                float zz[4], yb[4], zbv[4];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                  const bool on = (o < L::KM && o < K);
+                  const int rr = (cbs + o) * TP + pl;
+                  zz[o] = on ? *reinterpret_cast<const float*>(zb + rr * 128 + nn * 4) : 0.f;
+                  yb[o] = on ? *reinterpret_cast<const float*>(Xb + sw128_q(rr, nn >> 2) + nsw) : 0.f;
+                  zbv[o] = 0.f;
+                }
+                jet_adj_dir<float, L::KM>(sc, zz, yb, zbv, sb);
+#pragma unroll
+                for (int o = 0; o < L::KM; ++o)
+                  if (o < K) zb_out[(long long)(cbs + o) * g.oplane] = zbv[o];
+              }
+            }
+            zb_out[0] = jet_adj_z0<float, L::KM>(sc, y0b, sb);
+          }
         }
         fence_proxy_async();
         __syncthreads();
       }
+      if (dbgp && last < 48) g.dbg[last * 16 + 14] = clock64();
       tc_fence_before();
       __syncthreads();
     }
   }
+#undef DBG_STAMP
   cp_async_wait<0>();
   __syncthreads();
   if (warp == 1) tmem_dealloc(acc0, ncols);
@@ -741,32 +923,39 @@ struct TcDwArgs {
   long long Np;
   int PT;              // points per 32-row reduction chunk
   int chunks_per_split;
+  long long* dbg;      // optional timeline buffer (bring-up instrumentation; null in production)
 };
 
-// raw tiles of one reduction chunk: A rows [32][128 k] (16 KB) and Zbar rows [32][NC n] (NC*128 B)
-__host__ __device__ inline int tc_dw_raw_bytes(int NC) { return KCH * 128 * 4 + KCH * NC * 4; }
-constexpr int DW_RAW_STAGES = 3;  // raw-tile ring: two chunks of prefetch distance (a loaded HBM round trip is ~1.4 us)
 __host__ __device__ inline int tc_dw_smem_bytes(int NC) {
-  return 2 * tc_stage_bytes(NC) + DW_RAW_STAGES * tc_dw_raw_bytes(NC) + 1024 + 256;
+  return 2 * tc_stage_bytes(NC) + 1024 + 256;
 }
 
+constexpr int DW_NPW = 16;                      // producer warps of k_tc_dw (one 32-row x 16-reduction-row task each)
+constexpr int DW_THREADS = (DW_NPW + 1) * 32;   // + the MMA warp
+constexpr int DW_MMA_WARP = DW_NPW;
+
+// Producer geometry.  Both operands of dW are TRANSPOSES of row-major global data: tile row = dW row k (A') or dW
+// column n (B'), tile column kk = reduction row rr = (channel, point) of the chunk.  A thread owns a 4 x 4 block:
+// it loads rr = 4q..4q+3 as four LDG.128 (4 consecutive k / n each), transposes in registers (pure renaming) and
+// stores four 16-byte chunks (one per k / n row) into each of the hi and lo tiles.  A warp = 8 row quads x 4 q:
+// lane = rq_lo | q_lo << 1 | rq_hi << 3, so that a quarter warp's STS.128 hits 8 distinct 16-byte chunks
+// ((q ^ row) & 7 with row & 7 = 4 rq_lo + i) and every LDG.128 instruction reads four full 128-byte lines.
+// Tasks: A' = 4 row groups x 2 q groups, B' = N/32 row groups x 2 q groups  (16 tasks at N = 128).
 template <class L>
-__global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
+__global__ void __launch_bounds__(DW_THREADS, 1) k_tc_dw(TcDwArgs g) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
   const int N = g.Nout;  // columns of this CTA
   const int stage_bytes = tc_stage_bytes(N);
-  const int raw_bytes = tc_dw_raw_bytes(N);
-  const uint32_t raw_off = 2 * stage_bytes;
-  const uint32_t bars_off = raw_off + DW_RAW_STAGES * raw_bytes;
-  const uint32_t bars = base + bars_off;  // mma_done[2] at +16,+24
+  const uint32_t bars_off = 2 * stage_bytes;
+  const uint32_t bars = base + bars_off;  // mma_done[2] at +16,+24, a_ready[2] at +32,+40
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ncols = tc_pow2_cols(3 * N);
   const int PT = L::pt(g.PT);
   const int C = L::nchan(g.J);
   const int rows_used = C * PT;
-  tc_setup(base, base_ptr, bars_off, stage_bytes, stage_bytes, ncols);  // whole stages cleared (pad columns stay 0)
+  tc_setup(base, base_ptr, bars_off, stage_bytes, stage_bytes, ncols, DW_NPW);  // whole stages cleared (pad columns stay 0)
   // accX: 2N columns (A_hi B_hi | A_hi B_lo), accY: N columns (A_lo B_hi)
   const uint32_t accX = *reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 64), accY = accX + (uint32_t)(2 * N);
   const uint32_t idesc_2n = make_idesc_tf32(128, 2 * N), idesc_n = make_idesc_tf32(128, N);
@@ -783,136 +972,119 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
     const long long vp = g.Np - ch * PT;
     return vp >= PT ? PT : (vp > 0 ? (int)vp : 0);
   };
-  // cp.async pieces of one chunk: A rows (32 pieces of 16 B per 512-byte row) then Zbar rows (N/4 pieces per row);
-  // the piece -> (row, column) mapping is chunk-invariant and precomputed.
-  constexpr int DW_PIECES = (KCH * 32 + KCH * 32 + NPROD - 1) / NPROD;  // N <= 128
-  const int zb_pieces = N / 4;
-  long long psrc[DW_PIECES];
-  uint32_t pdst[DW_PIECES];
-  int ppl[DW_PIECES];  // -1 none; bit 8 set => Zbar piece
+  const bool is_mma = (warp == DW_MMA_WARP);
+  const int n_tasks = 8 + N / 16;
+  const bool has_task = !is_mma && warp < n_tasks;  // (N <= 128: at most one task per producer warp)
+  const bool t_isA = warp < 8;
+  uint32_t g_off[4];            // element offsets of the four source rows relative to the chunk's first point
+  uint32_t g_plb = 0xFFFFFFFFu; // their point-in-chunk, one byte each (0xFF: no such reduction row)
+  uint32_t d_off[4];            // byte offsets of the four destination chunks inside the hi tile
+  int d_lo = 0;                 // hi -> lo tile distance
+  {
+    const int tl = t_isA ? warp : warp - 8;
+    const int rowgroup = tl >> 1, qg = tl & 1;
+    const int rq = ((lane >> 3) << 1) | (lane & 1), q = qg * 4 + ((lane >> 1) & 3);
+    const int row0 = rowgroup * 32 + rq * 4;
+    uint32_t plb = 0;
 #pragma unroll
-  for (int jj = 0; jj < DW_PIECES; ++jj) {
-    const int i = tid + jj * NPROD;
-    ppl[jj] = -1;
-    psrc[jj] = 0;
-    pdst[jj] = 0;
-    if (tid >= NPROD) {
-    } else if (i < rows_used * 32) {
-      const int rr = i >> 5, q = i & 31;
-      const int c = rr / PT, pl = rr - c * PT;
-      ppl[jj] = pl;
-      psrc[jj] = (long long)c * g.aplane + (long long)pl * g.lda + k0 + q * 4;
-      pdst[jj] = (uint32_t)(rr * 512 + q * 16);
-    } else {
-      const int i2 = i - rows_used * 32;
-      if (i2 < rows_used * zb_pieces) {
-        const int rr = i2 / zb_pieces, q = i2 - rr * zb_pieces;
+    for (int e = 0; e < 4; ++e) {
+      const int rr = 4 * q + e;
+      uint32_t b8 = 0xFFu;
+      g_off[e] = 0;
+      if (has_task && rr < rows_used) {
         const int c = rr / PT, pl = rr - c * PT;
-        ppl[jj] = pl | 256;
-        psrc[jj] = (long long)c * g.zbplane + (long long)pl * g.ldzb + n0 + q * 4;
-        pdst[jj] = (uint32_t)(KCH * 512 + rr * N * 4 + q * 16);
+        b8 = (uint32_t)pl;
+        g_off[e] = t_isA ? (uint32_t)((long long)c * g.aplane + (long long)pl * g.lda + k0 + row0)
+                         : (uint32_t)((long long)c * g.zbplane + (long long)pl * g.ldzb + n0 + row0);
       }
+      plb |= b8 << (8 * e);
     }
-  }
-  auto issue_raw = [&](long long ch, uint32_t itr) {
-    const int vp = valid_pts(ch);
-    const uint32_t dst = base + raw_off + (itr % DW_RAW_STAGES) * raw_bytes;
-    const long long pb = ch * PT;
+    g_plb = plb;
 #pragma unroll
-    for (int jj = 0; jj < DW_PIECES; ++jj) {
-      if (ppl[jj] >= 0) {
-        const bool isz = (ppl[jj] & 256) != 0;
-        const bool ok = (ppl[jj] & 255) < vp;
-        const float* bp = isz ? g.Zbar : g.Aact;
-        cp_async16(dst + pdst[jj], ok ? bp + psrc[jj] + pb * (isz ? g.ldzb : g.lda) : bp, ok);
-      }
+    for (int i = 0; i < 4; ++i) d_off[i] = sw128_q(row0 + i, q) + (t_isA ? 0u : (uint32_t)(2 * A_TILE_BYTES));
+    d_lo = t_isA ? A_TILE_BYTES : N * KCH * 4;
+  }
+  auto prefetch = [&](float4 (&buf)[4], long long ch) {
+    const uint32_t vp = (uint32_t)valid_pts(ch);
+    const float* bp = t_isA ? g.Aact + ch * PT * (long long)g.lda : g.Zbar + ch * PT * (long long)g.ldzb;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool ok = ((g_plb >> (8 * e)) & 255u) < vp;
+      buf[e] = ok ? __ldg(reinterpret_cast<const float4*>(bp + g_off[e])) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-
-  // split/transpose items: [0, 128 nq) -> A'(row k, 16-byte chunk q) ; [128 nq, 128 nq + N nq) -> B'(row n, chunk q)
-  const int nq = (rows_used + 3) / 4;  // 16-byte chunks of 4 reduction rows
-  constexpr int DW_ITEMS = (128 * 8 + 128 * 8 + NPROD - 1) / NPROD;
-  int i_src[DW_ITEMS], i_stride[DW_ITEMS], i_ne[DW_ITEMS], i_lo[DW_ITEMS];
-  uint32_t i_dst[DW_ITEMS];
-#pragma unroll
-  for (int jj = 0; jj < DW_ITEMS; ++jj) {
-    const int item = tid + jj * NPROD;
-    const int itemsA = 128 * nq;
-    i_ne[jj] = 0;
-    i_src[jj] = 0;
-    i_stride[jj] = 0;
-    i_lo[jj] = 0;
-    i_dst[jj] = 0;
-    if (tid < NPROD && item < itemsA + N * nq) {
-      const bool isA = item < itemsA;
-      const int local = isA ? item : item - itemsA;
-      const int width = isA ? 128 : N;
-      const int row = local % width, q = local / width;
-      const int left = rows_used - 4 * q;
-      i_ne[jj] = left >= 4 ? 4 : left;
-      i_stride[jj] = width;
-      i_src[jj] = (isA ? 0 : KCH * 128) + 4 * q * width + row;
-      i_dst[jj] = sw128(row, 4 * q) + (isA ? 0u : (uint32_t)(2 * A_TILE_BYTES));
-      i_lo[jj] = isA ? A_TILE_BYTES : N * KCH * 4;
-    }
-  }
-  uint32_t it = 0;
-  if (ch_begin < ch_end) issue_raw(ch_begin, 0);
-  cp_async_commit();
-  if (ch_begin + 1 < ch_end) issue_raw(ch_begin + 1, 1);
-  cp_async_commit();
-  const bool is_mma = (warp == MMA_WARP);
-  for (long long ch = ch_begin; ch < ch_end; ++ch, ++it) {
+  const bool dbgp = g.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
+  const bool dbgm = g.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && is_mma && lane == 0;
+#define DBG_STAMP(cond, slot) do { if ((cond) && it < 48) g.dbg[it * 16 + (slot)] = clock64(); } while (0)
+  // one reduction chunk: producers split the register-resident block of chunk `ch` into the operand stage and
+  // refill the same registers with chunk ch+2; the MMA warp issues the chunk's 8 MMAs
+  auto step = [&](float4 (&buf)[4], long long ch, uint32_t it) {
     const uint32_t s = it & 1u, u = it >> 1;
     if (!is_mma) {
+      DBG_STAMP(dbgp, 0);
       unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-      cp_async_wait<1>();  // chunk `it` has landed (chunk it+1 may still be in flight)
-      producer_sync();     // visible to all producers, and everybody is done reading chunk it-1
-      if (ch + 2 < ch_end) issue_raw(ch + 2, it + 2);  // -> buffer (it+2)%3 == (it-1)%3
-      cp_async_commit();
-      if (u >= 1) mbar_wait(bars + 16 + 8 * s, (u - 1) & 1u);
-      // split + transpose: item descriptors were precomputed (chunk-invariant); invalid tail rows were zero-filled
-      // by cp.async, rows >= rows_used are masked by the per-item element count
-      const float* rawf = reinterpret_cast<const float*>(base_ptr + raw_off + (it % DW_RAW_STAGES) * raw_bytes);
+      if (u >= 1) mbar_wait_warp(bars + 16 + 8 * s, (u - 1) & 1u);  // MMAs that read this stage have retired
+      DBG_STAMP(dbgp, 3);
+      if (has_task) {
 #pragma unroll
-      for (int jj = 0; jj < DW_ITEMS; ++jj) {
-        if (i_ne[jj] > 0) {
-          const float* src = rawf + i_src[jj];
-          float hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float v = e < i_ne[jj] ? src[e * i_stride[jj]] : 0.f;
-            hi[e] = tf32_rn(v);
-            lo[e] = v - hi[e];
-          }
-          unsigned char* t_hi = stage_ptr + i_dst[jj];
-          *reinterpret_cast<float4*>(t_hi) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(t_hi + i_lo[jj]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        for (int i = 0; i < 4; ++i) {
+          auto comp = [&](const float4& v) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; };
+          const float v[4] = {comp(buf[0]), comp(buf[1]), comp(buf[2]), comp(buf[3])};
+          float4 h, l;
+          h.x = tf32_rn(v[0]); h.y = tf32_rn(v[1]); h.z = tf32_rn(v[2]); h.w = tf32_rn(v[3]);
+          l.x = v[0] - h.x; l.y = v[1] - h.y; l.z = v[2] - h.z; l.w = v[3] - h.w;
+          *reinterpret_cast<float4*>(stage_ptr + d_off[i]) = h;
+          *reinterpret_cast<float4*>(stage_ptr + d_off[i] + d_lo) = l;
         }
       }
+      DBG_STAMP(dbgp, 4);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + 32 + 8 * s);
+      DBG_STAMP(dbgp, 5);
+      if (has_task && ch + 2 < ch_end) prefetch(buf, ch + 2);
+      DBG_STAMP(dbgp, 6);
     }
     if (is_mma) {
       if (lane == 0) {
+        DBG_STAMP(dbgm, 8);
         mbar_wait(bars + 32 + 8 * s, u & 1u);
+        DBG_STAMP(dbgm, 9);
         tc_fence_after();
         issue_chunk_mmas_cat(accX, accY, descs, s, idesc_2n, idesc_n, it == 0);
         mma_commit(bars + 16 + 8 * s);
+        DBG_STAMP(dbgm, 10);
+        if (dbgm) {  // true completion time of THIS chunk's MMAs (non-suspending poll; instrumentation only)
+          while (!mbar_test_wait(bars + 16 + 8 * s, u & 1u)) {}
+          DBG_STAMP(dbgm, 11);
+        }
       }
       __syncwarp();
     }
+  };
+  float4 bufA[4], bufB[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) bufA[e] = bufB[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (has_task) {
+    if (ch_begin < ch_end) prefetch(bufA, ch_begin);
+    if (ch_begin + 1 < ch_end) prefetch(bufB, ch_begin + 1);
   }
-  if (it > 0) {
+  uint32_t it = 0;
+  for (long long ch = ch_begin; ch < ch_end; ch += 2, it += 2) {
+    step(bufA, ch, it);
+    if (ch + 1 < ch_end) step(bufB, ch + 1, it + 1);
+  }
+  it = ch_begin < ch_end ? (uint32_t)(ch_end - ch_begin) : 0u;
+#undef DBG_STAMP
+  if (it > 0 && !is_mma) {
     const uint32_t last = it - 1;
-    mbar_wait(bars + 16 + 8 * (last & 1u), (last >> 1) & 1u);
+    mbar_wait_warp(bars + 16 + 8 * (last & 1u), (last >> 1) & 1u);
     tc_fence_after();
     const int q = warp & 3, part = warp >> 2;
     const int k = k0 + q * 32 + lane;
     float* dw_row = g.dW + (long long)k * g.ldw + n0;
     const int ncb = N / 32;
-    for (int cb = part; cb < ncb; cb += THREADS / 128) {
+    for (int cb = part; cb < ncb; cb += DW_NPW / 4) {
       float v[32], w[32];
       load_acc_sum(accX, accX + (uint32_t)N, q, cb * 32, v);
       {
@@ -930,7 +1102,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dw(TcDwArgs g) {
       }
     }
   }
-  cp_async_wait<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(accX, ncols);
@@ -991,7 +1162,7 @@ inline int tc_pick_layout(const JetLayout& J, int act) {
   return TC_LAY_DYN;
 }
 
-#define PPSCI_TC_LAUNCH_L(KERNEL, lay, kmax, grid, smem, stream, args, err_expr)                                 \
+#define PPSCI_TC_LAUNCH_L(KERNEL, lay, kmax, grid, smem, stream, args, err_expr)  /* k_tc_dw: DW_THREADS */                               \
   do {                                                                                                            \
     void (*kfn_)(decltype(args)) = nullptr;                                                                       \
     switch (lay) {                                                                                                \
@@ -1003,7 +1174,7 @@ inline int tc_pick_layout(const JetLayout& J, int act) {
     }                                                                                                             \
     cudaError_t e_ = cudaFuncSetAttribute(kfn_, cudaFuncAttributeMaxDynamicSharedMemorySize, (smem));             \
     if (e_ != cudaSuccess) { err_expr; }                                                                          \
-    kfn_<<<(grid), dim3(tc::THREADS), (smem), (stream)>>>(args);                                                  \
+    kfn_<<<(grid), dim3(tc::DW_THREADS), (smem), (stream)>>>(args);                                                  \
   } while (0)
 
 #define PPSCI_TC_LAUNCH(KERNEL, lay, kmax, grid, smem, stream, args, err_expr)                                   \

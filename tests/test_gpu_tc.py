@@ -12,11 +12,26 @@ pytestmark = pytest.mark.gpu
 TOL_TC = dict(loss=2e-5, res=1e-5, grad=5e-5)
 
 
+# PPSCI_B200_TC_MASK selects the kernel variants: 31 = default (CTA-pair forward / dx, single-CTA dW),
+# 7 = single-CTA kernels only (the fallback the pair kernels replace)
+@pytest.mark.parametrize("mask", [31, 7])
 @pytest.mark.parametrize("name", sorted(TC_CASES))
-def test_tc_case_matches_oracle(name):
+def test_tc_case_matches_oracle(name, mask, monkeypatch):
     assert torch.cuda.is_available()
+    monkeypatch.setenv("PPSCI_B200_TC_MASK", str(mask))
     r = run_case(name, 3000, device="cuda:0", backend=2)
     assert r["tc"], "tcgen05 backend was not selected"
+    assert r["loss"] <= TOL_TC["loss"], r
+    assert r["res"] <= TOL_TC["res"], r
+    assert r["grad"] <= TOL_TC["grad"], r
+
+
+@pytest.mark.parametrize("n", [13, 3013, 70001])
+def test_tc_ragged_point_counts(n):
+    """Odd tile counts (one CTA of the last pair gets an empty tile), a partial last tile, fewer tiles than CTAs,
+    and more than one pass of the persistent loop + a second point chunk."""
+    r = run_case("ns_f32_tc_256", n, device="cuda:0", backend=2)
+    assert r["tc"]
     assert r["loss"] <= TOL_TC["loss"], r
     assert r["res"] <= TOL_TC["res"], r
     assert r["grad"] <= TOL_TC["grad"], r
