@@ -16,6 +16,7 @@
 #ifndef PPSCI_EMUL
 #include "kernels_tc.cuh"
 #include "kernels_tc2.cuh"
+#include "kernels_thin.cuh"
 #endif
 
 using namespace ppsci;
@@ -458,6 +459,11 @@ static int run(ppsci_plan* P, const CallArgs& a) {
   const bool thin_on = getenv("PPSCI_B200_NO_THIN") == nullptr;
   const bool thin_first = thin_on && L >= 2 && s.widths[0] <= THIN_MAXF;
   const bool thin_last = thin_on && L >= 2 && n_out <= THIN_MAXM && C * n_out <= THIN_MAXCM;
+#ifndef PPSCI_EMUL
+  // fp32 + one of the compile-time jet layouts: vectorised thin kernels (kernels_thin.cuh)
+  const int thin_lay = tc_pick_layout(P->J, PPSCI_ACT_TANH);
+  const bool thin_vec = sizeof(T) == 4 && thin_lay != TC_LAY_DYN && getenv("PPSCI_B200_NO_THINV") == nullptr;
+#endif
 
   if (a.want_loss) CK(cudaMemsetAsync(loss_acc, 0, PPSCI_MAX_RES * sizeof(double), st));
   const bool do_bwd = a.want_loss && grads != nullptr;
@@ -520,6 +526,18 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         f.oplane = (long long)nc_max * P->ld[1];
         f.Np = nc;
         const long long tot = (long long)nc * f.N;
+#ifndef PPSCI_EMUL
+        if constexpr (sizeof(T) == 4) {
+          if (thin_vec && f.N % 4 == 0) {  // compile-time layout, 128-bit stores, seeds staged once per point
+            void (*kv)(FirstArgs<float>) = nullptr;
+            PPSCI_THIN_PICK_L(k_first_fwd_v, thin_lay, KMAX, kv);
+            ProfScope ps_(P, CLS_FWD, st);
+            kv<<<dim3((unsigned)((nc + thin::PB - 1) / thin::PB)), dim3(256), 0, st>>>(f);
+            P->launches++;
+            continue;
+          }
+        }
+#endif
         auto k1 = k_first_fwd<T, KMAX>;
         ProfScope ps_(P, CLS_FWD, st);
         PPSCI_LAUNCH(k1, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, f);
@@ -539,6 +557,18 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         f.ldy = P->ld[L];
         f.yplane = (long long)nc_max * P->ld[L];
         f.Np = nc;
+#ifndef PPSCI_EMUL
+        if constexpr (sizeof(T) == 4) {
+          if (thin_vec && f.K % 4 == 0 && f.m <= 4) {
+            void (*kv)(LastArgs<float>) = nullptr;
+            PPSCI_THIN_PICK_LM(k_last_fwd_v, thin_lay, f.m, kv);
+            ProfScope ps_(P, CLS_FWD, st);
+            kv<<<dim3((unsigned)((nc + 7) / 8)), dim3(256), 0, st>>>(f);
+            P->launches++;
+            continue;
+          }
+        }
+#endif
         auto k2 = k_last_fwd<T, KMAX>;
         ProfScope ps_(P, CLS_FWD, st);
         PPSCI_LAUNCH(k2, dim3((unsigned)((nc + 7) / 8)), dim3(256), 0, st, f);
@@ -682,8 +712,22 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         f.db = grads + P->b_off[L];
         f.Np = nc;
         f.pts_per_block = 64;
-        auto k3 = k_last_bwd<T, KMAX>;
-        {
+        bool last_done = false;
+#ifndef PPSCI_EMUL
+        if constexpr (sizeof(T) == 4) {
+          if (thin_vec && f.K % 4 == 0 && f.m <= 4) {
+            f.pts_per_block = 128;
+            void (*kv)(LastArgs<float>) = nullptr;
+            PPSCI_THIN_PICK_LM(k_last_bwd_v, thin_lay, f.m, kv);
+            ProfScope ps_(P, CLS_DX, st);
+            kv<<<dim3((unsigned)((f.K + 255) / 256), (unsigned)((nc + 127) / 128)), dim3(256), 0, st>>>(f);
+            P->launches++;
+            last_done = true;
+          }
+        }
+#endif
+        if (!last_done) {
+          auto k3 = k_last_bwd<T, KMAX>;
           ProfScope ps_(P, CLS_DX, st);
           PPSCI_LAUNCH(k3, dim3((unsigned)((f.K + 255) / 256), (unsigned)((nc + 63) / 64)), dim3(256), 0, st, f);
           P->launches++;
@@ -707,6 +751,19 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         f.db = grads + P->b_off[1];
         f.Np = nc;
         f.pts_per_block = 32;
+#ifndef PPSCI_EMUL
+        if constexpr (sizeof(T) == 4) {
+          if (thin_vec && f.N % 4 == 0) {
+            f.pts_per_block = 256;
+            void (*kv)(FirstArgs<float>) = nullptr;
+            PPSCI_THIN_PICK_L(k_first_dw_v, thin_lay, KMAX, kv);
+            ProfScope ps_(P, CLS_DW, st);
+            kv<<<dim3((unsigned)((f.N + 255) / 256), (unsigned)((nc + 255) / 256)), dim3(256), 0, st>>>(f);
+            P->launches++;
+            break;
+          }
+        }
+#endif
         auto k4 = k_first_dw<T, KMAX>;
         ProfScope ps_(P, CLS_DW, st);
         PPSCI_LAUNCH(k4, dim3((unsigned)((f.N + 255) / 256), (unsigned)((nc + 31) / 32)), dim3(256), 0, st, f);
