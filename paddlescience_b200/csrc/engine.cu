@@ -51,7 +51,7 @@ struct ppsci_plan {
   int chunk = 0;
   int num_sms = 148;
   bool use_tc = false;
-  int tc_mask = 31;  // bit0 forward, bit1 dx, bit2 dW on the tensor cores; bit3 / bit4: CTA-pair forward / dx kernels (PPSCI_B200_TC_MASK, debugging)
+  int tc_mask = 63;  // bit0 forward, bit1 dx, bit2 dW on the tensor cores; bit3 / bit4 / bit5: CTA-pair forward / dx / dW kernels (PPSCI_B200_TC_MASK, debugging)
   // device copies of the residual program
   int* d_prog = nullptr;
   double* d_consts = nullptr;
@@ -793,8 +793,24 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           t.Nout = NC;
           t.n0_stride = NC;
           t.ldw = s.widths[l];
-          const unsigned kt = (unsigned)(t.Kdim / 128), nb = (unsigned)(s.widths[l] / NC);
           const long long total_chunks = (nc + PTt - 1) / PTt;
+          if ((P->tc_mask & 32) && t.Kdim % 256 == 0 && s.widths[l] % 256 == 0 && P->num_sms >= 2) {
+            // CTA pairs (cta_group::2): one pair per 256 x 256 block of dW and reduction split
+            const unsigned kt2 = (unsigned)(t.Kdim / 256), nb2 = (unsigned)(s.widths[l] / 256);
+            long long want2 = (P->num_sms / 2) / (kt2 * nb2);
+            if (want2 < 1) want2 = 1;
+            if (want2 > total_chunks) want2 = total_chunks;
+            const long long cps2 = (total_chunks + want2 - 1) / want2;
+            const unsigned splits2 = (unsigned)((total_chunks + cps2 - 1) / cps2);
+            t.chunks_per_split = (int)cps2;
+            t.dbg = debug_timeline_ptr(0);
+            const int smem2 = tc::tc2_smem_bytes(256);
+            ProfScope ps_(P, CLS_DW, st);
+            PPSCI_TC2_LAUNCH_L(k_tc2_dw, tc_pick_layout(P->J, PPSCI_ACT_TANH), dim3(2 * kt2, splits2, nb2), smem2, st, t,
+                               return fail(std::string("cudaFuncSetAttribute(k_tc2_dw): ") + cudaGetErrorString(e_)));
+            P->launches++;
+          } else {
+          const unsigned kt = (unsigned)(t.Kdim / 128), nb = (unsigned)(s.widths[l] / NC);
           long long want = P->num_sms / (kt * nb);
           if (want < 1) want = 1;
           if (want > total_chunks) want = total_chunks;
@@ -808,6 +824,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
             PPSCI_TC_LAUNCH_L(k_tc_dw, tc_pick_layout(P->J, PPSCI_ACT_TANH), KMAX, dim3(kt, splits, nb), smem_tc, st, t,
                             return fail(std::string("cudaFuncSetAttribute(k_tc_dw): ") + cudaGetErrorString(e_)));
             P->launches++;
+          }
           }
           {
             ProfScope ps_(P, CLS_DW, st);

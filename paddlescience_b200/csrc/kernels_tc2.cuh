@@ -26,6 +26,7 @@ constexpr int T2_MMA_WARP = 15;
 constexpr int T2_NSTAGE = 3;
 constexpr int T2_PROD_THREADS = T2_NPW * 32;
 
+__device__ __forceinline__ float f4comp(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -685,8 +686,190 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_dx
   if (warp == 1) tmem_dealloc2(acc0, ncols);
 }
 
+
+// =====================================================================================================
+// Backward dW on a CTA pair:  dW_l[k][n] += sum_rows A_{l-1}[row][k] Zbar_l[row][n]  for a 256 x 256 block of dW
+// (M = 256 = the block's k rows, 128 per CTA; N = 256, each CTA stages the 128 n rows of its half) over this
+// pair's range of 32-row reduction chunks.  Producers exactly as in k_tc_dw (16 warps, one 4x4-block task each:
+// 8 tasks transpose-split the a-stash block, 8 the Zbar block; registers double-buffered two chunks ahead), but
+// each CTA now feeds twice the flops per byte it pulls from L2.  17th warp: MMA issue (leader) / relay (peer).
+// grid (2 * K/256, splits, N/256), cluster (2, 1, 1).
+// =====================================================================================================
+template <class L>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DW_THREADS, 1) k_tc2_dw(TcDwArgs g) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
+  constexpr int N = 256, NH = 128;
+  const int stage_bytes = tc2_stage_bytes(N);
+  const uint32_t bars_off = T2_NSTAGE * stage_bytes;
+  const uint32_t bars = base + bars_off;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t ncols = 512;
+  const int PT = L::pt(g.PT);
+  const int C = L::nchan(g.J);
+  const int rows_used = C * PT;
+  const uint32_t acc0 = tc2_setup(base, base_ptr, bars_off, stage_bytes, ncols, DW_NPW), acc1 = acc0 + (uint32_t)N;
+  const uint32_t rank = cluster_ctarank();
+  const int k0 = (int)(blockIdx.x >> 1) * 256 + (int)rank * 128;  // this CTA's dW rows
+  const int n0 = (int)blockIdx.z * 256;
+  const int n0h = n0 + (int)rank * NH;                             // this CTA's half of the B operand
+  const long long total_chunks = (g.Np + PT - 1) / PT;
+  const long long ch_begin = (long long)blockIdx.y * g.chunks_per_split;
+  long long ch_end = ch_begin + g.chunks_per_split;
+  if (ch_end > total_chunks) ch_end = total_chunks;
+  const uint32_t n_it = ch_begin < ch_end ? (uint32_t)(ch_end - ch_begin) : 0u;
+  auto valid_pts = [&](long long ch) {
+    const long long vp = g.Np - ch * PT;
+    return vp >= PT ? PT : (vp > 0 ? (int)vp : 0);
+  };
+  const bool is_mma = (warp == DW_MMA_WARP);
+  const bool dbg0 = g.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#define DBG_STAMP(cond, slot) do { if (dbg0 && (cond) && it < 48) g.dbg[it * 16 + (slot)] = clock64(); } while (0)
+
+  if (is_mma) {
+    if (lane == 0) {
+      T2Stage st;
+      if (rank == 0) {
+        const uint32_t idesc = make_idesc_tf32(256, N);
+        const uint64_t d_a_hi = make_smem_desc(base), d_a_lo = make_smem_desc(base + A_TILE_BYTES);
+        const uint64_t d_b_hi = make_smem_desc(base + 2 * A_TILE_BYTES);
+        const uint64_t d_b_lo = make_smem_desc(base + 2 * A_TILE_BYTES + (uint32_t)(NH * KCH * 4));
+        const uint64_t stage_inc = (uint64_t)(stage_bytes >> 4);
+        for (uint32_t it = 0; it < n_it; ++it) {
+          DBG_STAMP(true, 8);
+          mbar_wait(bars + 48 + 8 * st.s, st.par);
+          DBG_STAMP(true, 9);
+          mbar_wait_cluster(bars + 72 + 8 * st.s, st.par);
+          DBG_STAMP(true, 15);
+          tc_fence_after();
+          const uint64_t so = (uint64_t)st.s * stage_inc;
+          issue_chunk_mmas_2(acc0, acc1, d_a_hi + so, d_a_lo + so, d_b_hi + so, d_b_lo + so, idesc, it == 0);
+          mma_commit_2(bars + 24 + 8 * st.s);
+          DBG_STAMP(true, 10);
+          st.next();
+        }
+      } else {
+        for (uint32_t it = 0; it < n_it; ++it) {
+          mbar_wait(bars + 48 + 8 * st.s, st.par);
+          mbar_remote_arrive(bars + 72 + 8 * st.s, 0);
+          st.next();
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // task geometry (see k_tc_dw): warps 0..7 -> A' (this CTA's 128 k rows), warps 8..15 -> B' (its 128 n rows)
+    const bool t_isA = warp < 8;
+    uint32_t g_off[4], d_off[4];
+    uint32_t g_plb = 0xFFFFFFFFu;
+    {
+      const int tl = t_isA ? warp : warp - 8;
+      const int rowgroup = tl >> 1, qg = tl & 1;
+      const int rq = ((lane >> 3) << 1) | (lane & 1), q = qg * 4 + ((lane >> 1) & 3);
+      const int row0 = rowgroup * 32 + rq * 4;
+      uint32_t plb = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int rr = 4 * q + e;
+        uint32_t b8 = 0xFFu;
+        g_off[e] = 0;
+        if (rr < rows_used) {
+          const int c = rr / PT, pl = rr - c * PT;
+          b8 = (uint32_t)pl;
+          g_off[e] = t_isA ? (uint32_t)((long long)c * g.aplane + (long long)pl * g.lda + k0 + row0)
+                           : (uint32_t)((long long)c * g.zbplane + (long long)pl * g.ldzb + n0h + row0);
+        }
+        plb |= b8 << (8 * e);
+      }
+      g_plb = plb;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d_off[i] = sw128_q(row0 + i, q) + (t_isA ? 0u : (uint32_t)(2 * A_TILE_BYTES));
+    }
+    const int d_lo = t_isA ? A_TILE_BYTES : NH * KCH * 4;
+    auto prefetch = [&](float4 (&buf)[4], long long ch) {
+      const uint32_t vp = (uint32_t)valid_pts(ch);
+      const float* bp = t_isA ? g.Aact + ch * PT * (long long)g.lda : g.Zbar + ch * PT * (long long)g.ldzb;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = ((g_plb >> (8 * e)) & 255u) < vp;
+        buf[e] = ok ? __ldg(reinterpret_cast<const float4*>(bp + g_off[e])) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto step = [&](float4 (&buf)[4], long long ch, uint32_t it) {
+      const uint32_t s = it % T2_NSTAGE;
+      DBG_STAMP(tid == 0, 0);
+      unsigned char* stage_ptr = base_ptr + s * stage_bytes;
+      if (it >= T2_NSTAGE) t2_wait_chunk_done(bars, it - T2_NSTAGE);  // MMAs that read this stage have retired
+      DBG_STAMP(tid == 0, 3);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float v[4] = {f4comp(buf[0], i), f4comp(buf[1], i), f4comp(buf[2], i), f4comp(buf[3], i)};
+        float4 h, l;
+        h.x = tf32_rn(v[0]); h.y = tf32_rn(v[1]); h.z = tf32_rn(v[2]); h.w = tf32_rn(v[3]);
+        l.x = v[0] - h.x; l.y = v[1] - h.y; l.z = v[2] - h.z; l.w = v[3] - h.w;
+        *reinterpret_cast<float4*>(stage_ptr + d_off[i]) = h;
+        *reinterpret_cast<float4*>(stage_ptr + d_off[i] + d_lo) = l;
+      }
+      DBG_STAMP(tid == 0, 4);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 48 + 8 * s);
+      DBG_STAMP(tid == 0, 5);
+      if (ch + 2 < ch_end) prefetch(buf, ch + 2);
+      DBG_STAMP(tid == 0, 6);
+    };
+    float4 bufA[4], bufB[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) bufA[e] = bufB[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ch_begin < ch_end) prefetch(bufA, ch_begin);
+    if (ch_begin + 1 < ch_end) prefetch(bufB, ch_begin + 1);
+    uint32_t it = 0;
+    for (long long ch = ch_begin; ch < ch_end; ch += 2, it += 2) {
+      step(bufA, ch, it);
+      if (ch + 1 < ch_end) step(bufB, ch + 1, it + 1);
+    }
+    // ---- flush: this CTA's 128 x 256 block of partial dW ----
+    if (n_it > 0) {
+      t2_wait_chunk_done(bars, n_it - 1);
+      tc_fence_after();
+      const int q = warp & 3, part = warp >> 2;
+      const int k = k0 + q * 32 + lane;
+      float* dw_row = g.dW + (long long)k * g.ldw + n0;
+      for (int cb = part; cb < N / 32; cb += DW_NPW / 4) {
+        float v[32];
+        load_acc_sum(acc0, acc1, q, cb * 32, v);
+        if (k < g.Kdim) {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) atomicAdd(dw_row + cb * 32 + t, v[t]);
+        }
+      }
+    }
+  }
+#undef DBG_STAMP
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc2(acc0, ncols);
+}
+
 }  // namespace tc
 }  // namespace ppsci
+
+#define PPSCI_TC2_LAUNCH_L(KERNEL, lay, grid, smem, stream, args, err_expr)                                         \
+  do {                                                                                                              \
+    void (*kfn_)(decltype(args)) = nullptr;                                                                         \
+    switch (lay) {                                                                                                  \
+      case ppsci::TC_LAY_22: kfn_ = ppsci::tc::KERNEL<ppsci::tc::SLay<2, 2, 0, 0>>; break;                          \
+      case ppsci::TC_LAY_12: kfn_ = ppsci::tc::KERNEL<ppsci::tc::SLay<1, 2, 0, 0>>; break;                          \
+      case ppsci::TC_LAY_222: kfn_ = ppsci::tc::KERNEL<ppsci::tc::SLay<2, 2, 2, 0>>; break;                         \
+      case ppsci::TC_LAY_VALUE: kfn_ = ppsci::tc::KERNEL<ppsci::tc::SLay<0, 0, 0, 0>>; break;                       \
+      default: kfn_ = ppsci::tc::KERNEL<ppsci::tc::DLay<4>>;                                                        \
+    }                                                                                                               \
+    cudaError_t e_ = cudaFuncSetAttribute(kfn_, cudaFuncAttributeMaxDynamicSharedMemorySize, (smem));               \
+    if (e_ != cudaSuccess) { err_expr; }                                                                            \
+    kfn_<<<(grid), dim3(ppsci::tc::DW_THREADS), (smem), (stream)>>>(args);                                          \
+  } while (0)
 
 // static jet layouts only (callers check lay != TC_LAY_DYN); tanh activation
 #define PPSCI_TC2_LAUNCH(KERNEL, lay, grid, smem, stream, args, err_expr)                                           \

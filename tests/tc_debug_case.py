@@ -1,5 +1,5 @@
 """GPU bring-up diagnostics: per-layer weight-gradient error of a tests.cases TC case under kernel-variant
-masks (PPSCI_B200_TC_MASK: 1 fwd, 2 dx, 4 dW, 8 pair-fwd, 16 pair-dx), against the SIMT backend."""
+masks (PPSCI_B200_TC_MASK: 1 fwd, 2 dx, 4 dW, 8 pair-fwd, 16 pair-dx, 32 pair-dW), against the SIMT backend."""
 import os
 import sys
 
@@ -50,4 +50,4 @@ def run(name, n, masks):
 
 if __name__ == "__main__":
     for name in sorted(TC_CASES):
-        run(name, 3000, (7, 15, 23, 31))
+        run(name, 3000, (7, 39, 63))
