@@ -10,9 +10,11 @@
 // Roles per CTA (512 threads): warps 0..13 produce the A operand (and run the epilogue), warp 14 lane 0 streams
 // this CTA's half of the weight images (free-running, up to 3 chunks ahead), warp 15 lane 0 issues the pair's
 // MMAs (leader CTA, cluster rank 0) or relays "my A tile and my B half are in place" to the leader (peer CTA).
-//   b_full[s]     tx-count barrier of the weight copies of stage s            (local)
-//   a_ready[s]    one arrival per producer warp                                  (local)
-//   peer_ready[s] one remote arrival from the peer's relay lane                  (leader only)
+//   full[s]       ONE barrier per stage collects everything the MMAs of a chunk need: one arrival per producer
+//                 warp, the weight streamer's arrive.expect_tx + the bytes of its two bulk copies and, on the
+//                 leader, one remote arrival from the peer's relay lane (which waits for the peer's own full[s]).
+//                 The issuing lane is the critical serial path of the main loop; each extra barrier it polls
+//                 costs ~200 cycles even when already complete (measured), hence a single one.
 //   mma_done[s]   tcgen05.commit, multicast to both CTAs: stage s may be overwritten / accumulators are final
 #pragma once
 #include "kernels_tc.cuh"
@@ -87,7 +89,7 @@ __device__ __forceinline__ void mma_commit_2(uint32_t bar) {
 }
 
 __host__ __device__ inline int tc2_stage_bytes(int N) { return 2 * A_TILE_BYTES + 2 * (N / 2) * KCH * 4; }
-// barriers: b_full[3] +0, mma_done[3] +24, a_ready[3] +48, peer_ready[3] +72, TMEM base slot +128
+// barriers: mma_done[3] +24, full[3] +48, TMEM base slot +128
 __host__ __device__ inline int tc2_smem_bytes(int N) { return T2_NSTAGE * tc2_stage_bytes(N) + 1024 + 256; }
 
 // 12 MMAs (3xTF32, split accumulators: see issue_chunk_mmas) of one K chunk, M = 256 over the CTA pair
@@ -132,15 +134,13 @@ struct T2Stage {  // running (stage, parity) pair of a 3-deep ring
 
 // Shared prologue: barriers, pair-wide TMEM allocation, zeroed A regions, cluster rendezvous.
 __device__ __forceinline__ uint32_t tc2_setup(uint32_t base, unsigned char* base_ptr, uint32_t bars_off, int stage_bytes,
-                                              uint32_t ncols, int a_count) {
+                                              uint32_t ncols, int full_count) {
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t bars = base + bars_off;
   if (tid == 0) {
     for (int i = 0; i < T2_NSTAGE; ++i) {
-      mbar_init(bars + 8 * i, 1);            // b_full
-      mbar_init(bars + 24 + 8 * i, 1);       // mma_done
-      mbar_init(bars + 48 + 8 * i, a_count); // a_ready: one arrival per warp that produces a share of the chunk
-      mbar_init(bars + 72 + 8 * i, 1);       // peer_ready
+      mbar_init(bars + 24 + 8 * i, 1);           // mma_done
+      mbar_init(bars + 48 + 8 * i, full_count);  // full
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -188,8 +188,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_fw
   constexpr int W1 = (TP + 3) / 4;
   constexpr int NG = (2 * W1 <= T2_NPW) ? 2 : 1;
   constexpr int WG = NG > 1 ? W1 : T2_NPW;  // warps per group
-  const uint32_t acc0 = tc2_setup(base, base_ptr, bars_off, stage_bytes, ncols, WG), acc1 = acc0 + (uint32_t)N;
   const uint32_t rank = cluster_ctarank();
+  // full[s]: producer warps of the chunk + weight streamer (+ the peer's relay on the leader)
+  const uint32_t acc0 = tc2_setup(base, base_ptr, bars_off, stage_bytes, ncols, WG + 1 + (rank == 0 ? 1 : 0)), acc1 = acc0 + (uint32_t)N;
   const int pair = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
   const int nchunks = g.Kdim / KCH;
   const int act = act_id<ACT>(g.A.act);
@@ -209,9 +210,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_fw
         if (it >= T2_NSTAGE) mbar_wait(bars + 24 + 8 * st.s, st.par ^ 1u);  // MMAs that read this stage have retired
         const float* img = g.Wimg + (long long)j * 2 * N * KCH + (long long)rank * NH * KCH;
         const uint32_t dst = base + st.s * stage_bytes + 2 * A_TILE_BYTES;
-        mbar_expect_tx(bars + 8 * st.s, 2 * half_bytes);
-        bulk_g2s(dst, img, half_bytes, bars + 8 * st.s);
-        bulk_g2s(dst + half_bytes, img + (long long)N * KCH, half_bytes, bars + 8 * st.s);
+        mbar_expect_tx(bars + 48 + 8 * st.s, 2 * half_bytes);
+        bulk_g2s(dst, img, half_bytes, bars + 48 + 8 * st.s);
+        bulk_g2s(dst + half_bytes, img + (long long)N * KCH, half_bytes, bars + 48 + 8 * st.s);
         DBG_STAMP(true, 7);
         st.next();
         if (++j == nchunks) j = 0;
@@ -230,11 +231,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_fw
         int j = 0;
         for (uint32_t it = 0; it < total_it; ++it) {
           DBG_STAMP(true, 8);
-          mbar_wait(bars + 48 + 8 * st.s, st.par);          // my A tile
-          DBG_STAMP(true, 9);
-          mbar_wait(bars + 8 * st.s, st.par);               // my half of the weights
-          DBG_STAMP(true, 12);
-          mbar_wait_cluster(bars + 72 + 8 * st.s, st.par);  // the peer's A tile and weight half
+          mbar_wait_cluster(bars + 48 + 8 * st.s, st.par);  // both A tiles and both weight halves are in place
           DBG_STAMP(true, 15);
           tc_fence_after();
           const uint64_t so = (uint64_t)st.s * stage_inc;
@@ -248,8 +245,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_fw
         // ---- relay: tell the leader when this CTA's operands of a chunk are in place ----
         for (uint32_t it = 0; it < total_it; ++it) {
           mbar_wait(bars + 48 + 8 * st.s, st.par);
-          mbar_wait(bars + 8 * st.s, st.par);
-          mbar_remote_arrive(bars + 72 + 8 * st.s, 0);
+          mbar_remote_arrive(bars + 48 + 8 * st.s, 0);
           st.next();
         }
       }
@@ -463,8 +459,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_dx
   constexpr int TP = 128 / CS;
   constexpr int rows_used = CS * TP;
   constexpr int NG = 2, WG = T2_NPW / NG;  // two producer groups own alternate chunks (see k_tc2_fwd)
-  const uint32_t acc0 = tc2_setup(base, base_ptr, bars_off, stage_bytes, ncols, WG), acc1 = acc0 + (uint32_t)N;
   const uint32_t rank = cluster_ctarank();
+  // full[s]: producer warps of the chunk + weight streamer (+ the peer's relay on the leader)
+  const uint32_t acc0 = tc2_setup(base, base_ptr, bars_off, stage_bytes, ncols, WG + 1 + (rank == 0 ? 1 : 0)), acc1 = acc0 + (uint32_t)N;
   const int pair = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
   const int nchunks = g.Kdim / KCH;
   const int act = act_id<ACT>(g.act);
@@ -483,9 +480,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_dx
         if (it >= T2_NSTAGE) mbar_wait(bars + 24 + 8 * st.s, st.par ^ 1u);
         const float* img = g.Wimg + (long long)j * 2 * N * KCH + (long long)rank * NH * KCH;
         const uint32_t dst = base + st.s * stage_bytes + 2 * A_TILE_BYTES;
-        mbar_expect_tx(bars + 8 * st.s, 2 * half_bytes);
-        bulk_g2s(dst, img, half_bytes, bars + 8 * st.s);
-        bulk_g2s(dst + half_bytes, img + (long long)N * KCH, half_bytes, bars + 8 * st.s);
+        mbar_expect_tx(bars + 48 + 8 * st.s, 2 * half_bytes);
+        bulk_g2s(dst, img, half_bytes, bars + 48 + 8 * st.s);
+        bulk_g2s(dst + half_bytes, img + (long long)N * KCH, half_bytes, bars + 48 + 8 * st.s);
         DBG_STAMP(true, 7);
         st.next();
         if (++j == nchunks) j = 0;
@@ -503,11 +500,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_dx
         int j = 0;
         for (uint32_t it = 0; it < total_it; ++it) {
           DBG_STAMP(true, 8);
-          mbar_wait(bars + 48 + 8 * st.s, st.par);
-          DBG_STAMP(true, 9);
-          mbar_wait(bars + 8 * st.s, st.par);
-          DBG_STAMP(true, 12);
-          mbar_wait_cluster(bars + 72 + 8 * st.s, st.par);
+          mbar_wait_cluster(bars + 48 + 8 * st.s, st.par);  // both A tiles and both weight halves are in place
           DBG_STAMP(true, 15);
           tc_fence_after();
           const uint64_t so = (uint64_t)st.s * stage_inc;
@@ -520,8 +513,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_dx
       } else {
         for (uint32_t it = 0; it < total_it; ++it) {
           mbar_wait(bars + 48 + 8 * st.s, st.par);
-          mbar_wait(bars + 8 * st.s, st.par);
-          mbar_remote_arrive(bars + 72 + 8 * st.s, 0);
+          mbar_remote_arrive(bars + 48 + 8 * st.s, 0);
           st.next();
         }
       }
@@ -595,42 +587,61 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_dx
         if (lane == 0) mbar_arrive(bars + 48 + 8 * s);
         DBG_STAMP(tid == 0, 5);
       }
-      // ---- epilogue ----
+      // ---- epilogue: two 32-column blocks of Abar per step, all 14 warps on the adjoint ----
+      // Scratch = the A regions of the three stages.  The stage of the tile's LAST chunk holds the two exchange
+      // tiles X0 / X1; the other two stages are free one chunk earlier (mma_done of the second-to-last chunk) and
+      // hold a 4-slot ring of Z_{l-1} blocks, so the first two block pairs are already in flight while the
+      // last chunk's MMAs run.  Step i: warps 0..3 / 7..10 move blocks 2i / 2i+1 from TMEM to X0 / X1, then warps
+      // 0..6 run the adjoint of block 2i and warps 7..13 of block 2i+1; the Z pair i+1 is requested at step i.
       {
         const uint32_t lastc = it - 1;
+        const int ncb = N / 32;
+        const int nsteps = (ncb + 1) / 2;
+        const uint32_t sc = lastc % T2_NSTAGE, sa = (lastc + 1) % T2_NSTAGE, sb = (lastc + 2) % T2_NSTAGE;
+        auto xbuf = [&](int i) { return base_ptr + sc * stage_bytes + (i & 1) * A_TILE_BYTES; };
+        auto zslot = [&](int i) { return (uint32_t)(((i & 2) ? sb : sa) * stage_bytes + (i & 1) * A_TILE_BYTES); };
+        auto issue_pair = [&](int i) {  // Z blocks 2i, 2i+1 -> ring slots 2(i&1), 2(i&1)+1; one cp.async group
+          if (i < nsteps) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int cb = 2 * i + h;
+              if (cb < ncb) zpcs.issue(base + zslot(2 * (i & 1) + h), g.Zprev, p0 * g.ldz + cb * 32, vpts);
+            }
+          }
+          cp_async_commit();
+        };
+        if (lastc >= 1) t2_wait_chunk_done(bars, lastc - 1);  // the two other stages are no longer read
+        issue_pair(0);
+        issue_pair(1);
         t2_wait_chunk_done(bars, lastc);
         tc_fence_after();
         if (dbg0 && tid == 0 && lastc < 48) g.dbg[lastc * 16 + 13] = clock64();
-        const int ncb = N / 32;
-        auto xbuf = [&](int i) { return base_ptr + (i & 1) * A_TILE_BYTES; };
-        auto zring_addr = [&](int i) { return base + (uint32_t)((1 + ((i >> 1) & 1)) * stage_bytes + (i & 1) * A_TILE_BYTES); };
-        auto zring_ptr = [&](int i) { return base_ptr + (1 + ((i >> 1) & 1)) * stage_bytes + (i & 1) * A_TILE_BYTES; };
-        auto fill_x = [&](int cb) {  // warps 8..11: 128 lanes x 32 columns of Abar -> X[cb & 1][row][chunk ^ (row & 7)]
-          float v[32];
-          load_acc_sum(acc0, acc1, warp & 3, cb * 32, v);
-          unsigned char* Xb = xbuf(cb);
-          const int row = (warp & 3) * 32 + lane;
+        const int grp = warp / 7, wg7 = warp - grp * 7;  // adjoint group (block parity) and warp within it
+        for (int i = 0; i < nsteps; ++i) {
+          if (i == 0) cp_async_wait<1>();  // Z pair i has landed (at step 0 pair 1 may still be in flight;
+          else cp_async_wait<0>();         //  later pairs are requested one step ahead)
+          t2_prod_sync();      // ... for every thread; all warps are done with step i-1 (X and its Z slots are free)
+          if (i >= 1) issue_pair(i + 1);  // -> the slots of pair i-1
+          {
+            const int fw = grp == 0 ? warp : warp - 7;  // warps 0..3 and 7..10 fill X0 / X1
+            const int cb = 2 * i + grp;
+            if (fw < 4 && cb < ncb) {
+              const int q = warp & 3;  // (7..10) & 3 = 3, 0, 1, 2: all four lane quadrants
+              float v[32];
+              load_acc_sum(acc0, acc1, q, cb * 32, v);
+              unsigned char* Xb = xbuf(grp);
+              const int row = q * 32 + lane;
 #pragma unroll
-          for (int t4 = 0; t4 < 8; ++t4)
-            *reinterpret_cast<float4*>(Xb + sw128_q(row, t4)) = make_float4(v[4 * t4], v[4 * t4 + 1], v[4 * t4 + 2], v[4 * t4 + 3]);
-        };
-#pragma unroll 1
-        for (int b = 0; b < 3; ++b) {
-          if (b < ncb) zpcs.issue(zring_addr(b), g.Zprev, p0 * g.ldz + b * 32, vpts);
-          cp_async_commit();
-        }
-        if (warp >= 8 && warp < 12) fill_x(0);
-        for (int cb = 0; cb < ncb; ++cb) {
-          cp_async_wait<2>();  // Z block cb has landed (blocks cb+1, cb+2 may be in flight)
-          t2_prod_sync();      // X[cb & 1] is filled; every warp is done with block cb-1
-          if (cb + 3 < ncb) zpcs.issue(zring_addr((cb + 3) & 3), g.Zprev, p0 * g.ldz + (cb + 3) * 32, vpts);
-          cp_async_commit();
-          if (warp >= 8 && warp < 12) {
-            if (cb + 1 < ncb) fill_x(cb + 1);
-          } else if (warp < 8) {
-            const unsigned char* zb = zring_ptr(cb & 3);
-            const unsigned char* Xb = xbuf(cb);
-            for (int pl = warp * 4 + psub; pl < vpts; pl += 32) {  // item = (point, k quad)
+              for (int t4 = 0; t4 < 8; ++t4)
+                *reinterpret_cast<float4*>(Xb + sw128_q(row, t4)) = make_float4(v[4 * t4], v[4 * t4 + 1], v[4 * t4 + 2], v[4 * t4 + 3]);
+            }
+          }
+          t2_prod_sync();  // X0 / X1 complete
+          const int cb = 2 * i + grp;
+          if (cb < ncb) {
+            const unsigned char* zb = base_ptr + zslot(2 * (i & 1) + grp);
+            const unsigned char* Xb = xbuf(grp);
+            for (int pl = wg7 * 4 + psub; pl < vpts; pl += 28) {  // item = (point, k quad)
               float4 zc[CS], xc[CS];
 #pragma unroll
               for (int c = 0; c < CS; ++c) {
@@ -642,10 +653,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_dx
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
                 auto comp = [&](const float4& v) { return t == 0 ? v.x : t == 1 ? v.y : t == 2 ? v.z : v.w; };
-                float sc[6];
+                float sc_[6];
                 float y0;
-                act_coef<float, L::KM + 1>(act, comp(zc[0]), y0, sc);
-                float sb[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+                act_coef<float, L::KM + 1>(act, comp(zc[0]), y0, sc_);
+                float sb_[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int d = 0; d < L::ND; ++d) {
                   const int K = L::order(g.J, d), cbs = L::cbase(g.J, d);
@@ -657,12 +668,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_dx
                     yb[o] = on ? comp(xc[on ? cbs + o : 0]) : 0.f;
                     zbv[o] = 0.f;
                   }
-                  jet_adj_dir<float, L::KM>(sc, zz, yb, zbv, sb);
+                  jet_adj_dir<float, L::KM>(sc_, zz, yb, zbv, sb_);
 #pragma unroll
                   for (int o = 0; o < L::KM; ++o)
                     if (o < K && cbs + o < CS) ob[cbs + o][t] = zbv[o];
                 }
-                ob[0][t] = jet_adj_z0<float, L::KM>(sc, comp(xc[0]), sb);
+                ob[0][t] = jet_adj_z0<float, L::KM>(sc_, comp(xc[0]), sb_);
               }
               float* out = g.Out + (p0 + pl) * g.ldo + cb * 32 + 4 * kq;
 #pragma unroll
@@ -709,8 +720,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DW_THREADS, 1) k_tc2
   const int PT = L::pt(g.PT);
   const int C = L::nchan(g.J);
   const int rows_used = C * PT;
-  const uint32_t acc0 = tc2_setup(base, base_ptr, bars_off, stage_bytes, ncols, DW_NPW), acc1 = acc0 + (uint32_t)N;
   const uint32_t rank = cluster_ctarank();
+  const uint32_t acc0 = tc2_setup(base, base_ptr, bars_off, stage_bytes, ncols, DW_NPW + (rank == 0 ? 1 : 0)), acc1 = acc0 + (uint32_t)N;
   const int k0 = (int)(blockIdx.x >> 1) * 256 + (int)rank * 128;  // this CTA's dW rows
   const int n0 = (int)blockIdx.z * 256;
   const int n0h = n0 + (int)rank * NH;                             // this CTA's half of the B operand
@@ -738,9 +749,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DW_THREADS, 1) k_tc2
         const uint64_t stage_inc = (uint64_t)(stage_bytes >> 4);
         for (uint32_t it = 0; it < n_it; ++it) {
           DBG_STAMP(true, 8);
-          mbar_wait(bars + 48 + 8 * st.s, st.par);
-          DBG_STAMP(true, 9);
-          mbar_wait_cluster(bars + 72 + 8 * st.s, st.par);
+          mbar_wait_cluster(bars + 48 + 8 * st.s, st.par);  // both A tiles and both weight halves are in place
           DBG_STAMP(true, 15);
           tc_fence_after();
           const uint64_t so = (uint64_t)st.s * stage_inc;
@@ -752,7 +761,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DW_THREADS, 1) k_tc2
       } else {
         for (uint32_t it = 0; it < n_it; ++it) {
           mbar_wait(bars + 48 + 8 * st.s, st.par);
-          mbar_remote_arrive(bars + 72 + 8 * st.s, 0);
+          mbar_remote_arrive(bars + 48 + 8 * st.s, 0);
           st.next();
         }
       }
