@@ -26,6 +26,9 @@ if ROOT not in sys.path:
 
 METRIC = "collocation-points/sec PDE residual loss+grad (LDC N-S)"
 UNIT = "points/s"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the hidden-layer kernels at the bench shape (one 65,536-point
+# chunk, C = 5, width 256), from the committed `ncu --set full` capture (profiles/r01_ncu_pair_kernels.md)
+NCU_TRAFFIC_BYTES = {"dx_gemm": 975.5e6, "dw_gemm": 676.9e6, "fwd_gemm": None}
 HIDDEN = [256] * 6
 N_PER_GPU = 1 << 20
 NU, RHO = 0.01, 1.0
@@ -279,20 +282,34 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     peaks = measured_peaks()
-    # dominant kernel class and its algorithmic flops per launch (fwd = C*F_v, dW = C*F_v, dx = C*F_v)
-    fv_c = fpp / 3.0
-    dom = max(("fwd_gemm", "dw_gemm", "dx_gemm"), key=lambda k: prof[k]["ms"])
-    dom_ms = prof[dom]["ms"]
-    dom_flops_step = fv_c * N
-    achieved = dom_flops_step / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else None
-    peak = peaks["bf16_tflops_sustained"]
+    # Dominant kernel class = the hidden-layer kernel (forward / dx / dW) with the largest device time.  Each of
+    # its launches streams whole [C][chunk][256] fp32 jet plane sets through HBM exactly once ("HBM
+    # layout" / "Kernels"): forward reads Z_{l-1}, writes Z_l and the post-activation stash a_{l-1} (3 plane sets),
+    # dx reads Zbar_l and Z_{l-1}, writes Zbar_{l-1} (3), dW reads a_{l-1} and Zbar_l (2).  Algorithmic bytes per
+    # launch = sets * C * chunk_points * width * 4; its algorithmic fp32 FLOPs = 2 * C * chunk * width^2.
+    width, chunk_pts = 256, 65536
+    sets = {"fwd_gemm": 3, "dx_gemm": 3, "dw_gemm": 2}
+    dom = max(sets, key=lambda k: prof[k]["ms"])
+    dom_ms, dom_launches = prof[dom]["ms"], max(1, prof[dom]["launches"])
+    n_hh = len(model.net_spec().widths) - 3  # hidden -> hidden layers (one launch per layer and point chunk)
+    launch_pts = N * n_hh / dom_launches     # points per launch
+    alg_bytes = sets[dom] * C * launch_pts * width * 4
+    alg_flops = 2.0 * C * launch_pts * width * width
+    avg_s = dom_ms * 1e-3 / dom_launches
+    achieved = alg_bytes / avg_s / 1e9 if dom_ms > 0 else None
+    peak = peaks["hbm_gbs"]
+    tf_alg = alg_flops / avg_s / 1e12 if dom_ms > 0 else None
     roofline = {
-        "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": (achieved / peak) if achieved else None, "traffic": None,
-        "note": f"algorithmic fp32 FLOPs of the {dom} class per step ({dom_flops_step / 1e12:.3f} T over "
-                f"{prof[dom]['launches']} launches) / its summed device time; peak = measured dense bf16 cuBLAS "
-                f"(sustained) from {peaks['source']}; the tf32 MMA kind peaks at half of it and 3xTF32 issues 3 MMA "
-                "flops per algorithmic flop (DESIGN.md)",
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": (achieved / peak) if achieved else None, "traffic": NCU_TRAFFIC_BYTES.get(dom),
+        "avg_launch_us": avg_s * 1e6, "alg_bytes_per_launch": alg_bytes,
+        "note": f"{dom}: {sets[dom]} fp32 jet plane sets of [C={C}][{int(launch_pts)} points][{width}] per launch / average "
+                f"launch time measured with CUDA events on the launch stream (untimed profile pass); peak = measured copy "
+                f"bandwidth from {peaks['source']}.  Second roof of the same kernel: {tf_alg:.1f} TFLOP/s algorithmic fp32 "
+                f"(x3 tf32 MMA flops issued = {3 * tf_alg:.0f} TFLOP/s) against the measured dense bf16 "
+                f"{peaks['bf16_tflops_sustained']:.0f} TFLOP/s (tf32 kind: half of it); `traffic` = dram bytes per launch "
+                "from the committed ncu capture (profiles/), not re-measured here",
+        "tensor_frac_tf32_issued": (3 * tf_alg) / (0.5 * peaks["bf16_tflops_sustained"]) if tf_alg else None,
         "whole_step_tflops": fpp * N / (ms_per_step * 1e-3) / 1e12,
         "class_ms": {k: round(v["ms"], 3) for k, v in prof.items()},
         "backend": "tcgen05" if plan.uses_tcgen05 else "simt-fp32",
@@ -310,9 +327,9 @@ def run_ours(args):
                    "flops_per_point": fpp, "l2": "256 MiB buffer written between timed iterations (L2 flush, untimed)",
                    "step": "fwd jets + residual + MSE + adjoint -> flat grad (+ NCCL all-reduce if N>1) + fused Adam"},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * N * 4, "d2h_bytes_per_step": d2h,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": world * 2 * N * 4, "d2h_bytes_per_step": world * d2h,
                 "api": "ppsci.utils.ExpressionSolver.train_forward + ppsci.optimizer.Adam.step, pinned host inputs"},
-        "gpu_launches": int(launches_per_step * args.steps),
+        "gpu_launches": int(world * launches_per_step * args.steps),
         "roofline": roofline,
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "loss": {k: float(v) for k, v in losses.items()},

@@ -194,9 +194,12 @@ int64_t ppsci_b200_plan_stash_offset(const ppsci_plan* plan, int64_t n_points, i
 /* Bench instrumentation: when on, every launch of the next calls is bracketed by CUDA events on
  * the caller's stream (no syncs).  get_profile returns, for the most recent call, the summed
  * device time [ms] and launch count per kernel class:
- *   0 forward-jet GEMM, 1 residual head, 2 dW GEMM, 3 dx GEMM (+activation adjoint), 4 misc. */
+ *   0 forward-jet GEMM, 1 residual head, 2 dW GEMM, 3 dx GEMM (+activation adjoint), 4 misc,
+ *   5 thin first/last-layer forward, 6 thin last-layer backward, 7 thin first-layer dW + bias gradients.
+ * Both arrays have PPSCI_PROFILE_CLASSES (8) entries. */
+#define PPSCI_PROFILE_CLASSES 8
 int ppsci_b200_plan_set_profile(ppsci_plan* plan, int32_t on);
-int ppsci_b200_plan_get_profile(ppsci_plan* plan, double* ms5, int64_t* count5);
+int ppsci_b200_plan_get_profile(ppsci_plan* plan, double* ms, int64_t* count);
 
 /* 1 if the tcgen05 (tensor-core) kernels serve this plan's hidden layers, else 0. */
 int32_t ppsci_b200_plan_uses_tcgen05(const ppsci_plan* plan);

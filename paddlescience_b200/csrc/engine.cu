@@ -67,7 +67,7 @@ struct ppsci_plan {
   std::vector<int> ev_cls;  // class of event pair i (events 2i, 2i+1)
 };
 
-enum { CLS_FWD = 0, CLS_HEAD = 1, CLS_DW = 2, CLS_DX = 3, CLS_MISC = 4, CLS_COUNT = 5 };
+enum { CLS_FWD = 0, CLS_HEAD = 1, CLS_DW = 2, CLS_DX = 3, CLS_MISC = 4, CLS_THIN_FWD = 5, CLS_THIN_DX = 6, CLS_THIN_DW = 7, CLS_COUNT = 8 };
 
 struct ProfScope {
   ppsci_plan* P;
@@ -531,7 +531,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           if (thin_vec && f.N % 4 == 0) {  // compile-time layout, 128-bit stores, seeds staged once per point
             void (*kv)(FirstArgs<float>) = nullptr;
             PPSCI_THIN_PICK_L(k_first_fwd_v, thin_lay, KMAX, kv);
-            ProfScope ps_(P, CLS_FWD, st);
+            ProfScope ps_(P, CLS_THIN_FWD, st);
             kv<<<dim3((unsigned)((nc + thin::PB - 1) / thin::PB)), dim3(256), 0, st>>>(f);
             P->launches++;
             continue;
@@ -539,7 +539,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         }
 #endif
         auto k1 = k_first_fwd<T, KMAX>;
-        ProfScope ps_(P, CLS_FWD, st);
+        ProfScope ps_(P, CLS_THIN_FWD, st);
         PPSCI_LAUNCH(k1, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, f);
         P->launches++;
         continue;
@@ -562,7 +562,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           if (thin_vec && f.K % 4 == 0 && f.m <= 4) {
             void (*kv)(LastArgs<float>) = nullptr;
             PPSCI_THIN_PICK_LM(k_last_fwd_v, thin_lay, f.m, kv);
-            ProfScope ps_(P, CLS_FWD, st);
+            ProfScope ps_(P, CLS_THIN_FWD, st);
             kv<<<dim3((unsigned)((nc + 7) / 8)), dim3(256), 0, st>>>(f);
             P->launches++;
             continue;
@@ -570,7 +570,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         }
 #endif
         auto k2 = k_last_fwd<T, KMAX>;
-        ProfScope ps_(P, CLS_FWD, st);
+        ProfScope ps_(P, CLS_THIN_FWD, st);
         PPSCI_LAUNCH(k2, dim3((unsigned)((nc + 7) / 8)), dim3(256), 0, st, f);
         P->launches++;
         continue;
@@ -719,7 +719,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
             f.pts_per_block = 128;
             void (*kv)(LastArgs<float>) = nullptr;
             PPSCI_THIN_PICK_LM(k_last_bwd_v, thin_lay, f.m, kv);
-            ProfScope ps_(P, CLS_DX, st);
+            ProfScope ps_(P, CLS_THIN_DX, st);
             kv<<<dim3((unsigned)((f.K + 255) / 256), (unsigned)((nc + 127) / 128)), dim3(256), 0, st>>>(f);
             P->launches++;
             last_done = true;
@@ -728,7 +728,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
 #endif
         if (!last_done) {
           auto k3 = k_last_bwd<T, KMAX>;
-          ProfScope ps_(P, CLS_DX, st);
+          ProfScope ps_(P, CLS_THIN_DX, st);
           PPSCI_LAUNCH(k3, dim3((unsigned)((f.K + 255) / 256), (unsigned)((nc + 63) / 64)), dim3(256), 0, st, f);
           P->launches++;
         }
@@ -757,7 +757,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
             f.pts_per_block = 256;
             void (*kv)(FirstArgs<float>) = nullptr;
             PPSCI_THIN_PICK_L(k_first_dw_v, thin_lay, KMAX, kv);
-            ProfScope ps_(P, CLS_DW, st);
+            ProfScope ps_(P, CLS_THIN_DW, st);
             kv<<<dim3((unsigned)((f.N + 255) / 256), (unsigned)((nc + 255) / 256)), dim3(256), 0, st>>>(f);
             P->launches++;
             break;
@@ -765,7 +765,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         }
 #endif
         auto k4 = k_first_dw<T, KMAX>;
-        ProfScope ps_(P, CLS_DW, st);
+        ProfScope ps_(P, CLS_THIN_DW, st);
         PPSCI_LAUNCH(k4, dim3((unsigned)((f.N + 255) / 256), (unsigned)((nc + 31) / 32)), dim3(256), 0, st, f);
         P->launches++;
         break;
@@ -794,6 +794,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           t.n0_stride = NC;
           t.ldw = s.widths[l];
           const long long total_chunks = (nc + PTt - 1) / PTt;
+          bool db_fused = false;
           if ((P->tc_mask & 32) && t.Kdim % 256 == 0 && s.widths[l] % 256 == 0 && P->num_sms >= 2) {
             // CTA pairs (cta_group::2): one pair per 256 x 256 block of dW and reduction split
             const unsigned kt2 = (unsigned)(t.Kdim / 256), nb2 = (unsigned)(s.widths[l] / 256);
@@ -804,6 +805,8 @@ static int run(ppsci_plan* P, const CallArgs& a) {
             const unsigned splits2 = (unsigned)((total_chunks + cps2 - 1) / cps2);
             t.chunks_per_split = (int)cps2;
             t.dbg = debug_timeline_ptr(0);
+            t.db = reinterpret_cast<float*>(grads) + P->b_off[l];  // bias gradient fused into the Zbar producer
+            db_fused = true;
             const int smem2 = tc::tc2_smem_bytes(256);
             ProfScope ps_(P, CLS_DW, st);
             PPSCI_TC2_LAUNCH_L(k_tc2_dw, tc_pick_layout(P->J, PPSCI_ACT_TANH), dim3(2 * kt2, splits2, nb2), smem2, st, t,
@@ -826,8 +829,8 @@ static int run(ppsci_plan* P, const CallArgs& a) {
             P->launches++;
           }
           }
-          {
-            ProfScope ps_(P, CLS_DW, st);
+          if (!db_fused) {
+            ProfScope ps_(P, CLS_THIN_DW, st);
             const int ppb = 512;
             tc::k_bias_grad<<<dim3((unsigned)((s.widths[l] + 127) / 128), (unsigned)((nc + ppb - 1) / ppb)), dim3(128), 0, st>>>(
                 reinterpret_cast<const float*>(zbar_cur), zbar_ld, (long long)nc, s.widths[l],

@@ -924,6 +924,7 @@ struct TcDwArgs {
   int PT;              // points per 32-row reduction chunk
   int chunks_per_split;
   long long* dbg;      // optional timeline buffer (bring-up instrumentation; null in production)
+  float* db;           // pair kernel only: bias gradient db_l[n] += sum_p Zbar_l[0][p][n] (null: not fused)
 };
 
 __host__ __device__ inline int tc_dw_smem_bytes(int NC) {

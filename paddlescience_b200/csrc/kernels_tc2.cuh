@@ -114,10 +114,14 @@ __device__ __forceinline__ void issue_chunk_mmas_2(uint32_t acc0, uint32_t acc1,
 // barrier among the producer / epilogue warps only
 __device__ __forceinline__ void t2_prod_sync() { asm volatile("bar.sync 2, %0;" ::"n"(T2_PROD_THREADS) : "memory"); }
 
-// mbarrier parity waits are only meaningful for the barrier's current or immediately preceding phase (an older
-// target aliases: the wait falls through early or blocks on a future phase).  Every producer warp therefore waits
-// for the retirement of chunk it-3 at EVERY chunk, whether or not it produces that chunk, which keeps all of its
-// later waits (stage reuse, the epilogue's wait for the tile's last chunk) adjacent.
+// mbarrier parity waits are only meaningful while the target is the barrier's current or immediately preceding phase
+// (an older target aliases: the wait falls through early, or blocks on a FUTURE phase and deadlocks).  Rule used by
+// the producer warps: a warp only waits on mma_done for (a) the chunk three before a chunk it produces itself and
+// (b) in the epilogue, a chunk its own group produced.  In both cases the previous phase of that barrier is known to
+// be complete (the warp's previous own chunk waited past it) and the next phase cannot complete before the wait
+// (it needs this warp's own production).  Warps that do not own the chunk are released through the producers'
+// named barrier instead of polling a phase they may be more than one phase away from (a timing-dependent deadlock
+// observed with two producer groups when one group lagged a full chunk cycle).
 __device__ __forceinline__ void t2_wait_chunk_done(uint32_t bars, uint32_t c) {
   mbar_wait_warp(bars + 24 + 8 * (c % T2_NSTAGE), (c / T2_NSTAGE) & 1u);
 }
@@ -256,10 +260,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_fw
     constexpr int MAXI = (TP + PPR - 1) / PPR;
     const int group = NG > 1 ? warp / W1 : 0, wg = warp - group * W1;
     const bool active = group < NG;
-    float4 zreg[MAXI][CS];
     const int kq = lane & 7, psub = lane >> 3;
-    auto prefetch = [&](long long tile_r, int jr) {
-      const long long p0r = tile_r * TP;
+    // operand rows of running chunk itn (of this CTA) -> registers
+    auto prefetch = [&](float4 (&buf)[MAXI][CS], uint32_t itn) {
+      const uint32_t tn = itn / (uint32_t)nchunks;
+      const int jr = (int)(itn - tn * (uint32_t)nchunks);
+      const long long p0r = (2LL * (pair + (long long)tn * npairs) + rank) * TP;
       const int col = jr * KCH + 4 * kq;
 #pragma unroll
       for (int i = 0; i < MAXI; ++i) {
@@ -269,85 +275,80 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_fw
         const float* src = g.A.Z + p * g.A.ld + col;
 #pragma unroll
         for (int c = 0; c < CS; ++c)
-          zreg[i][c] = ok ? __ldg(reinterpret_cast<const float4*>(src + (long long)c * g.A.plane)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          buf[i][c] = ok ? __ldg(reinterpret_cast<const float4*>(src + (long long)c * g.A.plane)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    if (active && (uint32_t)group < total_it) {
-      long long t0 = 2LL * pair + rank;
-      int j0 = group;
-      while (j0 >= nchunks) { j0 -= nchunks; t0 += 2LL * npairs; }
-      prefetch(t0, j0);
-    }
     uint32_t it = 0;
+    // one own chunk: produce from the register buffer that holds it, hand off, then refill the buffer with the own
+    // chunk after next (2 NG chunks ahead).  Two statically named buffers alternate: a loaded HBM round trip was
+    // measured at ~3,500 cycles, longer than one own-chunk period.  The refill comes AFTER the hand-off because
+    // fence.proxy.async also waits for the thread's outstanding global loads.
+    auto own_step = [&](float4 (&buf)[MAXI][CS], long long p0, int j) {
+      DBG_STAMP(tid == 0, 0);
+      const uint32_t s = it % T2_NSTAGE;
+      unsigned char* stage_ptr = base_ptr + s * stage_bytes;
+      if (it >= T2_NSTAGE) t2_wait_chunk_done(bars, it - T2_NSTAGE);  // stage free
+      DBG_STAMP(tid == 0, 3);
+#pragma unroll
+      for (int i = 0; i < MAXI; ++i) {
+        const int pl = wg * 4 + psub + i * PPR;
+        if (pl >= TP) continue;
+        const long long p = p0 + pl;
+        const bool valid = p < g.Np;
+        float yout[CS][4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          auto comp = [&](const float4& v) { return t == 0 ? v.x : t == 1 ? v.y : t == 2 ? v.z : v.w; };
+          float sc[6];
+          float y0;
+          act_coef<float, L::KM>(act, comp(buf[i][0]), y0, sc);
+          yout[0][t] = valid ? y0 : 0.f;
+#pragma unroll
+          for (int d = 0; d < L::ND; ++d) {
+            const int K = L::order(g.J, d), cb = L::cbase(g.J, d);
+            float zz[4], yy[4];
+#pragma unroll
+            for (int o = 0; o < 4; ++o) zz[o] = (o < L::KM && o < K) ? comp(buf[i][(cb + o) < CS ? (cb + o) : 0]) : 0.f;
+            jet_fwd_dir<float, L::KM>(sc, zz, yy);
+#pragma unroll
+            for (int o = 0; o < L::KM; ++o)
+              if (o < K && cb + o < CS) yout[cb + o][t] = valid ? yy[o] : 0.f;
+          }
+        }
+        float* ast = (g.Astash && valid) ? g.Astash + p * g.lda + j * KCH + 4 * kq : nullptr;
+#pragma unroll
+        for (int c = 0; c < CS; ++c) {
+          store_split4_at(stage_ptr, sw128_q(c * TP + pl, kq), yout[c]);
+          if (ast)
+            *reinterpret_cast<float4*>(ast + (long long)c * g.aplane) = make_float4(yout[c][0], yout[c][1], yout[c][2], yout[c][3]);
+        }
+      }
+      DBG_STAMP(tid == 0, 4);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 48 + 8 * s);
+      DBG_STAMP(tid == 0, 5);
+      if (it + 2 * NG < total_it) prefetch(buf, it + 2 * NG);
+      DBG_STAMP(tid == 0, 1);
+    };
+    float4 zA[MAXI][CS], zB[MAXI][CS];
+    if (active) {
+      if ((uint32_t)group < total_it) prefetch(zA, (uint32_t)group);
+      if ((uint32_t)(group + NG) < total_it) prefetch(zB, (uint32_t)(group + NG));
+    }
     for (int tp = pair; tp < n_tile_pairs; tp += npairs) {
       const long long tile = 2LL * tp + rank;
       const long long p0 = tile * TP;
       for (int j = 0; j < nchunks; ++j, ++it) {
-        if (!(active && (NG == 1 || (int)(it % NG) == group))) {  // not this warp's chunk: only keep the phase view adjacent
-          if (it >= T2_NSTAGE) t2_wait_chunk_done(bars, it - T2_NSTAGE);
-          continue;
-        }
-        DBG_STAMP(tid == 0, 0);
-        const uint32_t s = it % T2_NSTAGE;
-        unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-        float4 zcur[MAXI][CS];
-#pragma unroll
-        for (int i = 0; i < MAXI; ++i)
-#pragma unroll
-          for (int c = 0; c < CS; ++c) zcur[i][c] = zreg[i][c];
-        if (it + NG < total_it) {
-          long long ntile = tile;
-          int nj = j + NG;
-          while (nj >= nchunks) { nj -= nchunks; ntile += 2LL * npairs; }
-          prefetch(ntile, nj);
-        }
-        DBG_STAMP(tid == 0, 1);
-        if (it >= T2_NSTAGE) t2_wait_chunk_done(bars, it - T2_NSTAGE);  // stage free
-        DBG_STAMP(tid == 0, 3);
-#pragma unroll
-        for (int i = 0; i < MAXI; ++i) {
-          const int pl = wg * 4 + psub + i * PPR;
-          if (pl >= TP) continue;
-          const long long p = p0 + pl;
-          const bool valid = p < g.Np;
-          float yout[CS][4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            auto comp = [&](const float4& v) { return t == 0 ? v.x : t == 1 ? v.y : t == 2 ? v.z : v.w; };
-            float sc[6];
-            float y0;
-            act_coef<float, L::KM>(act, comp(zcur[i][0]), y0, sc);
-            yout[0][t] = valid ? y0 : 0.f;
-#pragma unroll
-            for (int d = 0; d < L::ND; ++d) {
-              const int K = L::order(g.J, d), cb = L::cbase(g.J, d);
-              float zz[4], yy[4];
-#pragma unroll
-              for (int o = 0; o < 4; ++o) zz[o] = (o < L::KM && o < K) ? comp(zcur[i][(cb + o) < CS ? (cb + o) : 0]) : 0.f;
-              jet_fwd_dir<float, L::KM>(sc, zz, yy);
-#pragma unroll
-              for (int o = 0; o < L::KM; ++o)
-                if (o < K && cb + o < CS) yout[cb + o][t] = valid ? yy[o] : 0.f;
-            }
-          }
-          float* ast = (g.Astash && valid) ? g.Astash + p * g.lda + j * KCH + 4 * kq : nullptr;
-#pragma unroll
-          for (int c = 0; c < CS; ++c) {
-            store_split4_at(stage_ptr, sw128_q(c * TP + pl, kq), yout[c]);
-            if (ast)
-              *reinterpret_cast<float4*>(ast + (long long)c * g.aplane) = make_float4(yout[c][0], yout[c][1], yout[c][2], yout[c][3]);
-          }
-        }
-        DBG_STAMP(tid == 0, 4);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars + 48 + 8 * s);
-        DBG_STAMP(tid == 0, 5);
+        if (!(active && (NG == 1 || (int)(it % NG) == group))) continue;  // the other group's chunk
+        if ((it / NG) & 1u) own_step(zB, p0, j);
+        else own_step(zA, p0, j);
       }
       // ---- epilogue (producer warps only): TMEM -> exchange tiles in the A regions of stages 0 / 1 -> Z_l ----
       {
         const uint32_t lastc = it - 1;  // the tile's last chunk
-        t2_wait_chunk_done(bars, lastc);
+        if (active && (NG == 1 || (int)(lastc % NG) == group)) t2_wait_chunk_done(bars, lastc);  // its producers wait ...
+        t2_prod_sync();                                                                           // ... and release the rest
         tc_fence_after();
         if (dbg0 && tid == 0 && it - 1 < 48) g.dbg[(it - 1) * 16 + 13] = clock64();
         const int ncb = N / 32;
@@ -369,27 +370,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_fw
                 *reinterpret_cast<float4*>(Xb + sw128_q(row, t4)) = make_float4(v[4 * t4], v[4 * t4 + 1], v[4 * t4 + 2], v[4 * t4 + 3]);
             }
           }
+          if (dbg0 && tid == 0 && lastc < 48) g.dbg[lastc * 16 + (cb0 == 0 ? 2 : 12)] = clock64();  // X tiles written
           t2_prod_sync();
-          for (int r = warp * 4 + psub; r < rows_used; r += T2_NPW * 4) {
+          if (dbg0 && tid == 0 && lastc < 48 && cb0 == 0) g.dbg[lastc * 16 + 6] = clock64();  // ... by every warp
+          // write-out: one warp instruction = one output row x 4 blocks = 512 contiguous bytes (lane = block x k quad)
+          for (int r = warp; r < rows_used; r += T2_NPW) {
             const int c = r / TP, pl = r - c * TP;
             const long long p = p0 + pl;
-            if (p < g.Np) {
-              float* out_row = g.Out + (long long)c * g.oplane + p * g.ldo + cb0 * 32 + 4 * kq;
-#pragma unroll
-              for (int b4 = 0; b4 < 4; ++b4) {
-                if (cb0 + b4 < ncb) {
-                  const unsigned char* Xr = base_ptr + (b4 >> 1) * stage_bytes + (b4 & 1) * A_TILE_BYTES;
-                  float4 val = *reinterpret_cast<const float4*>(Xr + sw128_q(r, kq));
-                  if (c == 0 && g.bias) {
-                    const float* bp = g.bias + (cb0 + b4) * 32 + 4 * kq;
-                    val.x += __ldg(bp); val.y += __ldg(bp + 1); val.z += __ldg(bp + 2); val.w += __ldg(bp + 3);
-                  }
-                  *reinterpret_cast<float4*>(out_row + b4 * 32) = val;
-                }
+            const int b4 = lane >> 3;
+            if (p < g.Np && cb0 + b4 < ncb) {
+              const unsigned char* Xr = base_ptr + (b4 >> 1) * stage_bytes + (b4 & 1) * A_TILE_BYTES;
+              float4 val = *reinterpret_cast<const float4*>(Xr + sw128_q(r, kq));
+              if (c == 0 && g.bias) {
+                const float* bp = g.bias + (cb0 + b4) * 32 + 4 * kq;
+                val.x += __ldg(bp); val.y += __ldg(bp + 1); val.z += __ldg(bp + 2); val.w += __ldg(bp + 3);
               }
+              *reinterpret_cast<float4*>(g.Out + (long long)c * g.oplane + p * g.ldo + (cb0 + b4) * 32 + 4 * kq) = val;
             }
           }
+          if (dbg0 && tid == 0 && lastc < 48 && cb0 == 0) g.dbg[lastc * 16 + 9] = clock64();  // my rows written out
           t2_prod_sync();
+          if (dbg0 && tid == 0 && lastc < 48 && cb0 == 0) g.dbg[lastc * 16 + 11] = clock64();
         }
         if (dbg0 && tid == 0 && it - 1 < 48) g.dbg[(it - 1) * 16 + 14] = clock64();
         tc_fence_before();  // accumulator reads ordered before the a_ready arrivals that release the next tile's MMAs
@@ -523,69 +524,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_dx
     constexpr int MAXR = (128 + RPP - 1) / RPP;
     const int group = warp / WG, wg = warp - group * WG;
     const int kq = lane & 7, psub = lane >> 3;
-    float4 zreg[MAXR];
     auto valid_pts = [&](long long p0r) {
       const long long vp = g.Np - p0r;
       return vp >= TP ? TP : (vp > 0 ? (int)vp : 0);
     };
-    auto prefetch = [&](long long tile_r, int jr) {
-      const long long p0r = tile_r * TP;
+    auto prefetch = [&](float4 (&buf)[MAXR], uint32_t itn) {
+      const uint32_t tn = itn / (uint32_t)nchunks;
+      const int jr = (int)(itn - tn * (uint32_t)nchunks);
+      const long long p0r = (2LL * (pair + (long long)tn * npairs) + rank) * TP;
       const int col = jr * KCH + 4 * kq;
 #pragma unroll
       for (int i = 0; i < MAXR; ++i) {
         const int r = wg * 4 + psub + i * RPP;
         const int c = r / TP, pl = r - c * TP;
         const bool ok = r < rows_used && p0r + pl < g.Np;
-        zreg[i] = ok ? __ldg(reinterpret_cast<const float4*>(g.A.Z + (long long)c * g.A.plane + (p0r + pl) * g.A.ld + col))
-                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        buf[i] = ok ? __ldg(reinterpret_cast<const float4*>(g.A.Z + (long long)c * g.A.plane + (p0r + pl) * g.A.ld + col))
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     T2RowPieces zpcs;
     zpcs.init(TP, rows_used, g.zplane, g.ldz);
-    if ((uint32_t)group < total_it) {
-      long long t0 = 2LL * pair + rank;
-      int j0 = group;
-      while (j0 >= nchunks) { j0 -= nchunks; t0 += 2LL * npairs; }
-      prefetch(t0, j0);
-    }
     uint32_t it = 0;
+    auto own_step = [&](float4 (&buf)[MAXR]) {  // see k_tc2_fwd: two register buffers, refilled after the hand-off
+      DBG_STAMP(tid == 0, 0);
+      const uint32_t s = it % T2_NSTAGE;
+      unsigned char* stage_ptr = base_ptr + s * stage_bytes;
+      if (it >= T2_NSTAGE) t2_wait_chunk_done(bars, it - T2_NSTAGE);  // stage free
+      DBG_STAMP(tid == 0, 3);
+#pragma unroll
+      for (int i = 0; i < MAXR; ++i) {
+        const int r = wg * 4 + psub + i * RPP;
+        if (r < rows_used) {
+          const float v[4] = {buf[i].x, buf[i].y, buf[i].z, buf[i].w};
+          store_split4_at(stage_ptr, sw128_q(r, kq), v);
+        }
+      }
+      DBG_STAMP(tid == 0, 4);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + 48 + 8 * s);
+      DBG_STAMP(tid == 0, 5);
+      if (it + 2 * NG < total_it) prefetch(buf, it + 2 * NG);
+      DBG_STAMP(tid == 0, 1);
+    };
+    float4 zA[MAXR], zB[MAXR];
+    if ((uint32_t)group < total_it) prefetch(zA, (uint32_t)group);
+    if ((uint32_t)(group + NG) < total_it) prefetch(zB, (uint32_t)(group + NG));
     for (int tp = pair; tp < n_tile_pairs; tp += npairs) {
       const long long tile = 2LL * tp + rank;
       const long long p0 = tile * TP;
       const int vpts = valid_pts(p0);
       for (int j = 0; j < nchunks; ++j, ++it) {
-        if ((int)(it % NG) != group) {  // not this warp's chunk: only keep the phase view adjacent (see t2_wait_chunk_done)
-          if (it >= T2_NSTAGE) t2_wait_chunk_done(bars, it - T2_NSTAGE);
-          continue;
-        }
-        DBG_STAMP(tid == 0, 0);
-        const uint32_t s = it % T2_NSTAGE;
-        unsigned char* stage_ptr = base_ptr + s * stage_bytes;
-        float4 zcur[MAXR];
-#pragma unroll
-        for (int i = 0; i < MAXR; ++i) zcur[i] = zreg[i];
-        if (it + NG < total_it) {
-          long long ntile = tile;
-          int nj = j + NG;
-          while (nj >= nchunks) { nj -= nchunks; ntile += 2LL * npairs; }
-          prefetch(ntile, nj);
-        }
-        DBG_STAMP(tid == 0, 1);
-        if (it >= T2_NSTAGE) t2_wait_chunk_done(bars, it - T2_NSTAGE);  // stage free
-        DBG_STAMP(tid == 0, 3);
-#pragma unroll
-        for (int i = 0; i < MAXR; ++i) {
-          const int r = wg * 4 + psub + i * RPP;
-          if (r < rows_used) {
-            const float v[4] = {zcur[i].x, zcur[i].y, zcur[i].z, zcur[i].w};
-            store_split4_at(stage_ptr, sw128_q(r, kq), v);
-          }
-        }
-        DBG_STAMP(tid == 0, 4);
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bars + 48 + 8 * s);
-        DBG_STAMP(tid == 0, 5);
+        if ((int)(it % NG) != group) continue;  // the other group's chunk
+        if ((it / NG) & 1u) own_step(zB);
+        else own_step(zA);
       }
       // ---- epilogue: two 32-column blocks of Abar per step, all 14 warps on the adjoint ----
       // Scratch = the A regions of the three stages.  The stage of the tile's LAST chunk holds the two exchange
@@ -610,10 +602,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_dx
           }
           cp_async_commit();
         };
-        if (lastc >= 1) t2_wait_chunk_done(bars, lastc - 1);  // the two other stages are no longer read
+        if (lastc >= 1) {  // the two other stages are no longer read once the second-to-last chunk has retired
+          if ((int)((lastc - 1) % NG) == group) t2_wait_chunk_done(bars, lastc - 1);  // (waited by its producers,
+          t2_prod_sync();                                                              //  see t2_wait_chunk_done)
+        }
         issue_pair(0);
         issue_pair(1);
-        t2_wait_chunk_done(bars, lastc);
+        if ((int)(lastc % NG) == group) t2_wait_chunk_done(bars, lastc);
+        t2_prod_sync();
         tc_fence_after();
         if (dbg0 && tid == 0 && lastc < 48) g.dbg[lastc * 16 + 13] = clock64();
         const int grp = warp / 7, wg7 = warp - grp * 7;  // adjoint group (block parity) and warp within it
@@ -796,6 +792,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DW_THREADS, 1) k_tc2
       for (int i = 0; i < 4; ++i) d_off[i] = sw128_q(row0 + i, q) + (t_isA ? 0u : (uint32_t)(2 * A_TILE_BYTES));
     }
     const int d_lo = t_isA ? A_TILE_BYTES : NH * KCH * 4;
+    // fused bias gradient: B' tasks of the first k block whose 4 reduction rows include value-channel rows (rr < PT)
+    const int db_q0 = 4 * ((warp & 1) * 4 + ((lane >> 1) & 3));
+    const bool db_on = g.db != nullptr && !t_isA && (blockIdx.x >> 1) == 0 && db_q0 < PT;
+    const int db_col = n0h + ((warp - 8) >> 1) * 32 + ((((lane >> 3) << 1) | (lane & 1)) * 4);
+    float4 db_acc = make_float4(0.f, 0.f, 0.f, 0.f);
     auto prefetch = [&](float4 (&buf)[4], long long ch) {
       const uint32_t vp = (uint32_t)valid_pts(ch);
       const float* bp = t_isA ? g.Aact + ch * PT * (long long)g.lda : g.Zbar + ch * PT * (long long)g.ldzb;
@@ -820,6 +821,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DW_THREADS, 1) k_tc2
         *reinterpret_cast<float4*>(stage_ptr + d_off[i]) = h;
         *reinterpret_cast<float4*>(stage_ptr + d_off[i] + d_lo) = l;
       }
+      if (db_on) {  // value-channel rows of the Zbar block are exactly the bias-gradient terms of my 4 columns
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (db_q0 + e < PT) {
+            db_acc.x += buf[e].x; db_acc.y += buf[e].y; db_acc.z += buf[e].z; db_acc.w += buf[e].w;
+          }
+      }
       DBG_STAMP(tid == 0, 4);
       fence_proxy_async();
       __syncwarp();
@@ -837,6 +845,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DW_THREADS, 1) k_tc2
     for (long long ch = ch_begin; ch < ch_end; ch += 2, it += 2) {
       step(bufA, ch, it);
       if (ch + 1 < ch_end) step(bufB, ch + 1, it + 1);
+    }
+    if (db_on && n_it > 0) {
+      atomicAdd(g.db + db_col, db_acc.x);
+      atomicAdd(g.db + db_col + 1, db_acc.y);
+      atomicAdd(g.db + db_col + 2, db_acc.z);
+      atomicAdd(g.db + db_col + 3, db_acc.w);
     }
     // ---- flush: this CTA's 128 x 256 block of partial dW ----
     if (n_it > 0) {

@@ -131,14 +131,14 @@ class ResidualPlan:
     def last_launches(self) -> int:
         return int(self.lib.lib.ppsci_b200_plan_last_launches(self.handle))
 
-    PROFILE_CLASSES = ("fwd_gemm", "head", "dw_gemm", "dx_gemm", "misc")
+    PROFILE_CLASSES = ("fwd_gemm", "head", "dw_gemm", "dx_gemm", "misc", "thin_fwd", "thin_dx", "thin_dw")
 
     def set_profile(self, on: bool):
         self.lib.check(self.lib.lib.ppsci_b200_plan_set_profile(self.handle, 1 if on else 0), "set_profile")
 
     def get_profile(self):
-        ms = (C.c_double * 5)()
-        cnt = (C.c_int64 * 5)()
+        ms = (C.c_double * 8)()
+        cnt = (C.c_int64 * 8)()
         self.lib.check(self.lib.lib.ppsci_b200_plan_get_profile(self.handle, ms, cnt), "get_profile")
         return {k: {"ms": ms[i], "launches": int(cnt[i])} for i, k in enumerate(self.PROFILE_CLASSES)}
 

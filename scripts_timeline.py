@@ -21,7 +21,7 @@ for _ in range(2):
 torch.cuda.synchronize()
 t = dbg.cpu().view(48, 16)
 t0 = int(t[2, 0])
-names = {0: "top", 1: "prefetch_issued", 3: "stage_free", 4: "items_done", 5: "arrived", 6: "refill_issued", 7: "b_issued", 8: "mma_top", 9: "a_ready", 12: "b_ready", 15: "peer_ready", 10: "committed", 11: "chunk_done", 13: "epi_start", 14: "epi_end"}
+names = {0: "top", 1: "prefetch_issued", 3: "stage_free", 4: "items_done", 5: "arrived", 6: "refill_issued", 7: "b_issued", 8: "mma_top", 9: "a_ready", 12: "b_ready", 15: "peer_ready", 10: "committed", 11: "chunk_done", 13: "epi_start", 2: "epi_fill0", 6: "epi_sync0a", 9: "epi_out0", 11: "epi_sync0b", 12: "epi_fill1", 14: "epi_end"}
 print("iteration timeline of CTA 0 (cycles relative to iteration 2 top); producer thread 0 | MMA lane")
 for it in range(2, 22):
     row = {names[k]: int(t[it, k]) - t0 for k in names if int(t[it, k]) != 0}
