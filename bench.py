@@ -28,7 +28,7 @@ METRIC = "collocation-points/sec PDE residual loss+grad (LDC N-S)"
 UNIT = "points/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the hidden-layer kernels at the bench shape (one 65,536-point
 # chunk, C = 5, width 256), from the committed `ncu --set full` capture (profiles/r01_ncu_pair_kernels.md)
-NCU_TRAFFIC_BYTES = {"dx_gemm": 975.5e6, "dw_gemm": 676.9e6, "fwd_gemm": None}
+NCU_TRAFFIC_BYTES = {"fwd_gemm": 950.0e6, "dx_gemm": 972.2e6, "dw_gemm": 675.0e6}
 HIDDEN = [256] * 6
 N_PER_GPU = 1 << 20
 NU, RHO = 0.01, 1.0
