@@ -4,13 +4,13 @@ The package mirrors the part of ``ppsci`` that lies on the hot path named in BAS
 (SURVEY.md §8): ``arch.MLP``, ``equation.PDE`` (+ Laplace/Poisson/NavierStokes/Biharmonic/
 AllenCahn/Helmholtz), ``autodiff.{jacobian,hessian}``, ``constraint.{Interior,Boundary,
 Supervised}Constraint``, ``geometry.{Interval,Rectangle,Cuboid,Hypercube}``, the three array
-datasets, ``loss.MSELoss`` / ``loss.mtl.Sum``, ``optimizer.Adam`` + LR schedules and
-``solver.Solver``.  All arithmetic of that path runs in hand-written sm_100a CUDA behind the
+datasets, ``loss.MSELoss`` / ``loss.mtl.Sum``, ``optimizer.Adam`` + LR schedules,
+``solver.Solver`` and the evaluation side of it (``validate.{Geometry,Supervised}Validator``, ``metric.*``).  All arithmetic of that path runs in hand-written sm_100a CUDA behind the
 C-ABI in ``include/ppsci_b200.h``; there is no CPU fallback."""
-from . import arch, autodiff, constraint, data, equation, geometry, loss, optimizer, solver, utils  # noqa: F401
+from . import arch, autodiff, constraint, data, equation, geometry, loss, metric, optimizer, solver, utils, validate  # noqa: F401
 from .utils import logger  # noqa: F401
 from .utils.symbolic import lambdify  # noqa: F401
 
 __version__ = "0.1.0"
-__all__ = ["arch", "autodiff", "constraint", "data", "equation", "geometry", "loss", "optimizer", "solver", "utils",
+__all__ = ["arch", "autodiff", "constraint", "data", "equation", "geometry", "loss", "metric", "optimizer", "solver", "utils", "validate",
            "logger", "lambdify"]

@@ -128,6 +128,15 @@ class Solver:
             train_mod.train_epoch_func(self, epoch_id, self.log_freq)
             if self.lr_scheduler is not None and self.lr_scheduler.by_epoch:
                 self.lr_scheduler.step()
+            # evaluation during training (solver.py:577-607): keep the best model by the target metric
+            if self.eval_during_train and self.validator and epoch_id % self.eval_freq == 0 and epoch_id >= self.start_eval_epoch:
+                cur_metric, _ = self.eval(epoch_id)
+                if cur_metric < self.best_metric["metric"]:
+                    self.best_metric.update({"metric": cur_metric, "epoch": epoch_id})
+                    if self.output_dir:
+                        save_load.save_checkpoint(self.model, self.optimizer, dict(self.best_metric), self.output_dir,
+                                                  "best_model", self.equation)
+                logger.info(f"[Eval][Epoch {epoch_id}][best metric: {self.best_metric['metric']}]")
             if self.save_freq > 0 and epoch_id % self.save_freq == 0:
                 save_load.save_checkpoint(self.model, self.optimizer, {"metric": self.last_loss, "epoch": epoch_id},
                                           self.output_dir, f"epoch_{epoch_id}", self.equation)

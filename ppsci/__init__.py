@@ -6,7 +6,8 @@ import paddlescience_b200 as _impl
 from paddlescience_b200 import *  # noqa: F401,F403
 from paddlescience_b200 import __all__ as _all
 
-for _name in ("arch", "autodiff", "constraint", "data", "equation", "geometry", "loss", "optimizer", "solver", "utils"):
+for _name in ("arch", "autodiff", "constraint", "data", "equation", "geometry", "loss", "metric", "optimizer", "solver", "utils",
+              "validate"):
     _sys.modules[f"ppsci.{_name}"] = getattr(_impl, _name)
 _sys.modules["ppsci.loss.mtl"] = _impl.loss.mtl
 _sys.modules["ppsci.utils.logger"] = _impl.utils.logger
