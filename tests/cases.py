@@ -41,6 +41,11 @@ def _biharm_exprs():
     return O.biharmonic_expr(2, q, 1.5)
 
 
+def _value_exprs():
+    x, y = sp.symbols("x y")
+    return {"u": sp.Function("u")(x, y), "v": sp.Function("v")(x, y)}
+
+
 def _mixed_exprs():
     x, y = sp.symbols("x y")
     u = sp.Function("u")(x, y)
@@ -90,6 +95,12 @@ TC_CASES = {
     "ac_f32_tc_128": dict(in_keys=("t", "x"), out_keys=("u",), hidden=[128] * 4, act="tanh", exprs=_ac_exprs,
                           dtype=torch.float32, periods={"x": (2.0, False)},
                           oracle_exprs=lambda: O.allen_cahn_callable(0.01), ranges={"x": (-1, 1)}),
+    # C = 7 (three second-order directions): pair kernels with two producer groups of 5 warps + 4 idle producer warps
+    "ns3d_f32_tc_256": dict(in_keys=("x", "y", "z"), out_keys=("u", "v", "w", "p"), hidden=[256, 256, 256], act="tanh",
+                            exprs=lambda: O.navier_stokes_expr(0.05, 1.0, 3, False), dtype=torch.float32),
+    # C = 1 (no derivatives: a boundary / supervised constraint): 128 points per tile, three producer passes
+    "value_f32_tc_256": dict(in_keys=("x", "y"), out_keys=("u", "v"), hidden=[256, 256, 256], act="tanh",
+                             exprs=lambda: _value_exprs(), dtype=torch.float32, labels_rand=True),
     "biharmonic_f32_tc_128": dict(in_keys=("x", "y"), out_keys=("u",), hidden=[128, 128, 128], act="tanh",
                                   exprs=_biharm_exprs, dtype=torch.float32, ranges={"x": (0, 2), "y": (0, 3)}),
 }
