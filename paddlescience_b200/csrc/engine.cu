@@ -236,6 +236,17 @@ extern "C" int ppsci_b200_plan_create(const ppsci_plan_spec* s, ppsci_plan** out
   }
   P->n_params = off;
   P->chunk = s->chunk_points > 0 ? s->chunk_points : (s->dtype == PPSCI_F64 ? 32768 : 65536);
+  if (s->chunk_points <= 0) {
+    if (const char* m = getenv("PPSCI_B200_CHUNK_POINTS")) {  // tuning knob: points per workspace chunk
+      const long long v = atoll(m);
+      if (v >= 1024 && v <= (1 << 22)) P->chunk = (int)v;
+    }
+  }
+  {  // the tensor-core dW kernels address a chunk's plane set with 32-bit element offsets
+    long long ld_max = 4;
+    for (int l = 0; l <= s->n_layers; ++l) ld_max = std::max<long long>(ld_max, (s->widths[l] + 3) / 4 * 4);
+    while ((long long)C * P->chunk * ld_max >= (1LL << 32) && P->chunk > 1024) P->chunk /= 2;
+  }
 
   int dev = 0;
   cudaDeviceProp prop;
