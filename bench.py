@@ -26,8 +26,9 @@ if ROOT not in sys.path:
 
 METRIC = "collocation-points/sec PDE residual loss+grad (LDC N-S)"
 UNIT = "points/s"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the hidden-layer kernels at the bench shape (one 65,536-point
-# chunk, C = 5, width 256), from the committed `ncu --set full` capture (profiles/r01_ncu_pair_kernels.md)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the hidden-layer kernels over one 65,536-point chunk (C = 5,
+# width 256) from the committed `ncu --set full` capture (profiles/r01_final_summary.md); scaled linearly to the
+# points per launch of the run (the traffic is one pass over the plane sets)
 NCU_TRAFFIC_BYTES = {"fwd_gemm": 950.0e6, "dx_gemm": 972.2e6, "dw_gemm": 675.0e6}
 HIDDEN = [256] * 6
 N_PER_GPU = 1 << 20
@@ -301,7 +302,8 @@ def run_ours(args):
     tf_alg = alg_flops / avg_s / 1e12 if dom_ms > 0 else None
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": (achieved / peak) if achieved else None, "traffic": NCU_TRAFFIC_BYTES.get(dom),
+        "frac": (achieved / peak) if achieved else None,
+        "traffic": (NCU_TRAFFIC_BYTES[dom] * launch_pts / chunk_pts) if NCU_TRAFFIC_BYTES.get(dom) else None,
         "avg_launch_us": avg_s * 1e6, "alg_bytes_per_launch": alg_bytes,
         "note": f"{dom}: {sets[dom]} fp32 jet plane sets of [C={C}][{int(launch_pts)} points][{width}] per launch / average "
                 f"launch time measured with CUDA events on the launch stream (untimed profile pass); peak = measured copy "

@@ -90,3 +90,68 @@ class Adam:
                 raise NotImplementedError("one optimizer over several models is not supported yet")
             model_list = model_list[0]
         return FlatAdam(model_list, self.learning_rate, self.beta1, self.beta2, self.epsilon, self.weight_decay)
+
+
+class FlatLBFGS:
+    """L-BFGS over ``model.flat`` (reference: ppsci/optimizer/optimizer.py:250-323 wraps ``paddle.optimizer.LBFGS``,
+    driven by the closure loop of ppsci/solver/train.py:216-319).  The two-loop recursion and the strong-Wolfe line
+    search are vector operations on the single flat parameter buffer (``torch.optim.LBFGS`` semantics); every
+    closure evaluation is one fused native loss + weight-gradient call per constraint."""
+
+    is_lbfgs = True
+
+    def __init__(self, model, learning_rate=1.0, max_iter=1, max_eval=None, tolerance_grad=1e-7, tolerance_change=1e-9,
+                 history_size=100, line_search_fn="strong_wolfe"):
+        self.model = model
+        self._opt = torch.optim.LBFGS([model.flat], lr=float(learning_rate() if callable(learning_rate) else learning_rate),
+                                      max_iter=max_iter, max_eval=max_eval, tolerance_grad=tolerance_grad,
+                                      tolerance_change=tolerance_change, history_size=history_size,
+                                      line_search_fn=line_search_fn)
+        self._lr = learning_rate
+        self.grad_scale = 1.0
+
+    def get_lr(self) -> float:
+        return float(self._opt.param_groups[0]["lr"])
+
+    def set_lr(self, lr: float):
+        self._opt.param_groups[0]["lr"] = float(lr)
+
+    def step(self, closure):
+        if self.model.flat.device.type != "cuda":
+            raise RuntimeError("FlatLBFGS.step needs parameters on a CUDA (B200) device: no CPU fallback")
+        if callable(self._lr):
+            self.set_lr(self._lr())
+        return self._opt.step(closure)
+
+    def clear_grad(self):
+        if self.model.flat.grad is not None:
+            self.model.flat.grad.zero_()
+
+    zero_grad = clear_grad
+
+    def state_dict(self):
+        return self._opt.state_dict()
+
+    def set_state_dict(self, sd):
+        self._opt.load_state_dict(sd)
+
+
+class LBFGS:
+    """``ppsci.optimizer.LBFGS`` factory (optimizer.py:250-323), same arguments and defaults."""
+
+    def __init__(self, learning_rate: float = 1.0, max_iter: int = 1, max_eval: Optional[int] = None,
+                 tolerance_grad: float = 1e-07, tolerance_change: float = 1e-09, history_size: int = 100,
+                 line_search_fn: Optional[str] = "strong_wolfe"):
+        if line_search_fn not in (None, "strong_wolfe"):
+            raise ValueError(f"line_search_fn should be 'strong_wolfe' or None, but got {line_search_fn}")
+        self.lr, self.max_iter, self.max_eval = learning_rate, max_iter, max_eval
+        self.tolerance_grad, self.tolerance_change = tolerance_grad, tolerance_change
+        self.history_size, self.line_search_fn = history_size, line_search_fn
+
+    def __call__(self, model_list):
+        if isinstance(model_list, (tuple, list)):
+            if len(model_list) != 1:
+                raise NotImplementedError("one optimizer over several models is not supported yet")
+            model_list = model_list[0]
+        return FlatLBFGS(model_list, self.lr, self.max_iter, self.max_eval, self.tolerance_grad, self.tolerance_change,
+                         self.history_size, self.line_search_fn)

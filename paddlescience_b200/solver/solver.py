@@ -125,7 +125,10 @@ class Solver:
         start_epoch = self.best_metric["epoch"] + 1
         self.global_step = (start_epoch - 1) * self.iters_per_epoch
         for epoch_id in range(start_epoch, self.epochs + 1):
-            train_mod.train_epoch_func(self, epoch_id, self.log_freq)
+            if getattr(self.optimizer, "is_lbfgs", False):
+                train_mod.train_LBFGS_epoch_func(self, epoch_id, self.log_freq)
+            else:
+                train_mod.train_epoch_func(self, epoch_id, self.log_freq)
             if self.lr_scheduler is not None and self.lr_scheduler.by_epoch:
                 self.lr_scheduler.step()
             # evaluation during training (solver.py:577-607): keep the best model by the target metric

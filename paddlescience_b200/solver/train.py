@@ -101,3 +101,60 @@ def train_epoch_func(solver, epoch_id: int, log_freq: int):
         batch_tic = time.perf_counter()
         if nvtx:
             torch.cuda.nvtx.range_pop()
+
+
+def train_LBFGS_epoch_func(solver, epoch_id: int, log_freq: int):
+    """One epoch with L-BFGS (reference: ppsci/solver/train.py:216-319): per iteration one batch per constraint and
+    ``optimizer.step(closure)``; the closure zeroes the flat gradient, runs the fused loss + weight-gradient call of
+    every constraint, all-reduces under data parallel and returns the total loss."""
+    batch_tic = time.perf_counter()
+    model = solver.model
+    device, dtype = model.flat.device, model.flat.dtype
+    for iter_id in range(1, solver.iters_per_epoch + 1):
+        total_batch_size = 0
+        reader_cost = 0.0
+        reader_tic = time.perf_counter()
+        input_dicts, label_dicts, weight_dicts = [], [], []
+        for _constraint in solver.constraint.values():
+            try:
+                input_dict, label_dict, weight_dict = next(_constraint.data_iter)
+            except StopIteration:
+                _constraint.data_iter = iter(_constraint.data_loader)
+                input_dict, label_dict, weight_dict = next(_constraint.data_iter)
+            input_dicts.append(_to_device(input_dict, device, dtype))
+            label_dicts.append(_to_device(label_dict, device, dtype))
+            weight_dicts.append(_to_device(weight_dict, device, dtype) if weight_dict else None)
+            total_batch_size += _compute_batch_size(input_dict)
+            reader_cost += time.perf_counter() - reader_tic
+            reader_tic = time.perf_counter()
+        last = {}
+
+        def closure():
+            solver.optimizer.clear_grad()
+            losses_all, losses_constraint = solver.forward_helper.train_forward(
+                tuple(c.output_expr for c in solver.constraint.values()), input_dicts, model, solver.constraint,
+                label_dicts, weight_dicts)
+            total_loss = solver.loss_aggregator(losses_all, solver.global_step).loss
+            if solver.world_size > 1:
+                import torch.distributed as dist
+
+                dist.all_reduce(model.flat.grad)
+                model.flat.grad.mul_(1.0 / solver.world_size)
+            last["loss"], last["constraint"] = total_loss, losses_constraint
+            return total_loss
+
+        solver.optimizer.step(closure)
+        if solver.lr_scheduler is not None and not solver.lr_scheduler.by_epoch:
+            solver.lr_scheduler.step()
+        if solver.benchmark_flag and device.type == "cuda":
+            torch.cuda.synchronize()
+        solver.global_step += 1
+        loss_dict = {"loss": float(last["loss"])}
+        loss_dict.update({k: float(v) for k, v in last["constraint"].items()})
+        solver.last_loss = loss_dict["loss"]
+        printer.update_train_loss(solver, loss_dict, total_batch_size)
+        solver.train_time_info["reader_cost"].update(reader_cost)
+        solver.train_time_info["batch_cost"].update(time.perf_counter() - batch_tic)
+        if solver.global_step % log_freq == 0 or solver.global_step == 1 or solver.global_step == solver.max_steps:
+            printer.log_train_info(solver, total_batch_size, epoch_id, iter_id)
+        batch_tic = time.perf_counter()

@@ -95,6 +95,10 @@ TC_CASES = {
     "ac_f32_tc_128": dict(in_keys=("t", "x"), out_keys=("u",), hidden=[128] * 4, act="tanh", exprs=_ac_exprs,
                           dtype=torch.float32, periods={"x": (2.0, False)},
                           oracle_exprs=lambda: O.allen_cahn_callable(0.01), ranges={"x": (-1, 1)}),
+    # several workspace chunks per call on the tensor-core path (chunk = ceil(n / 3))
+    "ns_f32_tc_256_chunks": dict(in_keys=("x", "y"), out_keys=("u", "v", "p"), hidden=[256, 256, 256], act="tanh",
+                                 exprs=lambda: O.navier_stokes_expr(0.01, 1.0, 2, False), dtype=torch.float32,
+                                 chunk_div=3, weights=True),
     # C = 7 (three second-order directions): pair kernels with two producer groups of 5 warps + 4 idle producer warps
     "ns3d_f32_tc_256": dict(in_keys=("x", "y", "z"), out_keys=("u", "v", "w", "p"), hidden=[256, 256, 256], act="tanh",
                             exprs=lambda: O.navier_stokes_expr(0.05, 1.0, 3, False), dtype=torch.float32),

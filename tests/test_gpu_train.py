@@ -1,0 +1,81 @@
+"""End-to-end training steps through the public API on a B200 (Solver.train: fused loss + weight-gradient call per
+constraint -> optimizer) against the same optimizer driven by the oracle's loss / gradient in fp64.
+
+Reference loops: ppsci/solver/train.py:58-213 (Adam), :216-319 (L-BFGS closure)."""
+import numpy as np
+import pytest
+import sympy as sp
+import torch
+
+import ppsci
+from oracle import ppsci_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(opt_factory, iters):
+    ppsci.utils.misc.set_random_seed(11)
+    model = ppsci.arch.MLP(("x", "y"), ("u",), 3, 20, "tanh")
+    eq = ppsci.equation.Laplace(2)
+    rect = ppsci.geometry.Rectangle((0, 0), (1, 1))
+    cfg = {"dataset": "IterableNamedArrayDataset", "iters_per_epoch": 1}
+    pde = ppsci.constraint.InteriorConstraint(eq.equations, {"laplace": 0}, rect, {**cfg, "batch_size": 512},
+                                              ppsci.loss.MSELoss("mean"), name="EQ")
+    bc = ppsci.constraint.BoundaryConstraint({"u": lambda out: out["u"]}, {"u": lambda d: d["x"] ** 2 - d["y"] ** 2}, rect,
+                                             {**cfg, "batch_size": 128}, ppsci.loss.MSELoss("mean"), name="BC")
+    params0 = model.flat.detach().cpu().double().clone()
+    solver = ppsci.solver.Solver(model, {"EQ": pde, "BC": bc}, None, opt_factory(model), epochs=1, iters_per_epoch=iters,
+                                 equation={"lap": eq})
+    return model, solver, pde, bc, params0
+
+
+def _oracle_loss_grad(om, p, pde, bc):
+    x, y = sp.symbols("x y")
+    tot, grad = 0.0, torch.zeros_like(p)
+    for cst, exprs in ((pde, O.laplace_expr(2)), (bc, {"u": sp.Function("u")(x, y)})):
+        ds = cst.data_loader.loader
+        inp = {k: v.detach().cpu().double() for k, v in ds.input.items() if k in ("x", "y")}
+        lab = {k: v.detach().cpu().double() for k, v in ds.label.items()}
+        losses, _, g = O.train_forward_backward(om, p, exprs, inp, lab, None, "mean", None)
+        tot = tot + sum(float(v) for v in losses.values())
+        grad = grad + g
+    return tot, grad
+
+
+def test_solver_train_adam_matches_oracle_adam():
+    model, solver, pde, bc, params0 = _problem(lambda m: ppsci.optimizer.Adam(1e-3)(m), 5)
+    solver.train()
+    om = O.OracleMLP(("x", "y"), ("u",), [20, 20, 20], "tanh")
+    p = params0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    for _ in range(5):
+        _, g = _oracle_loss_grad(om, p.detach(), pde, bc)
+        p.grad = g
+        opt.step()
+    got = model.flat.detach().cpu().double()
+    step = (p.detach() - params0).norm()
+    assert float((got - p.detach()).norm() / step) <= 2e-3  # fp32 engine vs fp64 oracle over 5 Adam steps
+    assert float(step) > 0
+
+
+def test_solver_train_lbfgs_decreases_loss_like_oracle_lbfgs():
+    kw = dict(learning_rate=1.0, max_iter=4, history_size=10, line_search_fn="strong_wolfe")
+    model, solver, pde, bc, params0 = _problem(lambda m: ppsci.optimizer.LBFGS(**kw)(m), 3)
+    om = O.OracleMLP(("x", "y"), ("u",), [20, 20, 20], "tanh")
+    loss0, _ = _oracle_loss_grad(om, params0, pde, bc)
+    solver.train()
+    p = params0.clone().requires_grad_(True)
+    opt = torch.optim.LBFGS([p], lr=1.0, max_iter=4, history_size=10, line_search_fn="strong_wolfe")
+
+    def closure():
+        loss, g = _oracle_loss_grad(om, p.detach(), pde, bc)
+        p.grad = g
+        return torch.tensor(loss, dtype=torch.float64)
+
+    for _ in range(3):
+        opt.step(closure)
+    loss_engine, _ = _oracle_loss_grad(om, model.flat.detach().cpu().double(), pde, bc)
+    loss_oracle, _ = _oracle_loss_grad(om, p.detach(), pde, bc)
+    assert loss_engine < 0.5 * loss0, (loss0, loss_engine)
+    # same algorithm, fp32 vs fp64 loss / gradient: the two trajectories reach the same loss level
+    assert abs(np.log10(loss_engine) - np.log10(loss_oracle)) < 0.5, (loss_engine, loss_oracle)
