@@ -1,6 +1,6 @@
 # first-contact GPU script: timing of the SIMT path on the headline config
 import sys, time, json, os
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from tests.cases import make_net
 from paddlescience_b200.engine.compiler import compile_residuals

@@ -1,6 +1,6 @@
 # short single-step workload for ncu captures (one 65536-point chunk of the headline config)
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from tests.cases import make_net
 from paddlescience_b200.engine.compiler import compile_residuals

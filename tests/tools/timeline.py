@@ -1,7 +1,7 @@
 # bring-up instrumentation: per-iteration clock64 timeline of CTA 0 in k_tc_dw / k_tc_fwd / k_tc_dx
-# usage: PPSCI_B200_DEBUG_KERNEL=<0 dW | 1 fwd | 2 dx> python scripts_timeline.py
+# usage: PPSCI_B200_DEBUG_KERNEL=<0 dW | 1 fwd | 2 dx> python tests/tools/timeline.py
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 dev = torch.device("cuda:0")
 dbg = torch.zeros(48 * 16, dtype=torch.int64, device=dev)
