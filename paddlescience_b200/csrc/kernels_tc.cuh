@@ -25,7 +25,7 @@ namespace ppsci {
 namespace tc {
 
 constexpr int KCH = 32;  // K elements per chunk = one 128-byte swizzle row of tf32
-constexpr int THREADS = 512;  // 16 warps: 15 operand-producer warps + 1 MMA/TMA-issue warp
+constexpr int THREADS = 512;  // 16 warps (single-CTA kernels: 15 operand-producer warps + 1 MMA / weight-copy warp)
 constexpr int NPROD = THREADS - 32;  // producer threads (warps 0..14)
 constexpr int NPW = NPROD / 32;      // producer warps
 constexpr int MMA_WARP = THREADS / 32 - 1;
@@ -210,10 +210,11 @@ struct DLay {
 template <int ACT>
 __device__ __forceinline__ int act_id(int rt) { return ACT >= 0 ? ACT : rt; }
 
-// ---- raw-tile staging with cp.async (LDGSTS) ----------------------------------------------------------
+// ---- block staging with cp.async (LDGSTS), used by the dx epilogue for the Z_{l-1} blocks -----------------
 // (Measured: one cp.async.bulk per 128-byte row costs ~100 issue cycles each and serialises; 16-byte
 // cp.async pieces spread over all threads are 2x faster here.)  The piece -> (row, 16-byte column) mapping
-// does not change from chunk to chunk, so each thread precomputes its pieces once.
+// does not change from block to block, so each thread precomputes its pieces once.  The main loops do NOT
+// stage operand rows this way any more: they go global -> registers -> swizzled tiles (see k_tc_fwd).
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, bool valid) {
   const int sz = valid ? 16 : 0;  // src-size 0 => the 16 destination bytes are zero-filled
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
@@ -224,11 +225,8 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-constexpr int RAW_TILE_BYTES = 128 * KCH * 4;  // 128 rows x 32 fp32, linear (row pitch 128 B)
 constexpr int ROW_PIECES = (128 * 8 + NPROD - 1) / NPROD;  // 16-byte pieces of a [128 x 32] tile per producer thread
 
-// barrier among the producer warps only (the MMA warp never joins it)
-__device__ __forceinline__ void producer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory"); }
 
 // pieces of a [rows_used x 32] tile whose row r = c*TP + pl comes from plane c, point p0 + pl
 struct RowPieces {
@@ -366,9 +364,8 @@ struct TcFwdArgs {
 };
 
 // Shared-memory map of k_tc_fwd / k_tc_dx (offsets from the 1024-aligned base):
-//   [0, 2*stage)                       two operand stages: A_hi | A_lo | B_hi | B_lo
-//   [2*stage, 2*stage + 2*RAW)         raw fp32 staging ring (TMA row copies), one K chunk ahead
-//   then mbarriers b_full[2] (+0,+8), mma_done[2] (+16,+24), raw_full[2] (+32,+40) and the TMEM base slot (+64)
+//   [0, 2*stage)   two operand stages: A_hi | A_lo | B_hi | B_lo
+//   then mbarriers b_full[2] (+0,+8), mma_done[2] (+16,+24), a_ready[2] (+32,+40) and the TMEM base slot (+64)
 __host__ __device__ inline int tc_fwd_smem_bytes(int N) { return 2 * tc_stage_bytes(N) + 1024 + 256; }
 
 // Shared prologue of the three kernels: barriers, TMEM, zeroed operand stages.
@@ -398,9 +395,10 @@ __device__ __forceinline__ void tc_setup(uint32_t base, unsigned char* base_ptr,
 
 // Forward layer  Z_l = act_jets(Z_{l-1}) W_l + b_l  on the tensor cores.
 // Persistent: CTA t handles tiles t, t+grid, ...; each tile = 128 rows = TP points x C channels.
-// Pipeline per K chunk `it`:  raw rows of chunk it+1 (TMA row copies, warp 0) and weight images of chunk it+1
-// (one TMA bulk copy) are requested, the A operand of chunk `it` is produced from the raw tile by all warps
-// (item = point x lane-column: all C channels), then thread 0 issues its 12 MMAs.
+// Pipeline per K chunk `it`: the operand rows of chunk it+1 are already in registers (prefetched while chunk `it`
+// was produced), the producer warps write the A operand of chunk `it` into its stage and arrive on a_ready, the
+// MMA warp's lane 0 waits for a_ready + the weight image (one TMA bulk copy per chunk) and issues the 12 MMAs.
+// This single-CTA kernel is the fallback / cross-check of the CTA-pair kernel k_tc2_fwd (kernels_tc2.cuh).
 template <class L, int ACT>
 __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
   extern __shared__ unsigned char smem_dyn[];
@@ -645,7 +643,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
 // Backward dx on the tensor cores:  Abar = Zbar_l W_l^T  (contraction over the layer's outputs), then the
 // activation adjoint  Zbar_{l-1} = adj(Abar, Z_{l-1}).  The C channels of one point live in different TMEM
 // lanes and the adjoint needs them together, so each 32-column block goes through a shared-memory
-// exchange tile; the matching Z_{l-1} block is prefetched by TMA row copies one block ahead.  During the
+// exchange tile; the matching Z_{l-1} block is prefetched by cp.async one block ahead.  During the
 // epilogue all MMAs have retired, so the exchange tile lives in stage 0's A_hi region and the two Z
 // buffers in stage 1's A_hi / A_lo regions (same 128-byte row pitch; pad rows stay zero).
 // =====================================================================================================
@@ -904,8 +902,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
 // Reduction dimension = jet rows (points x channels).  CTA (kt, split, nb) owns dW rows [128 kt, +128),
 // columns [NC nb, +NC) and a contiguous range of 32-row reduction chunks (PT points each); it accumulates in
 // TMEM across its whole range and flushes once with red.global.add.  A_{l-1} (post-activation jets) was
-// stashed by the forward kernel, so both operands are plain copies: raw rows arrive by TMA row copies
-// (one row per lane of warp 0) and all warps split + transpose them into K-major SW128 tiles.
+// stashed by the forward kernel, so both operands are plain copies: 4x4 blocks are gathered with 128-bit loads,
+// transposed in registers and split into K-major SW128 tiles (see the producer geometry note below).
 // =====================================================================================================
 struct TcDwArgs {
   const float* Aact;   // a_{l-1} [C][Np][lda]
