@@ -99,6 +99,9 @@ TC_CASES = {
     "ns_f32_tc_256_chunks": dict(in_keys=("x", "y"), out_keys=("u", "v", "p"), hidden=[256, 256, 256], act="tanh",
                                  exprs=lambda: O.navier_stokes_expr(0.01, 1.0, 2, False), dtype=torch.float32,
                                  chunk_div=3, weights=True),
+    # widths that give odd K-chunk counts (3, 5), odd 32-column block counts and a 16-row weight half per CTA
+    "ns_f32_tc_mixed": dict(in_keys=("x", "y"), out_keys=("u", "v", "p"), hidden=[96, 160, 64, 32], act="tanh",
+                            exprs=lambda: O.navier_stokes_expr(0.01, 1.0, 2, False), dtype=torch.float32),
     # C = 7 (three second-order directions): pair kernels with two producer groups of 5 warps + 4 idle producer warps
     "ns3d_f32_tc_256": dict(in_keys=("x", "y", "z"), out_keys=("u", "v", "w", "p"), hidden=[256, 256, 256], act="tanh",
                             exprs=lambda: O.navier_stokes_expr(0.05, 1.0, 3, False), dtype=torch.float32),
