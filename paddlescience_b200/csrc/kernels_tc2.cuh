@@ -187,8 +187,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_fw
   constexpr int rows_used = CS * TP;
   // Producer groups.  One chunk's items (TP points x 8 k quads) need W1 warps; when two such sets fit in the 14
   // producer warps, group g owns chunks it = g (mod NG): every warp then has NG chunk periods per chunk, and its
-  // register prefetch of the NEXT OWN chunk flies NG periods ahead (a loaded HBM round trip measured ~1.3 us is
-  // longer than one ~1 us chunk period; with a one-period prefetch the timeline showed producers stalled on it).
+  // two register buffers hold its next two own chunks (2 NG chunk periods of prefetch distance; a loaded HBM
+  // round trip was measured at ~3,500 cycles, about two chunk periods).
   constexpr int W1 = (TP + 3) / 4;
   constexpr int NG = (2 * W1 <= T2_NPW) ? 2 : 1;
   constexpr int WG = NG > 1 ? W1 : T2_NPW;  // warps per group
