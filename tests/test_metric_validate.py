@@ -82,3 +82,38 @@ def test_solver_eval_matches_oracle_forward():
     assert abs(metrics["L2Rel"]["u"] - l2) <= 1e-5 * l2
     assert abs(metrics["MSE"]["u"] - mse) <= 1e-5 * mse
     assert target == pytest.approx(metrics["L2Rel"]["u"])
+
+
+def test_build_metric_and_validator_from_config():
+    ppsci.utils.misc.set_random_seed(1)
+    m = ppsci.metric.build_metric([{"MSE": {"keep_batch": False}}, {"L2Rel": None}])
+    assert list(m) == ["MSE", "L2Rel"] and isinstance(m["L2Rel"], ppsci.metric.L2Rel)
+    geom = {"rect": ppsci.geometry.Rectangle((0, 0), (1, 1))}
+    v = ppsci.validate.build_validator([{"GeometryValidator": {
+        "output_expr": {"u": lambda out: out["u"]}, "label_dict": {"u": 0}, "geom": "rect",
+        "dataloader_cfg": {"dataset": "NamedArrayDataset", "total_size": 10, "batch_size": 4},
+        "loss": {"name": "MSELoss", "reduction": "mean"}, "metric": [{"MSE": None}], "name": "v0"}}], geom=geom)
+    assert list(v) == ["v0"] and isinstance(v["v0"].metric["MSE"], ppsci.metric.MSE)
+    assert ppsci.validate.build_validator(None) is None and ppsci.metric.build_metric(None) is None
+
+
+def test_supervised_validator_defaults_to_label_keys():
+    x = np.linspace(0, 1, 9, dtype=np.float32).reshape(-1, 1)
+    v = ppsci.validate.SupervisedValidator(
+        {"dataset": {"name": "NamedArrayDataset", "input": {"x": x}, "label": {"u": x ** 2}}, "batch_size": 4},
+        ppsci.loss.MSELoss("mean"), metric={"MAE": ppsci.metric.MAE()}, name="sup")
+    assert v.input_keys == ("x",) and v.output_keys == ("u",)
+    assert float(v.output_expr["u"]({"u": 3.0})) == 3.0
+    assert len(v.data_loader.loader) == 3
+
+
+def test_lbfgs_factory_arguments():
+    model = ppsci.arch.MLP(("x",), ("u",), 2, 8)
+    opt = ppsci.optimizer.LBFGS(0.5, max_iter=3, history_size=7)(model)
+    assert opt.is_lbfgs and opt.get_lr() == 0.5
+    opt.set_lr(0.25)
+    assert opt.get_lr() == 0.25
+    with pytest.raises(ValueError):
+        ppsci.optimizer.LBFGS(line_search_fn="armijo")
+    with pytest.raises(RuntimeError):  # parameters live on the CPU here: no CPU fallback
+        opt.step(lambda: torch.zeros(()))
