@@ -5,6 +5,12 @@ Parameters live in ONE flat fp32/fp64 buffer laid out [W_1 (in,out) | b_1 | W_2 
 (the reference's nn.Linear layout is [in,out], mlp.py:246,274).  ``linears[i].weight`` /
 ``.bias`` / ``last_fc`` are views into it, and ``state_dict()`` uses the reference's key names
 (``linears.0.weight`` ...) so checkpoints translate 1:1.
+
+``weight_norm=True`` (reference: ``WeightNormLinear``, mlp.py:31-53, used by the hidden layers): the trainable
+vector is ``[V_1 | b_1 | ... | W_last | b_last | g_1 ... g_{L-1}]`` and the buffer the kernels read holds the
+effective weights ``W_l = g_l * V_l / ||V_l||_col``; the engine call is unchanged, the reparametrisation and its
+chain rule are a handful of column-wise torch operations on the (small) weight matrices before / after it
+(``engine_params`` / ``engine_grads`` / ``finish_grads``).
 """
 from __future__ import annotations
 
@@ -30,9 +36,28 @@ class _LinearView:
 
     @property
     def weight(self) -> torch.Tensor:
+        """Effective weight [in, out] (a view for plain layers, g * V / ||V||_col for weight-normalised ones)."""
+        a, b = self._owner._shapes[self._index]
+        off = self._owner._w_off[self._index]
+        v = self._owner.flat.data[off: off + a * b].view(a, b)
+        if self._owner._wn_layer(self._index):
+            return v * (self.weight_g / v.norm(p=2, dim=0, keepdim=True))
+        return v
+
+    @property
+    def weight_v(self) -> torch.Tensor:
+        if not self._owner._wn_layer(self._index):
+            raise AttributeError("weight_v exists only for weight-normalised layers")
         a, b = self._owner._shapes[self._index]
         off = self._owner._w_off[self._index]
         return self._owner.flat.data[off: off + a * b].view(a, b)
+
+    @property
+    def weight_g(self) -> torch.Tensor:
+        if not self._owner._wn_layer(self._index):
+            raise AttributeError("weight_g exists only for weight-normalised layers")
+        off = self._owner._g_off[self._index]
+        return self._owner.flat.data[off: off + self._owner._shapes[self._index][1]]
 
     @property
     def bias(self) -> torch.Tensor:
@@ -63,7 +88,7 @@ class MLP(base.Arch):
     """Multi layer perceptron network (same arguments as the reference, mlp.py:179-193).
 
     Not yet supported by the jet kernels (raise ``NotImplementedError`` at construction):
-    ``skip_connection``, ``fourier``, ``random_weight``, trainable periods, ``weight_norm``.
+    ``skip_connection``, ``fourier``, ``random_weight``, trainable periods.
     """
 
     def __init__(
@@ -96,8 +121,8 @@ class MLP(base.Arch):
             hidden = [hidden_size] * num_layers
         else:
             raise ValueError(f"hidden_size should be list of int or int, but got {type(hidden_size)}")
-        for flag, name in ((skip_connection, "skip_connection"), (weight_norm, "weight_norm"), (fourier, "fourier"),
-                           (random_weight, "random_weight")):
+        self.weight_norm = bool(weight_norm)
+        for flag, name in ((skip_connection, "skip_connection"), (fourier, "fourier"), (random_weight, "random_weight")):
             if flag:
                 raise NotImplementedError(f"MLP({name}=...) is not supported by the jet kernels yet")
         if input_dim is not None and input_dim != len(self.input_keys) + (len(self.periods) if self.periods else 0):
@@ -136,6 +161,14 @@ class MLP(base.Arch):
             off += a * b
             self._b_off.append(off)
             off += b
+        self._n_eff = off  # length of the [W | b] buffer the kernels read
+        self._g_off = []   # weight_norm: per hidden layer, offset of its gain vector g_l (appended after the last bias)
+        if self.weight_norm:
+            for a, b in self._shapes[:-1]:
+                self._g_off.append(off)
+                off += b
+            self.register_buffer("_eff", torch.zeros(self._n_eff, dtype=dtype), persistent=False)
+            self.register_buffer("_eff_grad", torch.zeros(self._n_eff, dtype=dtype), persistent=False)
         self.flat = nn.Parameter(torch.zeros(off, dtype=dtype))
         self.linears = [_LinearView(self, i) for i in range(len(hidden))]
         self.last_fc = _LinearView(self, len(hidden))
@@ -152,9 +185,53 @@ class MLP(base.Arch):
                 w = (torch.rand(a * b, dtype=torch.float64) * 2 - 1) * lim
                 self.flat.data[self._w_off[i]: self._w_off[i] + a * b] = w.to(self.flat.dtype)
                 self.flat.data[self._b_off[i]: self._b_off[i] + b] = 0
+                if self._wn_layer(i):  # WeightNormLinear._init_weights: V xavier-uniform, g = 1, bias = 0
+                    self.flat.data[self._g_off[i]: self._g_off[i] + b] = 1
 
     def net_spec(self) -> NetSpec:
         return self._net
+
+    # ---- what the engine reads / accumulates into ---------------------------------------------------
+    def _wn_layer(self, i: int) -> bool:
+        return self.weight_norm and i < len(self._shapes) - 1  # hidden layers only (mlp.py:234-246); last_fc is plain
+
+    def engine_params(self) -> torch.Tensor:
+        """The flat [W_1 | b_1 | ...] buffer passed to the native calls (effective weights under weight_norm)."""
+        if not self.weight_norm:
+            return self.flat.data
+        with torch.no_grad():
+            self._eff.copy_(self.flat.data[: self._n_eff])
+            for i, (a, b) in enumerate(self._shapes[:-1]):
+                v = self.flat.data[self._w_off[i]: self._w_off[i] + a * b].view(a, b)
+                g = self.flat.data[self._g_off[i]: self._g_off[i] + b]
+                self._eff[self._w_off[i]: self._w_off[i] + a * b].view(a, b).copy_(v * (g / v.norm(p=2, dim=0, keepdim=True)))
+        return self._eff
+
+    def engine_grads(self) -> torch.Tensor:
+        """Buffer the native calls accumulate the weight gradient into (same layout as ``engine_params``)."""
+        if self.flat.grad is None:
+            self.flat.grad = torch.zeros_like(self.flat.data)
+        return self._eff_grad if self.weight_norm else self.flat.grad
+
+    def finish_grads(self):
+        """Chain rule of the weight normalisation: gradients w.r.t. the effective weights -> (V, g); then the
+        staging buffer is cleared.  No-op for plain layers (the kernels accumulated into ``flat.grad`` directly)."""
+        if not self.weight_norm:
+            return
+        with torch.no_grad():
+            gr = self.flat.grad
+            gr[: self._n_eff] += self._eff_grad  # biases and the plain last layer pass through; V parts are fixed below
+            for i, (a, b) in enumerate(self._shapes[:-1]):
+                sl = slice(self._w_off[i], self._w_off[i] + a * b)
+                v = self.flat.data[sl].view(a, b)
+                g = self.flat.data[self._g_off[i]: self._g_off[i] + b]
+                dw = self._eff_grad[sl].view(a, b)
+                norm = v.norm(p=2, dim=0, keepdim=True)
+                dot = (dw * v).sum(dim=0, keepdim=True)  # [1, out]
+                dv = (g / norm) * (dw - v * (dot / (norm * norm)))
+                gr[sl].view(a, b).add_(dv - dw)  # replace the pass-through dW by dV
+                gr[self._g_off[i]: self._g_off[i] + b] += (dot / norm).view(-1)
+            self._eff_grad.zero_()
 
     @property
     def dtype(self) -> torch.dtype:
@@ -167,8 +244,12 @@ class MLP(base.Arch):
     def state_dict(self, *args, **kwargs):  # reference-style keys
         out = OrderedDict()
         views = self.linears + [self.last_fc]
-        for name, v in zip(self._layer_names(), views):
-            out[f"{name}.weight"] = v.weight.detach().clone()
+        for i, (name, v) in enumerate(zip(self._layer_names(), views)):
+            if self._wn_layer(i):
+                out[f"{name}.weight_v"] = v.weight_v.detach().clone()
+                out[f"{name}.weight_g"] = v.weight_g.detach().clone()
+            else:
+                out[f"{name}.weight"] = v.weight.detach().clone()
             out[f"{name}.bias"] = v.bias.detach().clone()
         return out
 
@@ -176,8 +257,8 @@ class MLP(base.Arch):
         views = self.linears + [self.last_fc]
         missing, unexpected = [], [k for k in state_dict if k.rsplit(".", 1)[0] not in self._layer_names()]
         with torch.no_grad():
-            for name, v in zip(self._layer_names(), views):
-                for part in ("weight", "bias"):
+            for i, (name, v) in enumerate(zip(self._layer_names(), views)):
+                for part in (("weight_v", "weight_g", "bias") if self._wn_layer(i) else ("weight", "bias")):
                     key = f"{name}.{part}"
                     if key not in state_dict:
                         missing.append(key)
@@ -214,7 +295,7 @@ class MLP(base.Arch):
                 f"CPU fallback (inputs on {first.device}, parameters on {self.flat.device})")
         plan = self._plan_values()
         cols = {k: x[k].to(self.flat.dtype) for k in self.input_keys}
-        jets, _ = plan.forward(cols, self.flat.data, want_jets=True, want_residuals=False)
+        jets, _ = plan.forward(cols, self.engine_params(), want_jets=True, want_residuals=False)
         y = jets[0]  # [N, n_out]
         shape = tuple(first.shape[:-1]) + (1,) if first.dim() > 1 else (first.numel(), 1)
         out = {k: y[:, j].reshape(shape) for j, k in enumerate(self.output_keys)}

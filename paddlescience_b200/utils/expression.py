@@ -87,8 +87,7 @@ class ExpressionSolver(nn.Module):
         losses_all: Dict[str, torch.Tensor] = {}
         losses_constraint: Dict[str, torch.Tensor] = {}
         flat = model.flat
-        if flat.grad is None:
-            flat.grad = torch.zeros_like(flat.data)
+        params, grads = model.engine_params(), model.engine_grads()  # effective weights / staging grads under weight_norm
         for i, cst_name in enumerate(constraint):
             cst = constraint[cst_name]
             use_nvtx = self.nvtx_flag and flat.is_cuda
@@ -100,13 +99,14 @@ class ExpressionSolver(nn.Module):
             if "area" in input_dicts[i]:  # mse.py:92-93 multiplies by the area column when present
                 area = input_dicts[i]["area"]
                 weights = {k: (weights[k] * area if weights and k in weights else area) for k in cc.names}
-            loss_vec = plan.loss_fwd_bwd(input_dicts[i], flat.data, flat.grad, labels=label_dicts[i], weights=weights)
+            loss_vec = plan.loss_fwd_bwd(input_dicts[i], params, grads, labels=label_dicts[i], weights=weights)
             loss_vec = loss_vec.clone()
             losses_constraint[cst_name] = loss_vec.sum()
             for k, key in enumerate(cc.names):
                 losses_all[key] = losses_all[key] + loss_vec[k] if key in losses_all else loss_vec[k]
             if use_nvtx:
                 torch.cuda.nvtx.range_pop()
+        model.finish_grads()  # weight_norm chain rule into model.flat.grad (no-op otherwise)
         return losses_all, losses_constraint
 
     def eval_forward(self, expr_dict, input_dict, model, validator, label_dict, weight_dict):

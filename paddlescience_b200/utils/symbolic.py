@@ -63,7 +63,7 @@ class CompiledExpr:
         plan = self._plan(self.model.dtype)
         keys = list(self.model.input_keys) + list(plan.compiled.aux_keys)
         cols = {k: data_dict[k] for k in keys}
-        _, res = plan.forward(cols, self.model.flat.data, want_jets=False, want_residuals=True)
+        _, res = plan.forward(cols, self.model.engine_params(), want_jets=False, want_residuals=True)
         return res[self.name]
 
     def __repr__(self):
