@@ -70,11 +70,16 @@ def test_state_dict_uses_reference_keys_and_round_trips():
     np.testing.assert_array_equal(m2.flat.data.numpy(), m.flat.data.numpy())
 
 
-def test_train_forward_through_emulated_kernels_matches_oracle(monkeypatch):
+@pytest.mark.parametrize("weight_norm", [True, False])
+def test_train_forward_through_emulated_kernels_matches_oracle(monkeypatch, weight_norm):
     from tests.emul.build_emul import build
 
     monkeypatch.setattr(B, "_default", B.Library(build()))  # test infrastructure: same kernel sources, compiled for the CPU
-    m = _model()
+    if weight_norm:
+        m = _model()
+    else:  # the plain model goes through the same call sites (engine_params / engine_grads / finish_grads are pass-throughs)
+        ppsci.utils.misc.set_random_seed(3)
+        m = ppsci.arch.MLP(("x", "y"), ("u",), 3, 12, "tanh", dtype=torch.float64)
     eq = ppsci.equation.Laplace(2)
     rect = ppsci.geometry.Rectangle((0, 0), (1, 1))
     cst = ppsci.constraint.InteriorConstraint(eq.equations, {"laplace": 0}, rect,
@@ -89,7 +94,7 @@ def test_train_forward_through_emulated_kernels_matches_oracle(monkeypatch):
     raw = m.flat.data.clone().requires_grad_(True)
     om = O.OracleMLP(("x", "y"), ("u",), [12, 12, 12], "tanh")
     x = {k: inp[k].clone().requires_grad_(True) for k in ("x", "y")}
-    out = om(_eff_from_raw(m, raw), x)
+    out = om(_eff_from_raw(m, raw) if weight_norm else raw, x)
     data = dict(x)
     data.update(out)
     res = O.eval_expr(O.laplace_expr(2)["laplace"], data)
