@@ -130,6 +130,10 @@ typedef struct ppsci_plan_spec {
   /* tuning */
   int32_t chunk_points; /* points per internal chunk (0 = default) */
   int32_t backend;      /* 0 = auto, 1 = force SIMT kernels, 2 = force tcgen05 kernels */
+  /* Dense first-layer operand (DeepONet branch net, ppsci/arch/deeponet.py:96-106: MLP(input_dim=num_loc)):
+   * when non-zero, n_in must be 1, x_cols[0] is a row-major [n_points][n_feat] matrix (n_feat up to 4096, the
+   * feat_* arrays are ignored) and no input derivatives are available (n_dir must be 0). */
+  int32_t dense_in;
 } ppsci_plan_spec;
 
 typedef struct ppsci_plan ppsci_plan;
@@ -190,6 +194,15 @@ int64_t ppsci_b200_plan_last_launches(const ppsci_plan* plan);
 /* Test accessor: byte offset inside the (256-aligned) workspace of the jet planes of `layer`
  * ([C][min(n_points, chunk)][round4(width)]); layer == n_layers addresses the output jets. */
 int64_t ppsci_b200_plan_stash_offset(const ppsci_plan* plan, int64_t n_points, int32_t layer);
+
+/* Forward + adjoint of the network VALUES for caller-supplied output adjoints: runs the forward pass (stash), seeds
+ * the value channel of the output adjoints with ybar[n_points][n_out] (row-major, dL/dy computed by the caller),
+ * and accumulates dL/d(params) into grads.  No residual program, no loss.  This is how a model that combines
+ * several MLPs outside the kernels (DeepONet: G = sum_i branch_i * act(trunk_i) + b, deeponet.py:129-154) gets its
+ * weight gradients: the combination and the loss are elementwise work on [N, features] done by the caller. */
+int ppsci_b200_values_fwd_bwd(ppsci_plan* plan, const void* const* x_cols, const void* const* aux_cols,
+                              int64_t n_points, const void* params, void* grads, const void* ybar,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* Bench instrumentation: when on, every launch of the next calls is bracketed by CUDA events on
  * the caller's stream (no syncs).  get_profile returns, for the most recent call, the summed

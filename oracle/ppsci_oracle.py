@@ -372,3 +372,40 @@ def hypercube_random_points(xmin, xmax, n: int) -> np.ndarray:
     xmax = np.array(xmax, dtype="float32")
     x = np.random.random(size=(n, len(xmin))).astype("float32")
     return (xmax - xmin) * x + xmin
+
+
+# ------------------------------------------------------------------------------------------------
+# ppsci/arch/deeponet.py:91-154  DeepONet:  G = einsum("bi,bi->b", branch(u), act(trunk(y))) [+ b]
+# ------------------------------------------------------------------------------------------------
+class OracleDeepONet:
+    """Functional DeepONet over flat parameter vectors of its two MLPs (each laid out like OracleMLP) and the scalar
+    bias.  branch: MLP((u,), ("b",), ..., input_dim=num_loc, output_dim=num_features) on the [N, num_loc] matrix
+    (deeponet.py:96-106); trunk: MLP((y,), ("t",), ..., input_dim=1, output_dim=num_features) followed by the trunk
+    activation (deeponet.py:108-119, 141-142); output reshaped to [N, 1] plus b (deeponet.py:144-149)."""
+
+    def __init__(self, num_loc: int, num_features: int, branch_hidden: Sequence[int], trunk_hidden: Sequence[int],
+                 branch_activation: str = "tanh", trunk_activation: str = "tanh", use_bias: bool = True):
+        self.bw = [num_loc] + list(branch_hidden) + [num_features]
+        self.tw = [1] + list(trunk_hidden) + [num_features]
+        self.bact, self.tact = get_activation(branch_activation), get_activation(trunk_activation)
+        self.use_bias = use_bias
+
+    @staticmethod
+    def _mlp(flat: torch.Tensor, widths: Sequence[int], act, x: torch.Tensor) -> torch.Tensor:
+        off, y = 0, x
+        n = len(widths) - 1
+        for i, (a, b) in enumerate(zip(widths[:-1], widths[1:])):
+            W = flat[off: off + a * b].view(a, b)
+            off += a * b
+            bias = flat[off: off + b]
+            off += b
+            y = y @ W + bias  # nn.Linear with [in, out] weights (mlp.py:246,274)
+            if i < n - 1:
+                y = act(y)  # mlp.py:281-296: activation after every hidden layer, none after last_fc
+        return y
+
+    def __call__(self, branch_params, trunk_params, b, u: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        u_features = self._mlp(branch_params, self.bw, self.bact, u)
+        y_features = self.tact(self._mlp(trunk_params, self.tw, self.tact, y))
+        g = (u_features * y_features).sum(dim=-1).reshape(-1, 1)
+        return g + b if self.use_bias else g

@@ -1,7 +1,7 @@
 """paddlescience_b200 — B200-native PINN PDE-residual engine behind the PaddleScience API.
 
 The package mirrors the part of ``ppsci`` that lies on the hot path named in BASELINE.json
-(SURVEY.md §8): ``arch.MLP``, ``equation.PDE`` (+ Laplace/Poisson/NavierStokes/Biharmonic/
+(SURVEY.md §8): ``arch.MLP``, ``arch.DeepONet``, ``equation.PDE`` (+ Laplace/Poisson/NavierStokes/Biharmonic/
 AllenCahn/Helmholtz), ``autodiff.{jacobian,hessian}``, ``constraint.{Interior,Boundary,
 Supervised}Constraint``, ``geometry.{Interval,Rectangle,Cuboid,Hypercube}``, the three array
 datasets, ``loss.MSELoss`` / ``loss.mtl.Sum``, ``optimizer.Adam`` + LR schedules,

@@ -1,8 +1,9 @@
 from .base import Arch
 from .mlp import MLP
+from .deeponet import DeepONet
 from .activation import get_activation
 
-__all__ = ["Arch", "MLP", "get_activation", "build_model"]
+__all__ = ["Arch", "MLP", "DeepONet", "get_activation", "build_model"]
 
 
 def build_model(cfg):

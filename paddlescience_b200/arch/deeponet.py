@@ -1,0 +1,201 @@
+"""``DeepONet`` (reference: ppsci/arch/deeponet.py:28-154):  G(u)(y) = sum_i branch(u)_i * act(trunk(y))_i + b.
+
+Both sub-networks run in the native kernels (values only, C = 1): the branch net reads its ``[N, num_loc]`` sensor
+matrix as a dense first-layer operand (``dense_in``), the trunk net its coordinate column as an input seed.  The
+combination, the loss and their derivatives are elementwise work on ``[N, num_features]`` done with torch on the
+device; the weight gradients of the two MLPs come from ``ppsci_b200_values_fwd_bwd`` fed with dL/d(branch),
+dL/d(trunk).  One flat parameter buffer  [branch | trunk | b]  so the flat optimizers apply unchanged."""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict, List, Tuple, Union
+
+import torch
+from torch import nn
+
+from ..engine.compiler import NetSpec, compile_residuals
+from . import activation as act_mod
+from . import base
+
+_TORCH_ACT = {
+    "tanh": torch.tanh, "sin": torch.sin, "cos": torch.cos, "sigmoid": torch.sigmoid, "silu": torch.nn.functional.silu,
+    "swish": torch.nn.functional.silu, "gelu": torch.nn.functional.gelu, "relu": torch.relu, "identity": lambda t: t,
+}
+
+
+def _hidden(num_layers, hidden_size) -> List[int]:
+    if isinstance(hidden_size, (tuple, list)):
+        if num_layers is not None:
+            raise ValueError("num_layers should be None when hidden_size is specified")
+        return [int(h) for h in hidden_size]
+    if not isinstance(num_layers, int):
+        raise ValueError("num_layers should be an int when hidden_size is an int")
+    return [int(hidden_size)] * num_layers
+
+
+class DeepONet(base.Arch):
+    """Same arguments as the reference (deeponet.py:71-89).  ``*_skip_connection`` / ``*_weight_norm`` are not
+    supported yet and raise ``NotImplementedError``."""
+
+    def __init__(
+        self,
+        u_key: str,
+        y_key: str,
+        G_key: str,
+        num_loc: int,
+        num_features: int,
+        branch_num_layers: int,
+        trunk_num_layers: int,
+        branch_hidden_size: Union[int, Tuple[int, ...]],
+        trunk_hidden_size: Union[int, Tuple[int, ...]],
+        branch_skip_connection: bool = False,
+        trunk_skip_connection: bool = False,
+        branch_activation: str = "tanh",
+        trunk_activation: str = "tanh",
+        branch_weight_norm: bool = False,
+        trunk_weight_norm: bool = False,
+        use_bias: bool = True,
+        dtype: torch.dtype = torch.float32,
+    ):
+        super().__init__()
+        for flag, name in ((branch_skip_connection, "branch_skip_connection"), (trunk_skip_connection, "trunk_skip_connection"),
+                           (branch_weight_norm, "branch_weight_norm"), (trunk_weight_norm, "trunk_weight_norm")):
+            if flag:
+                raise NotImplementedError(f"DeepONet({name}=True) is not supported yet")
+        self.u_key, self.y_key = u_key, y_key
+        self.input_keys = (u_key, y_key)
+        self.output_keys = (G_key,)
+        self.num_loc, self.num_features, self.use_bias = int(num_loc), int(num_features), bool(use_bias)
+        self.branch_activation = act_mod.get_activation(branch_activation)
+        self.trunk_activation = act_mod.get_activation(trunk_activation)
+        bw = [self.num_loc] + _hidden(branch_num_layers, branch_hidden_size) + [self.num_features]
+        tw = [1] + _hidden(trunk_num_layers, trunk_hidden_size) + [self.num_features]
+        feats = tuple(f"f{i}" for i in range(self.num_features))
+        self._branch = NetSpec((u_key,), feats, [], [], [], bw, self.branch_activation, dense_in=True)
+        self._trunk = NetSpec((y_key,), feats, [0], [0], [0.0], tw, self.trunk_activation)
+        nb, nt = self._branch.n_params, self._trunk.n_params
+        self._b_rng = (0, nb)
+        t0 = (nb + 3) // 4 * 4
+        self._t_rng = (t0, t0 + nt)
+        self._bias_off = (t0 + nt + 3) // 4 * 4
+        self.flat = nn.Parameter(torch.zeros(self._bias_off + (1 if self.use_bias else 0), dtype=dtype))
+        self.reset_parameters()
+        self._plans = None
+
+    # ---- parameters ------------------------------------------------------------------------------
+    def _layers(self, which: str):
+        net, (lo, _) = (self._branch, self._b_rng) if which == "branch_net" else (self._trunk, self._t_rng)
+        off = lo
+        n = len(net.widths) - 1
+        for i, (a, b) in enumerate(zip(net.widths[:-1], net.widths[1:])):
+            name = f"{which}.linears.{i}" if i < n - 1 else f"{which}.last_fc"
+            yield name, (a, b), off, off + a * b
+            off += a * b + b
+
+    def reset_parameters(self):
+        """Xavier-uniform weights, zero biases, b = 0 (Paddle nn.Linear defaults; deeponet.py:121-125)."""
+        with torch.no_grad():
+            self.flat.data.zero_()
+            for which in ("branch_net", "trunk_net"):
+                for _, (a, b), w0, w1 in self._layers(which):
+                    lim = math.sqrt(6.0 / (a + b))
+                    self.flat.data[w0:w1] = ((torch.rand(a * b, dtype=torch.float64) * 2 - 1) * lim).to(self.flat.dtype)
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return self.flat.dtype
+
+    def state_dict(self, *args, **kwargs):  # reference-style keys
+        out = OrderedDict()
+        for which in ("branch_net", "trunk_net"):
+            for name, (a, b), w0, w1 in self._layers(which):
+                out[f"{name}.weight"] = self.flat.data[w0:w1].view(a, b).detach().clone()
+                out[f"{name}.bias"] = self.flat.data[w1: w1 + b].detach().clone()
+        if self.use_bias:
+            out["b"] = self.flat.data[self._bias_off: self._bias_off + 1].detach().clone()
+        return out
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        missing = []
+        with torch.no_grad():
+            for which in ("branch_net", "trunk_net"):
+                for name, (a, b), w0, w1 in self._layers(which):
+                    for key, lo, hi in ((f"{name}.weight", w0, w1), (f"{name}.bias", w1, w1 + b)):
+                        if key not in state_dict:
+                            missing.append(key)
+                            continue
+                        self.flat.data[lo:hi] = torch.as_tensor(state_dict[key]).reshape(-1).to(self.flat.dtype).to(self.flat.device)
+            if self.use_bias:
+                if "b" in state_dict:
+                    self.flat.data[self._bias_off] = float(torch.as_tensor(state_dict["b"]).reshape(-1)[0])
+                else:
+                    missing.append("b")
+        if strict and missing:
+            raise KeyError(f"missing keys {missing}")
+        return missing, []
+
+    set_state_dict = load_state_dict
+
+    # ---- native plans ----------------------------------------------------------------------------
+    def _get_plans(self):
+        from ..engine.plan import ResidualPlan
+
+        if self._plans is None or self._plans[0].dtype != self.flat.dtype:
+            self._plans = tuple(ResidualPlan(compile_residuals(net, {}, with_grad=False), self.flat.dtype, [], [])
+                                for net in (self._branch, self._trunk))
+        return self._plans
+
+    def _features(self, x: Dict[str, torch.Tensor]):
+        pb, pt = self._get_plans()
+        dt = self.flat.dtype
+        u = x[self.u_key].to(dt)
+        y = x[self.y_key].to(dt)
+        b = pb.forward({self.u_key: u}, self.flat.data[self._b_rng[0]: self._b_rng[1]], want_jets=True, want_residuals=False)[0][0]
+        t = pt.forward({self.y_key: y}, self.flat.data[self._t_rng[0]: self._t_rng[1]], want_jets=True, want_residuals=False)[0][0]
+        return u, y, b, t
+
+    def _combine(self, b: torch.Tensor, t: torch.Tensor, bias) -> torch.Tensor:
+        g = (b * _TORCH_ACT[self.trunk_activation](t)).sum(dim=-1, keepdim=True)  # einsum("bi,bi->b") + reshape [-1, 1]
+        return g + bias if bias is not None else g
+
+    def forward(self, x: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        if self._input_transform is not None:
+            x = self._input_transform(x)
+        first = x[self.u_key]
+        if first.device.type != "cuda" or self.flat.device != first.device:
+            raise RuntimeError(
+                "paddlescience_b200.arch.DeepONet.forward runs only on a CUDA (B200) device: the engine has no "
+                f"CPU fallback (inputs on {first.device}, parameters on {self.flat.device})")
+        _, _, b, t = self._features(x)
+        bias = self.flat.data[self._bias_off: self._bias_off + 1] if self.use_bias else None
+        out = {self.output_keys[0]: self._combine(b, t, bias)}
+        if self._output_transform is not None:
+            out = self._output_transform(x, out)
+        return out
+
+    def fused_train_forward(self, loss_fn, input_dict, label_dict, weight_dict) -> Dict[str, torch.Tensor]:
+        """Loss of one constraint + accumulation of its gradient into ``self.flat.grad``.
+
+        Replaces expression.py:96-129 + train.py:158 for this model: native forward of both sub-nets, the
+        product / loss / their derivatives on ``[N, num_features]`` in torch, native adjoints of both sub-nets."""
+        if self._input_transform is not None or self._output_transform is not None:
+            raise NotImplementedError("input / output transforms are not supported on the fused DeepONet training path")
+        flat = self.flat
+        if flat.grad is None:
+            flat.grad = torch.zeros_like(flat.data)
+        u, y, b, t = self._features(input_dict)
+        pb, pt = self._get_plans()
+        with torch.enable_grad():
+            bq, tq = b.detach().requires_grad_(True), t.detach().requires_grad_(True)
+            bias = flat.data[self._bias_off: self._bias_off + 1].detach().clone().requires_grad_(True) if self.use_bias else None
+            out = {self.output_keys[0]: self._combine(bq, tq, bias)}
+            if "area" in input_dict:
+                out["area"] = input_dict["area"]
+            losses = loss_fn(out, label_dict, weight_dict)
+            sum(losses.values()).backward()
+        pb.values_fwd_bwd({self.u_key: u}, flat.data[self._b_rng[0]: self._b_rng[1]], flat.grad[self._b_rng[0]: self._b_rng[1]], bq.grad)
+        pt.values_fwd_bwd({self.y_key: y}, flat.data[self._t_rng[0]: self._t_rng[1]], flat.grad[self._t_rng[0]: self._t_rng[1]], tq.grad)
+        if bias is not None:
+            flat.grad[self._bias_off: self._bias_off + 1] += bias.grad
+        return {k: v.detach() for k, v in losses.items()}

@@ -157,13 +157,19 @@ extern "C" int ppsci_b200_plan_create(const ppsci_plan_spec* s, ppsci_plan** out
   *out = nullptr;
   if (s->dtype != PPSCI_F32 && s->dtype != PPSCI_F64) return fail("plan_create: dtype must be f32 or f64");
   if (s->n_in < 1 || s->n_in > PPSCI_MAX_IN) return fail("plan_create: n_in out of range");
-  if (s->n_feat < 1 || s->n_feat > PPSCI_MAX_FEAT) return fail("plan_create: n_feat out of range");
+  if (s->dense_in) {  // dense [n_points][n_feat] first-layer operand (header: dense_in)
+    if (s->n_in != 1) return fail("plan_create: dense_in needs n_in == 1 (one row-major matrix)");
+    if (s->n_dir != 0) return fail("plan_create: dense_in has no input derivatives (n_dir must be 0)");
+    if (s->n_feat < 1 || s->n_feat > 4096) return fail("plan_create: n_feat out of range");
+  } else if (s->n_feat < 1 || s->n_feat > PPSCI_MAX_FEAT) {
+    return fail("plan_create: n_feat out of range");
+  }
   if (s->n_layers < 1 || s->n_layers > PPSCI_MAX_LAYERS) return fail("plan_create: n_layers out of range");
   if (s->widths[0] != s->n_feat) return fail("plan_create: widths[0] must equal n_feat");
   for (int l = 0; l <= s->n_layers; ++l)
     if (s->widths[l] < 1 || s->widths[l] > 4096) return fail("plan_create: layer width out of range");
   if (s->act < 0 || s->act > PPSCI_ACT_GELU) return fail("plan_create: unknown activation");
-  for (int f = 0; f < s->n_feat; ++f) {
+  for (int f = 0; f < (s->dense_in ? 0 : s->n_feat); ++f) {
     if (s->feat_src[f] < 0 || s->feat_src[f] >= s->n_in) return fail("plan_create: feat_src out of range");
     if (s->feat_kind[f] < 0 || s->feat_kind[f] > PPSCI_FEAT_SIN) return fail("plan_create: bad feat_kind");
   }
@@ -425,6 +431,17 @@ static void fill_act(const ppsci_plan* P, const T* Z, int ld, int64_t nc, int mo
   memset(&A->seed, 0, sizeof(SeedSpec));
 }
 
+// first-layer operand: input seeds, or (dense_in) the caller's row-major [n_points][n_feat] matrix as a plain operand
+template <typename T>
+static void fill_first(const ppsci_plan* P, const void* const* x_cols, int64_t x_off, int64_t nc, AOperand<T>* A) {
+  if (P->spec.dense_in) {
+    const int nf = P->spec.n_feat;
+    fill_act<T>(P, reinterpret_cast<const T*>(x_cols[0]) + x_off * nf, nf, nc, A_PLAIN, A);
+  } else {
+    fill_seed<T>(P, x_cols, x_off, A);
+  }
+}
+
 struct CallArgs {
   const void* const* x_cols;
   const void* const* aux_cols;
@@ -442,6 +459,7 @@ struct CallArgs {
   size_t workspace_bytes;
   void* stream;
   bool want_loss;
+  const void* ybar_in = nullptr;  // values_fwd_bwd: caller-supplied dL/dy [n_points][n_out]
 };
 
 template <typename T, int KMAX>
@@ -479,7 +497,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
   const int TP = TM / C;
   const int PT = RC / C;
   const bool thin_on = getenv("PPSCI_B200_NO_THIN") == nullptr;
-  const bool thin_first = thin_on && L >= 2 && s.widths[0] <= THIN_MAXF;
+  const bool thin_first = thin_on && L >= 2 && s.widths[0] <= THIN_MAXF && !s.dense_in;
   const bool thin_last = thin_on && L >= 2 && n_out <= THIN_MAXM && C * n_out <= THIN_MAXCM;
 #ifndef PPSCI_EMUL
   // fp32 + one of the compile-time jet layouts: vectorised thin kernels (kernels_thin.cuh)
@@ -488,7 +506,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
 #endif
 
   if (a.want_loss) CK(cudaMemsetAsync(loss_acc, 0, PPSCI_MAX_RES * sizeof(double), st));
-  const bool do_bwd = a.want_loss && grads != nullptr;
+  const bool do_bwd = (a.want_loss || a.ybar_in) && grads != nullptr;
   if (do_bwd) {
     for (int l = 2; l <= L; ++l) {
       const int K = s.widths[l - 1], N = s.widths[l];
@@ -643,7 +661,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
 #endif
       GemmArgs<T> g;
       memset(&g, 0, sizeof(g));
-      if (l == 1) fill_seed<T>(P, a.x_cols, c0, &g.A);
+      if (l == 1) fill_first<T>(P, a.x_cols, c0, nc_max, &g.A);
       else fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[l - 1]), P->ld[l - 1], nc_max, A_ACT, &g.A);
       g.J = P->J;
       g.B = params + P->w_off[l];
@@ -671,7 +689,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
                    reinterpret_cast<T*>(a.jets_out), (long long)a.n_points, (long long)c0, (long long)nc, C, n_out);
       P->launches++;
     }
-    if (s.n_res > 0 && (a.want_loss || a.residual_out)) {
+    if (s.n_res > 0 && (a.want_loss || a.residual_out) && !a.ybar_in) {
       HeadArgs<T> h;
       memset(&h, 0, sizeof(h));
       h.P.prog = P->d_prog;
@@ -710,6 +728,15 @@ static int run(ppsci_plan* P, const CallArgs& a) {
       P->launches++;
     }
     if (!do_bwd) continue;
+    if (a.ybar_in) {  // output adjoints from the caller instead of the residual head
+      const long long tot = (long long)nc * P->ld[L];
+      auto ks = k_seed_ybar<T>;
+      ProfScope ps_(P, CLS_MISC, st);
+      PPSCI_LAUNCH(ks, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, reinterpret_cast<const T*>(a.ybar_in),
+                   (long long)c0, (long long)nc, n_out, C, reinterpret_cast<T*>(ws + cv.ybar), P->ld[L],
+                   (long long)nc_max * P->ld[L]);
+      P->launches++;
+    }
     // ---------------- adjoint ----------------
     const T* zbar_cur = reinterpret_cast<const T*>(ws + cv.ybar);
     int zbar_ld = P->ld[L];
@@ -867,7 +894,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
       {  // dW_l, db_l
         DwArgs<T> g;
         memset(&g, 0, sizeof(g));
-        if (l == 1) fill_seed<T>(P, a.x_cols, c0, &g.A);
+        if (l == 1) fill_first<T>(P, a.x_cols, c0, nc_max, &g.A);
         else fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[l - 1]), P->ld[l - 1], nc_max, A_ACT, &g.A);
         g.J = P->J;
         g.Zbar = zbar_cur;
@@ -1000,6 +1027,26 @@ static int dispatch(ppsci_plan* P, const CallArgs& a) {
   }
   if (P->spec.dtype == PPSCI_F64) return dispatch_k<double>(P, a);
   return dispatch_k<float>(P, a);
+}
+
+extern "C" int ppsci_b200_values_fwd_bwd(ppsci_plan* plan, const void* const* x_cols, const void* const* aux_cols,
+                                         int64_t n_points, const void* params, void* grads, const void* ybar,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (!ybar || !grads) return fail("values_fwd_bwd: null ybar / grads");
+  CallArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x_cols = x_cols;
+  a.aux_cols = aux_cols;
+  a.n_points = n_points;
+  a.n_norm = n_points;
+  a.params = params;
+  a.grads = grads;
+  a.workspace = workspace;
+  a.workspace_bytes = workspace_bytes;
+  a.stream = stream;
+  a.want_loss = false;
+  a.ybar_in = ybar;
+  return dispatch(plan, a);
 }
 
 extern "C" int ppsci_b200_residual_loss_fwd_bwd(ppsci_plan* plan, const void* const* x_cols,

@@ -617,6 +617,18 @@ __global__ void __launch_bounds__(256) k_last_bwd(LastArgs<T> g) {
   }
 }
 
+// Output adjoints supplied by the caller (ppsci_b200_values_fwd_bwd): value channel <- ybar[p][j], other channels 0.
+template <typename T>
+__global__ void k_seed_ybar(const T* __restrict__ ybar_in, long long x_off, long long Np, int n_out, int C, T* __restrict__ Ybar,
+                            int ldy, long long yplane) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Np * ldy) return;
+  const long long p = i / ldy;
+  const int j = (int)(i - p * ldy);
+  Ybar[i] = j < n_out ? ybar_in[(x_off + p) * n_out + j] : T(0);
+  for (int c = 1; c < C; ++c) Ybar[(long long)c * yplane + i] = T(0);
+}
+
 // ---- small helpers ---------------------------------------------------------------------------
 template <typename T>
 __global__ void k_transpose(const T* W, T* WT, int K, int N) {  // WT[n][k] = W[k][n]

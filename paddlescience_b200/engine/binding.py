@@ -73,6 +73,7 @@ class PlanSpec(C.Structure):
         ("loss_weight", C.c_double * MAX_RES),
         ("chunk_points", C.c_int32),
         ("backend", C.c_int32),
+        ("dense_in", C.c_int32),
     ]
 
 
@@ -84,6 +85,7 @@ EXPORTED_SYMBOLS = (
     "ppsci_b200_plan_workspace_bytes",
     "ppsci_b200_residual_loss_fwd_bwd",
     "ppsci_b200_residual_fwd",
+    "ppsci_b200_values_fwd_bwd",
     "ppsci_b200_plan_last_launches",
     "ppsci_b200_plan_uses_tcgen05",
     "ppsci_b200_plan_stash_offset",
@@ -137,6 +139,8 @@ class Library:
             vp, C.POINTER(vp), C.POINTER(vp), i64, vp, vp, C.POINTER(vp), vp, C.c_size_t, vp,
         ]
         L.ppsci_b200_residual_fwd.restype = C.c_int
+        L.ppsci_b200_values_fwd_bwd.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), i64, vp, vp, vp, vp, C.c_size_t, vp]
+        L.ppsci_b200_values_fwd_bwd.restype = C.c_int
         L.ppsci_b200_plan_last_launches.argtypes = [vp]
         L.ppsci_b200_plan_last_launches.restype = i64
         L.ppsci_b200_plan_uses_tcgen05.argtypes = [vp]

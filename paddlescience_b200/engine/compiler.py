@@ -54,6 +54,7 @@ class NetSpec:
     feat_omega: List[float]
     widths: List[int]  # [n_feat, hidden..., n_out]
     act: str = "tanh"
+    dense_in: bool = False  # the single input key is a row-major [N, n_feat] matrix (DeepONet branch net); values only
 
     @property
     def n_params(self) -> int:

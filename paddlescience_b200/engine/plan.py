@@ -62,10 +62,13 @@ class ResidualPlan:
         s.dtype = _dtype_id(dtype)
         s.n_in = len(net.input_keys)
         s.n_feat = net.widths[0]
-        for f in range(s.n_feat):
-            s.feat_src[f] = net.feat_src[f]
-            s.feat_kind[f] = net.feat_kind[f]
-            s.feat_omega[f] = net.feat_omega[f]
+        self.dense_in = bool(getattr(net, "dense_in", False))
+        s.dense_in = 1 if self.dense_in else 0
+        if not self.dense_in:
+            for f in range(s.n_feat):
+                s.feat_src[f] = net.feat_src[f]
+                s.feat_kind[f] = net.feat_kind[f]
+                s.feat_omega[f] = net.feat_omega[f]
         s.n_layers = len(net.widths) - 1
         for i, w in enumerate(net.widths):
             s.widths[i] = w
@@ -232,6 +235,38 @@ class ResidualPlan:
         del keep
         return self._loss[: self.n_res]
 
+    def _inputs(self, inputs: Dict[str, torch.Tensor], device):
+        """(n_points, [input tensors in column order]); a dense-input net takes ONE row-major [N, n_feat] matrix."""
+        net = self.compiled.net
+        if self.dense_in:
+            m = inputs[net.input_keys[0]]
+            if m.dim() != 2 or m.shape[1] != net.widths[0]:
+                raise ValueError(f"input '{net.input_keys[0]}' must be [N, {net.widths[0]}], got {tuple(m.shape)}")
+            if m.device != device:
+                raise ValueError(f"input '{net.input_keys[0]}': tensor is on {m.device}, parameters are on {device}")
+            return int(m.shape[0]), [m.to(self.dtype).contiguous()]
+        n = inputs[net.input_keys[0]].numel()
+        return n, [_col(inputs[k], n, self.dtype, device, f"input '{k}'") for k in net.input_keys]
+
+    def values_fwd_bwd(self, inputs: Dict[str, torch.Tensor], params: torch.Tensor, grads: torch.Tensor, ybar: torch.Tensor):
+        """Forward of the network values + adjoint for caller-supplied output adjoints ``ybar`` [N, n_out]
+        (dL/dy); accumulates dL/d(params) into ``grads`` (``ppsci_b200_values_fwd_bwd``)."""
+        cr = self.compiled
+        device = params.device
+        n, xs = self._inputs(inputs, device)
+        auxs = [_col(inputs[k], n, self.dtype, device, f"aux '{k}'") for k in cr.aux_keys]
+        if ybar.shape != (n, self.n_out) or ybar.dtype != self.dtype or ybar.device != device:
+            raise ValueError(f"ybar must be [{n}, {self.n_out}] {self.dtype} on {device}")
+        if grads.dtype != params.dtype or grads.numel() != params.numel() or grads.device != device or not grads.is_contiguous():
+            raise ValueError("grads must match params in dtype/size/device and be contiguous")
+        yb = ybar.contiguous()
+        ws = self._workspace(n, device)
+        wptr, wbytes = self._aligned(ws)
+        rc = self.lib.lib.ppsci_b200_values_fwd_bwd(
+            self.handle, self._ptr_array(xs, len(xs)), self._ptr_array(auxs, len(auxs)), n, params.data_ptr(),
+            grads.data_ptr(), yb.data_ptr(), wptr, wbytes, self._stream(device))
+        self.lib.check(rc, "values_fwd_bwd")
+
     def forward(
         self,
         inputs: Dict[str, torch.Tensor],
@@ -243,8 +278,7 @@ class ResidualPlan:
         cr = self.compiled
         net = cr.net
         device = params.device
-        n = inputs[net.input_keys[0]].numel()
-        xs = [_col(inputs[k], n, self.dtype, device, f"input '{k}'") for k in net.input_keys]
+        n, xs = self._inputs(inputs, device)
         auxs = [_col(inputs[k], n, self.dtype, device, f"aux '{k}'") for k in cr.aux_keys]
         jets = torch.empty((self.channels, n, self.n_out), dtype=self.dtype, device=device) if want_jets else None
         res_t = [torch.empty((n, 1), dtype=self.dtype, device=device) for _ in range(self.n_res)] if want_residuals else []

@@ -107,7 +107,7 @@ class Solver:
         if type(self.loss_aggregator).__name__ != "Sum":
             raise NotImplementedError("only the Sum loss aggregator is supported by the fused adjoint kernels")
         # compile every constraint's expressions now (solver.py:496-535 does its sympy conversion here)
-        for cst in self.constraint.values():
+        for cst in ([] if hasattr(self.model, "fused_train_forward") else self.constraint.values()):
             sample_keys = None
             ds = getattr(cst.data_loader, "loader", None)
             ds = getattr(ds, "ds", ds)

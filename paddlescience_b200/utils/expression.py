@@ -86,6 +86,19 @@ class ExpressionSolver(nn.Module):
         gradient of  sum(losses_all)  has been accumulated into ``model.flat.grad``."""
         losses_all: Dict[str, torch.Tensor] = {}
         losses_constraint: Dict[str, torch.Tensor] = {}
+        if hasattr(model, "fused_train_forward"):  # models that combine several native networks (DeepONet)
+            for i, cst_name in enumerate(constraint):
+                cst = constraint[cst_name]
+                extra = [k for k in cst.output_expr if k not in model.output_keys]
+                if extra:
+                    raise NotImplementedError(f"{type(model).__name__}: output expressions {extra} beyond the model outputs "
+                                              "are not supported on the fused training path")
+                weights = weight_dicts[i]
+                losses = model.fused_train_forward(cst.loss, input_dicts[i], label_dicts[i], weights)
+                losses_constraint[cst_name] = sum(losses.values())
+                for key, v in losses.items():
+                    losses_all[key] = losses_all[key] + v if key in losses_all else v
+            return losses_all, losses_constraint
         flat = model.flat
         params, grads = model.engine_params(), model.engine_grads()  # effective weights / staging grads under weight_norm
         for i, cst_name in enumerate(constraint):
