@@ -100,6 +100,14 @@ def _need_sym(t, what: str):
             "graph through the network to differentiate real tensors.")
 
 
+def _diff(expr: sp.Basic, x: sp.Basic, order: int) -> sp.Basic:
+    """d^order expr / dx^order with the product / chain rule expanded down to derivatives of network outputs
+    (``jacobian(nu * u__x, x)`` or ``jacobian(u * u, x)`` in a user PDE callable — the reference differentiates
+    whatever tensor it is handed, ad.py:56-77).  A bare network output stays an unevaluated ``Derivative`` node,
+    which is what the residual compiler lowers to jet registers."""
+    return sp.diff(expr, x, order)
+
+
 class Jacobians:
     """``jacobian(ys, xs, i=0, j=None, retain_graph=None, create_graph=True)`` — ad.py:95-160."""
 
@@ -111,11 +119,11 @@ class Jacobians:
         if isinstance(xs, (list, tuple)):
             for x in xs:
                 _need_sym(x, "xs[k]")
-            return [SymTensor(sp.Derivative(ys.expr, x.expr)) for x in xs]
+            return [SymTensor(_diff(ys.expr, x.expr, 1)) for x in xs]
         _need_sym(xs, "xs")
         if j not in (None, 0):
             raise ValueError(f"j={j} is not valid: xs is a single-column proxy")
-        return SymTensor(sp.Derivative(ys.expr, xs.expr))
+        return SymTensor(_diff(ys.expr, xs.expr, 1))
 
     def _clear(self):
         pass
@@ -130,7 +138,7 @@ class Hessians:
         _need_sym(xs, "xs")
         if component not in (None, 0) or i != 0 or j != 0:
             raise ValueError("component / i / j must be 0 for single-column proxies")
-        return SymTensor(sp.Derivative(ys.expr, xs.expr, 2))
+        return SymTensor(_diff(ys.expr, xs.expr, 2))
 
     def _clear(self):
         pass

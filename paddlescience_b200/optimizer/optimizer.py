@@ -65,11 +65,18 @@ class FlatAdam:
     zero_grad = clear_grad
 
     def state_dict(self):
-        return {"t": self.t, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
+        # like paddle's optimizer state ("LR_Scheduler" entry): a resumed run continues the warm-up / decay where it
+        # stopped instead of replaying it from step 0
+        sd = {"t": self.t, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
+        if hasattr(self._lr, "state_dict"):
+            sd["LR_Scheduler"] = self._lr.state_dict()
+        return sd
 
     def set_state_dict(self, sd):
         self.t = int(sd["t"])
         self.exp_avg, self.exp_avg_sq = sd["exp_avg"], sd["exp_avg_sq"]
+        if "LR_Scheduler" in sd and hasattr(self._lr, "set_state_dict"):
+            self._lr.set_state_dict(sd["LR_Scheduler"])
 
 
 class Adam:
@@ -130,10 +137,17 @@ class FlatLBFGS:
     zero_grad = clear_grad
 
     def state_dict(self):
-        return self._opt.state_dict()
+        sd = self._opt.state_dict()
+        if hasattr(self._lr, "state_dict"):
+            sd["LR_Scheduler"] = self._lr.state_dict()
+        return sd
 
     def set_state_dict(self, sd):
+        sd = dict(sd)
+        lr_sd = sd.pop("LR_Scheduler", None)
         self._opt.load_state_dict(sd)
+        if lr_sd is not None and hasattr(self._lr, "set_state_dict"):
+            self._lr.set_state_dict(lr_sd)
 
 
 class LBFGS:

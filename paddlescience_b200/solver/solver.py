@@ -88,6 +88,8 @@ class Solver:
         if device in ("gpu", "cuda") and torch.cuda.is_available():
             local = int(os.environ.get("LOCAL_RANK", "0"))
             self.device = torch.device("cuda", local if local < torch.cuda.device_count() else 0)
+            # the native library allocates / launches on the CURRENT device (plan_create: cudaGetDevice + cudaMalloc)
+            torch.cuda.set_device(self.device)
             self.model.to(self.device)
         else:
             self.device = torch.device("cpu")  # construction / host logic only; train() raises
@@ -100,6 +102,11 @@ class Solver:
             save_load.load_pretrain(self.model, pretrained_model_path, self.equation)
         if checkpoint_path is not None:
             self.best_metric.update(save_load.load_checkpoint(checkpoint_path, self.model, self.optimizer, self.equation) or {})
+
+        if self.world_size > 1 and hasattr(self.model, "flat"):
+            # Paddle's DataParallel broadcasts rank 0's parameters at wrap time (solver.py:299-310); ranks seeded
+            # differently would otherwise train diverging replicas without any error
+            dist.broadcast(self.model.flat.data, src=0)
 
         self.forward_helper = expression.ExpressionSolver()
         self.forward_helper.nvtx_flag = self.nvtx_flag

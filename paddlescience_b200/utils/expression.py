@@ -62,6 +62,7 @@ class ExpressionSolver(nn.Module):
     def __init__(self):
         super().__init__()
         self._compiled: Dict[int, CompiledConstraint] = {}
+        self._eval_exprs: Dict[tuple, symbolic.CompiledExpr] = {}  # (id(expr), name, id(model), extra keys) -> compiled
 
     def forward(self, *args, **kwargs):
         raise NotImplementedError("Use train_forward/eval_forward/visu_forward instead of forward.")
@@ -99,6 +100,12 @@ class ExpressionSolver(nn.Module):
                 for key, v in losses.items():
                     losses_all[key] = losses_all[key] + v if key in losses_all else v
             return losses_all, losses_constraint
+        if getattr(model, "_input_transform", None) is not None or getattr(model, "_output_transform", None) is not None:
+            # MLP.forward (eval / predict / validators) applies the registered transforms; the fused residual kernels
+            # differentiate the bare network.  Training a different function than the one evaluated must not be silent.
+            raise NotImplementedError(f"{type(model).__name__}: registered input / output transforms are not traced into "
+                                      "the fused residual kernels; express the transform inside the constraint's "
+                                      "output_expr (or the equation) instead")
         flat = model.flat
         params, grads = model.engine_params(), model.engine_grads()  # effective weights / staging grads under weight_norm
         for i, cst_name in enumerate(constraint):
@@ -128,10 +135,18 @@ class ExpressionSolver(nn.Module):
         for name, expr in expr_dict.items():
             if name in output_dict and not isinstance(expr, (sp.Basic, symbolic.CompiledExpr)):
                 continue  # plain "lambda out: out['u']" style pass-through
-            ce = expr if isinstance(expr, symbolic.CompiledExpr) else symbolic.CompiledExpr(
-                expr if isinstance(expr, sp.Basic) else symbolic.trace_to_sympy(
-                    expr, model.input_keys, model.output_keys, [k for k in input_dict if k not in model.input_keys]),
-                model, name)
+            if isinstance(expr, symbolic.CompiledExpr):
+                ce = expr
+            else:  # compile once per (expression, model): sympy CSE + plan_create + workspace are not per-batch work
+                extra = tuple(k for k in input_dict if k not in model.input_keys)
+                ck = (id(expr), name, id(model), extra)
+                ce = self._eval_exprs.get(ck)
+                if ce is None or ce._src is not expr:
+                    ce = symbolic.CompiledExpr(
+                        expr if isinstance(expr, sp.Basic) else symbolic.trace_to_sympy(
+                            expr, model.input_keys, model.output_keys, list(extra)), model, name)
+                    ce._src = expr  # keeps the key's id() alive and guards against id reuse
+                    self._eval_exprs[ck] = ce
             output_dict[name] = ce(input_dict)
         if "area" in input_dict:
             output_dict["area"] = input_dict["area"]

@@ -112,14 +112,62 @@ TC_CASES = {
                                   exprs=_biharm_exprs, dtype=torch.float32, ranges={"x": (0, 2), "y": (0, 3)}),
 }
 
+# The five BASELINE.json configs at their named shapes.  Network widths / depths, jet channels,
+# reductions and point counts follow SURVEY.md section 8(d); "n" is the point count of the GPU test.
+NAMED_CASES = {
+    # cfg1: examples/laplace/laplace2d.py:48-59 — 101 x 101 evenly spaced interior grid, MSELoss("sum")
+    "cfg1_laplace_4x20": dict(in_keys=("x", "y"), out_keys=("u",), hidden=[20] * 4, act="tanh",
+                              exprs=lambda: O.laplace_expr(2), dtype=torch.float32, reduction="sum",
+                              grid=((0.0, 0.0), (1.0, 1.0)), n=10201),
+    "cfg1_laplace_5x20": dict(in_keys=("x", "y"), out_keys=("u",), hidden=[20] * 5, act="tanh",
+                              exprs=lambda: O.laplace_expr(2), dtype=torch.float32, reduction="sum",
+                              grid=((0.0, 0.0), (1.0, 1.0)), n=10201),
+    # cfg2: Allen-Cahn, 4 x 128, periodic in x, 2^18 points
+    "cfg2_allen_cahn_4x128": dict(in_keys=("t", "x"), out_keys=("u",), hidden=[128] * 4, act="tanh", exprs=_ac_exprs,
+                                  dtype=torch.float32, periods={"x": (2.0, False)},
+                                  oracle_exprs=lambda: O.allen_cahn_callable(0.01), ranges={"x": (-1, 1)}, n=1 << 18),
+    # cfg3: LDC Navier-Stokes Re=100, 6 x 256 — the headline shape
+    "cfg3_ldc_6x256": dict(in_keys=("x", "y"), out_keys=("u", "v", "p"), hidden=[256] * 6, act="tanh",
+                           exprs=lambda: O.navier_stokes_expr(0.01, 1.0, 2, False), dtype=torch.float32, n=1 << 16),
+    # cfg4: Biharmonic2D, 5 x 128, fp64, C = 17 (x, y, x+y, x-y to order 4)
+    "cfg4_biharmonic_5x128_f64": dict(in_keys=("x", "y"), out_keys=("u",), hidden=[128] * 5, act="tanh",
+                                      exprs=_biharm_exprs, dtype=torch.float64, ranges={"x": (0, 2), "y": (0, 3)},
+                                      n=1 << 15),
+}
+
 TOL = {  # (loss rel, residual rel-L2, grad rel-L2)
     torch.float32: (2e-6, 5e-6, 1e-5),
     torch.float64: (1e-12, 1e-11, 1e-11),
 }
 
 
-def run_case(name: str, n: int, library=None, device="cpu", backend: int = 0, seed: int = 0) -> Dict[str, float]:
-    c = CASES[name] if name in CASES else TC_CASES[name]
+def oracle_in_blocks(om, params, exprs, inputs, labels, wts, reduction, lw, block: int = 8192):
+    """O.train_forward_backward over blocks of points (the fp64 double-backward graph of 6 x 256 holds ~0.6 MB per
+    point): per-point residuals concatenate, "sum" losses and their gradients add, "mean" = sum / n."""
+    n = next(iter(inputs.values())).shape[0]
+    if n <= block:
+        return O.train_forward_backward(om, params, exprs, inputs, labels, wts, reduction, lw)
+    losses, res, grad = {}, {}, None
+    for s in range(0, n, block):
+        sl = slice(s, min(n, s + block))
+        l_, r_, g_ = O.train_forward_backward(om, params, exprs, {k: v[sl] for k, v in inputs.items()},
+                                              {k: v[sl] for k, v in labels.items()},
+                                              {k: v[sl] for k, v in wts.items()} if wts else None, "sum", lw)
+        for k, v in l_.items():
+            losses[k] = losses.get(k, 0.0) + v
+        for k, v in r_.items():
+            res.setdefault(k, []).append(v)
+        grad = g_ if grad is None else grad + g_
+    scale = 1.0 / n if reduction == "mean" else 1.0
+    return ({k: v * scale for k, v in losses.items()}, {k: torch.cat(v) for k, v in res.items()}, grad * scale)
+
+
+def run_case(name, n: int, library=None, device="cpu", backend: int = 0, seed: int = 0,
+             oracle_subset: int = 0) -> Dict[str, float]:
+    """``name``: key of CASES / TC_CASES / NAMED_CASES, or a case dict.  ``oracle_subset`` > 0: the engine runs all
+    ``n`` points, the oracle only ``oracle_subset`` evenly strided points; residuals are compared on that subset and
+    the engine's loss against the mean / sum of its own residuals (loss / grad errors are then not oracle errors)."""
+    c = name if isinstance(name, dict) else (CASES.get(name) or TC_CASES.get(name) or NAMED_CASES[name])
     torch.manual_seed(seed)
     dtype = c["dtype"]
     exprs = c["exprs"]()
@@ -132,9 +180,15 @@ def run_case(name: str, n: int, library=None, device="cpu", backend: int = 0, se
     plan = ResidualPlan(cr, dtype, [reduction] * nres, [1.0 + 0.5 * k for k in range(nres)], chunk_points=chunk,
                         backend=backend, library=library)
     inputs = {}
-    for k in c["in_keys"]:
-        lo, hi = (c.get("ranges") or {}).get(k, (0, 1))
-        inputs[k] = (torch.rand(n, 1, dtype=torch.float64) * (hi - lo) + lo).to(dtype)
+    if c.get("grid"):  # the reference's evenly=True interior set (geometry_nd.py:83-110): itertools.product order
+        pts = O.hypercube_uniform_points(*c["grid"], n, boundary=True)
+        n = pts.shape[0]
+        for i, k in enumerate(c["in_keys"]):
+            inputs[k] = torch.as_tensor(pts[:, i:i + 1], dtype=torch.float64).to(dtype)
+    else:
+        for k in c["in_keys"]:
+            lo, hi = (c.get("ranges") or {}).get(k, (0, 1))
+            inputs[k] = (torch.rand(n, 1, dtype=torch.float64) * (hi - lo) + lo).to(dtype)
     om = O.OracleMLP(c["in_keys"], c["out_keys"], c["hidden"], c["act"], periods)
     params = O.xavier_uniform_params(om.widths, 1, torch.float64)
     params = (params + 0.1 * torch.randn_like(params)).to(dtype)
@@ -143,9 +197,13 @@ def run_case(name: str, n: int, library=None, device="cpu", backend: int = 0, se
     wts = {k: torch.rand(n, 1, dtype=torch.float64).to(dtype) for k in cr.names} if c.get("weights") else None
     lw = {k: 1.0 + 0.5 * i for i, k in enumerate(cr.names)}
     oracle_exprs = c["oracle_exprs"]() if c.get("oracle_exprs") else exprs
-    lo_, ro, go = O.train_forward_backward(
-        om, params.double(), oracle_exprs, {k: v.double() for k, v in inputs.items()},
-        {k: v.double() for k, v in labels.items()}, {k: v.double() for k, v in wts.items()} if wts else None,
+    sub = None
+    if oracle_subset and oracle_subset < n:
+        sub = torch.arange(0, n, n // oracle_subset)[:oracle_subset]
+    pick = (lambda v: v[sub]) if sub is not None else (lambda v: v)
+    lo_, ro, go = oracle_in_blocks(
+        om, params.double(), oracle_exprs, {k: pick(v).double() for k, v in inputs.items()},
+        {k: pick(v).double() for k, v in labels.items()}, {k: pick(v).double() for k, v in wts.items()} if wts else None,
         reduction, lw)
     dev = torch.device(device)
     d_in = {k: v.to(dev) for k, v in inputs.items()}
@@ -156,9 +214,21 @@ def run_case(name: str, n: int, library=None, device="cpu", backend: int = 0, se
     d_res = {k: torch.empty(n, 1, dtype=dtype, device=dev) for k in cr.names}
     loss = plan.loss_fwd_bwd(d_in, d_par, d_grads, labels=d_lab, weights=d_w, residual_out=d_res)
     loss = loss.cpu()
-    lerr = max(abs(float(loss[i]) - float(lo_[k])) / max(1e-30, abs(float(lo_[k]))) for i, k in enumerate(cr.names))
-    rerr = max(float((d_res[k].cpu().double() - ro[k]).norm() / ro[k].norm().clamp_min(1e-30)) for k in cr.names)
-    gerr = float((d_grads.cpu().double() - go).norm() / go.norm())
+    if sub is not None:
+        # loss: against the engine's own residuals reduced in fp64 (self-consistency at full size)
+        def own(i, k):
+            r = d_res[k].cpu().double()
+            e2 = (r - labels[k].double()) ** 2
+            if wts:
+                e2 = e2 * wts[k].double()
+            return float(lw[k] * (e2.mean() if reduction == "mean" else e2.sum()))
+        lerr = max(abs(float(loss[i]) - own(i, k)) / max(1e-30, abs(own(i, k))) for i, k in enumerate(cr.names))
+        rerr = max(float((d_res[k].cpu().double()[sub] - ro[k]).norm() / ro[k].norm().clamp_min(1e-30)) for k in cr.names)
+        gerr = float("nan")
+    else:
+        lerr = max(abs(float(loss[i]) - float(lo_[k])) / max(1e-30, abs(float(lo_[k]))) for i, k in enumerate(cr.names))
+        rerr = max(float((d_res[k].cpu().double() - ro[k]).norm() / ro[k].norm().clamp_min(1e-30)) for k in cr.names)
+        gerr = float((d_grads.cpu().double() - go).norm() / go.norm())
     # forward-only entry point must agree with the fused call
     _, res2 = plan.forward(d_in, d_par, want_jets=False)
     ferr = max(float((res2[k] - d_res[k]).abs().max()) for k in cr.names)

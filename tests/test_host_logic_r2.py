@@ -1,0 +1,61 @@
+"""Host-side behaviours fixed in round 2: composite jacobians, transform guard on the fused path,
+LR-scheduler state in optimizer checkpoints."""
+import pytest
+import sympy as sp
+import torch
+
+import ppsci
+from paddlescience_b200.autodiff.ad import SymTensor, hessian, jacobian
+from paddlescience_b200.engine.compiler import compile_residuals
+
+
+def test_jacobian_of_composite_expression_expands_to_output_derivatives():
+    """``jacobian(u * u, x)`` / ``jacobian(nu * u__x, x)`` (reference ad.py:56-77 differentiates any tensor)."""
+    x, y = sp.symbols("x y")
+    u = sp.Function("u")(x, y)
+    su, sx = SymTensor(u), SymTensor(x)
+    d = jacobian(su * su, sx).expr
+    assert sp.simplify(d - 2 * u * u.diff(x)) == 0
+    ux = jacobian(su, sx)
+    assert ux.expr == u.diff(x)  # a bare output stays an unevaluated Derivative node
+    d2 = jacobian(0.3 * ux, sx).expr
+    assert sp.simplify(d2 - 0.3 * u.diff(x, 2)) == 0
+    h = hessian(su * sx, sx).expr
+    assert sp.simplify(h - (2 * u.diff(x) + x * u.diff(x, 2))) == 0
+    # and the result compiles (it used to raise "derivative of ... is not supported")
+    m = ppsci.arch.MLP(("x", "y"), ("u",), 2, 8, "tanh")
+    cr = compile_residuals(m.net_spec(), {"r": d + h})
+    assert cr.channels == 3  # value + x to order 2
+
+
+def test_train_forward_refuses_models_with_registered_transforms():
+    m = ppsci.arch.MLP(("x", "y"), ("u",), 2, 8, "tanh")
+    m.register_output_transform(lambda inp, out: {"u": out["u"] * inp["x"]})
+    eq = ppsci.equation.Laplace(2)
+    rect = ppsci.geometry.Rectangle((0, 0), (1, 1))
+    cst = ppsci.constraint.InteriorConstraint(eq.equations, {"laplace": 0}, rect,
+                                              {"dataset": "IterableNamedArrayDataset", "iters_per_epoch": 1, "batch_size": 8},
+                                              ppsci.loss.MSELoss("mean"), name="EQ")
+    ds = cst.data_loader.loader
+    fh = ppsci.utils.ExpressionSolver()
+    with pytest.raises(NotImplementedError, match="transform"):
+        fh.train_forward((cst.output_expr,), [ds.input], m, {"EQ": cst}, [ds.label], [None])
+
+
+def test_optimizer_checkpoint_carries_the_lr_schedule_position():
+    m = ppsci.arch.MLP(("x", "y"), ("u",), 2, 8, "tanh")
+    sched = ppsci.optimizer.lr_scheduler.ExponentialDecay(10, 5, 1e-3, 0.9, 3, warmup_epoch=1)()
+    opt = ppsci.optimizer.Adam(sched)(m)
+    for _ in range(7):
+        sched.step()
+    opt.t = 7
+    opt.exp_avg = torch.zeros(3)
+    opt.exp_avg_sq = torch.zeros(3)
+    sd = opt.state_dict()
+    assert sd["LR_Scheduler"] == {"last_epoch": 7}
+    sched2 = ppsci.optimizer.lr_scheduler.ExponentialDecay(10, 5, 1e-3, 0.9, 3, warmup_epoch=1)()
+    opt2 = ppsci.optimizer.Adam(sched2)(m)
+    opt2.set_state_dict(sd)
+    assert opt2.t == 7 and sched2.last_epoch == 7
+    assert opt2.get_lr() == pytest.approx(opt.get_lr())
+    assert opt2.get_lr() != pytest.approx(1e-3 * 0 + sched2.warmup_start_lr)  # not replaying the warm-up
