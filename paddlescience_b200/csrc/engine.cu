@@ -13,11 +13,9 @@
 #include <vector>
 
 #include "kernels_simt.cuh"
-#ifndef PPSCI_EMUL
 #include "kernels_tc.cuh"
 #include "kernels_tc2.cuh"
 #include "kernels_thin.cuh"
-#endif
 
 using namespace ppsci;
 
@@ -271,17 +269,16 @@ extern "C" int ppsci_b200_plan_create(const ppsci_plan_spec* s, ppsci_plan** out
     delete P;
     return fail("plan_create: no CUDA device available (the engine has no CPU fallback)");
   }
-#ifndef PPSCI_EMUL
   P->use_tc = tc_plan_supported(P->spec, P->C, P->kmax) && s->backend != 1;
+#ifdef PPSCI_EMUL
+  if (s->backend != 2) P->use_tc = false;  // the emulated tensor-core kernels (1,024 OS threads per CTA pair) run on request only
+#endif
   if (const char* m = getenv("PPSCI_B200_TC_MASK")) P->tc_mask = atoi(m);
   if (s->backend == 2 && !P->use_tc) {
     delete P;
     return fail("plan_create: backend=2 (tcgen05) requested but the plan is not eligible "
                 "(needs f32, tanh, hidden widths in {128,256}, order<=2)");
   }
-#else
-  if (s->backend == 2) { delete P; return fail("plan_create: tcgen05 backend is not emulated"); }
-#endif
 
   auto up = [&](const void* src, size_t bytes, void** dst) -> cudaError_t {
     cudaError_t e = cudaMalloc(dst, bytes ? bytes : 16);
@@ -499,11 +496,9 @@ static int run(ppsci_plan* P, const CallArgs& a) {
   const bool thin_on = getenv("PPSCI_B200_NO_THIN") == nullptr;
   const bool thin_first = thin_on && L >= 2 && s.widths[0] <= THIN_MAXF && !s.dense_in;
   const bool thin_last = thin_on && L >= 2 && n_out <= THIN_MAXM && C * n_out <= THIN_MAXCM;
-#ifndef PPSCI_EMUL
   // fp32 + one of the compile-time jet layouts: vectorised thin kernels (kernels_thin.cuh)
   const int thin_lay = tc_pick_layout(P->J, PPSCI_ACT_TANH);
   const bool thin_vec = sizeof(T) == 4 && thin_lay != TC_LAY_DYN && getenv("PPSCI_B200_NO_THINV") == nullptr;
-#endif
 
   if (a.want_loss) CK(cudaMemsetAsync(loss_acc, 0, PPSCI_MAX_RES * sizeof(double), st));
   const bool do_bwd = (a.want_loss || a.ybar_in) && grads != nullptr;
@@ -519,7 +514,6 @@ static int run(ppsci_plan* P, const CallArgs& a) {
     }
   }
 
-#ifndef PPSCI_EMUL
   if constexpr (sizeof(T) == 4) {
     if (P->use_tc) {
       for (int l = 2; l < L; ++l) {
@@ -527,9 +521,9 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         const int K = s.widths[l - 1], N = s.widths[l];
         const long long tot = (long long)K * N;
         ProfScope ps_(P, CLS_MISC, st);
-        tc::k_tc_prep_w<<<dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st>>>(
-            reinterpret_cast<const float*>(params) + P->w_off[l],
-            reinterpret_cast<float*>(ws + cv.tc + tc_img_offset(s, l)), K, N, 0);
+        PPSCI_LAUNCH(tc::k_tc_prep_w, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st,
+                     reinterpret_cast<const float*>(params) + P->w_off[l],
+                     reinterpret_cast<float*>(ws + cv.tc + tc_img_offset(s, l)), K, N, 0);
         P->launches++;
       }
       if (do_bwd && (P->tc_mask & 2)) {
@@ -538,15 +532,14 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           const int K = s.widths[l], N = s.widths[l - 1];  // gemm K = fan-out, gemm N = fan-in
           const long long tot = (long long)K * N;
           ProfScope ps_(P, CLS_MISC, st);
-          tc::k_tc_prep_w<<<dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st>>>(
-              reinterpret_cast<const float*>(params) + P->w_off[l],
-              reinterpret_cast<float*>(ws + cv.tc + tc_imgT_offset(s, l)), K, N, 1);
+          PPSCI_LAUNCH(tc::k_tc_prep_w, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st,
+                       reinterpret_cast<const float*>(params) + P->w_off[l],
+                       reinterpret_cast<float*>(ws + cv.tc + tc_imgT_offset(s, l)), K, N, 1);
           P->launches++;
         }
       }
     }
   }
-#endif
   for (int64_t c0 = 0; c0 < a.n_points; c0 += nc_max) {
     const int64_t nc = (a.n_points - c0) < nc_max ? (a.n_points - c0) : nc_max;
     const unsigned ptiles = (unsigned)((nc + TP - 1) / TP);
@@ -566,18 +559,16 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         f.oplane = (long long)nc_max * P->ld[1];
         f.Np = nc;
         const long long tot = (long long)nc * f.N;
-#ifndef PPSCI_EMUL
         if constexpr (sizeof(T) == 4) {
           if (thin_vec && f.N % 4 == 0) {  // compile-time layout, 128-bit stores, seeds staged once per point
             void (*kv)(FirstArgs<float>) = nullptr;
             PPSCI_THIN_PICK_L(k_first_fwd_v, thin_lay, KMAX, kv);
             ProfScope ps_(P, CLS_THIN_FWD, st);
-            kv<<<dim3((unsigned)((nc + thin::PB - 1) / thin::PB)), dim3(256), 0, st>>>(f);
+            PPSCI_LAUNCH(kv, dim3((unsigned)((nc + thin::PB - 1) / thin::PB)), dim3(256), 0, st, f);
             P->launches++;
             continue;
           }
         }
-#endif
         auto k1 = k_first_fwd<T, KMAX>;
         ProfScope ps_(P, CLS_THIN_FWD, st);
         PPSCI_LAUNCH(k1, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, f);
@@ -597,25 +588,22 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         f.ldy = P->ld[L];
         f.yplane = (long long)nc_max * P->ld[L];
         f.Np = nc;
-#ifndef PPSCI_EMUL
         if constexpr (sizeof(T) == 4) {
           if (thin_vec && f.K % 4 == 0 && f.m <= 4) {
             void (*kv)(LastArgs<float>) = nullptr;
             PPSCI_THIN_PICK_LM(k_last_fwd_v, thin_lay, f.m, kv);
             ProfScope ps_(P, CLS_THIN_FWD, st);
-            kv<<<dim3((unsigned)((nc + 7) / 8)), dim3(256), 0, st>>>(f);
+            PPSCI_LAUNCH(kv, dim3((unsigned)((nc + 7) / 8)), dim3(256), 0, st, f);
             P->launches++;
             continue;
           }
         }
-#endif
         auto k2 = k_last_fwd<T, KMAX>;
         ProfScope ps_(P, CLS_THIN_FWD, st);
         PPSCI_LAUNCH(k2, dim3((unsigned)((nc + 7) / 8)), dim3(256), 0, st, f);
         P->launches++;
         continue;
       }
-#ifndef PPSCI_EMUL
       if constexpr (sizeof(T) == 4) {
         if (P->use_tc && (P->tc_mask & 1) && tc_layer_ok(s, l)) {
           tc::TcFwdArgs t;
@@ -658,7 +646,6 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           continue;
         }
       }
-#endif
       GemmArgs<T> g;
       memset(&g, 0, sizeof(g));
       if (l == 1) fill_first<T>(P, a.x_cols, c0, nc_max, &g.A);
@@ -762,19 +749,17 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         f.Np = nc;
         f.pts_per_block = 64;
         bool last_done = false;
-#ifndef PPSCI_EMUL
         if constexpr (sizeof(T) == 4) {
           if (thin_vec && f.K % 4 == 0 && f.m <= 4) {
             f.pts_per_block = 128;
             void (*kv)(LastArgs<float>) = nullptr;
             PPSCI_THIN_PICK_LM(k_last_bwd_v, thin_lay, f.m, kv);
             ProfScope ps_(P, CLS_THIN_DX, st);
-            kv<<<dim3((unsigned)((f.K + 255) / 256), (unsigned)((nc + 127) / 128)), dim3(256), 0, st>>>(f);
+            PPSCI_LAUNCH(kv, dim3((unsigned)((f.K + 255) / 256), (unsigned)((nc + 127) / 128)), dim3(256), 0, st, f);
             P->launches++;
             last_done = true;
           }
         }
-#endif
         if (!last_done) {
           auto k3 = k_last_bwd<T, KMAX>;
           ProfScope ps_(P, CLS_THIN_DX, st);
@@ -800,26 +785,23 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         f.db = grads + P->b_off[1];
         f.Np = nc;
         f.pts_per_block = 32;
-#ifndef PPSCI_EMUL
         if constexpr (sizeof(T) == 4) {
           if (thin_vec && f.N % 4 == 0) {
             f.pts_per_block = 256;
             void (*kv)(FirstArgs<float>) = nullptr;
             PPSCI_THIN_PICK_L(k_first_dw_v, thin_lay, KMAX, kv);
             ProfScope ps_(P, CLS_THIN_DW, st);
-            kv<<<dim3((unsigned)((f.N + 255) / 256), (unsigned)((nc + 255) / 256)), dim3(256), 0, st>>>(f);
+            PPSCI_LAUNCH(kv, dim3((unsigned)((f.N + 255) / 256), (unsigned)((nc + 255) / 256)), dim3(256), 0, st, f);
             P->launches++;
             break;
           }
         }
-#endif
         auto k4 = k_first_dw<T, KMAX>;
         ProfScope ps_(P, CLS_THIN_DW, st);
         PPSCI_LAUNCH(k4, dim3((unsigned)((f.N + 255) / 256), (unsigned)((nc + 31) / 32)), dim3(256), 0, st, f);
         P->launches++;
         break;
       }
-#ifndef PPSCI_EMUL
       bool dw_done = false;
       if constexpr (sizeof(T) == 4) {
         if (tc_astash_needed(P, l - 1)) {
@@ -881,16 +863,15 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           if (!db_fused) {
             ProfScope ps_(P, CLS_THIN_DW, st);
             const int ppb = 512;
-            tc::k_bias_grad<<<dim3((unsigned)((s.widths[l] + 127) / 128), (unsigned)((nc + ppb - 1) / ppb)), dim3(128), 0, st>>>(
-                reinterpret_cast<const float*>(zbar_cur), zbar_ld, (long long)nc, s.widths[l],
-                reinterpret_cast<float*>(grads) + P->b_off[l], ppb);
+            PPSCI_LAUNCH(tc::k_bias_grad, dim3((unsigned)((s.widths[l] + 127) / 128), (unsigned)((nc + ppb - 1) / ppb)), dim3(128), 0, st,
+                         reinterpret_cast<const float*>(zbar_cur), zbar_ld, (long long)nc, s.widths[l],
+                         reinterpret_cast<float*>(grads) + P->b_off[l], ppb);
             P->launches++;
           }
           dw_done = true;
         }
       }
       if (!dw_done)
-#endif
       {  // dW_l, db_l
         DwArgs<T> g;
         memset(&g, 0, sizeof(g));
@@ -919,7 +900,6 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         P->launches++;
       }
       if (l == 1) break;
-#ifndef PPSCI_EMUL
       if constexpr (sizeof(T) == 4) {
         if (P->use_tc && (P->tc_mask & 2) && tc_dx_ok(s, l)) {
           tc::TcDxArgs t;
@@ -966,7 +946,6 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           continue;
         }
       }
-#endif
       {  // Zbar_{l-1}
         GemmArgs<T> g;
         memset(&g, 0, sizeof(g));
@@ -1093,10 +1072,6 @@ extern "C" int ppsci_b200_adam_step(int32_t dtype, void* params, const void* gra
   return 0;
 }
 
-#ifdef PPSCI_EMUL
-static size_t tc_scratch_bytes(const ppsci_plan*, int64_t) { return 0; }
-static bool tc_astash_needed(const ppsci_plan*, int) { return false; }
-#else
 // a_l is stashed by the tensor-core forward of layer l+1 and consumed by the tensor-core dW of layer l+1
 static bool tc_astash_needed(const ppsci_plan* P, int l) {
   const int lay = l + 1;
@@ -1106,4 +1081,3 @@ static bool tc_astash_needed(const ppsci_plan* P, int l) {
 static size_t tc_scratch_bytes(const ppsci_plan* P, int64_t nc) {
   return P->use_tc ? tc_scratch_bytes_impl(P->spec, P->C, nc) : 0;
 }
-#endif

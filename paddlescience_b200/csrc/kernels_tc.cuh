@@ -14,7 +14,9 @@
 // Accumulator: 128 lanes x N fp32 columns in TMEM; read back with tcgen05.ld.32x32b.
 #pragma once
 
+#ifndef PPSCI_EMUL
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include <string>
@@ -31,12 +33,36 @@ constexpr int NPW = NPROD / 32;      // producer warps
 constexpr int MMA_WARP = THREADS / 32 - 1;
 constexpr int A_TILE_BYTES = 128 * KCH * 4;  // 16 KB (one of hi / lo)
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 // byte offset of element (row, kk) inside a [rows x 32 fp32] K-major SWIZZLE_128B tile
 __host__ __device__ __forceinline__ uint32_t sw128(int row, int kk) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((kk >> 2) ^ row) & 7) << 4) + ((kk & 3) << 2));
 }
+
+// ---- UMMA descriptors ---------------------------------------------------------------------------------
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_128B,
+// 8-row group pitch (SBO) 1024 B, LBO unused for swizzled K-major (=1), version 1 (Blackwell).
+__host__ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                    // leading byte offset >> 4, bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset >> 4, bits [32,46)
+  d |= (uint64_t)1 << 46;                    // version, bits [46,48)
+  d |= (uint64_t)2 << 61;                    // layout type SWIZZLE_128B, bits [61,64)
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate, K-major A and B.
+__host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// ---- PTX wrappers (sm_100a).  The -DPPSCI_EMUL test build (tests/emul/) swaps in CPU emulations with the same names. ----
+#ifdef PPSCI_EMUL
+}  // namespace tc
+}  // namespace ppsci
+#include "tc_emul_prims.h"
+namespace ppsci {
+namespace tc {
+#else
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ float tf32_rn(float x) {
   uint32_t u;
@@ -128,22 +154,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// ---- UMMA descriptors ---------------------------------------------------------------------------------
-// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): K-major, SWIZZLE_128B,
-// 8-row group pitch (SBO) 1024 B, LBO unused for swizzled K-major (=1), version 1 (Blackwell).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, bits [0,14)
-  d |= (uint64_t)1 << 16;                    // leading byte offset >> 4, bits [16,30)
-  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset >> 4, bits [32,46)
-  d |= (uint64_t)1 << 46;                    // version, bits [46,48)
-  d |= (uint64_t)2 << 61;                    // layout type SWIZZLE_128B, bits [61,64)
-  return d;
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate, K-major A and B.
-__host__ __device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -155,6 +165,11 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+#endif  // PPSCI_EMUL
 
 // ---- weight image: Wimg[j][part][sw128(n, kk)] = split(W_as_B[n][32 j + kk]) ---------------------------
 // transposed = 0: B[n][k] = W[k * N + n]   (forward: W is [K=in][N=out] row-major)
@@ -215,6 +230,7 @@ __device__ __forceinline__ int act_id(int rt) { return ACT >= 0 ? ACT : rt; }
 // cp.async pieces spread over all threads are 2x faster here.)  The piece -> (row, 16-byte column) mapping
 // does not change from block to block, so each thread precomputes its pieces once.  The main loops do NOT
 // stage operand rows this way any more: they go global -> registers -> swizzled tiles (see k_tc_fwd).
+#ifndef PPSCI_EMUL
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, bool valid) {
   const int sz = valid ? 16 : 0;  // src-size 0 => the 16 destination bytes are zero-filled
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
@@ -224,6 +240,8 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
+
+#endif
 
 constexpr int ROW_PIECES = (128 * 8 + NPROD - 1) / NPROD;  // 16-byte pieces of a [128 x 32] tile per producer thread
 
@@ -313,15 +331,31 @@ __device__ __forceinline__ void issue_chunk_mmas_cat(uint32_t accX, uint32_t acc
   }
 }
 
-// acc0 + acc1 for 32 lanes x 32 columns
-__device__ __forceinline__ void load_acc_sum(uint32_t acc0, uint32_t acc1, int q, int col, float (&out)[32]) {
+// ---- compensation of the accumulator's round-toward-zero --------------------------------------------------
+// Measured (tests/microbench/tc_numerics.cu, profiles/r02_tc_numerics.txt): tcgen05 adds the exactly summed K = 8
+// products of one instruction to the fp32 accumulator with ROUND TOWARD ZERO.  Every accumulate therefore shrinks the
+// partial sum by 0.72 * 2^-24 of its magnitude on average; for exchangeable terms E[partial_k | total] = (k / n)
+// total, so n accumulations of significant magnitude shrink the result by a factor 1 - c0 * n / 2 — a pure, data
+// independent bias (the three trials of the micro-benchmark, row magnitudes 1e-9 .. 1e3, agree to 3 digits):
+//   c0 = 3.35e-8 per accumulation (model 0.5 * 0.7213 * 2^-23 = 4.3e-8, measured 78 % of it)
+// The epilogues multiply the accumulator sum by (1 + c0 * sum_acc events_acc / 2 * share_acc); what remains is the
+// zero-mean part of the rounding (fp32-chain level).
+constexpr float TC_RZ_C0 = 3.35e-8f;
+// split scheme of issue_chunk_mmas(_2): acc0 sees 2 significant accumulations per 32-wide chunk, acc1 sees 10
+// (2 exact-product + 8 small cross terms rounded at acc1's magnitude), each accumulator holds half of the result
+__host__ __device__ __forceinline__ float tc_rz_comp_split(long long nchunks) { return 1.f + TC_RZ_C0 * 3.f * (float)nchunks; }
+// concatenated scheme of issue_chunk_mmas_cat: 4 accumulations of the exact-product term per chunk, full magnitude
+__host__ __device__ __forceinline__ float tc_rz_comp_cat(long long nchunks) { return 1.f + TC_RZ_C0 * 2.f * (float)nchunks; }
+
+// (acc0 + acc1) * comp for 32 lanes x 32 columns
+__device__ __forceinline__ void load_acc_sum(uint32_t acc0, uint32_t acc1, int q, int col, float (&out)[32], float comp) {
   uint32_t v0[32], v1[32];
   const uint32_t lane_off = (uint32_t)(q * 32) << 16;
   tmem_ld32(acc0 + lane_off + (uint32_t)col, v0);
   tmem_ld32(acc1 + lane_off + (uint32_t)col, v1);
   tmem_ld_wait();
 #pragma unroll
-  for (int t = 0; t < 32; ++t) out[t] = __uint_as_float(v0[t]) + __uint_as_float(v1[t]);
+  for (int t = 0; t < 32; ++t) out[t] = (__uint_as_float(v0[t]) + __uint_as_float(v1[t])) * comp;
 }
 
 // store v = hi + lo into the (hi, lo) pair of K-major SW128 tiles; `off` = sw128(row, col)
@@ -401,7 +435,7 @@ __device__ __forceinline__ void tc_setup(uint32_t base, unsigned char* base_ptr,
 // This single-CTA kernel is the fallback / cross-check of the CTA-pair kernel k_tc2_fwd (kernels_tc2.cuh).
 template <class L, int ACT>
 __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
-  extern __shared__ unsigned char smem_dyn[];
+  PPSCI_DYN_SMEM(smem_dyn);
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
   const int N = g.Nout;
@@ -598,7 +632,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
         unsigned char* Xb = base_ptr + (part >> 1) * stage_bytes + (part & 1) * A_TILE_BYTES;
         if (cb < ncb) {
           float v[32];
-          load_acc_sum(acc0, acc1, q, cb * 32, v);
+          load_acc_sum(acc0, acc1, q, cb * 32, v, tc_rz_comp_split(nchunks));
           const int row = q * 32 + lane;
 #pragma unroll
           for (int t4 = 0; t4 < 8; ++t4)
@@ -668,7 +702,7 @@ struct TcDxArgs {
 
 template <class L, int ACT>
 __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
-  extern __shared__ unsigned char smem_dyn[];
+  PPSCI_DYN_SMEM(smem_dyn);
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
   const int N = g.Nout;
@@ -801,7 +835,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
         cp_async_commit();
         if (warp < 4) {  // 128 lanes x 32 columns of Abar
           float v[32];
-          load_acc_sum(acc0, acc1, warp, cb * 32, v);
+          load_acc_sum(acc0, acc1, warp, cb * 32, v, tc_rz_comp_split(nchunks));
           const int row = warp * 32 + lane;
 #pragma unroll
           for (int t4 = 0; t4 < 8; ++t4)
@@ -942,7 +976,7 @@ constexpr int DW_MMA_WARP = DW_NPW;
 // Tasks: A' = 4 row groups x 2 q groups, B' = N/32 row groups x 2 q groups  (16 tasks at N = 128).
 template <class L>
 __global__ void __launch_bounds__(DW_THREADS, 1) k_tc_dw(TcDwArgs g) {
-  extern __shared__ unsigned char smem_dyn[];
+  PPSCI_DYN_SMEM(smem_dyn);
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
   const int N = g.Nout;  // columns of this CTA
@@ -1083,9 +1117,10 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_tc_dw(TcDwArgs g) {
     const int k = k0 + q * 32 + lane;
     float* dw_row = g.dW + (long long)k * g.ldw + n0;
     const int ncb = N / 32;
+    const float rz_comp = tc_rz_comp_cat((long long)it);
     for (int cb = part; cb < ncb; cb += DW_NPW / 4) {
       float v[32], w[32];
-      load_acc_sum(accX, accX + (uint32_t)N, q, cb * 32, v);
+      load_acc_sum(accX, accX + (uint32_t)N, q, cb * 32, v, 1.f);
       {
         uint32_t y[32];
         tmem_ld32(accY + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), y);
@@ -1094,7 +1129,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_tc_dw(TcDwArgs g) {
         for (int t = 0; t < 32; ++t) w[t] = __uint_as_float(y[t]);
       }
 #pragma unroll
-      for (int t = 0; t < 32; ++t) v[t] += w[t];
+      for (int t = 0; t < 32; ++t) v[t] = (v[t] + w[t]) * rz_comp;
       if (k < g.Kdim) {
 #pragma unroll
         for (int t = 0; t < 32; ++t) atomicAdd(dw_row + cb * 32 + t, v[t]);
@@ -1173,7 +1208,7 @@ inline int tc_pick_layout(const JetLayout& J, int act) {
     }                                                                                                             \
     cudaError_t e_ = cudaFuncSetAttribute(kfn_, cudaFuncAttributeMaxDynamicSharedMemorySize, (smem));             \
     if (e_ != cudaSuccess) { err_expr; }                                                                          \
-    kfn_<<<(grid), dim3(tc::DW_THREADS), (smem), (stream)>>>(args);                                                  \
+    PPSCI_KLAUNCH(kfn_, (grid), dim3(tc::DW_THREADS), (smem), (stream), 1, args);                                  \
   } while (0)
 
 #define PPSCI_TC_LAUNCH(KERNEL, lay, kmax, grid, smem, stream, args, err_expr)                                   \
@@ -1190,7 +1225,7 @@ inline int tc_pick_layout(const JetLayout& J, int act) {
     }                                                                                                             \
     cudaError_t e_ = cudaFuncSetAttribute(kfn_, cudaFuncAttributeMaxDynamicSharedMemorySize, (smem));             \
     if (e_ != cudaSuccess) { err_expr; }                                                                          \
-    kfn_<<<(grid), dim3(tc::THREADS), (smem), (stream)>>>(args);                                                  \
+    PPSCI_KLAUNCH(kfn_, (grid), dim3(tc::THREADS), (smem), (stream), 1, args);                                     \
   } while (0)
 
 

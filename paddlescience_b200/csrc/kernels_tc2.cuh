@@ -29,6 +29,7 @@ constexpr int T2_NSTAGE = 3;
 constexpr int T2_PROD_THREADS = T2_NPW * 32;
 
 __device__ __forceinline__ float f4comp(const float4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+#ifndef PPSCI_EMUL
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -88,6 +89,8 @@ __device__ __forceinline__ void mma_commit_2(uint32_t bar) {
                : "memory");
 }
 
+#endif  // PPSCI_EMUL (tests/emul/tc_emul_prims.h provides the same names)
+
 __host__ __device__ inline int tc2_stage_bytes(int N) { return 2 * A_TILE_BYTES + 2 * (N / 2) * KCH * 4; }
 // barriers: mma_done[3] +24, full[3] +48, TMEM base slot +128
 __host__ __device__ inline int tc2_smem_bytes(int N) { return T2_NSTAGE * tc2_stage_bytes(N) + 1024 + 256; }
@@ -112,7 +115,7 @@ __device__ __forceinline__ void issue_chunk_mmas_2(uint32_t acc0, uint32_t acc1,
 }
 
 // barrier among the producer / epilogue warps only
-__device__ __forceinline__ void t2_prod_sync() { asm volatile("bar.sync 2, %0;" ::"n"(T2_PROD_THREADS) : "memory"); }
+__device__ __forceinline__ void t2_prod_sync() { named_bar_sync(2, T2_PROD_THREADS); }
 
 // mbarrier parity waits are only meaningful while the target is the barrier's current or immediately preceding phase
 // (an older target aliases: the wait falls through early, or blocks on a FUTURE phase and deadlocks).  Rule used by
@@ -173,7 +176,7 @@ __device__ __forceinline__ uint32_t tc2_setup(uint32_t base, unsigned char* base
 template <class L, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_fwd(TcFwdArgs g) {
   static_assert(L::kStatic, "pair kernels are specialised for the static jet layouts");
-  extern __shared__ unsigned char smem_dyn[];
+  PPSCI_DYN_SMEM(smem_dyn);
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
   const int N = g.Nout, NH = N / 2;
@@ -363,7 +366,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_fw
             unsigned char* Xb = base_ptr + (part >> 1) * stage_bytes + (part & 1) * A_TILE_BYTES;
             if (cb < ncb) {
               float v[32];
-              load_acc_sum(acc0, acc1, q, cb * 32, v);
+              load_acc_sum(acc0, acc1, q, cb * 32, v, tc_rz_comp_split(nchunks));
               const int row = q * 32 + lane;
 #pragma unroll
               for (int t4 = 0; t4 < 8; ++t4)
@@ -447,7 +450,7 @@ struct T2RowPieces {
 template <class L, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_dx(TcDxArgs g) {
   static_assert(L::kStatic, "pair kernels are specialised for the static jet layouts");
-  extern __shared__ unsigned char smem_dyn[];
+  PPSCI_DYN_SMEM(smem_dyn);
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
   const int N = g.Nout, NH = N / 2;
@@ -624,7 +627,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_dx
             if (fw < 4 && cb < ncb) {
               const int q = warp & 3;  // (7..10) & 3 = 3, 0, 1, 2: all four lane quadrants
               float v[32];
-              load_acc_sum(acc0, acc1, q, cb * 32, v);
+              load_acc_sum(acc0, acc1, q, cb * 32, v, tc_rz_comp_split(nchunks));
               unsigned char* Xb = xbuf(grp);
               const int row = q * 32 + lane;
 #pragma unroll
@@ -704,7 +707,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_dx
 // =====================================================================================================
 template <class L>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DW_THREADS, 1) k_tc2_dw(TcDwArgs g) {
-  extern __shared__ unsigned char smem_dyn[];
+  PPSCI_DYN_SMEM(smem_dyn);
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
   constexpr int N = 256, NH = 128;
@@ -861,7 +864,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DW_THREADS, 1) k_tc2
       float* dw_row = g.dW + (long long)k * g.ldw + n0;
       for (int cb = part; cb < N / 32; cb += DW_NPW / 4) {
         float v[32];
-        load_acc_sum(acc0, acc1, q, cb * 32, v);
+        load_acc_sum(acc0, acc1, q, cb * 32, v, tc_rz_comp_split(n_it));
         if (k < g.Kdim) {
 #pragma unroll
           for (int t = 0; t < 32; ++t) atomicAdd(dw_row + cb * 32 + t, v[t]);
@@ -891,7 +894,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DW_THREADS, 1) k_tc2
     }                                                                                                               \
     cudaError_t e_ = cudaFuncSetAttribute(kfn_, cudaFuncAttributeMaxDynamicSharedMemorySize, (smem));               \
     if (e_ != cudaSuccess) { err_expr; }                                                                            \
-    kfn_<<<(grid), dim3(ppsci::tc::DW_THREADS), (smem), (stream)>>>(args);                                          \
+    PPSCI_KLAUNCH(kfn_, (grid), dim3(ppsci::tc::DW_THREADS), (smem), (stream), 2, args);                            \
   } while (0)
 
 // static jet layouts only (callers check lay != TC_LAY_DYN); tanh activation
@@ -906,5 +909,5 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DW_THREADS, 1) k_tc2
     }                                                                                                               \
     cudaError_t e_ = cudaFuncSetAttribute(kfn_, cudaFuncAttributeMaxDynamicSharedMemorySize, (smem));               \
     if (e_ != cudaSuccess) { err_expr; }                                                                            \
-    kfn_<<<(grid), dim3(ppsci::tc::THREADS), (smem), (stream)>>>(args);                                             \
+    PPSCI_KLAUNCH(kfn_, (grid), dim3(ppsci::tc::THREADS), (smem), (stream), 2, args);                               \
   } while (0)
