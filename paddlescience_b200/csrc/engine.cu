@@ -15,6 +15,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_tc2.cuh"
+#include "kernels_fused.cuh"
 #include "kernels_thin.cuh"
 
 using namespace ppsci;
@@ -49,7 +50,10 @@ struct ppsci_plan {
   int chunk = 0;
   int num_sms = 148;
   bool use_tc = false;
-  int tc_mask = 63;  // bit0 forward, bit1 dx, bit2 dW on the tensor cores; bit3 / bit4 / bit5: CTA-pair forward / dx / dW kernels (PPSCI_B200_TC_MASK, debugging)
+  // bit0 forward, bit1 dx, bit2 dW on the tensor cores; bit3 / bit4 / bit5: CTA-pair forward / dx / dW kernels;
+  // bit6: layer-fused forward (kernels_fused.cuh).  PPSCI_B200_TC_MASK selects subsets (debugging / cross-checks).
+  // bit7: layer-fused dx chain.
+  int tc_mask = 255;
   // device copies of the residual program
   int* d_prog = nullptr;
   double* d_consts = nullptr;
@@ -97,6 +101,7 @@ struct Carve {
   size_t z[PPSCI_MAX_LAYERS + 1];  // z[l] for l = 1..n_layers-1 (hidden pre-activations)
   size_t a[PPSCI_MAX_LAYERS + 1];  // a[l] = act_jets(z[l]) stashed by the tcgen05 forward for the dW kernel
   size_t y, ybar, zbar0, zbar1;
+  size_t zb[PPSCI_MAX_LAYERS + 1];  // zb[l] = Zbar_l, one buffer per hidden layer (fused dx chain: every Zbar_l outlives the chain)
   size_t wt[PPSCI_MAX_LAYERS + 1];
   size_t loss_acc;
   size_t tc;  // scratch of the tcgen05 backend
@@ -105,6 +110,8 @@ struct Carve {
 
 static size_t tc_scratch_bytes(const ppsci_plan* P, int64_t nc);
 static bool tc_astash_needed(const ppsci_plan* P, int l);
+static bool fused_fwd_ok(const ppsci_plan* P);
+static bool fused_dx_ok(const ppsci_plan* P);
 
 static void carve(const ppsci_plan* P, int64_t nc, Carve* cv) {
   const size_t es = P->spec.dtype == PPSCI_F64 ? 8 : 4;
@@ -118,8 +125,10 @@ static void carve(const ppsci_plan* P, int64_t nc, Carve* cv) {
   for (int l = 1; l < L; ++l) cv->z[l] = take((size_t)P->C * nc * P->ld[l] * es);
   cv->y = take((size_t)P->C * nc * P->ld[L] * es);
   cv->ybar = take((size_t)P->C * nc * P->ld[L] * es);
-  cv->zbar0 = take((size_t)P->C * nc * P->ld_hidden_max * es);
-  cv->zbar1 = take((size_t)P->C * nc * P->ld_hidden_max * es);
+  const bool fdx = fused_dx_ok(P);
+  cv->zbar0 = take(fdx ? 0 : (size_t)P->C * nc * P->ld_hidden_max * es);
+  cv->zbar1 = take(fdx ? 0 : (size_t)P->C * nc * P->ld_hidden_max * es);
+  for (int l = 1; l < L; ++l) cv->zb[l] = take(fdx ? (size_t)P->C * nc * P->ld[l] * es : 0);
   for (int l = 2; l <= L; ++l) cv->wt[l] = take((size_t)P->spec.widths[l] * P->spec.widths[l - 1] * es);
   cv->loss_acc = take(PPSCI_MAX_RES * sizeof(double));
   cv->tc = take(tc_scratch_bytes(P, nc));
@@ -605,6 +614,37 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         continue;
       }
       if constexpr (sizeof(T) == 4) {
+        if (l == 2 && fused_fwd_ok(P)) {  // every hidden -> hidden layer in ONE launch, jets stay on chip between layers
+          tc::FusedFwdArgs t;
+          memset(&t, 0, sizeof(t));
+          t.J = P->J;
+          t.act = s.act;
+          t.H = s.widths[1];
+          t.n_fused = L - 2;
+          t.Zin = reinterpret_cast<const float*>(ws + cv.z[1]);
+          t.ld = P->ld[1];
+          t.plane = (long long)nc_max * P->ld[1];
+          for (int i = 0; i < L - 2; ++i) {
+            t.Wimg[i] = reinterpret_cast<const float*>(ws + cv.tc + tc_img_offset(s, 2 + i));
+            t.bias[i] = reinterpret_cast<const float*>(params) + P->b_off[2 + i];
+            t.Zout[i] = reinterpret_cast<float*>(ws + cv.z[2 + i]);
+            t.Astash[i] = (do_bwd && tc_astash_needed(P, 1 + i)) ? reinterpret_cast<float*>(ws + cv.a[1 + i]) : nullptr;
+          }
+          t.Np = nc;
+          t.num_tiles = (int)ptiles;
+          t.dbg = debug_timeline_ptr(3);
+          const int smemf = tc::fused_fwd_smem_bytes(t.H);
+          const unsigned tile_pairs = (ptiles + 1) / 2, sm_pairs = (unsigned)P->num_sms / 2;
+          const unsigned gridf = 2 * (tile_pairs < sm_pairs ? tile_pairs : sm_pairs);
+          ProfScope ps_(P, CLS_FWD, st);
+          PPSCI_FUSED_LAUNCH(k_fused_fwd, tc_pick_layout(P->J, s.act), dim3(gridf), smemf, st, t,
+                             return fail(std::string("cudaFuncSetAttribute(k_fused_fwd): ") + cudaGetErrorString(e_)));
+          P->launches++;
+          l = L - 1;  // the loop's ++l continues with the output layer
+          continue;
+        }
+      }
+      if constexpr (sizeof(T) == 4) {
         if (P->use_tc && (P->tc_mask & 1) && tc_layer_ok(s, l)) {
           tc::TcFwdArgs t;
           memset(&t, 0, sizeof(t));
@@ -728,7 +768,43 @@ static int run(ppsci_plan* P, const CallArgs& a) {
     const T* zbar_cur = reinterpret_cast<const T*>(ws + cv.ybar);
     int zbar_ld = P->ld[L];
     int flip = 0;
+    const bool fdx = fused_dx_ok(P);
+    bool fdx_done = false;
+    // destination of Zbar_{lower}: its own buffer under the fused dx chain, the two ping-pong buffers otherwise
+    auto zbar_dst = [&](int lower) -> T* {
+      return reinterpret_cast<T*>(ws + (fdx ? cv.zb[lower] : (flip ? cv.zbar1 : cv.zbar0)));
+    };
     for (int l = L; l >= 1; --l) {
+      if constexpr (sizeof(T) == 4) {
+        if (fdx && l == L - 1 && !fdx_done) {  // Zbar_{L-1} is in place: Zbar_{L-2} .. Zbar_1 in ONE launch
+          tc::FusedDxArgs t;
+          memset(&t, 0, sizeof(t));
+          t.J = P->J;
+          t.act = s.act;
+          t.H = s.widths[1];
+          t.n_fused = L - 2;
+          t.ZbarIn = reinterpret_cast<const float*>(ws + cv.zb[L - 1]);
+          t.ld = P->ld[1];
+          t.plane = (long long)nc_max * P->ld[1];
+          for (int i = 0; i < L - 2; ++i) {
+            const int ll = L - 1 - i;
+            t.WimgT[i] = reinterpret_cast<const float*>(ws + cv.tc + tc_imgT_offset(s, ll));
+            t.Zprev[i] = reinterpret_cast<const float*>(ws + cv.z[ll - 1]);
+            t.ZbarOut[i] = reinterpret_cast<float*>(ws + cv.zb[ll - 1]);
+          }
+          t.Np = nc;
+          t.num_tiles = (int)ptiles;
+          t.dbg = debug_timeline_ptr(4);
+          const int smemf = tc::fused_fwd_smem_bytes(t.H);
+          const unsigned tile_pairs = (ptiles + 1) / 2, sm_pairs = (unsigned)P->num_sms / 2;
+          const unsigned gridf = 2 * (tile_pairs < sm_pairs ? tile_pairs : sm_pairs);
+          ProfScope ps_(P, CLS_DX, st);
+          PPSCI_FUSED_LAUNCH(k_fused_dx, tc_pick_layout(P->J, s.act), dim3(gridf), smemf, st, t,
+                             return fail(std::string("cudaFuncSetAttribute(k_fused_dx): ") + cudaGetErrorString(e_)));
+          P->launches++;
+          fdx_done = true;
+        }
+      }
       if (l == L && thin_last) {  // dW_L, db_L and Zbar_{L-1} in one streaming pass
         LastArgs<T> f;
         memset(&f, 0, sizeof(f));
@@ -740,7 +816,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         f.Ybar = zbar_cur;
         f.ldy = P->ld[L];
         f.yplane = (long long)nc_max * P->ld[L];
-        T* outp = reinterpret_cast<T*>(ws + (flip ? cv.zbar1 : cv.zbar0));
+        T* outp = zbar_dst(L - 1);
         f.ZbarOut = outp;
         f.ldo = P->ld[L - 1];
         f.oplane = (long long)nc_max * P->ld[L - 1];
@@ -900,6 +976,11 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         P->launches++;
       }
       if (l == 1) break;
+      if (fdx && l <= L - 1) {  // Zbar_{l-1} was produced by the fused chain
+        zbar_cur = reinterpret_cast<const T*>(ws + cv.zb[l - 1]);
+        zbar_ld = P->ld[l - 1];
+        continue;
+      }
       if constexpr (sizeof(T) == 4) {
         if (P->use_tc && (P->tc_mask & 2) && tc_dx_ok(s, l)) {
           tc::TcDxArgs t;
@@ -913,7 +994,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           t.ldz = P->ld[l - 1];
           t.zplane = (long long)nc_max * P->ld[l - 1];
           t.act = s.act;
-          float* outp = reinterpret_cast<float*>(ws + (flip ? cv.zbar1 : cv.zbar0));
+          float* outp = reinterpret_cast<float*>(zbar_dst(l - 1));
           t.Out = outp;
           t.ldo = P->ld[l - 1];
           t.oplane = (long long)nc_max * P->ld[l - 1];
@@ -956,7 +1037,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         g.Nout = s.widths[l - 1];
         g.ldb = s.widths[l - 1];
         g.bias = nullptr;
-        T* outp = reinterpret_cast<T*>(ws + (flip ? cv.zbar1 : cv.zbar0));
+        T* outp = zbar_dst(l - 1);
         g.Out = outp;
         g.ldo = P->ld[l - 1];
         g.oplane = (long long)nc_max * P->ld[l - 1];
@@ -1080,4 +1161,29 @@ static bool tc_astash_needed(const ppsci_plan* P, int l) {
 }
 static size_t tc_scratch_bytes(const ppsci_plan* P, int64_t nc) {
   return P->use_tc ? tc_scratch_bytes_impl(P->spec, P->C, nc) : 0;
+}
+
+// layer-fused forward: fp32 tanh, one of the static jet layouts, at least one hidden -> hidden layer, all hidden
+// widths equal (K = N = H, a multiple of 32 up to 256)
+static bool fused_fwd_ok(const ppsci_plan* P) {
+  const ppsci_plan_spec& s = P->spec;
+  const int L = s.n_layers;
+  if (!P->use_tc || !(P->tc_mask & 1) || !(P->tc_mask & 8) || !(P->tc_mask & 64) || P->num_sms < 2) return false;
+  if (L < 3 || L - 2 > tc::FUSE_MAXL) return false;
+  if (tc_pick_layout(P->J, s.act) == TC_LAY_DYN) return false;
+  for (int l = 2; l < L; ++l)
+    if (!tc_layer_ok(s, l) || s.widths[l] != s.widths[1]) return false;
+  return s.widths[1] <= 256;
+}
+
+// layer-fused dx chain: same shape constraints as the fused forward, dx of every hidden -> hidden layer tensor-core eligible
+static bool fused_dx_ok(const ppsci_plan* P) {
+  const ppsci_plan_spec& s = P->spec;
+  const int L = s.n_layers;
+  if (!P->use_tc || !(P->tc_mask & 2) || !(P->tc_mask & 16) || !(P->tc_mask & 128) || P->num_sms < 2) return false;
+  if (L < 3 || L - 2 > tc::FUSE_MAXL) return false;
+  if (tc_pick_layout(P->J, s.act) == TC_LAY_DYN) return false;
+  for (int l = 2; l < L; ++l)
+    if (!tc_dx_ok(s, l) || s.widths[l] != s.widths[1]) return false;
+  return s.widths[1] <= 256;
 }

@@ -280,10 +280,12 @@ __host__ __device__ inline uint32_t tc_pow2_cols(int n) {
   return c;
 }
 
-// 3xTF32 MMAs of one 32-wide K chunk.  Two accumulators: the exact-product "big" term A_hi B_hi
-// alternates between acc0 / acc1 per 8-wide k-step, the small cross terms always go to acc1, so each
-// accumulator sees half as many fp32 round-toward-zero accumulation steps of significant magnitude
-// (tensor cores accumulate with truncation); the epilogue adds acc0 + acc1 with round-to-nearest.
+// 3xTF32 MMAs of one 32-wide K chunk.  Two accumulators: acc0 takes ONLY the exact-product "big" term A_hi B_hi
+// (4 accumulations per chunk), acc1 the two small cross terms.  The accumulator rounds toward zero at its own
+// magnitude (measured, tests/microbench/tc_numerics.cu), so the cross terms — 2^-11 of the result — must not be added
+// into the big accumulator: acc0 sees 4 instead of 12 truncations per chunk (error of a 256-deep contraction
+// 6.3e-7 instead of 1.9e-6; the round-1 alternating split gave 1.1e-6), acc1's truncations are 2^-11 smaller.
+// The epilogue adds acc0 * (1 + rz compensation) + acc1 with round-to-nearest.
 // The issuing lane is the kernel's critical serial path: descriptors are a precomputed base (stage 0,
 // k-step 0) plus increments of the 14-bit start-address field (units of 16 bytes).
 struct ChunkDescs {
@@ -305,13 +307,8 @@ __device__ __forceinline__ void issue_chunk_mmas(uint32_t acc0, uint32_t acc1, c
     const uint64_t inc = so + (uint64_t)(2 * ks);
     const uint64_t dah = D.a_hi + inc, dal = D.a_lo + inc, dbh = D.b_hi + inc, dbl = D.b_lo + inc;
     const bool first = first_chunk && ks == 0;
-    if ((ks & 1) == 0) {
-      mma_tf32(acc0, dah, dbh, idesc, first ? 0u : 1u);
-      mma_tf32(acc1, dal, dbh, idesc, first ? 0u : 1u);
-    } else {
-      mma_tf32(acc1, dah, dbh, idesc, 1u);
-      mma_tf32(acc1, dal, dbh, idesc, 1u);
-    }
+    mma_tf32(acc0, dah, dbh, idesc, first ? 0u : 1u);
+    mma_tf32(acc1, dal, dbh, idesc, first ? 0u : 1u);
     mma_tf32(acc1, dah, dbl, idesc, 1u);
   }
 }
@@ -341,10 +338,9 @@ __device__ __forceinline__ void issue_chunk_mmas_cat(uint32_t accX, uint32_t acc
 // The epilogues multiply the accumulator sum by (1 + c0 * sum_acc events_acc / 2 * share_acc); what remains is the
 // zero-mean part of the rounding (fp32-chain level).
 constexpr float TC_RZ_C0 = 3.35e-8f;
-// split scheme of issue_chunk_mmas(_2): acc0 sees 2 significant accumulations per 32-wide chunk, acc1 sees 10
-// (2 exact-product + 8 small cross terms rounded at acc1's magnitude), each accumulator holds half of the result
-__host__ __device__ __forceinline__ float tc_rz_comp_split(long long nchunks) { return 1.f + TC_RZ_C0 * 3.f * (float)nchunks; }
-// concatenated scheme of issue_chunk_mmas_cat: 4 accumulations of the exact-product term per chunk, full magnitude
+// issue_chunk_mmas(_2) and issue_chunk_mmas_cat: 4 accumulations of the exact-product term per 32-wide chunk at the
+// full magnitude of the result (the cross terms live in their own accumulator / columns, 2^-11 of it)
+__host__ __device__ __forceinline__ float tc_rz_comp_split(long long nchunks) { return 1.f + TC_RZ_C0 * 2.f * (float)nchunks; }
 __host__ __device__ __forceinline__ float tc_rz_comp_cat(long long nchunks) { return 1.f + TC_RZ_C0 * 2.f * (float)nchunks; }
 
 // (acc0 + acc1) * comp for 32 lanes x 32 columns
@@ -355,7 +351,7 @@ __device__ __forceinline__ void load_acc_sum(uint32_t acc0, uint32_t acc1, int q
   tmem_ld32(acc1 + lane_off + (uint32_t)col, v1);
   tmem_ld_wait();
 #pragma unroll
-  for (int t = 0; t < 32; ++t) out[t] = (__uint_as_float(v0[t]) + __uint_as_float(v1[t])) * comp;
+  for (int t = 0; t < 32; ++t) out[t] = fmaf(__uint_as_float(v0[t]), comp, __uint_as_float(v1[t]));
 }
 
 // store v = hi + lo into the (hi, lo) pair of K-major SW128 tiles; `off` = sw128(row, col)

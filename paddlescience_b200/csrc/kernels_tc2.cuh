@@ -95,7 +95,7 @@ __host__ __device__ inline int tc2_stage_bytes(int N) { return 2 * A_TILE_BYTES 
 // barriers: mma_done[3] +24, full[3] +48, TMEM base slot +128
 __host__ __device__ inline int tc2_smem_bytes(int N) { return T2_NSTAGE * tc2_stage_bytes(N) + 1024 + 256; }
 
-// 12 MMAs (3xTF32, split accumulators: see issue_chunk_mmas) of one K chunk, M = 256 over the CTA pair
+// 12 MMAs (3xTF32, exact-product | cross-term accumulators: see issue_chunk_mmas) of one K chunk, M = 256 over the pair
 __device__ __forceinline__ void issue_chunk_mmas_2(uint32_t acc0, uint32_t acc1, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi,
                                                    uint64_t b_lo, uint32_t idesc, bool first_chunk) {
 #pragma unroll
@@ -103,13 +103,8 @@ __device__ __forceinline__ void issue_chunk_mmas_2(uint32_t acc0, uint32_t acc1,
     const uint64_t inc = (uint64_t)(2 * ks);
     const uint64_t dah = a_hi + inc, dal = a_lo + inc, dbh = b_hi + inc, dbl = b_lo + inc;
     const bool first = first_chunk && ks == 0;
-    if ((ks & 1) == 0) {
-      mma_tf32_2(acc0, dah, dbh, idesc, first ? 0u : 1u);
-      mma_tf32_2(acc1, dal, dbh, idesc, first ? 0u : 1u);
-    } else {
-      mma_tf32_2(acc1, dah, dbh, idesc, 1u);
-      mma_tf32_2(acc1, dal, dbh, idesc, 1u);
-    }
+    mma_tf32_2(acc0, dah, dbh, idesc, first ? 0u : 1u);  // exact-product term alone in acc0
+    mma_tf32_2(acc1, dal, dbh, idesc, first ? 0u : 1u);  // cross terms (2^-11 of the result) in acc1
     mma_tf32_2(acc1, dah, dbl, idesc, 1u);
   }
 }
