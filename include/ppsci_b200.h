@@ -138,7 +138,8 @@ typedef struct ppsci_plan_spec {
 
 typedef struct ppsci_plan ppsci_plan;
 
-/* Build a plan.  Validates the spec, copies programs, allocates NO device memory. */
+/* Build a plan.  Validates the spec, copies the residual program to the device (five small buffers, freed by
+ * plan_destroy); every other byte of device memory the calls touch is caller-owned workspace. */
 int ppsci_b200_plan_create(const ppsci_plan_spec* spec, ppsci_plan** out);
 void ppsci_b200_plan_destroy(ppsci_plan* plan);
 
@@ -203,6 +204,31 @@ int64_t ppsci_b200_plan_stash_offset(const ppsci_plan* plan, int64_t n_points, i
 int ppsci_b200_values_fwd_bwd(ppsci_plan* plan, const void* const* x_cols, const void* const* aux_cols,
                               int64_t n_points, const void* params, void* grads, const void* ybar,
                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* Two-phase variant of values_fwd_bwd for callers whose output adjoints depend on the outputs (DeepONet: the product /
+ * loss head sits between the forward and the adjoint of its two MLPs): values_fwd_keep runs the forward exactly as a
+ * training call does (everything the adjoint reads stays in `workspace`) and writes the network outputs
+ * y_out[n_points][n_out]; values_bwd_kept then runs ONLY the adjoint from that stash — the forward is not recomputed.
+ * Both calls take at most plan_chunk_points points, the same inputs / params / workspace, and nothing else may use the
+ * workspace in between. */
+int32_t ppsci_b200_plan_chunk_points(const ppsci_plan* plan);
+int ppsci_b200_values_fwd_keep(ppsci_plan* plan, const void* const* x_cols, const void* const* aux_cols,
+                               int64_t n_points, const void* params, void* y_out, void* workspace,
+                               size_t workspace_bytes, void* stream);
+int ppsci_b200_values_bwd_kept(ppsci_plan* plan, const void* const* x_cols, const void* const* aux_cols,
+                               int64_t n_points, const void* params, void* grads, const void* ybar,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* DeepONet head — replaces, for one batch, deeponet.py:141-149 (G = sum_i branch_i * act(trunk_i) + b), the MSE of
+ * ppsci/loss/mse.py:82-106 on G and their derivatives (no framework autograd graph):
+ *   b, t      [n][n_features] row-major branch / trunk features;  bias: device scalar or NULL
+ *   g_out     optional [n] outputs
+ *   loss_acc  optional device double, ACCUMULATES  coef * sum_p w_p (G_p - label_p)^2   (coef = loss weight / n_norm for "mean")
+ *   bbar/tbar optional [n][n_features] adjoints dL/db, dL/dt (may alias b / t);  dbias: device scalar, accumulated
+ * With bbar == tbar == NULL only g_out is produced (eval / predict). */
+int ppsci_b200_deeponet_head(int32_t dtype, int32_t act, const void* b, const void* t, const void* bias,
+                             const void* label, const void* weight, int64_t n, int32_t n_features, double coef,
+                             void* g_out, double* loss_acc, void* bbar, void* tbar, void* dbias, void* stream);
 
 /* Bench instrumentation: when on, every launch of the next calls is bracketed by CUDA events on
  * the caller's stream (no syncs).  get_profile returns, for the most recent call, the summed

@@ -177,25 +177,59 @@ class DeepONet(base.Arch):
     def fused_train_forward(self, loss_fn, input_dict, label_dict, weight_dict) -> Dict[str, torch.Tensor]:
         """Loss of one constraint + accumulation of its gradient into ``self.flat.grad``.
 
-        Replaces expression.py:96-129 + train.py:158 for this model: native forward of both sub-nets, the
-        product / loss / their derivatives on ``[N, num_features]`` in torch, native adjoints of both sub-nets."""
+        Replaces expression.py:96-129 + train.py:158 for this model without any framework autograd graph: native forward
+        of both sub-nets with the adjoint's stash kept (``values_fwd_keep``), ONE head kernel for the product, the MSE and
+        the two adjoint seeds dL/d(branch), dL/d(trunk) (``ppsci_b200_deeponet_head``), native adjoints of both sub-nets
+        from the kept stash (``values_bwd_kept`` — the forward is not recomputed).  Batches larger than the plans'
+        workspace chunk are processed slice by slice."""
+        from ..engine import binding as B
+
         if self._input_transform is not None or self._output_transform is not None:
             raise NotImplementedError("input / output transforms are not supported on the fused DeepONet training path")
+        if type(loss_fn).__name__ != "MSELoss":
+            raise NotImplementedError(f"{type(loss_fn).__name__} has no fused head kernel; only MSELoss is on the hot path")
         flat = self.flat
         if flat.grad is None:
             flat.grad = torch.zeros_like(flat.data)
-        u, y, b, t = self._features(input_dict)
+        key = self.output_keys[0]
+        dt, dev = flat.dtype, flat.device
+        u = input_dict[self.u_key].to(dt)
+        y = input_dict[self.y_key].to(dt)
+        if dev != u.device:
+            raise ValueError(f"inputs are on {u.device}, parameters on {dev}")
+        n = u.shape[0]
+        label = label_dict[key].to(dt).reshape(-1).contiguous()
+        weight = None
+        if weight_dict is not None and key in weight_dict:
+            weight = weight_dict[key].to(dt).reshape(-1)
+        if "area" in input_dict:  # mse.py:92-93
+            area = input_dict["area"].to(dt).reshape(-1)
+            weight = area if weight is None else weight * area
+        if weight is not None:
+            weight = weight.expand(n).contiguous()
+        red = getattr(loss_fn, "reduction", "mean")
+        coef = float(loss_fn.weight_of(key) if hasattr(loss_fn, "weight_of") else 1.0) * (1.0 / n if red == "mean" else 1.0)
         pb, pt = self._get_plans()
-        with torch.enable_grad():
-            bq, tq = b.detach().requires_grad_(True), t.detach().requires_grad_(True)
-            bias = flat.data[self._bias_off: self._bias_off + 1].detach().clone().requires_grad_(True) if self.use_bias else None
-            out = {self.output_keys[0]: self._combine(bq, tq, bias)}
-            if "area" in input_dict:
-                out["area"] = input_dict["area"]
-            losses = loss_fn(out, label_dict, weight_dict)
-            sum(losses.values()).backward()
-        pb.values_fwd_bwd({self.u_key: u}, flat.data[self._b_rng[0]: self._b_rng[1]], flat.grad[self._b_rng[0]: self._b_rng[1]], bq.grad)
-        pt.values_fwd_bwd({self.y_key: y}, flat.data[self._t_rng[0]: self._t_rng[1]], flat.grad[self._t_rng[0]: self._t_rng[1]], tq.grad)
-        if bias is not None:
-            flat.grad[self._bias_off: self._bias_off + 1] += bias.grad
-        return {k: v.detach() for k, v in losses.items()}
+        lib = pb.lib
+        pbr, ptr_ = flat.data[self._b_rng[0]: self._b_rng[1]], flat.data[self._t_rng[0]: self._t_rng[1]]
+        gbr, gtr = flat.grad[self._b_rng[0]: self._b_rng[1]], flat.grad[self._t_rng[0]: self._t_rng[1]]
+        loss_acc = torch.zeros(1, dtype=torch.float64, device=dev)
+        bias = flat.data[self._bias_off: self._bias_off + 1] if self.use_bias else None
+        dbias = flat.grad[self._bias_off: self._bias_off + 1] if self.use_bias else None
+        act = B.ACT_IDS[self._trunk.act.lower()]
+        chunk = min(pb.chunk_points, pt.chunk_points)
+        stream = torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else 0
+        for s0 in range(0, n, chunk):
+            sl = slice(s0, min(n, s0 + chunk))
+            bf = pb.values_fwd_keep({self.u_key: u[sl]}, pbr)
+            tf = pt.values_fwd_keep({self.y_key: y[sl]}, ptr_)
+            m = bf.shape[0]
+            rc = lib.lib.ppsci_b200_deeponet_head(
+                B.F64 if dt == torch.float64 else B.F32, act, bf.data_ptr(), tf.data_ptr(),
+                bias.data_ptr() if bias is not None else None, label[sl].data_ptr(),
+                weight[sl].data_ptr() if weight is not None else None, m, self.num_features, coef, None,
+                loss_acc.data_ptr(), bf.data_ptr(), tf.data_ptr(), dbias.data_ptr() if dbias is not None else None, stream)
+            lib.check(rc, "deeponet_head")
+            pb.values_bwd_kept(pbr, gbr, bf)  # bf / tf now hold dL/d(branch), dL/d(trunk)
+            pt.values_bwd_kept(ptr_, gtr, tf)
+        return {key: loss_acc[0].to(dt)}

@@ -466,6 +466,7 @@ struct CallArgs {
   void* stream;
   bool want_loss;
   const void* ybar_in = nullptr;  // values_fwd_bwd: caller-supplied dL/dy [n_points][n_out]
+  int phase = 0;                  // 0: forward + adjoint; 1: forward only, stash kept for a later adjoint; 2: adjoint from the kept stash
 };
 
 template <typename T, int KMAX>
@@ -510,7 +511,11 @@ static int run(ppsci_plan* P, const CallArgs& a) {
   const bool thin_vec = sizeof(T) == 4 && thin_lay != TC_LAY_DYN && getenv("PPSCI_B200_NO_THINV") == nullptr;
 
   if (a.want_loss) CK(cudaMemsetAsync(loss_acc, 0, PPSCI_MAX_RES * sizeof(double), st));
-  const bool do_bwd = (a.want_loss || a.ybar_in) && grads != nullptr;
+  // phase 1 runs the forward exactly as a training call would (stash of everything the adjoint reads), phase 2 only the adjoint
+  const bool do_bwd = ((a.want_loss || a.ybar_in) && grads != nullptr) || a.phase == 1;
+  if (a.phase == 2 && a.n_points > nc_max)
+    return fail("values_bwd_kept: the kept stash covers one workspace chunk (" + std::to_string(nc_max) + " points); got " +
+                std::to_string(a.n_points));
   if (do_bwd) {
     for (int l = 2; l <= L; ++l) {
       const int K = s.widths[l - 1], N = s.widths[l];
@@ -553,7 +558,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
     const int64_t nc = (a.n_points - c0) < nc_max ? (a.n_points - c0) : nc_max;
     const unsigned ptiles = (unsigned)((nc + TP - 1) / TP);
     // ---------------- forward ----------------
-    for (int l = 1; l <= L; ++l) {
+    for (int l = (a.phase == 2 ? L + 1 : 1); l <= L; ++l) {
       if (l == 1 && thin_first) {
         FirstArgs<T> f;
         memset(&f, 0, sizeof(f));
@@ -754,7 +759,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
       PPSCI_LAUNCH(kh, dim3((unsigned)((nc + HEAD_THREADS - 1) / HEAD_THREADS)), dim3(HEAD_THREADS), 0, st, h);
       P->launches++;
     }
-    if (!do_bwd) continue;
+    if (!do_bwd || a.phase == 1) continue;
     if (a.ybar_in) {  // output adjoints from the caller instead of the residual head
       const long long tot = (long long)nc * P->ld[L];
       auto ks = k_seed_ybar<T>;
@@ -1132,6 +1137,73 @@ extern "C" int ppsci_b200_residual_fwd(ppsci_plan* plan, const void* const* x_co
   return dispatch(plan, a);
 }
 
+extern "C" int32_t ppsci_b200_plan_chunk_points(const ppsci_plan* P) { return P ? P->chunk : -1; }
+
+extern "C" int ppsci_b200_values_fwd_keep(ppsci_plan* plan, const void* const* x_cols, const void* const* aux_cols, int64_t n_points,
+                                          const void* params, void* y_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!y_out) return fail("values_fwd_keep: null y_out");
+  if (plan && n_points > plan->chunk) return fail("values_fwd_keep: at most plan_chunk_points points per call");
+  CallArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x_cols = x_cols;
+  a.aux_cols = aux_cols;
+  a.n_points = n_points;
+  a.n_norm = n_points;
+  a.params = params;
+  a.jets_out = y_out;  // C = 1: [n_points][n_out]
+  a.workspace = workspace;
+  a.workspace_bytes = workspace_bytes;
+  a.stream = stream;
+  a.phase = 1;
+  if (plan && plan->C != 1) return fail("values_fwd_keep: the plan must have no input derivatives (C == 1)");
+  return dispatch(plan, a);
+}
+
+extern "C" int ppsci_b200_values_bwd_kept(ppsci_plan* plan, const void* const* x_cols, const void* const* aux_cols, int64_t n_points,
+                                          const void* params, void* grads, const void* ybar, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+  if (!ybar || !grads) return fail("values_bwd_kept: null ybar / grads");
+  CallArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x_cols = x_cols;
+  a.aux_cols = aux_cols;
+  a.n_points = n_points;
+  a.n_norm = n_points;
+  a.params = params;
+  a.grads = grads;
+  a.workspace = workspace;
+  a.workspace_bytes = workspace_bytes;
+  a.stream = stream;
+  a.ybar_in = ybar;
+  a.phase = 2;
+  return dispatch(plan, a);
+}
+
+extern "C" int ppsci_b200_deeponet_head(int32_t dtype, int32_t act, const void* b, const void* t, const void* bias,
+                                        const void* label, const void* weight, int64_t n, int32_t n_features, double coef,
+                                        void* g_out, double* loss_acc, void* bbar, void* tbar, void* dbias, void* stream) {
+  if (!b || !t || n <= 0 || n_features <= 0) return fail("deeponet_head: bad arguments");
+  if ((bbar == nullptr) != (tbar == nullptr)) return fail("deeponet_head: bbar and tbar must both be given or both be null");
+  if (act < 0 || act > PPSCI_ACT_GELU) return fail("deeponet_head: unknown activation");
+  const long long warps = n < 148LL * 64 ? n : 148LL * 64;  // 8 warps per block
+  const unsigned blocks = (unsigned)((warps + 7) / 8);
+  if (dtype == PPSCI_F64) {
+    auto k = k_deeponet_head<double>;
+    PPSCI_LAUNCH(k, dim3(blocks), dim3(256), 0, stream, (const double*)b, (const double*)t, (const double*)bias, act,
+                 (const double*)label, (const double*)weight, (long long)n, n_features, coef, (double*)g_out, loss_acc,
+                 (double*)bbar, (double*)tbar, (double*)dbias);
+  } else if (dtype == PPSCI_F32) {
+    auto k = k_deeponet_head<float>;
+    PPSCI_LAUNCH(k, dim3(blocks), dim3(256), 0, stream, (const float*)b, (const float*)t, (const float*)bias, act,
+                 (const float*)label, (const float*)weight, (long long)n, n_features, coef, (float*)g_out, loss_acc,
+                 (float*)bbar, (float*)tbar, (float*)dbias);
+  } else {
+    return fail("deeponet_head: bad dtype");
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int ppsci_b200_adam_step(int32_t dtype, void* params, const void* grads, void* exp_avg, void* exp_avg_sq,
                                     int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay,
                                     int64_t step, double grad_scale, void* stream) {
@@ -1173,6 +1245,13 @@ static bool fused_fwd_ok(const ppsci_plan* P) {
   if (tc_pick_layout(P->J, s.act) == TC_LAY_DYN) return false;
   for (int l = 2; l < L; ++l)
     if (!tc_layer_ok(s, l) || s.widths[l] != s.widths[1]) return false;
+  // Accuracy gate.  The fused forward double-buffers ONE accumulator per layer (2 x 256 TMEM columns), i.e. all 12
+  // round-toward-zero accumulations of a 32-wide chunk land in the big accumulator: measured on cfg3 (6 x 256) the
+  // residual error is 1.3e-5 against 4.4e-6 for the layer-at-a-time kernels, whose exact-product | cross-term split
+  // needs all 512 columns.  Up to 128-wide layers the contraction is short enough (cfg2: 1.8e-6) and the fused kernel is
+  // the default; wider layers take it only on request (PPSCI_B200_TC_MASK bit 8).  The dx chain has no such gate: its
+  // rounding only enters the weight gradient (cfg3: 1.1e-5 against a 5e-5 tolerance).
+  if (s.widths[1] > 128 && !(P->tc_mask & 256)) return false;
   return s.widths[1] <= 256;
 }
 

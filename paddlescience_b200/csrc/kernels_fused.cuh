@@ -72,15 +72,21 @@ __device__ __forceinline__ void issue_chunk_mmas_2_single(uint32_t acc, uint64_t
 // (timeline of the first version, three combined stages: the workers idled ~2,600 cycles per step waiting for a stage
 // and the MMAs started ~1,700 cycles after the hand-off — nothing overlapped).  Weights only need double buffering:
 // a 32 KB half-chunk arrives from L2 in ~800 cycles, a chunk's MMAs take ~1,900.
-//   [0, 4 * 32 KB)            A stages: A_hi | A_lo of chunk it % 4
-//   then 2 weight slots       B_hi half | B_lo half of chunk it % 2   (N/2 rows each)
-//   then 2 exchange tiles     X0 | X1
+// Second version (4 A stages + 2 weight slots + 2 exchange tiles): the stage wait disappeared but the MMAs still
+// started 2,500 - 3,800 cycles after the hand-off — with two weight slots a chunk's weights can only be requested when
+// the chunk two before has retired, one chunk time (1,900 cycles) before they are needed, and the loaded L2 -> SMEM
+// round trip is longer than that (round-1 finding: weights must be three chunks ahead).  Three weight slots need the
+// 32 KB of the exchange tiles back, so the exchange now happens IN PLACE: the raw fp32 accumulator block of 32
+// columns is written into the A_lo region of the very stage its operand chunk will occupy, and every (point, k-quad)
+// item reads exactly the 16-byte cells it later overwrites with its own hi / lo output.
+//   [0, 4 * 32 KB)            A stages: A_hi | A_lo of chunk it % 4   (A_lo doubles as the exchange tile)
+//   then 3 weight slots       B_hi half | B_lo half of chunk it % 3   (N/2 rows each)
 //   then barriers: mma_done[4] +0.., full[4] +64.., TMEM base slot +192
 constexpr int FA = 4;
-constexpr int FB = 2;
+constexpr int FB = 3;
 __host__ __device__ inline int fused_bslot_bytes(int N) { return 2 * (N / 2) * KCH * 4; }
 __host__ __device__ inline int fused_fwd_smem_bytes(int N) {
-  return FA * 2 * A_TILE_BYTES + FB * fused_bslot_bytes(N) + 2 * FUSE_X_BYTES + 1024 + 256;
+  return FA * 2 * A_TILE_BYTES + FB * fused_bslot_bytes(N) + 1024 + 256;
 }
 // chunk c has retired (its A stage, its weight slot and its full barrier may be reused)
 __device__ __forceinline__ void f_wait_done(uint32_t bars, uint32_t c) { mbar_wait_warp(bars + 8 * (c % FA), (c / FA) & 1u); }
@@ -112,7 +118,7 @@ __device__ __forceinline__ uint32_t fused_setup(uint32_t base, unsigned char* ba
   return *reinterpret_cast<volatile uint32_t*>(base_ptr + bars_off + 192);
 }
 
-// weight streamer lane: this CTA's N/2 rows of W_hi and W_lo of every (tile, layer, chunk), two chunks ahead
+// weight streamer lane: this CTA's N/2 rows of W_hi and W_lo of every (tile, layer, chunk), three chunks ahead
 __device__ __forceinline__ void fused_stream_weights(uint32_t base, uint32_t bars, uint32_t b_off, const float* const* Wimg, int my_tp,
                                                      int NLf, int nchunks, int N, uint32_t rank) {
   const int NH = N / 2;
@@ -206,8 +212,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
   unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
   const int N = g.H;
   const uint32_t b_off = (uint32_t)(FA * 2 * A_TILE_BYTES);
-  const uint32_t x_off = b_off + (uint32_t)(FB * fused_bslot_bytes(N));
-  const uint32_t bars_off = x_off + 2 * FUSE_X_BYTES;
+  const uint32_t bars_off = b_off + (uint32_t)(FB * fused_bslot_bytes(N));
   const uint32_t bars = base + bars_off;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ncols = tc_pow2_cols(2 * N);
@@ -238,7 +243,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
     const int pl0 = wg7 * 4 + psub;               // this thread's point in the first item pass (28 points per pass)
     constexpr int MAXI = (TP + 27) / 28;
     const float comp = tc_rz_comp_single(nchunks);
-    unsigned char* Xbuf[2] = {base_ptr + x_off, base_ptr + x_off + FUSE_X_BYTES};
     uint32_t it = 0, lay = 0;
     // hand-off of the two chunks of a step: every warp arrives on both full barriers (see the file header)
     auto hand_off = [&](uint32_t it0, bool has1) {
@@ -328,15 +332,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
           const bool has1 = 2 * i + 1 < ncb;
           const uint32_t drow = produce_next ? it0 : 47u;
           FDBG(tid == 0, drow, 0);
-          t2_prod_sync();  // both exchange tiles are free (the previous step's / layer's items are done)
+          // the two stages of this step (operand chunks AND exchange tiles) have been released; the last layer's
+          // epilogue only borrows them as scratch (every MMA issued so far has retired, nothing to wait for)
+          if (produce_next) wait_stages(it0, has1);
           FDBG(tid == 0, drow, 1);
           const int cb = 2 * i + grp;
-          if (wg7 < 4 && cb < ncb) {  // warps 0..3 and 7..10 move blocks 2i / 2i+1 into X0 / X1
+          // exchange tile of block cb = the A_lo region of the stage its operand chunk goes to
+          unsigned char* stage_ptr = base_ptr + ((it + (uint32_t)cb) % FA) * (2 * A_TILE_BYTES);
+          unsigned char* Xb = stage_ptr + A_TILE_BYTES;
+          if (wg7 < 4 && cb < ncb) {  // warps 0..3 and 7..10 move blocks 2i / 2i+1 out of TMEM
             const int q = warp & 3;   // (7..10) & 3 = 3, 0, 1, 2: all four lane quadrants
             uint32_t v[32];
             tmem_ld32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), v);
             tmem_ld_wait();
-            unsigned char* Xb = Xbuf[grp];
             const int row = q * 32 + lane;
 #pragma unroll
             for (int t4 = 0; t4 < 8; ++t4)
@@ -345,13 +353,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
                               __uint_as_float(v[4 * t4 + 2]) * comp, __uint_as_float(v[4 * t4 + 3]) * comp);
           }
           FDBG(tid == 0, drow, 2);
-          t2_prod_sync();  // X0 / X1 complete
+          t2_prod_sync();  // exchange tiles complete
           FDBG(tid == 0, drow, 3);
-          if (produce_next) wait_stages(it0, has1);
           FDBG(tid == 0, drow, 4);
           if (cb < ncb) {
-            const unsigned char* Xb = Xbuf[grp];
-            unsigned char* stage_ptr = base_ptr + ((it + (uint32_t)cb) % FA) * (2 * A_TILE_BYTES);
             const int col = cb * 32 + 4 * kq;
             const float4 b4 = bias ? make_float4(__ldg(bias + col), __ldg(bias + col + 1), __ldg(bias + col + 2), __ldg(bias + col + 3))
                                    : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -436,8 +441,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
   unsigned char* base_ptr = smem_dyn + (base - smem_u32(smem_dyn));
   const int N = g.H;
   const uint32_t b_off = (uint32_t)(FA * 2 * A_TILE_BYTES);
-  const uint32_t x_off = b_off + (uint32_t)(FB * fused_bslot_bytes(N));
-  const uint32_t bars_off = x_off + 2 * FUSE_X_BYTES;
+  const uint32_t bars_off = b_off + (uint32_t)(FB * fused_bslot_bytes(N));
   const uint32_t bars = base + bars_off;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ncols = tc_pow2_cols(2 * N);
@@ -465,7 +469,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
     const int pl0 = wg7 * 4 + psub;
     constexpr int MAXR = (128 + 27) / 28;  // P0 item = (row, 4 consecutive k), 28 rows per pass and group
     const float comp = tc_rz_comp_single(nchunks);
-    unsigned char* Xbuf[2] = {base_ptr + x_off, base_ptr + x_off + FUSE_X_BYTES};
     uint32_t it = 0, lay = 0;
     auto hand_off = [&](uint32_t it0, bool has1) {
       fence_proxy_async();
@@ -547,8 +550,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
         for (int i = 0; i < nsteps; ++i) {
           const uint32_t it0 = it + 2 * (uint32_t)i;
           const bool has1 = 2 * i + 1 < ncb;
-          t2_prod_sync();  // both exchange tiles are free
+          // the two stages of this step (operand chunks AND exchange tiles) have been released; the last layer's
+          // epilogue only borrows them as scratch (every MMA issued so far has retired, nothing to wait for)
+          if (produce_next) wait_stages(it0, has1);
           const int cb = 2 * i + grp;
+          unsigned char* stage_ptr = base_ptr + ((it + (uint32_t)cb) % FA) * (2 * A_TILE_BYTES);
+          unsigned char* Xb = stage_ptr + A_TILE_BYTES;  // exchange tile = the A_lo region of the destination stage
           if (cb + 2 < ncb && pl0 < vpts) {  // pull the next step's Z block towards L2 while this step runs
 #pragma unroll
             for (int c = 0; c < CS; ++c) prefetch_l2(zprev + (long long)c * g.plane + (p0 + pl0) * g.ld + (cb + 2) * 32 + 4 * kq);
@@ -558,7 +565,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
             uint32_t v[32];
             tmem_ld32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cb * 32), v);
             tmem_ld_wait();
-            unsigned char* Xb = Xbuf[grp];
             const int row = q * 32 + lane;
 #pragma unroll
             for (int t4 = 0; t4 < 8; ++t4)
@@ -566,11 +572,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
                   make_float4(__uint_as_float(v[4 * t4]) * comp, __uint_as_float(v[4 * t4 + 1]) * comp,
                               __uint_as_float(v[4 * t4 + 2]) * comp, __uint_as_float(v[4 * t4 + 3]) * comp);
           }
-          t2_prod_sync();  // X0 / X1 complete
-          if (produce_next) wait_stages(it0, has1);
+          t2_prod_sync();  // exchange tiles complete
           if (cb < ncb) {
-            const unsigned char* Xb = Xbuf[grp];
-            unsigned char* stage_ptr = base_ptr + ((it + (uint32_t)cb) % FA) * (2 * A_TILE_BYTES);
             for (int pl = pl0; pl < TP; pl += 28) {
               const bool valid = pl < vpts;
               float4 zc[CS], xc[CS];

@@ -784,6 +784,53 @@ __global__ void __launch_bounds__(HEAD_THREADS) k_head(HeadArgs<T> h) {
   }
 }
 
+// DeepONet head (reference: ppsci/arch/deeponet.py:141-149 + ppsci/loss/mse.py:82-106 for the one output G):
+//   G[p] = sum_i b[p][i] * sigma(t[p][i]) + bias ,  e = G - label ,  loss += coef * w[p] * e^2 ,
+//   gbar = 2 coef w e ,  bbar[p][i] = gbar sigma(t_i) ,  tbar[p][i] = gbar b_i sigma'(t_i) ,  dbias += gbar.
+// One warp per point and pass (lanes stride the feature dimension: coalesced rows); bbar / tbar may alias b / t.
+template <typename T>
+__global__ void __launch_bounds__(256) k_deeponet_head(const T* b, const T* t, const T* __restrict__ bias, int act,
+                                                       const T* __restrict__ label, const T* __restrict__ weight, long long n, int F,
+                                                       double coef, T* __restrict__ g_out, double* __restrict__ loss_acc, T* bbar,
+                                                       T* tbar, T* __restrict__ dbias) {
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const T bias_v = bias ? bias[0] : T(0);
+  double loss_part = 0.0;
+  T db_part = T(0);
+  for (long long p = (long long)blockIdx.x * wpb + wib; p < n; p += (long long)gridDim.x * wpb) {
+    const T* bp = b + p * F;
+    const T* tp = t + p * F;
+    T acc = T(0);
+    for (int i = lane; i < F; i += 32) {
+      T y0, sc[6];
+      act_coef<T, 1>(act, tp[i], y0, sc);
+      acc += bp[i] * y0;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const T gval = acc + bias_v;
+    if (g_out && lane == 0) g_out[p] = gval;
+    if (!bbar) continue;
+    const T e = gval - (label ? label[p] : T(0));
+    const T w = weight ? weight[p] : T(1);
+    const T gbar = (T)(2.0 * coef) * w * e;
+    if (lane == 0) {
+      loss_part += coef * (double)w * (double)e * (double)e;
+      db_part += gbar;
+    }
+    for (int i = lane; i < F; i += 32) {
+      T y0, sc[6];
+      const T bv = bp[i];
+      act_coef<T, 1>(act, tp[i], y0, sc);
+      bbar[p * F + i] = gbar * y0;
+      tbar[p * F + i] = gbar * bv * sc[1];
+    }
+  }
+  if (bbar && lane == 0) {
+    if (loss_acc) atomicAdd(loss_acc, loss_part);
+    if (dbias) atomicAdd(dbias, db_part);
+  }
+}
+
 template <typename T>
 __global__ void k_finalize_loss(const double* acc, T* out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -86,6 +86,10 @@ EXPORTED_SYMBOLS = (
     "ppsci_b200_residual_loss_fwd_bwd",
     "ppsci_b200_residual_fwd",
     "ppsci_b200_values_fwd_bwd",
+    "ppsci_b200_values_fwd_keep",
+    "ppsci_b200_values_bwd_kept",
+    "ppsci_b200_plan_chunk_points",
+    "ppsci_b200_deeponet_head",
     "ppsci_b200_plan_last_launches",
     "ppsci_b200_plan_uses_tcgen05",
     "ppsci_b200_plan_stash_offset",
@@ -141,6 +145,14 @@ class Library:
         L.ppsci_b200_residual_fwd.restype = C.c_int
         L.ppsci_b200_values_fwd_bwd.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), i64, vp, vp, vp, vp, C.c_size_t, vp]
         L.ppsci_b200_values_fwd_bwd.restype = C.c_int
+        L.ppsci_b200_values_fwd_keep.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), i64, vp, vp, vp, C.c_size_t, vp]
+        L.ppsci_b200_values_fwd_keep.restype = C.c_int
+        L.ppsci_b200_values_bwd_kept.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), i64, vp, vp, vp, vp, C.c_size_t, vp]
+        L.ppsci_b200_values_bwd_kept.restype = C.c_int
+        L.ppsci_b200_plan_chunk_points.argtypes = [vp]
+        L.ppsci_b200_plan_chunk_points.restype = i32
+        L.ppsci_b200_deeponet_head.argtypes = [i32, i32, vp, vp, vp, vp, vp, i64, i32, dbl, vp, vp, vp, vp, vp, vp]
+        L.ppsci_b200_deeponet_head.restype = C.c_int
         L.ppsci_b200_plan_last_launches.argtypes = [vp]
         L.ppsci_b200_plan_last_launches.restype = i64
         L.ppsci_b200_plan_uses_tcgen05.argtypes = [vp]

@@ -267,6 +267,40 @@ class ResidualPlan:
             grads.data_ptr(), yb.data_ptr(), wptr, wbytes, self._stream(device))
         self.lib.check(rc, "values_fwd_bwd")
 
+    @property
+    def chunk_points(self) -> int:
+        return int(self.lib.lib.ppsci_b200_plan_chunk_points(self.handle))
+
+    def values_fwd_keep(self, inputs: Dict[str, torch.Tensor], params: torch.Tensor) -> torch.Tensor:
+        """Forward of the network values with the adjoint's stash kept in this plan's workspace; returns y [N, n_out].
+        At most ``chunk_points`` points (``ppsci_b200_values_fwd_keep``); follow with ``values_bwd_kept``."""
+        device = params.device
+        n, xs = self._inputs(inputs, device)
+        auxs = [_col(inputs[k], n, self.dtype, device, f"aux '{k}'") for k in self.compiled.aux_keys]
+        y = torch.empty((n, self.n_out), dtype=self.dtype, device=device)
+        ws = self._workspace(n, device)
+        wptr, wbytes = self._aligned(ws)
+        self._kept = (xs, auxs, n)  # the same input buffers must be handed to the adjoint call
+        rc = self.lib.lib.ppsci_b200_values_fwd_keep(self.handle, self._ptr_array(xs, len(xs)), self._ptr_array(auxs, len(auxs)), n,
+                                                     params.data_ptr(), y.data_ptr(), wptr, wbytes, self._stream(device))
+        self.lib.check(rc, "values_fwd_keep")
+        return y
+
+    def values_bwd_kept(self, params: torch.Tensor, grads: torch.Tensor, ybar: torch.Tensor):
+        """Adjoint of the most recent ``values_fwd_keep`` (its forward is NOT recomputed); accumulates into ``grads``."""
+        xs, auxs, n = self._kept
+        device = params.device
+        if ybar.shape != (n, self.n_out) or ybar.dtype != self.dtype or ybar.device != device:
+            raise ValueError(f"ybar must be [{n}, {self.n_out}] {self.dtype} on {device}")
+        yb = ybar.contiguous()
+        ws = self._workspace(n, device)
+        wptr, wbytes = self._aligned(ws)
+        rc = self.lib.lib.ppsci_b200_values_bwd_kept(self.handle, self._ptr_array(xs, len(xs)), self._ptr_array(auxs, len(auxs)), n,
+                                                     params.data_ptr(), grads.data_ptr(), yb.data_ptr(), wptr, wbytes,
+                                                     self._stream(device))
+        self.lib.check(rc, "values_bwd_kept")
+        self._kept = None
+
     def forward(
         self,
         inputs: Dict[str, torch.Tensor],
