@@ -513,6 +513,14 @@ def run_ours(args):
                     "; `traffic` (ncu dram bytes) is in profiles/, not re-measured here; hbm_gbs_design_traffic = plane sets this "
                     "design streams for the class / its time",
         })
+    if roofline is None:  # DeepONet (C = 1, no input derivatives): SURVEY section 8(d) gives 408 algorithmic bytes per pair
+        alg_bytes = 408.0 * N
+        hbm = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "whole step (branch + trunk MLPs, head, adjoints, Adam)", "achieved": hbm,
+                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm / peaks["hbm_gbs"], "traffic": None,
+                    "whole_step_tflops": fpp * N / (ms_per_step * 1e-3) / 1e12,
+                    "note": "algorithmic bytes = 408 B per (u, y) pair (the 100-float sensor row + y + label) over the whole "
+                            "step time; the step is compute / stash bound, not input bound"}
     log("profile pass done; timing the CPU baseline")
     cb = cpu_reference_leg(cfg, CPU_SAMPLE[cfg], 8, 1)
     log("cpu baseline done")

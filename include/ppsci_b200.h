@@ -29,7 +29,7 @@ extern "C" {
 #define PPSCI_MAX_LAYERS 16 /* linear layers (hidden + last_fc)                          */
 #define PPSCI_MAX_DIR 8     /* univariate Taylor directions                              */
 #define PPSCI_MAX_ORDER 4   /* highest Taylor order per direction                        */
-#define PPSCI_MAX_RES 8     /* residual (equation) outputs per constraint                */
+#define PPSCI_MAX_RES 16    /* residual (equation) outputs per call (one constraint, or a batch of them) */
 #define PPSCI_MAX_REG 256   /* register file of the residual program                     */
 
 /* dtype */

@@ -52,7 +52,7 @@ struct ppsci_plan {
   bool use_tc = false;
   // bit0 forward, bit1 dx, bit2 dW on the tensor cores; bit3 / bit4 / bit5: CTA-pair forward / dx / dW kernels;
   // bit6: layer-fused forward (kernels_fused.cuh).  PPSCI_B200_TC_MASK selects subsets (debugging / cross-checks).
-  // bit7: layer-fused dx chain.
+  // bit7: layer-fused dx chain.  bit8: tf32 fused forward also for layers wider than 128.  bit9: fp16 fused forward also for narrow layers.
   int tc_mask = 255;
   // device copies of the residual program
   int* d_prog = nullptr;
@@ -105,6 +105,7 @@ struct Carve {
   size_t wt[PPSCI_MAX_LAYERS + 1];
   size_t loss_acc;
   size_t tc;  // scratch of the tcgen05 backend
+  size_t w16;  // fp16 hi / lo weight images of the fused forward's layers 2.. (+ per-layer |W|max and scale words)
   size_t total;
 };
 
@@ -112,6 +113,7 @@ static size_t tc_scratch_bytes(const ppsci_plan* P, int64_t nc);
 static bool tc_astash_needed(const ppsci_plan* P, int l);
 static bool fused_fwd_ok(const ppsci_plan* P);
 static bool fused_dx_ok(const ppsci_plan* P);
+static bool fused_fwd16_ok(const ppsci_plan* P);
 
 static void carve(const ppsci_plan* P, int64_t nc, Carve* cv) {
   const size_t es = P->spec.dtype == PPSCI_F64 ? 8 : 4;
@@ -132,6 +134,7 @@ static void carve(const ppsci_plan* P, int64_t nc, Carve* cv) {
   for (int l = 2; l <= L; ++l) cv->wt[l] = take((size_t)P->spec.widths[l] * P->spec.widths[l - 1] * es);
   cv->loss_acc = take(PPSCI_MAX_RES * sizeof(double));
   cv->tc = take(tc_scratch_bytes(P, nc));
+  cv->w16 = take(fused_fwd16_ok(P) ? (size_t)(L - 3 > 0 ? L - 3 : 0) * P->spec.widths[1] * P->spec.widths[1] * 4 + 16 * PPSCI_MAX_LAYERS : 0);
   for (int l = 1; l < L; ++l) cv->a[l] = take(tc_astash_needed(P, l) ? (size_t)P->C * nc * P->ld[l] * es : 0);
   cv->total = off;
 }
@@ -358,10 +361,13 @@ extern "C" int32_t ppsci_b200_plan_uses_tcgen05(const ppsci_plan* P) { return (P
 // `layer` for a call with n_points points: layer in [1, n_layers) -> hidden pre-activations Z_l,
 // layer == n_layers -> output jets Y.  Layout [C][min(n_points, chunk)][ld], ld = round4(width).
 extern "C" int64_t ppsci_b200_plan_stash_offset(const ppsci_plan* P, int64_t n_points, int32_t layer) {
-  if (!P || n_points <= 0 || layer < 1 || layer > P->spec.n_layers) return -1;
+  if (!P || n_points <= 0) return -1;
   const int64_t nc = n_points < P->chunk ? n_points : P->chunk;
   Carve cv;
   carve(P, nc, &cv);
+  if (layer > 100 && layer - 100 < P->spec.n_layers) return (int64_t)cv.zb[layer - 100];   // debug: Zbar_l (fused dx chain)
+  if (layer > 200 && layer - 200 < P->spec.n_layers) return (int64_t)cv.a[layer - 200];    // debug: a-stash of layer l
+  if (layer < 1 || layer > P->spec.n_layers) return -1;
   return (int64_t)(layer < P->spec.n_layers ? cv.z[layer] : cv.y);
 }
 
@@ -619,6 +625,54 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         continue;
       }
       if constexpr (sizeof(T) == 4) {
+        if (l == 2 && fused_fwd16_ok(P)) {  // fused forward, fp16 hi / lo operands after the first layer (accurate for wide layers)
+          const int H = s.widths[1], NLf = L - 2;
+          unsigned char* w16 = ws + cv.w16;
+          const size_t img_bytes = (size_t)H * H * 4;
+          unsigned* absmax = reinterpret_cast<unsigned*>(w16 + (size_t)(NLf - 1) * img_bytes);
+          float* wscale = reinterpret_cast<float*>(absmax + PPSCI_MAX_LAYERS);
+          if (c0 == 0) {  // weight scales + fp16 images once per call
+            ProfScope ps_(P, CLS_MISC, st);
+            CK(cudaMemsetAsync(absmax, 0, 2 * sizeof(unsigned) * PPSCI_MAX_LAYERS, st));
+            for (int i = 1; i < NLf; ++i) {
+              const float* Wl = reinterpret_cast<const float*>(params) + P->w_off[2 + i];
+              PPSCI_LAUNCH(tc::k_w16_absmax, dim3(64), dim3(256), 0, st, Wl, (long long)H * H, absmax + i);
+              PPSCI_LAUNCH(tc::k_w16_scale, dim3(1), dim3(1), 0, st, absmax + i, wscale + i);
+              PPSCI_LAUNCH(tc::k_tc_prep_w16, dim3((unsigned)(((long long)H * H + 255) / 256)), dim3(256), 0, st, Wl,
+                           reinterpret_cast<unsigned short*>(w16 + (size_t)(i - 1) * img_bytes), H, H, wscale + i);
+              P->launches += 3;
+            }
+          }
+          tc::FusedFwd16Args ta;
+          memset(&ta, 0, sizeof(ta));
+          tc::FusedFwdArgs& t = ta.f;
+          t.J = P->J;
+          t.act = s.act;
+          t.H = H;
+          t.n_fused = NLf;
+          t.Zin = reinterpret_cast<const float*>(ws + cv.z[1]);
+          t.ld = P->ld[1];
+          t.plane = (long long)nc_max * P->ld[1];
+          for (int i = 0; i < NLf; ++i) {
+            t.Wimg[i] = i == 0 ? reinterpret_cast<const float*>(ws + cv.tc + tc_img_offset(s, 2))
+                               : reinterpret_cast<const float*>(w16 + (size_t)(i - 1) * img_bytes);
+            t.bias[i] = reinterpret_cast<const float*>(params) + P->b_off[2 + i];
+            t.Zout[i] = reinterpret_cast<float*>(ws + cv.z[2 + i]);
+            t.Astash[i] = (do_bwd && tc_astash_needed(P, 1 + i)) ? reinterpret_cast<float*>(ws + cv.a[1 + i]) : nullptr;
+          }
+          t.Np = nc;
+          t.num_tiles = (int)ptiles;
+          ta.wscale = wscale;
+          const int smemf = tc::fused_fwd16_smem_bytes(H);
+          const unsigned tile_pairs = (ptiles + 1) / 2, sm_pairs = (unsigned)P->num_sms / 2;
+          const unsigned gridf = 2 * (tile_pairs < sm_pairs ? tile_pairs : sm_pairs);
+          ProfScope ps_(P, CLS_FWD, st);
+          PPSCI_FUSED_LAUNCH(k_fused_fwd16, tc_pick_layout(P->J, s.act), dim3(gridf), smemf, st, ta,
+                             return fail(std::string("cudaFuncSetAttribute(k_fused_fwd16): ") + cudaGetErrorString(e_)));
+          P->launches++;
+          l = L - 1;
+          continue;
+        }
         if (l == 2 && fused_fwd_ok(P)) {  // every hidden -> hidden layer in ONE launch, jets stay on chip between layers
           tc::FusedFwdArgs t;
           memset(&t, 0, sizeof(t));
@@ -1265,4 +1319,20 @@ static bool fused_dx_ok(const ppsci_plan* P) {
   for (int l = 2; l < L; ++l)
     if (!tc_dx_ok(s, l) || s.widths[l] != s.widths[1]) return false;
   return s.widths[1] <= 256;
+}
+
+// fp16-operand fused forward (k_fused_fwd16): the shape constraints of the fused forward, width a multiple of 64, at
+// least two fused layers; the default for layers wider than 128 (where the single tf32 accumulator is not accurate
+// enough), on request (PPSCI_B200_TC_MASK bit 9) for narrower ones
+static bool fused_fwd16_ok(const ppsci_plan* P) {
+  const ppsci_plan_spec& s = P->spec;
+  const int L = s.n_layers;
+  if (!P->use_tc || !(P->tc_mask & 1) || !(P->tc_mask & 8) || !(P->tc_mask & 64) || P->num_sms < 2) return false;
+  if (L < 4 || L - 2 > tc::FUSE_MAXL) return false;
+  if (tc_pick_layout(P->J, s.act) == TC_LAY_DYN || s.act != PPSCI_ACT_TANH) return false;
+  for (int l = 2; l < L; ++l)
+    if (!tc_layer_ok(s, l) || s.widths[l] != s.widths[1]) return false;
+  if (s.widths[1] % 64 != 0 || s.widths[1] > 256) return false;
+  if (P->tc_mask & 256) return false;  // bit 8: force the tf32 fused forward (cross-check)
+  return s.widths[1] > 128 || (P->tc_mask & 512);
 }

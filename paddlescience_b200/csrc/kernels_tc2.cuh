@@ -81,6 +81,25 @@ __device__ __forceinline__ void mma_tf32_2(uint32_t d_tmem, uint64_t adesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void mma_f16_2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// fp32 <-> fp16 bit patterns (round to nearest even)
+__device__ __forceinline__ uint32_t f32_to_f16_bits(float x) {
+  uint16_t h;
+  asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  return (uint32_t)h;
+}
+__device__ __forceinline__ float f16_bits_to_f32(uint32_t h) {
+  float f;
+  asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"((uint16_t)h));
+  return f;
+}
 // completion of all MMAs issued so far -> one arrival on the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void mma_commit_2(uint32_t bar) {
   const uint16_t mask = 3;

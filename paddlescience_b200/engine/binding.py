@@ -15,7 +15,7 @@ MAX_FEAT = 32
 MAX_LAYERS = 16
 MAX_DIR = 8
 MAX_ORDER = 4
-MAX_RES = 8
+MAX_RES = 16
 MAX_REG = 256
 
 F32, F64 = 0, 1

@@ -26,20 +26,8 @@ class CompiledConstraint:
     def __init__(self, model, cst, extra_keys=()):
         self.model = model
         self.cst = cst
-        exprs: Dict[str, sp.Basic] = {}
-        out_keys = tuple(model.output_keys)
-        for name, e in cst.output_expr.items():
-            if isinstance(e, symbolic.CompiledExpr):
-                exprs[name] = e.expr
-            elif isinstance(e, sp.Basic):
-                exprs[name] = e
-            elif callable(e):
-                exprs[name] = symbolic.trace_to_sympy(e, model.input_keys, out_keys, extra_keys)
-            else:
-                raise TypeError(f"output_expr['{name}'] must be a sympy expression or a callable, got {type(e)}")
-        # the loss iterates label keys (mse.py:85); keep that order
-        self.names = [k for k in cst.output_keys if k in exprs] if hasattr(cst, "output_keys") else list(exprs)
-        self.exprs = {k: exprs[k] for k in self.names}
+        self.exprs = _constraint_exprs(model, cst, extra_keys)  # the loss iterates label keys (mse.py:85); same order
+        self.names = list(self.exprs)
         self.compiled = compile_residuals(model.net_spec(), self.exprs)
         self._plans: Dict[torch.dtype, ResidualPlan] = {}
 
@@ -54,8 +42,102 @@ class CompiledConstraint:
         return self._plans[dtype]
 
 
+def _constraint_exprs(model, cst, extra_keys) -> Dict[str, sp.Basic]:
+    """sympy residual expressions of one constraint, keyed and ordered like its label dict (mse.py:85)."""
+    exprs: Dict[str, sp.Basic] = {}
+    out_keys = tuple(model.output_keys)
+    for name, e in cst.output_expr.items():
+        if isinstance(e, symbolic.CompiledExpr):
+            exprs[name] = e.expr
+        elif isinstance(e, sp.Basic):
+            exprs[name] = e
+        elif callable(e):
+            exprs[name] = symbolic.trace_to_sympy(e, model.input_keys, out_keys, extra_keys)
+        else:
+            raise TypeError(f"output_expr['{name}'] must be a sympy expression or a callable, got {type(e)}")
+    names = [k for k in cst.output_keys if k in exprs] if hasattr(cst, "output_keys") else list(exprs)
+    return {k: exprs[k] for k in names}
+
+
+class BatchedConstraints:
+    """Several constraints that share one MLP evaluated by ONE native call (the reference
+    loops ``for i, cst_name in enumerate(constraint)`` in expression.py:89-129 — for LDC that is the interior equation
+    plus four ~100-point wall constraints, i.e. five times the per-call launch train for 0.1 % more points).
+
+    The point sets are concatenated; every residual of every constraint becomes one slot of a single residual program
+    (shared jet directions, common sub-expressions merged by the compiler); a slot only counts on its own constraint's
+    range because its per-point weight column is zero elsewhere.  "mean" of constraint i over its own N_i points is
+    expressed through the weights: w(p) = N_total / N_i on the range, with the call normalised by N_total."""
+
+    def __init__(self, model, csts: Dict[str, "object"], input_dicts):
+        from ..engine import binding as B
+
+        self.model = model
+        self.cst_names = list(csts)
+        self.slots = []  # (constraint index, key, slot name)
+        exprs: Dict[str, sp.Basic] = {}
+        self.reductions, self.loss_weights = [], []
+        for i, (cname, cst) in enumerate(csts.items()):
+            if type(cst.loss).__name__ != "MSELoss":
+                raise NotImplementedError(f"{type(cst.loss).__name__} has no fused head kernel; only MSELoss is on the hot path")
+            extra = [k for k in (input_dicts[i] or {}) if k not in model.input_keys]
+            for key, e in _constraint_exprs(model, cst, extra).items():
+                slot = f"{cname}::{key}"
+                exprs[slot] = e
+                self.slots.append((i, key, slot))
+                self.reductions.append(getattr(cst.loss, "reduction", "mean"))
+                self.loss_weights.append(cst.loss.weight_of(key) if hasattr(cst.loss, "weight_of") else 1.0)
+        if len(self.slots) > B.MAX_RES:
+            raise NotImplementedError(f"{len(self.slots)} residuals in one batch (max {B.MAX_RES})")
+        self.compiled = compile_residuals(model.net_spec(), exprs)
+        self._plans: Dict[torch.dtype, ResidualPlan] = {}
+        self._mask_cache = {}
+
+    def plan(self, dtype) -> ResidualPlan:
+        if dtype not in self._plans:
+            self._plans[dtype] = ResidualPlan(self.compiled, dtype, self.reductions, self.loss_weights)
+        return self._plans[dtype]
+
+    def run(self, input_dicts, label_dicts, weight_dicts, params, grads):
+        """Returns the per-slot loss vector (device tensor, no host sync)."""
+        dtype, dev = params.dtype, params.device
+        plan = self.plan(dtype)
+        cr = self.compiled
+        ns = [next(iter(d.values())).shape[0] for d in input_dicts]
+        offs = [0]
+        for n in ns:
+            offs.append(offs[-1] + n)
+        ntot = offs[-1]
+        cols = {}
+        for k in list(cr.net.input_keys) + list(cr.aux_keys):
+            buf = torch.zeros(ntot, 1, dtype=dtype, device=dev)
+            for i, d in enumerate(input_dicts):
+                if k in d:
+                    buf[offs[i]: offs[i + 1]] = d[k].to(dtype).reshape(-1, 1)
+            cols[k] = buf
+        labels, weights = {}, {}
+        for (i, key, slot), red in zip(self.slots, self.reductions):
+            lab = torch.zeros(ntot, 1, dtype=dtype, device=dev)
+            lv = label_dicts[i][key]
+            lab[offs[i]: offs[i + 1]] = lv.to(dtype).reshape(-1, 1) if torch.is_tensor(lv) else float(lv)
+            labels[slot] = lab
+            w = torch.zeros(ntot, 1, dtype=dtype, device=dev)
+            scale = (ntot / ns[i]) if red == "mean" else 1.0  # mean over the constraint's own points
+            wi = weight_dicts[i].get(key) if weight_dicts[i] else None
+            rng = w[offs[i]: offs[i + 1]]
+            rng.fill_(scale)
+            if wi is not None:
+                rng.mul_(wi.to(dtype).reshape(-1, 1) if torch.is_tensor(wi) else float(wi))
+            if "area" in input_dicts[i]:  # mse.py:92-93
+                rng.mul_(input_dicts[i]["area"].to(dtype).reshape(-1, 1))
+            weights[slot] = w
+        return plan.loss_fwd_bwd(cols, params, grads, labels=labels, weights=weights, n_norm=ntot).clone()
+
+
 class ExpressionSolver(nn.Module):
     """Expression computing helper (same public methods as the reference)."""
+
+    batch_constraints: bool = True  # constraints sharing the MLP go through ONE native call (BatchedConstraints)
 
     nvtx_flag: bool = False
 
@@ -63,6 +145,7 @@ class ExpressionSolver(nn.Module):
         super().__init__()
         self._compiled: Dict[int, CompiledConstraint] = {}
         self._eval_exprs: Dict[tuple, symbolic.CompiledExpr] = {}  # (id(expr), name, id(model), extra keys) -> compiled
+        self._batched: Dict[tuple, BatchedConstraints] = {}
 
     def forward(self, *args, **kwargs):
         raise NotImplementedError("Use train_forward/eval_forward/visu_forward instead of forward.")
@@ -108,6 +191,22 @@ class ExpressionSolver(nn.Module):
                                       "output_expr (or the equation) instead")
         flat = model.flat
         params, grads = model.engine_params(), model.engine_grads()  # effective weights / staging grads under weight_norm
+        if self.batch_constraints and len(constraint) > 1:
+            from ..engine import binding as B
+
+            n_slots = sum(len([k for k in cst.output_expr]) for cst in constraint.values())
+            if n_slots <= B.MAX_RES and all(type(c.loss).__name__ == "MSELoss" for c in constraint.values()):
+                bkey = tuple(id(c) for c in constraint.values())
+                if bkey not in self._batched:
+                    self._batched[bkey] = BatchedConstraints(model, constraint, input_dicts)
+                bc = self._batched[bkey]
+                loss_vec = bc.run(input_dicts, label_dicts, weight_dicts, params, grads)
+                for k, (i, key, _) in enumerate(bc.slots):
+                    cname = bc.cst_names[i]
+                    losses_constraint[cname] = losses_constraint[cname] + loss_vec[k] if cname in losses_constraint else loss_vec[k]
+                    losses_all[key] = losses_all[key] + loss_vec[k] if key in losses_all else loss_vec[k]
+                model.finish_grads()
+                return losses_all, losses_constraint
         for i, cst_name in enumerate(constraint):
             cst = constraint[cst_name]
             use_nvtx = self.nvtx_flag and flat.is_cuda

@@ -185,6 +185,11 @@ inline float atomicAdd(float* addr, float v) {
     if (__atomic_compare_exchange_n(ia, &old, ni, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) return f;
   }
 }
+inline unsigned atomicMax(unsigned* addr, unsigned v) {
+  unsigned old = __atomic_load_n(addr, __ATOMIC_RELAXED);
+  while (old < v && !__atomic_compare_exchange_n(addr, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+  return old;
+}
 inline double atomicAdd(double* addr, double v) {
   uint64_t* ia = reinterpret_cast<uint64_t*>(addr);
   uint64_t old = __atomic_load_n(ia, __ATOMIC_RELAXED);

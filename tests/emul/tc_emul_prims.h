@@ -62,6 +62,18 @@ inline void mma_f16_2(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32
   emul::mma_issue(2, ((idesc >> 7) & 7u) == 1u ? 2 : 1, d, a, b, idesc, acc);
 }
 inline void mma_commit_2(uint32_t bar) { emul::mma_commit(2, bar, 3u); }
+inline uint32_t f32_to_f16_bits(float x) {
+  const _Float16 h = (_Float16)x;  // round to nearest even
+  uint16_t u;
+  memcpy(&u, &h, 2);
+  return (uint32_t)u;
+}
+inline float f16_bits_to_f32(uint32_t b) {
+  const uint16_t u = (uint16_t)b;
+  _Float16 h;
+  memcpy(&h, &u, 2);
+  return (float)h;
+}
 // bar.sync id, nthreads
 inline void named_bar_sync(int id, int nthreads) { emul::t_cta->named[id].wait_n((unsigned)nthreads); }
 

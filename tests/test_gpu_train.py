@@ -79,3 +79,33 @@ def test_solver_train_lbfgs_decreases_loss_like_oracle_lbfgs():
     assert loss_engine < 0.5 * loss0, (loss0, loss_engine)
     # same algorithm, fp32 vs fp64 loss / gradient: the two trajectories reach the same loss level
     assert abs(np.log10(loss_engine) - np.log10(loss_oracle)) < 0.5, (loss_engine, loss_oracle)
+
+
+def test_batched_constraints_equal_the_loop_on_gpu():
+    """Three constraints sharing the MLP through ONE native call (BatchedConstraints) == the reference's loop over
+    constraints (expression.py:89-129), on the real kernels."""
+    import ppsci as _p
+    from tests.test_batching import _problem
+
+    outs = []
+    for batched in (True, False):
+        model, csts = _problem(torch.float32)
+        model = model.to("cuda")
+        fh = _p.utils.ExpressionSolver()
+        fh.batch_constraints = batched
+        loaders = [c.data_loader.loader for c in csts.values()]
+        dev = lambda d: None if d is None else {k: v.to("cuda", torch.float32) for k, v in d.items()}  # noqa: E731
+        ins, labs = [dev(ld.input) for ld in loaders], [dev(ld.label) for ld in loaders]
+        ws = [dev(ld.weight) if getattr(ld, "weight", None) else None for ld in loaders]
+        la, lc = fh.train_forward(tuple(c.output_expr for c in csts.values()), ins, model, csts, labs, ws)
+        outs.append(({k: float(v) for k, v in la.items()}, {k: float(v) for k, v in lc.items()}, model.flat.grad.detach().cpu().double()))
+    for k in outs[1][0]:
+        assert outs[0][0][k] == pytest.approx(outs[1][0][k], rel=2e-6)
+    for k in outs[1][1]:
+        assert outs[0][1][k] == pytest.approx(outs[1][1][k], rel=2e-6)
+    assert float((outs[0][2] - outs[1][2]).norm() / outs[1][2].norm()) <= 1e-5
+
+
+def test_run_check_trains_and_evaluates():
+    """ppsci.utils.run_check (reference ppsci/utils/checker.py:34-117): two epochs of N-S + one evaluation."""
+    assert ppsci.utils.run_check() is True
