@@ -230,6 +230,14 @@ int ppsci_b200_deeponet_head(int32_t dtype, int32_t act, const void* b, const vo
                              const void* label, const void* weight, int64_t n, int32_t n_features, double coef,
                              void* g_out, double* loss_acc, void* bbar, void* tbar, void* dbias, void* stream);
 
+/* Device-side collocation sampling — replaces, for axis-aligned boxes, the per-step numpy RNG + host-to-device copy of
+ * ContinuousNamedArrayDataset.__iter__ (ppsci/data/dataset/array_dataset.py:208-228).  out_cols[d][i] = lo[d] +
+ * (hi[d] - lo[d]) * U(seed; offset + i, d), U in [0, 1) from Philox4x32-10 (counter-based: the same (seed, offset)
+ * reproduce the same points on any launch geometry).  Not numpy's stream: bit-exact reference sampling stays on the host
+ * (geometry/*.py). */
+int ppsci_b200_sample_uniform(int32_t dtype, uint64_t seed, uint64_t offset, int64_t n, int32_t ndim, const double* lo,
+                              const double* hi, void* const* out_cols, void* stream);
+
 /* Bench instrumentation: when on, every launch of the next calls is bracketed by CUDA events on
  * the caller's stream (no syncs).  get_profile returns, for the most recent call, the summed
  * device time [ms] and launch count per kernel class:

@@ -1258,6 +1258,35 @@ extern "C" int ppsci_b200_deeponet_head(int32_t dtype, int32_t act, const void* 
   return 0;
 }
 
+extern "C" int ppsci_b200_sample_uniform(int32_t dtype, uint64_t seed, uint64_t offset, int64_t n, int32_t ndim, const double* lo,
+                                         const double* hi, void* const* out_cols, void* stream) {
+  if (n <= 0 || ndim < 1 || ndim > PPSCI_MAX_IN || !lo || !hi || !out_cols) return fail("sample_uniform: bad arguments");
+  SampleArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int d = 0; d < ndim; ++d) {
+    if (!out_cols[d]) return fail("sample_uniform: null output column");
+    a.cols[d] = out_cols[d];
+    a.lo[d] = lo[d];
+    a.hi[d] = hi[d];
+  }
+  a.ndim = ndim;
+  a.n = n;
+  a.seed = seed;
+  a.offset = offset;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (dtype == PPSCI_F64) {
+    auto k = k_sample_uniform<double>;
+    PPSCI_LAUNCH(k, dim3(blocks), dim3(256), 0, stream, a);
+  } else if (dtype == PPSCI_F32) {
+    auto k = k_sample_uniform<float>;
+    PPSCI_LAUNCH(k, dim3(blocks), dim3(256), 0, stream, a);
+  } else {
+    return fail("sample_uniform: bad dtype");
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int ppsci_b200_adam_step(int32_t dtype, void* params, const void* grads, void* exp_avg, void* exp_avg_sq,
                                     int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay,
                                     int64_t step, double grad_scale, void* stream) {

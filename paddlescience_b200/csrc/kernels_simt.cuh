@@ -831,6 +831,43 @@ __global__ void __launch_bounds__(256) k_deeponet_head(const T* b, const T* t, c
   }
 }
 
+// Device-side collocation sampling: uniform points in a box, Philox4x32-10 counter-based
+// generator (Salmon et al., SC'11) keyed by `seed`, counter = (point index + offset, dimension group).  Replaces the
+// per-step numpy RNG + H2D copy of ContinuousNamedArrayDataset (ppsci/data/dataset/array_dataset.py:208-228) for boxes;
+// the stream is NOT numpy's (MT19937 cannot be reproduced on the device) — host sampling stays the bit-exact mode.
+__host__ __device__ inline void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+struct SampleArgs {
+  void* cols[PPSCI_MAX_IN];
+  double lo[PPSCI_MAX_IN], hi[PPSCI_MAX_IN];
+  int ndim;
+  long long n;
+  unsigned long long seed, offset;
+};
+template <typename T>
+__global__ void k_sample_uniform(SampleArgs a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const unsigned long long ctr = a.offset + (unsigned long long)i;
+  for (int d0 = 0; d0 < a.ndim; d0 += 2) {  // one Philox block = 4 words = two 53-bit (or four 24-bit) uniforms
+    uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)(d0 >> 1), 0u};
+    philox4x32_10(c, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    for (int j = 0; j < 2 && d0 + j < a.ndim; ++j) {
+      double u;
+      if (sizeof(T) == 8) u = (double)((((unsigned long long)c[2 * j] << 32) | c[2 * j + 1]) >> 11) * (1.0 / 9007199254740992.0);
+      else u = (double)(c[2 * j] >> 8) * (1.0 / 16777216.0);
+      reinterpret_cast<T*>(a.cols[d0 + j])[i] = (T)(a.lo[d0 + j] + (a.hi[d0 + j] - a.lo[d0 + j]) * u);
+    }
+  }
+}
+
 template <typename T>
 __global__ void k_finalize_loss(const double* acc, T* out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

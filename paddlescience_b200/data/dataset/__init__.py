@@ -1,6 +1,7 @@
-from .array_dataset import ContinuousNamedArrayDataset, IterableNamedArrayDataset, NamedArrayDataset
+from .array_dataset import (ContinuousNamedArrayDataset, DeviceUniformSampler, IterableNamedArrayDataset,
+                            NamedArrayDataset)
 
-__all__ = ["NamedArrayDataset", "IterableNamedArrayDataset", "ContinuousNamedArrayDataset", "build_dataset"]
+__all__ = ["NamedArrayDataset", "IterableNamedArrayDataset", "ContinuousNamedArrayDataset", "DeviceUniformSampler", "build_dataset"]
 
 
 def build_dataset(cfg):

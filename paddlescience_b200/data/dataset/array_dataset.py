@@ -107,3 +107,46 @@ class ContinuousNamedArrayDataset:
 
     def __len__(self):
         return 1
+
+
+class DeviceUniformSampler:
+    """``input`` callable for ``ContinuousNamedArrayDataset`` that draws its batch ON the device: ``n`` points uniform in
+    the box ``[lo, hi]`` per call (the reference draws with numpy on the host and copies every
+    step, array_dataset.py:208-228).  Counter-based Philox stream (``ppsci_b200_sample_uniform``): call ``k`` uses the
+    counter range ``[k n, (k + 1) n)``, so a run is reproducible from ``seed`` alone; under data parallelism give every
+    rank the same seed and ``rank_offset = rank`` (disjoint counter ranges)."""
+
+    def __init__(self, keys, lo, hi, n: int, seed: int = 42, dtype=None, device="cuda", rank_offset: int = 0, world: int = 1):
+        import torch
+
+        self.keys = tuple(keys)
+        self.lo = [float(v) for v in lo]
+        self.hi = [float(v) for v in hi]
+        if not (len(self.keys) == len(self.lo) == len(self.hi)):
+            raise ValueError("keys, lo and hi must have the same length")
+        self.n, self.seed = int(n), int(seed)
+        self.dtype = dtype or torch.float32
+        self.device = torch.device(device)
+        self.rank_offset, self.world = int(rank_offset), int(world)
+        self.calls = 0
+
+    def __call__(self):
+        import ctypes as C
+
+        import torch
+
+        from ...engine import binding as B
+
+        lib = B.get_library()
+        cols = [torch.empty(self.n, 1, dtype=self.dtype, device=self.device) for _ in self.keys]
+        nd = len(self.keys)
+        lo = (C.c_double * nd)(*self.lo)
+        hi = (C.c_double * nd)(*self.hi)
+        ptrs = (C.c_void_p * nd)(*[c.data_ptr() for c in cols])
+        offset = (self.calls * self.world + self.rank_offset) * self.n
+        stream = torch.cuda.current_stream(self.device).cuda_stream if self.device.type == "cuda" else 0
+        rc = lib.lib.ppsci_b200_sample_uniform(B.F64 if self.dtype == torch.float64 else B.F32, self.seed, offset, self.n, nd, lo, hi,
+                                               ptrs, stream)
+        lib.check(rc, "sample_uniform")
+        self.calls += 1
+        return dict(zip(self.keys, cols))

@@ -90,6 +90,7 @@ EXPORTED_SYMBOLS = (
     "ppsci_b200_values_bwd_kept",
     "ppsci_b200_plan_chunk_points",
     "ppsci_b200_deeponet_head",
+    "ppsci_b200_sample_uniform",
     "ppsci_b200_plan_last_launches",
     "ppsci_b200_plan_uses_tcgen05",
     "ppsci_b200_plan_stash_offset",
@@ -153,6 +154,8 @@ class Library:
         L.ppsci_b200_plan_chunk_points.restype = i32
         L.ppsci_b200_deeponet_head.argtypes = [i32, i32, vp, vp, vp, vp, vp, i64, i32, dbl, vp, vp, vp, vp, vp, vp]
         L.ppsci_b200_deeponet_head.restype = C.c_int
+        L.ppsci_b200_sample_uniform.argtypes = [i32, C.c_uint64, C.c_uint64, i64, i32, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(vp), vp]
+        L.ppsci_b200_sample_uniform.restype = C.c_int
         L.ppsci_b200_plan_last_launches.argtypes = [vp]
         L.ppsci_b200_plan_last_launches.restype = i64
         L.ppsci_b200_plan_uses_tcgen05.argtypes = [vp]

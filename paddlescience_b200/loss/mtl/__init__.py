@@ -1,7 +1,8 @@
 from .base import LossAggregator
+from .pcgrad import PCGrad
 from .sum import Sum
 
-__all__ = ["LossAggregator", "Sum", "build_mtl_aggregator"]
+__all__ = ["LossAggregator", "Sum", "PCGrad", "build_mtl_aggregator"]
 
 
 def build_mtl_aggregator(cfg):

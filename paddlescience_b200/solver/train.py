@@ -57,15 +57,21 @@ def train_epoch_func(solver, epoch_id: int, log_freq: int):
 
         if nvtx:
             torch.cuda.nvtx.range_push("Loss computation")
-        losses_all, losses_constraint = solver.forward_helper.train_forward(
+        per_key = bool(getattr(solver.loss_aggregator, "needs_per_key_grads", False))
+        out = solver.forward_helper.train_forward(
             tuple(c.output_expr for c in solver.constraint.values()), input_dicts, model, solver.constraint,
-            label_dicts, weight_dicts)
+            label_dicts, weight_dicts, per_key_grads=per_key)
+        losses_all, losses_constraint = out[0], out[1]
         assert "loss" not in losses_all, (
             "Key 'loss' is not allowed in loss_dict for it is an preserved key representing total loss, "
             "please use other name instead.")
         if nvtx:
             torch.cuda.nvtx.range_pop()
-        total_loss = solver.loss_aggregator(losses_all, solver.global_step).loss
+        agg = solver.loss_aggregator(losses_all, solver.global_step)
+        total_loss = agg.loss
+        if per_key:  # the aggregator combines the per-term gradients into model.flat.grad (train.py:158 agg.backward())
+            agg.set_grads(out[2])
+            agg.backward()
 
         if iter_id % solver.update_freq == 0 or iter_id == solver.iters_per_epoch:
             if nvtx:

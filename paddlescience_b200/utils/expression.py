@@ -30,6 +30,17 @@ class CompiledConstraint:
         self.names = list(self.exprs)
         self.compiled = compile_residuals(model.net_spec(), self.exprs)
         self._plans: Dict[torch.dtype, ResidualPlan] = {}
+        self._key_plans: Dict[tuple, ResidualPlan] = {}
+
+    def plan_for_key(self, dtype, k: int) -> ResidualPlan:
+        """The same residual program with a one-hot loss weight: the adjoint yields d(loss of residual k)/d(params) alone
+        (per-equation gradients for mtl.PCGrad and friends; the reference calls losses[key].backward() per key)."""
+        if (dtype, k) not in self._key_plans:
+            loss = self.cst.loss
+            red = getattr(loss, "reduction", "mean")
+            lw = [(loss.weight_of(key) if hasattr(loss, "weight_of") else 1.0) if j == k else 0.0 for j, key in enumerate(self.names)]
+            self._key_plans[(dtype, k)] = ResidualPlan(self.compiled, dtype, [red] * len(self.names), lw)
+        return self._key_plans[(dtype, k)]
 
     def plan(self, dtype) -> ResidualPlan:
         if dtype not in self._plans:
@@ -165,11 +176,36 @@ class ExpressionSolver(nn.Module):
         constraint: Dict[str, "object"],
         label_dicts: Tuple[Dict[str, torch.Tensor], ...],
         weight_dicts: Tuple[Dict[str, torch.Tensor], ...],
+        per_key_grads: bool = False,
     ):
         """Returns (losses_all, losses_constraint) like the reference; additionally the weight
-        gradient of  sum(losses_all)  has been accumulated into ``model.flat.grad``."""
+        gradient of  sum(losses_all)  has been accumulated into ``model.flat.grad``.
+
+        ``per_key_grads=True`` (loss aggregators that need the gradient of every loss term, mtl.PCGrad): nothing is
+        accumulated into ``model.flat.grad``; a third value ``{key: flat gradient of losses_all[key]}`` is returned, each
+        produced by one fused call with a one-hot loss weight."""
         losses_all: Dict[str, torch.Tensor] = {}
         losses_constraint: Dict[str, torch.Tensor] = {}
+        if per_key_grads:
+            if hasattr(model, "fused_train_forward") or getattr(model, "weight_norm", False):
+                raise NotImplementedError("per-term gradients are implemented for plain MLP models")
+            flat = model.flat
+            params = model.engine_params()
+            grads_by_key: Dict[str, torch.Tensor] = {}
+            for i, cst_name in enumerate(constraint):
+                cst = constraint[cst_name]
+                cc = self.compiled_for(model, cst, input_dicts[i])
+                weights = weight_dicts[i]
+                if "area" in input_dicts[i]:
+                    area = input_dicts[i]["area"]
+                    weights = {k: (weights[k] * area if weights and k in weights else area) for k in cc.names}
+                for k, key in enumerate(cc.names):
+                    g = grads_by_key.setdefault(key, torch.zeros_like(flat.data))
+                    lv = cc.plan_for_key(flat.dtype, k).loss_fwd_bwd(input_dicts[i], params, g, labels=label_dicts[i],
+                                                                     weights=weights)[k].clone()
+                    losses_all[key] = losses_all[key] + lv if key in losses_all else lv
+                    losses_constraint[cst_name] = losses_constraint[cst_name] + lv if cst_name in losses_constraint else lv
+            return losses_all, losses_constraint, grads_by_key
         if hasattr(model, "fused_train_forward"):  # models that combine several native networks (DeepONet)
             for i, cst_name in enumerate(constraint):
                 cst = constraint[cst_name]

@@ -1,0 +1,54 @@
+"""mtl.PCGrad on per-term gradients from the adjoint kernels (reference: ppsci/loss/mtl/pcgrad.py:62-124)."""
+import numpy as np
+import pytest
+import torch
+
+import ppsci
+from oracle import ppsci_oracle as O
+from paddlescience_b200.engine import binding as B
+
+
+def test_per_key_gradients_and_projection_match_autograd(monkeypatch):
+    from tests.emul.build_emul import build
+
+    monkeypatch.setattr(B, "_default", B.Library(build()))  # test infrastructure: same kernel sources, compiled for the CPU
+    ppsci.utils.misc.set_random_seed(5)
+    model = ppsci.arch.MLP(("x", "y"), ("u", "v", "p"), 2, 12, "tanh", dtype=torch.float64)
+    eq = ppsci.equation.NavierStokes(0.1, 1.0, 2, False)
+    rect = ppsci.geometry.Rectangle((0, 0), (1, 1))
+    cst = ppsci.constraint.InteriorConstraint(eq.equations, {"continuity": 0, "momentum_x": 0, "momentum_y": 0}, rect,
+                                              {"dataset": "IterableNamedArrayDataset", "iters_per_epoch": 1, "batch_size": 40},
+                                              ppsci.loss.MSELoss("mean"), name="EQ")
+    ds = cst.data_loader.loader
+    inp = {k: v.double() for k, v in ds.input.items()}
+    lab = {k: v.double() for k, v in ds.label.items()}
+    fh = ppsci.utils.ExpressionSolver()
+    la, lc, gk = fh.train_forward((cst.output_expr,), [inp], model, {"EQ": cst}, [lab], [None], per_key_grads=True)
+    assert set(gk) == {"continuity", "momentum_x", "momentum_y"} and model.flat.grad is None or float(model.flat.grad.abs().max()) == 0.0
+    # oracle: gradient of each loss term alone
+    om = O.OracleMLP(("x", "y"), ("u", "v", "p"), [12, 12], "tanh")
+    exprs = O.navier_stokes_expr(0.1, 1.0, 2, False)
+    p = model.flat.data.clone()
+    ref = {}
+    for key in exprs:
+        _, _, g = O.train_forward_backward(om, p, exprs, {k: inp[k] for k in ("x", "y")}, lab, None, "mean",
+                                           {k: (1.0 if k == key else 0.0) for k in exprs})
+        ref[key] = g
+        np.testing.assert_allclose(gk[key].numpy(), g.numpy(), rtol=1e-8, atol=1e-12 * float(g.abs().max()))
+    # the aggregator's projection (same shuffle seed on both sides)
+    agg = ppsci.loss.mtl.PCGrad(model)
+    np.random.seed(3)
+    a = agg(la, 0)
+    a.set_grads(gk)
+    a.backward()
+    np.random.seed(3)
+    keys = list(la.keys())
+    np.random.shuffle(keys)
+    gl = [ref[k] for k in keys]
+    tot = torch.zeros_like(p)
+    for g in gl:
+        grad = g.clone()
+        for g2 in gl:
+            grad = grad - torch.clamp(torch.sum(grad * g2) / torch.sum(g2 * g2), max=0.0) * g2
+        tot += grad
+    np.testing.assert_allclose(model.flat.grad.numpy(), tot.numpy(), rtol=1e-7, atol=1e-12 * float(tot.abs().max()))
