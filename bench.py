@@ -430,6 +430,7 @@ def run_ours(args):
 
     # ---------------- per-kernel-class shares (separate, untimed pass) ----------------
     prof = None
+    don_prof = None
     if plan is not None:
         plan.set_profile(True)
         prof_acc = None
@@ -440,6 +441,15 @@ def run_ours(args):
             prof_acc = p if prof_acc is None else {k: {"ms": prof_acc[k]["ms"] + v["ms"], "launches": v["launches"]} for k, v in p.items()}
         plan.set_profile(False)
         prof = {k: {"ms": v["ms"] / 2, "launches": v["launches"]} for k, v in prof_acc.items()}
+    else:  # DeepONet: the LAST native call of each sub-network's plan in the step (its adjoint over the last slice)
+        plans = model._get_plans()
+        for p_ in plans:
+            p_.set_profile(True)
+        step(dev_in)
+        torch.cuda.synchronize(dev)
+        don_prof = {name: {k: round(v["ms"], 3) for k, v in p_.get_profile().items()} for name, p_ in zip(("branch", "trunk"), plans)}
+        for p_ in plans:
+            p_.set_profile(False)
 
     # ---------------- parity of THIS run's residuals against the fp64 oracle on a fixed subset (untimed) ----------------
     parity = None
@@ -519,6 +529,7 @@ def run_ours(args):
         roofline = {"bound": "hbm", "kernel": "whole step (branch + trunk MLPs, head, adjoints, Adam)", "achieved": hbm,
                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm / peaks["hbm_gbs"], "traffic": None,
                     "whole_step_tflops": fpp * N / (ms_per_step * 1e-3) / 1e12,
+                    "last_adjoint_call_class_ms": don_prof,
                     "note": "algorithmic bytes = 408 B per (u, y) pair (the 100-float sensor row + y + label) over the whole "
                             "step time; the step is compute / stash bound, not input bound"}
     log("profile pass done; timing the CPU baseline")

@@ -68,10 +68,12 @@ class OracleMLP:
         hidden: Sequence[int],
         activation: str = "tanh",
         periods: Optional[Dict[str, Tuple[float, bool]]] = None,
+        skip_connection: bool = False,
     ):
         self.input_keys = tuple(input_keys)
         self.output_keys = tuple(output_keys)
         self.periods = periods or {}
+        self.skip_connection = skip_connection
         n_feat = len(self.input_keys) + len(self.periods)  # mlp.py:222-226
         self.widths = [n_feat] + list(hidden) + [len(self.output_keys)]
         self.act = get_activation(activation)
@@ -100,8 +102,16 @@ class OracleMLP:
                 feats.append(x[k])
         y = torch.cat(feats, dim=-1) if len(feats) > 1 else feats[0]
         layers = self.split_params(flat)
-        for W, b in layers[:-1]:  # mlp.py:281-296
-            y = self.act(y @ W + b)
+        skip = None
+        for i, (W, b) in enumerate(layers[:-1]):  # mlp.py:281-296, statement by statement
+            y = y @ W + b
+            if self.skip_connection and i % 2 == 0:
+                if skip is not None:
+                    skip = y
+                    y = y + skip
+                else:
+                    skip = y
+            y = self.act(y)
         W, b = layers[-1]
         y = y @ W + b
         if len(self.output_keys) == 1:

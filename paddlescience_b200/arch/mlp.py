@@ -122,9 +122,11 @@ class MLP(base.Arch):
         else:
             raise ValueError(f"hidden_size should be list of int or int, but got {type(hidden_size)}")
         self.weight_norm = bool(weight_norm)
-        for flag, name in ((skip_connection, "skip_connection"), (fourier, "fourier"), (random_weight, "random_weight")):
+        for flag, name in ((fourier, "fourier"), (random_weight, "random_weight")):
             if flag:
                 raise NotImplementedError(f"MLP({name}=...) is not supported by the jet kernels yet")
+        if skip_connection and weight_norm:
+            raise NotImplementedError("MLP(skip_connection=True, weight_norm=True) is not supported yet")
         if input_dim is not None and input_dim != len(self.input_keys) + (len(self.periods) if self.periods else 0):
             raise NotImplementedError("input_dim different from the (period-embedded) key count is not supported")
         if output_dim is not None and output_dim != len(self.output_keys):
@@ -172,7 +174,16 @@ class MLP(base.Arch):
         self.flat = nn.Parameter(torch.zeros(off, dtype=dtype))
         self.linears = [_LinearView(self, i) for i in range(len(hidden))]
         self.last_fc = _LinearView(self, len(hidden))
-        self.skip_connection = False
+        # Reference semantics of skip_connection (mlp.py:281-296), restated exactly: at every even hidden layer i >= 2
+        # the code executes ``skip = y; y = y + skip`` — the freshly assigned skip IS y, so the pre-activation is
+        # doubled (the first even layer only records skip).  A doubled pre-activation is the same linear layer with
+        # W and b scaled by 2: the kernels read effective weights 2 W_i, 2 b_i for those layers and the chain rule
+        # returns 2 x their gradients (host-side reparametrisation, like weight_norm).
+        self.skip_connection = bool(skip_connection)
+        self._skip_layers = [i for i in range(len(hidden)) if self.skip_connection and i % 2 == 0 and i >= 2]
+        if self._skip_layers:
+            self.register_buffer("_eff", torch.zeros(self._n_eff, dtype=dtype), persistent=False)
+            self.register_buffer("_eff_grad", torch.zeros(self._n_eff, dtype=dtype), persistent=False)
         self.reset_parameters()
         self._value_plan = None
 
@@ -197,6 +208,13 @@ class MLP(base.Arch):
 
     def engine_params(self) -> torch.Tensor:
         """The flat [W_1 | b_1 | ...] buffer passed to the native calls (effective weights under weight_norm)."""
+        if self._skip_layers:
+            with torch.no_grad():
+                self._eff.copy_(self.flat.data[: self._n_eff])
+                for i in self._skip_layers:
+                    a, b = self._shapes[i]
+                    self._eff[self._w_off[i]: self._b_off[i] + b].mul_(2.0)  # W_i and b_i are contiguous
+            return self._eff
         if not self.weight_norm:
             return self.flat.data
         with torch.no_grad():
@@ -211,11 +229,19 @@ class MLP(base.Arch):
         """Buffer the native calls accumulate the weight gradient into (same layout as ``engine_params``)."""
         if self.flat.grad is None:
             self.flat.grad = torch.zeros_like(self.flat.data)
-        return self._eff_grad if self.weight_norm else self.flat.grad
+        return self._eff_grad if (self.weight_norm or self._skip_layers) else self.flat.grad
 
     def finish_grads(self):
         """Chain rule of the weight normalisation: gradients w.r.t. the effective weights -> (V, g); then the
         staging buffer is cleared.  No-op for plain layers (the kernels accumulated into ``flat.grad`` directly)."""
+        if self._skip_layers:
+            with torch.no_grad():
+                for i in self._skip_layers:
+                    a, b = self._shapes[i]
+                    self._eff_grad[self._w_off[i]: self._b_off[i] + b].mul_(2.0)  # d/dW = 2 d/dW_eff
+                self.flat.grad[: self._n_eff] += self._eff_grad
+                self._eff_grad.zero_()
+            return
         if not self.weight_norm:
             return
         with torch.no_grad():

@@ -187,7 +187,7 @@ class ExpressionSolver(nn.Module):
         losses_all: Dict[str, torch.Tensor] = {}
         losses_constraint: Dict[str, torch.Tensor] = {}
         if per_key_grads:
-            if hasattr(model, "fused_train_forward") or getattr(model, "weight_norm", False):
+            if hasattr(model, "fused_train_forward") or getattr(model, "weight_norm", False) or getattr(model, "_skip_layers", None):
                 raise NotImplementedError("per-term gradients are implemented for plain MLP models")
             flat = model.flat
             params = model.engine_params()

@@ -59,3 +59,34 @@ def test_optimizer_checkpoint_carries_the_lr_schedule_position():
     assert opt2.t == 7 and sched2.last_epoch == 7
     assert opt2.get_lr() == pytest.approx(opt.get_lr())
     assert opt2.get_lr() != pytest.approx(1e-3 * 0 + sched2.warmup_start_lr)  # not replaying the warm-up
+
+
+def test_skip_connection_follows_the_reference_loop(monkeypatch):
+    """MLP(skip_connection=True): the reference's loop (mlp.py:281-296, restated statement by statement in the oracle)
+    against the engine's effective-weight reparametrisation, through the CPU emulation of the real kernels."""
+    import numpy as np
+
+    from oracle import ppsci_oracle as O
+    from paddlescience_b200.engine import binding as B
+    from tests.emul.build_emul import build
+
+    monkeypatch.setattr(B, "_default", B.Library(build()))
+    ppsci.utils.misc.set_random_seed(9)
+    m = ppsci.arch.MLP(("x", "y"), ("u",), 5, 10, "tanh", skip_connection=True, dtype=torch.float64)
+    with torch.no_grad():
+        m.flat.data += 0.1 * torch.randn_like(m.flat.data)
+    assert m._skip_layers == [2, 4]
+    eq = ppsci.equation.Laplace(2)
+    rect = ppsci.geometry.Rectangle((0, 0), (1, 1))
+    cst = ppsci.constraint.InteriorConstraint(eq.equations, {"laplace": 0}, rect,
+                                              {"dataset": "IterableNamedArrayDataset", "iters_per_epoch": 1, "batch_size": 30},
+                                              ppsci.loss.MSELoss("mean"), name="EQ")
+    ds = cst.data_loader.loader
+    inp = {k: v.double() for k, v in ds.input.items()}
+    lab = {k: v.double() for k, v in ds.label.items()}
+    fh = ppsci.utils.ExpressionSolver()
+    losses_all, _ = fh.train_forward((cst.output_expr,), [inp], m, {"EQ": cst}, [lab], [None])
+    om = O.OracleMLP(("x", "y"), ("u",), [10] * 5, "tanh", skip_connection=True)
+    lo, _, g = O.train_forward_backward(om, m.flat.data.clone(), O.laplace_expr(2), {k: inp[k] for k in ("x", "y")}, lab, None, "mean")
+    assert float(losses_all["laplace"]) == pytest.approx(float(lo["laplace"]), rel=1e-11)
+    np.testing.assert_allclose(m.flat.grad.numpy(), g.numpy(), rtol=1e-8, atol=1e-12 * float(g.abs().max()))

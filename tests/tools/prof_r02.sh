@@ -12,6 +12,7 @@ for spec in "k_fused_fwd16 1" "k_fused_dx 1" "k_tc2_dw 7"; do
   ncu --set full --clock-control none --import-source on -k regex:$1 --launch-skip $2 -c 1 -f -o gpurun_out/r02_$1 python tests/tools/ncu_target.py > gpurun_out/r02_ncu_$1.log 2>&1
   ncu -i gpurun_out/r02_$1.ncu-rep --page details > gpurun_out/r02_ncu_$1_details.txt 2>&1
   ncu -i gpurun_out/r02_$1.ncu-rep --page raw --csv > gpurun_out/r02_ncu_$1_raw.csv 2>&1
+  rm -f gpurun_out/r02_$1.ncu-rep   # the report files are 10-25 MB each; gpurun_out/ travels back only below 64 MiB
 done
 python bench.py --config 5 --steps 5 --warmup 3 > gpurun_out/bench_r2f_cfg5.json 2> gpurun_out/bench_r2f_cfg5.err
 python bench.py --config 2 --steps 8 --warmup 3 > gpurun_out/bench_r2f_cfg2.json 2> gpurun_out/bench_r2f_cfg2.err
