@@ -662,6 +662,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           }
           t.Np = nc;
           t.num_tiles = (int)ptiles;
+          t.dbg = debug_timeline_ptr(3);
           ta.wscale = wscale;
           const int smemf = tc::fused_fwd16_smem_bytes(H);
           const unsigned tile_pairs = (ptiles + 1) / 2, sm_pairs = (unsigned)P->num_sms / 2;

@@ -334,11 +334,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
           const bool has1 = 2 * i + 1 < ncb;
           const uint32_t drow = produce_next ? it0 : 47u;
           FDBG(tid == 0, drow, 0);
+          const int cb = 2 * i + grp;
+          // this item's bias quad: requested before the stage wait / fill / barrier so that its latency is hidden
+          const int col = (cb < ncb ? cb : 0) * 32 + 4 * kq;
+          const float4 b4 = bias ? make_float4(__ldg(bias + col), __ldg(bias + col + 1), __ldg(bias + col + 2), __ldg(bias + col + 3))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
           // the two stages of this step (operand chunks AND exchange tiles) have been released; the last layer's
           // epilogue only borrows them as scratch (every MMA issued so far has retired, nothing to wait for)
           if (produce_next) wait_stages(it0, has1);
           FDBG(tid == 0, drow, 1);
-          const int cb = 2 * i + grp;
           // exchange tile of block cb = the A_lo region of the stage its operand chunk goes to
           unsigned char* stage_ptr = base_ptr + ((it + (uint32_t)cb) % FA) * (2 * A_TILE_BYTES);
           unsigned char* Xb = stage_ptr + A_TILE_BYTES;
@@ -359,9 +363,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
           FDBG(tid == 0, drow, 3);
           FDBG(tid == 0, drow, 4);
           if (cb < ncb) {
-            const int col = cb * 32 + 4 * kq;
-            const float4 b4 = bias ? make_float4(__ldg(bias + col), __ldg(bias + col + 1), __ldg(bias + col + 2), __ldg(bias + col + 3))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
             for (int pl = pl0; pl < TP; pl += 28) {
               const bool valid = pl < vpts;
               float4 z[CS];
@@ -518,6 +519,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
   const int n_tile_pairs = (g.num_tiles + 1) / 2;
   const int my_tp = pair < n_tile_pairs ? (n_tile_pairs - 1 - pair) / npairs + 1 : 0;
   const uint32_t chunks_per_tile = (uint32_t)(nch32 + (NLf - 1) * nch64);
+  const bool dbg0 = g.dbg && blockIdx.x == 0;
+#define FDBG(cond, row, slot) do { if (dbg0 && (cond) && (row) < 48u) g.dbg[(row) * 16 + (slot)] = clock64(); } while (0)
 
   if (warp == T2_TMA_WARP) {
     if (lane == 0) {  // weight streamer (see fused_stream_weights): layer 0 has nch32 chunks, the others nch64; same bytes per chunk
@@ -555,7 +558,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
             const uint32_t acc = acc_base + (lay & 1u) * (uint32_t)N;
             const int nch = l == 0 ? nch32 : nch64;
             for (int j = 0; j < nch; ++j, ++it) {
+              FDBG(true, it, 8);
               mbar_wait_cluster(bars + 64 + 8 * (it % FA), (it / FA) & 1u);
+              FDBG(true, it, 9);
               tc_fence_after();
               const uint64_t ao = (uint64_t)(it % FA) * a_inc, bo = (uint64_t)(it % FB) * b_inc;
               if (l == 0) {
@@ -570,6 +575,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
                 }
               }
               mma_commit_2(bars + 8 * (it % FA));
+              FDBG(true, it, 10);
             }
           }
       } else {
@@ -664,6 +670,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
         // accumulator -> true pre-activation: rz compensation, weight scale, operand row scale
         const float unw = l == 0 ? tc_rz_comp_single(nch32) : tc_rz_comp_single16(nch64) / __ldg(ga.wscale + l);
         const int nsteps = ncb / 2;
+        FDBG(tid == 0, produce_next ? it : 46u, 11);
         if (tid < 128) rowmax[tid] = 0u;
         t2_prod_sync();  // rs_cur (written by other warps in P0 / the previous epilogue) and the cleared maxima are visible
         if (produce_next) {
@@ -701,8 +708,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
         }
         for (int i = 0; i < nsteps; ++i) {
           const uint32_t itc = it + (uint32_t)i;  // the ONE 64-wide chunk this step produces (both groups, one row half each)
-          if (produce_next && itc >= FA) f_wait_done(bars, itc - FA);
+          const uint32_t drow = produce_next ? itc : 47u;
+          FDBG(tid == 0, drow, 0);
           const int cb = 2 * i + grp;
+          // this item's bias quad: requested before the stage wait / fill / barrier so that its latency is hidden
+          const int col = cb * 32 + 4 * kq;
+          const float4 b4 = bias ? make_float4(__ldg(bias + col), __ldg(bias + col + 1), __ldg(bias + col + 2), __ldg(bias + col + 3))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (produce_next && itc >= FA) f_wait_done(bars, itc - FA);
+          FDBG(tid == 0, drow, 1);
           unsigned char* stage_ptr = base_ptr + (itc % FA) * (2 * A_TILE_BYTES);
           if (wg7 < 4) {  // raw block -> the 8-byte cells its items will overwrite: (v0, v1) -> hi cell, (v2, v3) -> lo cell
             const int q = warp & 3, row = q * 32 + lane;
@@ -718,11 +732,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
                   make_float2(__uint_as_float(v[4 * t4 + 2]) * f, __uint_as_float(v[4 * t4 + 3]) * f);
             }
           }
+          FDBG(tid == 0, drow, 2);
           t2_prod_sync();  // exchange cells complete
+          FDBG(tid == 0, drow, 3);
           {
-            const int col = cb * 32 + 4 * kq;
-            const float4 b4 = bias ? make_float4(__ldg(bias + col), __ldg(bias + col + 1), __ldg(bias + col + 2), __ldg(bias + col + 3))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
             for (int pl = pl0; pl < TP; pl += 28) {
               const bool valid = pl < vpts;
               float4 z[CS];
@@ -762,14 +775,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
               }
             }
           }
+          FDBG(tid == 0, drow, 5);
           if (produce_next) hand_off(itc, false);
           else t2_prod_sync();  // scratch stage reuse two steps later is ordered by the next step's sync; keep groups together
+          FDBG(tid == 0, drow, 6);
         }
         if (produce_next) it += (uint32_t)nsteps;
         else tc_fence_before();
       }
     }
   }
+#undef FDBG
   __syncwarp();
   tc_fence_before();
   __syncthreads();

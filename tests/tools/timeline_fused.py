@@ -23,7 +23,7 @@ for _ in range(2):
 torch.cuda.synchronize()
 t = dbg.cpu().view(48, 16)
 t0 = min(int(v) for v in t.flatten() if int(v) != 0)
-names = {0: "top", 1: "sync1", 2: "filled", 3: "sync2", 4: "stage_free", 5: "items_done", 6: "arrived", 8: "mma_wait", 9: "mma_go", 10: "mma_committed"}
+names = {11: "epi_start", 0: "top", 1: "sync1", 2: "filled", 3: "sync2", 4: "stage_free", 5: "items_done", 6: "arrived", 8: "mma_wait", 9: "mma_go", 10: "mma_committed"}
 print("chunk timeline of CTA 0 (cycles relative to the first stamp); worker thread 0 | MMA lane")
 for it in range(48):
     row = {names[k]: int(t[it, k]) - t0 for k in names if int(t[it, k]) != 0}
