@@ -28,6 +28,11 @@ if ROOT not in sys.path:
 
 UNIT = "points/s"
 NU, RHO = 0.01, 1.0
+# dram__bytes_read.sum + dram__bytes_write.sum of the hidden-layer kernels of cfg3 from the committed `ncu --set full`
+# captures of this round (profiles/r02_summary.md; one 65,536-point chunk, all five hidden->hidden layers): bytes PER POINT.
+# Equal to the plane sets the design streams (no re-reads): fwd 1 read + 10 written sets, dx 6 read + 5 written, dW 10 read.
+NCU_DRAM_BYTES_PER_POINT_CFG3 = {"fwd_gemm": (368.6e6 + 3299.8e6) / 65536, "dx_gemm": (2064.9e6 + 1661.3e6) / 65536,
+                                 "dw_gemm": 5 * (671.5e6 + 3.6e6) / 65536}
 
 # name, metric label, points per GPU, dtype
 CONFIGS = {
@@ -496,7 +501,8 @@ def run_ours(args):
         n_hh = max(1, len(w) - 3)
         H = w[1]
         esz = 8 if dt == torch.float64 else 4
-        fused = on_tc and prof["fwd_gemm"]["launches"] * n_hh > 0 and prof["fwd_gemm"]["launches"] < n_hh * math.ceil(N / 262144) * 1 + 1
+        n_chunks = math.ceil(N / max(1, plan.chunk_points))
+        fused = on_tc and 0 < prof["fwd_gemm"]["launches"] <= n_chunks  # one launch per point chunk instead of one per layer
         sets = {"fwd_gemm": (2 * n_hh + 1) if fused else 3 * n_hh, "dx_gemm": (2 * n_hh + 1) if fused else 3 * n_hh, "dw_gemm": 2 * n_hh}
         design_bytes = sets[dom] * C * N * H * esz
         if on_tc:
@@ -508,7 +514,7 @@ def run_ours(args):
             roofline = {"bound": "hbm", "kernel": dom, "achieved": hbm, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": hbm / peaks["hbm_gbs"] if hbm else None}
         roofline.update({
-            "traffic": None,
+            "traffic": (NCU_DRAM_BYTES_PER_POINT_CFG3[dom] * N / dom_launches) if cfg == 3 else None,
             "class_ms_per_step": round(dom_ms, 3), "launches_per_step": dom_launches,
             "alg_flops_per_step": classes[dom] * N,
             "hbm_gbs_design_traffic": design_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else None,
@@ -520,8 +526,9 @@ def run_ours(args):
                     "measured with CUDA events around every launch on the launch stream (untimed profile pass); peak = dense tf32 "
                     "GEMM throughput measured in this run (cuBLAS 8192^3, best of 8)" +
                     (f"; bf16 sustained peak from {peaks['source']}: {peaks['bf16_tflops_sustained']}" if on_tc else "") +
-                    "; `traffic` (ncu dram bytes) is in profiles/, not re-measured here; hbm_gbs_design_traffic = plane sets this "
-                    "design streams for the class / its time",
+                    "; `traffic` = dram bytes per launch of this class from the committed ncu capture (profiles/r02_summary.md), "
+                    "scaled to the points per launch, not re-measured here; hbm_gbs_design_traffic = plane sets this design "
+                    "streams for the class / its time",
         })
     if roofline is None:  # DeepONet (C = 1, no input derivatives): SURVEY section 8(d) gives 408 algorithmic bytes per pair
         alg_bytes = 408.0 * N

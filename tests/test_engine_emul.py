@@ -41,9 +41,9 @@ def test_tcgen05_kernels_through_the_emulated_primitives(emul_lib, mask, monkeyp
     k_tc2_dw, thin first / last layers) compiled for the CPU: UMMA descriptors decoded, 128-byte swizzle, mbarrier
     phases, TMEM lane quadrants, cta_group::2 operand split, kind::tf32 / kind::f16 operands, round-toward-zero
     accumulation, MMAs executed at the commit (tests/emul/cuda_emul.h).  60 points = 3 point tiles: one full tile pair
-    + a pair whose second CTA has an empty tile; 4 x 256 hidden layers = three fused layers."""
+    + a pair whose second CTA has an empty tile; 3 x 256 hidden layers = two fused layers."""
     monkeypatch.setenv("PPSCI_B200_TC_MASK", str(mask))
-    case = dict(in_keys=("x", "y"), out_keys=("u", "v", "p"), hidden=[256] * 4, act="tanh",
+    case = dict(in_keys=("x", "y"), out_keys=("u", "v", "p"), hidden=[256] * 3, act="tanh",
                 exprs=lambda: __import__("oracle.ppsci_oracle", fromlist=["x"]).navier_stokes_expr(0.01, 1.0, 2, False),
                 dtype=torch.float32)
     r = run_case(case, 60, library=emul_lib, device="cpu", backend=2)
