@@ -41,6 +41,8 @@ class _LinearView:
         off = self._owner._w_off[self._index]
         v = self._owner.flat.data[off: off + a * b].view(a, b)
         if self._owner._wn_layer(self._index):
+            if self._owner.random_weight:
+                return v * self.weight_g
             return v * (self.weight_g / v.norm(p=2, dim=0, keepdim=True))
         return v
 
@@ -87,8 +89,9 @@ class _LinearView:
 class MLP(base.Arch):
     """Multi layer perceptron network (same arguments as the reference, mlp.py:179-193).
 
-    Not yet supported by the jet kernels (raise ``NotImplementedError`` at construction):
-    ``skip_connection``, ``fourier``, ``random_weight``, trainable periods.
+    ``weight_norm``, ``random_weight`` and ``skip_connection`` are host-side reparametrisations around the unchanged
+    engine call (effective [W | b] before it, chain rule after it).  Not yet supported by the jet kernels (raise
+    ``NotImplementedError`` at construction): ``fourier``, trainable periods.
     """
 
     def __init__(
@@ -122,11 +125,16 @@ class MLP(base.Arch):
         else:
             raise ValueError(f"hidden_size should be list of int or int, but got {type(hidden_size)}")
         self.weight_norm = bool(weight_norm)
-        for flag, name in ((fourier, "fourier"), (random_weight, "random_weight")):
-            if flag:
-                raise NotImplementedError(f"MLP({name}=...) is not supported by the jet kernels yet")
-        if skip_connection and weight_norm:
-            raise NotImplementedError("MLP(skip_connection=True, weight_norm=True) is not supported yet")
+        if fourier:
+            raise NotImplementedError("MLP(fourier=...) is not supported by the jet kernels yet")
+        # random_weight = {"mean": m, "std": s}: RandomWeightFactorization on EVERY layer incl. last_fc (mlp.py:56-92,
+        # 248-256, 262-270): W = g * V (column scaling), g = exp(N(m, s)), V = glorot_normal / g
+        self.random_weight = dict(random_weight) if random_weight else None
+        if (skip_connection or self.random_weight) and weight_norm:
+            raise NotImplementedError("weight_norm cannot be combined with skip_connection / random_weight (the reference "
+                                      "picks weight_norm first, mlp.py:238-250)")
+        if skip_connection and self.random_weight:
+            raise NotImplementedError("MLP(skip_connection=True, random_weight=...) is not supported yet")
         if input_dim is not None and input_dim != len(self.input_keys) + (len(self.periods) if self.periods else 0):
             raise NotImplementedError("input_dim different from the (period-embedded) key count is not supported")
         if output_dim is not None and output_dim != len(self.output_keys):
@@ -165,8 +173,8 @@ class MLP(base.Arch):
             off += b
         self._n_eff = off  # length of the [W | b] buffer the kernels read
         self._g_off = []   # weight_norm: per hidden layer, offset of its gain vector g_l (appended after the last bias)
-        if self.weight_norm:
-            for a, b in self._shapes[:-1]:
+        if self.weight_norm or self.random_weight:
+            for a, b in (self._shapes if self.random_weight else self._shapes[:-1]):
                 self._g_off.append(off)
                 off += b
             self.register_buffer("_eff", torch.zeros(self._n_eff, dtype=dtype), persistent=False)
@@ -196,15 +204,24 @@ class MLP(base.Arch):
                 w = (torch.rand(a * b, dtype=torch.float64) * 2 - 1) * lim
                 self.flat.data[self._w_off[i]: self._w_off[i] + a * b] = w.to(self.flat.dtype)
                 self.flat.data[self._b_off[i]: self._b_off[i] + b] = 0
-                if self._wn_layer(i):  # WeightNormLinear._init_weights: V xavier-uniform, g = 1, bias = 0
+                if self._wn_layer(i) and not self.random_weight:  # WeightNormLinear._init_weights: V xavier-uniform, g = 1, bias = 0
                     self.flat.data[self._g_off[i]: self._g_off[i] + b] = 1
+                if self.random_weight:  # RandomWeightFactorization._init_weights (mlp.py:77-88)
+                    v = torch.randn(a, b, dtype=torch.float64) * math.sqrt(2.0 / (a + b))  # glorot normal
+                    g = torch.exp(self.random_weight["mean"] + self.random_weight["std"] * torch.randn(b, dtype=torch.float64))
+                    self.flat.data[self._w_off[i]: self._w_off[i] + a * b] = (v / g).reshape(-1).to(self.flat.dtype)
+                    self.flat.data[self._g_off[i]: self._g_off[i] + b] = g.to(self.flat.dtype)
 
     def net_spec(self) -> NetSpec:
         return self._net
 
     # ---- what the engine reads / accumulates into ---------------------------------------------------
     def _wn_layer(self, i: int) -> bool:
-        return self.weight_norm and i < len(self._shapes) - 1  # hidden layers only (mlp.py:234-246); last_fc is plain
+        """Layer i is stored factored as (weight_v, weight_g): weight-normalised hidden layers (mlp.py:234-246; last_fc is
+        plain) or every layer under random weight factorization."""
+        if self.random_weight:
+            return True
+        return self.weight_norm and i < len(self._shapes) - 1
 
     def engine_params(self) -> torch.Tensor:
         """The flat [W_1 | b_1 | ...] buffer passed to the native calls (effective weights under weight_norm)."""
@@ -215,21 +232,24 @@ class MLP(base.Arch):
                     a, b = self._shapes[i]
                     self._eff[self._w_off[i]: self._b_off[i] + b].mul_(2.0)  # W_i and b_i are contiguous
             return self._eff
-        if not self.weight_norm:
+        if not (self.weight_norm or self.random_weight):
             return self.flat.data
         with torch.no_grad():
             self._eff.copy_(self.flat.data[: self._n_eff])
-            for i, (a, b) in enumerate(self._shapes[:-1]):
+            for i, (a, b) in enumerate(self._shapes):
+                if not self._wn_layer(i):
+                    continue
                 v = self.flat.data[self._w_off[i]: self._w_off[i] + a * b].view(a, b)
                 g = self.flat.data[self._g_off[i]: self._g_off[i] + b]
-                self._eff[self._w_off[i]: self._w_off[i] + a * b].view(a, b).copy_(v * (g / v.norm(p=2, dim=0, keepdim=True)))
+                scale = g if self.random_weight else g / v.norm(p=2, dim=0, keepdim=True)
+                self._eff[self._w_off[i]: self._w_off[i] + a * b].view(a, b).copy_(v * scale)
         return self._eff
 
     def engine_grads(self) -> torch.Tensor:
         """Buffer the native calls accumulate the weight gradient into (same layout as ``engine_params``)."""
         if self.flat.grad is None:
             self.flat.grad = torch.zeros_like(self.flat.data)
-        return self._eff_grad if (self.weight_norm or self._skip_layers) else self.flat.grad
+        return self._eff_grad if (self.weight_norm or self.random_weight or self._skip_layers) else self.flat.grad
 
     def finish_grads(self):
         """Chain rule of the weight normalisation: gradients w.r.t. the effective weights -> (V, g); then the
@@ -242,16 +262,22 @@ class MLP(base.Arch):
                 self.flat.grad[: self._n_eff] += self._eff_grad
                 self._eff_grad.zero_()
             return
-        if not self.weight_norm:
+        if not (self.weight_norm or self.random_weight):
             return
         with torch.no_grad():
             gr = self.flat.grad
             gr[: self._n_eff] += self._eff_grad  # biases and the plain last layer pass through; V parts are fixed below
-            for i, (a, b) in enumerate(self._shapes[:-1]):
+            for i, (a, b) in enumerate(self._shapes):
+                if not self._wn_layer(i):
+                    continue
                 sl = slice(self._w_off[i], self._w_off[i] + a * b)
                 v = self.flat.data[sl].view(a, b)
                 g = self.flat.data[self._g_off[i]: self._g_off[i] + b]
                 dw = self._eff_grad[sl].view(a, b)
+                if self.random_weight:  # W = g * V  ->  dV = g * dW,  dg = sum_in V * dW
+                    gr[sl].view(a, b).add_(g * dw - dw)
+                    gr[self._g_off[i]: self._g_off[i] + b] += (v * dw).sum(dim=0)
+                    continue
                 norm = v.norm(p=2, dim=0, keepdim=True)
                 dot = (dw * v).sum(dim=0, keepdim=True)  # [1, out]
                 dv = (g / norm) * (dw - v * (dot / (norm * norm)))

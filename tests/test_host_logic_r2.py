@@ -90,3 +90,45 @@ def test_skip_connection_follows_the_reference_loop(monkeypatch):
     lo, _, g = O.train_forward_backward(om, m.flat.data.clone(), O.laplace_expr(2), {k: inp[k] for k in ("x", "y")}, lab, None, "mean")
     assert float(losses_all["laplace"]) == pytest.approx(float(lo["laplace"]), rel=1e-11)
     np.testing.assert_allclose(m.flat.grad.numpy(), g.numpy(), rtol=1e-8, atol=1e-12 * float(g.abs().max()))
+
+
+def test_random_weight_factorization_reparametrisation(monkeypatch):
+    """MLP(random_weight={"mean", "std"}) — RandomWeightFactorization on every layer incl. last_fc (mlp.py:56-92):
+    W = g * V; loss / gradient w.r.t. (V, g, b) through the emulated kernels against autograd over the same factorisation."""
+    import numpy as np
+
+    from oracle import ppsci_oracle as O
+    from paddlescience_b200.engine import binding as B
+    from tests.emul.build_emul import build
+
+    monkeypatch.setattr(B, "_default", B.Library(build()))
+    ppsci.utils.misc.set_random_seed(4)
+    m = ppsci.arch.MLP(("x", "y"), ("u",), 3, 10, "tanh", random_weight={"mean": 0.5, "std": 0.1}, dtype=torch.float64)
+    sd = m.state_dict()
+    assert list(sd)[:3] == ["linears.0.weight_v", "linears.0.weight_g", "linears.0.bias"] and "last_fc.weight_g" in sd
+    assert float(m.linears[0].weight_g.min()) > 1.0  # exp(N(0.5, 0.1))
+    eq = ppsci.equation.Laplace(2)
+    rect = ppsci.geometry.Rectangle((0, 0), (1, 1))
+    cst = ppsci.constraint.InteriorConstraint(eq.equations, {"laplace": 0}, rect,
+                                              {"dataset": "IterableNamedArrayDataset", "iters_per_epoch": 1, "batch_size": 30},
+                                              ppsci.loss.MSELoss("mean"), name="EQ")
+    ds = cst.data_loader.loader
+    inp = {k: v.double() for k, v in ds.input.items()}
+    lab = {k: v.double() for k, v in ds.label.items()}
+    fh = ppsci.utils.ExpressionSolver()
+    losses_all, _ = fh.train_forward((cst.output_expr,), [inp], m, {"EQ": cst}, [lab], [None])
+    raw = m.flat.data.clone().requires_grad_(True)
+    parts = []
+    for i, (a, b) in enumerate(m._shapes):
+        v = raw[m._w_off[i]: m._w_off[i] + a * b].view(a, b)
+        g = raw[m._g_off[i]: m._g_off[i] + b]
+        parts += [(v * g).reshape(-1), raw[m._b_off[i]: m._b_off[i] + b]]
+    om = O.OracleMLP(("x", "y"), ("u",), [10] * 3, "tanh")
+    x = {k: inp[k].clone().requires_grad_(True) for k in ("x", "y")}
+    out = om(torch.cat(parts), x)
+    data = dict(x)
+    data.update(out)
+    loss = (O.eval_expr(O.laplace_expr(2)["laplace"], data) ** 2).mean()
+    loss.backward()
+    assert float(losses_all["laplace"]) == pytest.approx(float(loss.detach()), rel=1e-11)
+    np.testing.assert_allclose(m.flat.grad.numpy(), raw.grad.numpy(), rtol=1e-8, atol=1e-12 * float(raw.grad.abs().max()))
