@@ -591,6 +591,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
     const int pl0 = wg7 * 4 + psub;
     constexpr int MAXI = (TP + 27) / 28;
     uint32_t it = 0, lay = 0;
+    // exchange / operand cells of this thread's first-pass item (constant over steps, layers and tiles)
+    uint32_t coff0[CS];
+#pragma unroll
+    for (int c = 0; c < CS; ++c) coff0[c] = cell16(c * TP + (pl0 < TP ? pl0 : 0), grp, kq);
     auto hand_off = [&](uint32_t it0, bool has1) {
       fence_proxy_async();
       tc_fence_before();
@@ -741,7 +745,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
               float4 z[CS];
 #pragma unroll
               for (int c = 0; c < CS; ++c) {
-                const uint32_t off = cell16(c * TP + pl, grp, kq);
+                const uint32_t off = (TP <= 28) ? coff0[c] : cell16(c * TP + pl, grp, kq);  // one item pass: hoisted offsets
                 const float2 a = *reinterpret_cast<const float2*>(stage_ptr + off);
                 const float2 b = *reinterpret_cast<const float2*>(stage_ptr + A_TILE_BYTES + off);
                 z[c] = make_float4(a.x, a.y, b.x, b.y);
@@ -754,20 +758,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
               }
               if (produce_next) {
                 float yout[CS][4];
-                act_jets4<L>(act, g.J, z, valid, yout);
+                act_jets4<L>(act, g.J, z, true, yout);
 #pragma unroll
                 for (int c = 0; c < CS; ++c) {
-                  const float sc = rs_next[c * TP + pl];
-                  uint32_t hb[4], lb[4];
-#pragma unroll
-                  for (int t = 0; t < 4; ++t) {
-                    const float ys = yout[c][t] * sc;
-                    hb[t] = f32_to_f16_bits(ys);
-                    lb[t] = f32_to_f16_bits(ys - f16_bits_to_f32(hb[t]));
-                  }
-                  const uint32_t off = cell16(c * TP + pl, grp, kq);
-                  *reinterpret_cast<uint2*>(stage_ptr + off) = make_uint2(hb[0] | (hb[1] << 16), hb[2] | (hb[3] << 16));
-                  *reinterpret_cast<uint2*>(stage_ptr + A_TILE_BYTES + off) = make_uint2(lb[0] | (lb[1] << 16), lb[2] | (lb[3] << 16));
+                  // rows of points beyond the batch are written as zeros: one select on the row scale instead of 20
+                  const float sc = valid ? rs_next[c * TP + pl] : 0.f;
+                  const float y0 = yout[c][0] * sc, y1 = yout[c][1] * sc, y2 = yout[c][2] * sc, y3 = yout[c][3] * sc;
+                  const uint32_t h01 = f32x2_to_f16x2_bits(y0, y1), h23 = f32x2_to_f16x2_bits(y2, y3);  // packed conversions
+                  float b0, b1, b2, b3;
+                  f16x2_bits_to_f32x2(h01, b0, b1);
+                  f16x2_bits_to_f32x2(h23, b2, b3);
+                  const uint32_t l01 = f32x2_to_f16x2_bits(y0 - b0, y1 - b1), l23 = f32x2_to_f16x2_bits(y2 - b2, y3 - b3);
+                  const uint32_t off = (TP <= 28) ? coff0[c] : cell16(c * TP + pl, grp, kq);
+                  *reinterpret_cast<uint2*>(stage_ptr + off) = make_uint2(h01, h23);
+                  *reinterpret_cast<uint2*>(stage_ptr + A_TILE_BYTES + off) = make_uint2(l01, l23);
                   if (ast_next && valid)
                     *reinterpret_cast<float4*>(ast_next + (long long)c * g.plane + goff) =
                         make_float4(yout[c][0], yout[c][1], yout[c][2], yout[c][3]);
@@ -861,6 +865,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
     const int pl0 = wg7 * 4 + psub;
     constexpr int MAXR = (128 + 27) / 28;  // P0 item = (row, 4 consecutive k), 28 rows per pass and group
     const float comp = tc_rz_comp_single(nchunks);
+    // swizzled 16-byte cells of this thread's first-pass item (constant over steps, layers and tiles)
+    uint32_t coff0[CS];
+#pragma unroll
+    for (int c = 0; c < CS; ++c) coff0[c] = sw128_q(c * TP + (pl0 < TP ? pl0 : 0), kq);
     uint32_t it = 0, lay = 0;
     auto hand_off = [&](uint32_t it0, bool has1) {
       fence_proxy_async();
@@ -981,7 +989,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
                 for (int c = 0; c < CS; ++c) zc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
               }
 #pragma unroll
-              for (int c = 0; c < CS; ++c) xc[c] = *reinterpret_cast<const float4*>(Xb + sw128_q(c * TP + pl, kq));
+              for (int c = 0; c < CS; ++c)
+                xc[c] = *reinterpret_cast<const float4*>(Xb + ((TP <= 28) ? coff0[c] : sw128_q(c * TP + pl, kq)));
               float ob[CS][4];
 #pragma unroll
               for (int t = 0; t < 4; ++t) {
@@ -1003,9 +1012,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
                   jet_adj_dir<float, L::KM>(sc_, zz, yb, zbv, sb_);
 #pragma unroll
                   for (int o = 0; o < L::KM; ++o)
-                    if (o < K && cbs + o < CS) ob[cbs + o][t] = valid ? zbv[o] : 0.f;
+                    if (o < K && cbs + o < CS) ob[cbs + o][t] = zbv[o];
                 }
-                ob[0][t] = valid ? jet_adj_z0<float, L::KM>(sc_, f4comp(xc[0], t), sb_) : 0.f;
+                // points beyond the batch: their operand rows were zero, so Abar = 0 exactly and (with z = 0) every
+                // adjoint below is zero without a select
+                ob[0][t] = jet_adj_z0<float, L::KM>(sc_, f4comp(xc[0], t), sb_);
               }
               if (valid) {
                 float* out = zbout + (p0 + pl) * g.ld + cb * 32 + 4 * kq;
@@ -1015,7 +1026,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
               }
               if (produce_next) {
 #pragma unroll
-                for (int c = 0; c < CS; ++c) store_split4_at(stage_ptr, sw128_q(c * TP + pl, kq), ob[c]);
+                for (int c = 0; c < CS; ++c) store_split4_at(stage_ptr, (TP <= 28) ? coff0[c] : sw128_q(c * TP + pl, kq), ob[c]);
               }
             }
           }

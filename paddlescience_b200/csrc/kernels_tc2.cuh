@@ -100,6 +100,15 @@ __device__ __forceinline__ float f16_bits_to_f32(uint32_t h) {
   asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"((uint16_t)h));
   return f;
 }
+// two floats -> packed half2 bits (low half = a, high half = b), one instruction; and back
+__device__ __forceinline__ uint32_t f32x2_to_f16x2_bits(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+__device__ __forceinline__ void f16x2_bits_to_f32x2(uint32_t h, float& a, float& b) {
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(a), "=f"(b) : "r"(h));
+}
 // completion of all MMAs issued so far -> one arrival on the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void mma_commit_2(uint32_t bar) {
   const uint16_t mask = 3;

@@ -74,6 +74,11 @@ inline float f16_bits_to_f32(uint32_t b) {
   memcpy(&h, &u, 2);
   return (float)h;
 }
+inline uint32_t f32x2_to_f16x2_bits(float a, float b) { return f32_to_f16_bits(a) | (f32_to_f16_bits(b) << 16); }
+inline void f16x2_bits_to_f32x2(uint32_t h, float& a, float& b) {
+  a = f16_bits_to_f32(h & 0xFFFFu);
+  b = f16_bits_to_f32(h >> 16);
+}
 // bar.sync id, nthreads
 inline void named_bar_sync(int id, int nthreads) { emul::t_cta->named[id].wait_n((unsigned)nthreads); }
 
