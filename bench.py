@@ -420,6 +420,39 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     log(f"e2e done: {float(ms_e2e) / args.steps:.2f} ms/step")
 
+    # ---------------- the same step replayed as ONE CUDA graph (Solver(to_static=True)), single process ----------------
+    graph_rec = None
+    if world == 1 and not is_don and args.graph != "off":
+        import types
+
+        from paddlescience_b200.solver.graph_step import GraphedTrainStep
+
+        gs = GraphedTrainStep(types.SimpleNamespace(model=model, constraint=constraint, forward_helper=helper,
+                                                    loss_aggregator=ppsci.loss.mtl.Sum(), optimizer=opt, world_size=1,
+                                                    update_freq=1, global_step=0))
+
+        def gstep(inp):
+            return gs((inp,), (labels,), (None,))[0]
+
+        for _ in range(GraphedTrainStep.WARMUP + 3):  # eager iterations, the capture, replays
+            gstep(dev_in)
+        ms_g, _ = timed(gstep, dev_in, args.steps)
+        gs.always_copy = True  # the end-to-end figure pays the H2D copy of every input on every step
+        for _ in range(2):
+            gstep(host).cpu()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            gstep(host).cpu()  # pinned host inputs -> the graph's static buffers, D2H read of the total loss
+        e1.record()
+        sync_all()
+        graph_rec = {"ms_per_step": ms_g, "value": N / (ms_g * 1e-3), "unit": UNIT,
+                     "e2e_value": N / (e0.elapsed_time(e1) / args.steps * 1e-3), "replays": gs.replays,
+                     "note": "the identical step (same kernels, same inputs) captured once and replayed with one graph launch; "
+                             "lr / Adam bias corrections read from device memory (ppsci_b200_adam_step_dev)"}
+        log(f"cuda-graph pass done: {ms_g:.3f} ms/step")
+
     # ---------------- strong scaling: the SAME global batch (N points) split over the ranks ----------------
     strong = None
     if world > 1:
@@ -563,6 +596,8 @@ def run_ours(args):
     }
     if strong is not None:
         line["strong_scaling"] = strong
+    if graph_rec is not None:
+        line["cuda_graph"] = graph_rec
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -575,6 +610,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=3, choices=[1, 2, 3, 4, 5])
+    ap.add_argument("--graph", default="on", choices=["on", "off"],
+                    help="also time the step replayed as a CUDA graph (sub-record `cuda_graph`; the headline stays the eager step)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

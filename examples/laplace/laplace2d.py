@@ -55,7 +55,7 @@ def train(cfg, output_dir):
     solver = ppsci.solver.Solver(
         model, constraint, output_dir, optimizer, epochs=cfg["TRAIN"]["epochs"], iters_per_epoch=cfg["TRAIN"]["iters_per_epoch"],
         eval_during_train=cfg["TRAIN"]["eval_during_train"], eval_freq=cfg["TRAIN"]["eval_freq"], equation=equation, geom=geom,
-        validator=validator, log_freq=1000)
+        validator=validator, log_freq=1000, to_static=bool(cfg.get("to_static", False)))
     t0 = time.perf_counter()
     solver.train()
     train_s = time.perf_counter() - t0
@@ -70,8 +70,10 @@ if __name__ == "__main__":
     ap.add_argument("--epochs", type=int, default=CFG["TRAIN"]["epochs"])
     ap.add_argument("--output_dir", default="./output_laplace2d")
     ap.add_argument("--result_json", default=None)
+    ap.add_argument("--to_static", action="store_true", help="replay the training iteration as a CUDA graph (the reference's to_static flag)")
     a = ap.parse_args()
     CFG["TRAIN"]["epochs"] = a.epochs
+    CFG["to_static"] = a.to_static
     res = train(CFG, a.output_dir)
     print(json.dumps(res))
     if a.result_json:

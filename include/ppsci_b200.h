@@ -259,6 +259,15 @@ int ppsci_b200_adam_step(int32_t dtype, void* params, const void* grads, void* e
                          double eps, double weight_decay, int64_t step, double grad_scale,
                          void* stream);
 
+/* The same Adam update with the per-step scalars in DEVICE memory: hyper_dev[4] = {lr, 1 - beta1^t, 1 - beta2^t,
+ * grad_scale}.  No argument of the launch changes from step to step, so the call can be recorded into a CUDA graph
+ * together with ppsci_b200_residual_loss_fwd_bwd and replayed (the B200 counterpart of the reference's
+ * to_static=True, ppsci/solver/solver.py:487, 907-937: one captured launch train instead of a traced program).
+ * zero_grads != 0 also clears the gradient buffer it consumed (optimizer.clear_grad, ppsci/solver/train.py:178). */
+int ppsci_b200_adam_step_dev(int32_t dtype, void* params, void* grads, void* exp_avg, void* exp_avg_sq,
+                             int64_t n, const double* hyper_dev, double beta1, double beta2, double eps,
+                             double weight_decay, int32_t zero_grads, void* stream);
+
 const char* ppsci_b200_last_error(void);
 const char* ppsci_b200_version(void);
 

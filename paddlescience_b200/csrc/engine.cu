@@ -1309,6 +1309,26 @@ extern "C" int ppsci_b200_adam_step(int32_t dtype, void* params, const void* gra
   return 0;
 }
 
+extern "C" int ppsci_b200_adam_step_dev(int32_t dtype, void* params, void* grads, void* exp_avg, void* exp_avg_sq,
+                                        int64_t n, const double* hyper_dev, double beta1, double beta2, double eps,
+                                        double weight_decay, int32_t zero_grads, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !hyper_dev || n <= 0) return fail("adam_step_dev: bad arguments");
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (dtype == PPSCI_F64) {
+    auto k = k_adam_dev<double>;
+    PPSCI_LAUNCH(k, dim3(blocks), dim3(256), 0, stream, (double*)params, (double*)grads, (double*)exp_avg,
+                 (double*)exp_avg_sq, (long long)n, hyper_dev, beta1, beta2, eps, weight_decay, (int)zero_grads);
+  } else if (dtype == PPSCI_F32) {
+    auto k = k_adam_dev<float>;
+    PPSCI_LAUNCH(k, dim3(blocks), dim3(256), 0, stream, (float*)params, (float*)grads, (float*)exp_avg,
+                 (float*)exp_avg_sq, (long long)n, hyper_dev, beta1, beta2, eps, weight_decay, (int)zero_grads);
+  } else {
+    return fail("adam_step_dev: bad dtype");
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // a_l is stashed by the tensor-core forward of layer l+1 and consumed by the tensor-core dW of layer l+1
 static bool tc_astash_needed(const ppsci_plan* P, int l) {
   const int lay = l + 1;

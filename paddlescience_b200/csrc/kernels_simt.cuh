@@ -904,4 +904,25 @@ __global__ void k_adam(T* p, const T* g, T* m, T* v, long long n, double lr, dou
   p[i] = T(pi - (lr / bc1) * mi / denom);
 }
 
+// Same update with the per-step scalars read from device memory (hyper = {lr, 1 - beta1^t, 1 - beta2^t, grad_scale}) so
+// that the launch can sit inside a captured CUDA graph and be replayed with new values; optionally clears the gradient
+// it consumed (the step's  clear_grad  without another launch).
+template <typename T>
+__global__ void k_adam_dev(T* p, T* g, T* m, T* v, long long n, const double* __restrict__ hyper, double b1, double b2,
+                           double eps, double wd, int zero_grads) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double lr = hyper[0], bc1 = hyper[1], bc2 = hyper[2], gscale = hyper[3];
+  double gi = (double)g[i] * gscale;
+  double pi = (double)p[i];
+  if (wd != 0.0) gi += wd * pi;
+  const double mi = b1 * (double)m[i] + (1.0 - b1) * gi;
+  const double vi = b2 * (double)v[i] + (1.0 - b2) * gi * gi;
+  m[i] = T(mi);
+  v[i] = T(vi);
+  const double denom = sqrt(vi) / sqrt(bc2) + eps;
+  p[i] = T(pi - (lr / bc1) * mi / denom);
+  if (zero_grads) g[i] = T(0);
+}
+
 }  // namespace ppsci

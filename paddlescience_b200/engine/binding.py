@@ -97,6 +97,7 @@ EXPORTED_SYMBOLS = (
     "ppsci_b200_plan_set_profile",
     "ppsci_b200_plan_get_profile",
     "ppsci_b200_adam_step",
+    "ppsci_b200_adam_step_dev",
     "ppsci_b200_last_error",
     "ppsci_b200_version",
 )
@@ -168,6 +169,8 @@ class Library:
         L.ppsci_b200_plan_get_profile.restype = C.c_int
         L.ppsci_b200_adam_step.argtypes = [i32, vp, vp, vp, vp, i64, dbl, dbl, dbl, dbl, dbl, i64, dbl, vp]
         L.ppsci_b200_adam_step.restype = C.c_int
+        L.ppsci_b200_adam_step_dev.argtypes = [i32, vp, vp, vp, vp, i64, vp, dbl, dbl, dbl, dbl, i32, vp]
+        L.ppsci_b200_adam_step_dev.restype = C.c_int
         L.ppsci_b200_last_error.argtypes = []
         L.ppsci_b200_last_error.restype = C.c_char_p
         L.ppsci_b200_version.argtypes = []

@@ -58,6 +58,29 @@ class FlatAdam:
                                           torch.cuda.current_stream(p.device).cuda_stream)
         lib.check(rc, "adam_step")
 
+    # -- the same step split for CUDA-graph replay (solver/graph_step.py): ``step_dev`` is the launch (recorded once,
+    #    every scalar that changes per step is read from ``hyper_dev``), ``advance`` the host-side bookkeeping that
+    #    produces those scalars for the coming step.
+    def advance(self):
+        """t += 1; returns [lr, 1 - beta1^t, 1 - beta2^t, grad_scale] of this step."""
+        self.t += 1
+        return [self.get_lr(), 1.0 - self.beta1 ** self.t, 1.0 - self.beta2 ** self.t, float(self.grad_scale)]
+
+    def step_dev(self, hyper_dev: torch.Tensor, zero_grads: bool = True):
+        p = self.model.flat
+        if p.device.type != "cuda":
+            raise RuntimeError("FlatAdam.step_dev needs parameters on a CUDA (B200) device: no CPU fallback")
+        if hyper_dev.dtype != torch.float64 or hyper_dev.numel() < 4 or hyper_dev.device != p.device:
+            raise ValueError("hyper_dev must be a float64 tensor of 4 values on the parameters' device")
+        self._ensure_state()
+        lib = B.get_library()
+        dtype = B.F64 if p.dtype == torch.float64 else B.F32
+        rc = lib.lib.ppsci_b200_adam_step_dev(dtype, p.data.data_ptr(), p.grad.data_ptr(), self.exp_avg.data_ptr(),
+                                              self.exp_avg_sq.data_ptr(), p.numel(), hyper_dev.data_ptr(), self.beta1,
+                                              self.beta2, self.epsilon, self.weight_decay, 1 if zero_grads else 0,
+                                              torch.cuda.current_stream(p.device).cuda_stream)
+        lib.check(rc, "adam_step_dev")
+
     def clear_grad(self):
         if self.model.flat.grad is not None:
             self.model.flat.grad.zero_()

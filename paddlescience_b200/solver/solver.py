@@ -4,7 +4,8 @@
 Kept: ``Solver(model, constraint, output_dir, optimizer, lr_scheduler, epochs, iters_per_epoch,
 update_freq, save_freq, log_freq, ..., equation, geom, validator, ...)``, ``train()``, ``eval()``,
 ``predict()``, checkpoint save/resume.  Out of scope: export/ONNX,
-VisualDL/WandB writers, AMP, to_static, LBFGS."""
+VisualDL/WandB writers, AMP.  ``to_static=True`` records the training iteration as a CUDA graph
+(solver/graph_step.py) instead of tracing a static program."""
 from __future__ import annotations
 
 import os
@@ -70,6 +71,8 @@ class Solver:
         self.compute_metric_by_batch = compute_metric_by_batch
         self.eval_with_no_grad = eval_with_no_grad
         self.global_step = 0
+        self.to_static = bool(to_static)
+        self._graph_step = None  # GraphedTrainStep, created by the first training iteration when to_static is set
         self.max_steps = self.epochs * self.iters_per_epoch
         self.train_output_info: Dict[str, misc.AverageMeter] = {}
         self.train_time_info = {"reader_cost": misc.AverageMeter("reader_cost", ".5f", postfix="s"),

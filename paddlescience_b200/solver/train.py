@@ -42,18 +42,57 @@ def train_epoch_func(solver, epoch_id: int, log_freq: int):
         reader_cost = 0.0
         reader_tic = time.perf_counter()
         input_dicts, label_dicts, weight_dicts = [], [], []
+        # graph replay copies each batch tensor straight into the graph's static device buffers (host tensors included)
+        conv = (lambda d, *_: d) if getattr(solver, "to_static", False) else _to_device
         for _constraint in solver.constraint.values():
             try:
                 input_dict, label_dict, weight_dict = next(_constraint.data_iter)
             except StopIteration:
                 _constraint.data_iter = iter(_constraint.data_loader)
                 input_dict, label_dict, weight_dict = next(_constraint.data_iter)
-            input_dicts.append(_to_device(input_dict, device, dtype))
-            label_dicts.append(_to_device(label_dict, device, dtype))
-            weight_dicts.append(_to_device(weight_dict, device, dtype) if weight_dict else None)
+            input_dicts.append(conv(input_dict, device, dtype))
+            label_dicts.append(conv(label_dict, device, dtype))
+            weight_dicts.append(conv(weight_dict, device, dtype) if weight_dict else None)
             total_batch_size += _compute_batch_size(input_dict)
             reader_cost += time.perf_counter() - reader_tic
             reader_tic = time.perf_counter()
+
+        if getattr(solver, "to_static", False):
+            gs = solver._graph_step
+            if gs is None:
+                from .graph_step import GraphedTrainStep
+
+                gs = solver._graph_step = GraphedTrainStep(solver)
+                why = gs.unsupported_reason()
+                if why is not None:
+                    from ..utils import logger
+
+                    logger.message(f"to_static: the iteration is not replayed as a CUDA graph ({why}); running eagerly.")
+                    solver.to_static = False
+                    input_dicts = [_to_device(d, device, dtype) for d in input_dicts]
+                    label_dicts = [_to_device(d, device, dtype) for d in label_dicts]
+                    weight_dicts = [_to_device(d, device, dtype) if d else None for d in weight_dicts]
+            if solver.to_static:
+                total_loss, losses_constraint = gs(input_dicts, label_dicts, weight_dicts)
+                if solver.lr_scheduler is not None and not solver.lr_scheduler.by_epoch:
+                    solver.lr_scheduler.step()
+                if solver.benchmark_flag:
+                    torch.cuda.synchronize()
+                solver.global_step += 1
+                log_now = (solver.global_step % log_freq == 0 or solver.global_step == 1 or solver.global_step == solver.max_steps)
+                if log_now:
+                    loss_dict = {"loss": float(total_loss)}
+                    loss_dict.update({k: float(v) for k, v in losses_constraint.items()})
+                    solver.last_loss = loss_dict["loss"]
+                    printer.update_train_loss(solver, loss_dict, total_batch_size)
+                solver.train_time_info["reader_cost"].update(reader_cost)
+                solver.train_time_info["batch_cost"].update(time.perf_counter() - batch_tic)
+                if log_now:
+                    printer.log_train_info(solver, total_batch_size, epoch_id, iter_id)
+                batch_tic = time.perf_counter()
+                if nvtx:
+                    torch.cuda.nvtx.range_pop()
+                continue
 
         if nvtx:
             torch.cuda.nvtx.range_push("Loss computation")

@@ -109,3 +109,48 @@ def test_batched_constraints_equal_the_loop_on_gpu():
 def test_run_check_trains_and_evaluates():
     """ppsci.utils.run_check (reference ppsci/utils/checker.py:34-117): two epochs of N-S + one evaluation."""
     assert ppsci.utils.run_check() is True
+
+
+def _train_params(to_static, iters, sched=True, dataset="IterableNamedArrayDataset"):
+    ppsci.utils.misc.set_random_seed(11)
+    model = ppsci.arch.MLP(("x", "y"), ("u",), 3, 20, "tanh")
+    eq = ppsci.equation.Laplace(2)
+    rect = ppsci.geometry.Rectangle((0, 0), (1, 1))
+    cfg = {"dataset": dataset, "iters_per_epoch": iters}
+    if dataset == "NamedArrayDataset":
+        cfg["sampler"] = {"name": "BatchSampler", "shuffle": True, "drop_last": True}
+    pde = ppsci.constraint.InteriorConstraint(eq.equations, {"laplace": 0}, rect, {**cfg, "batch_size": 512},
+                                              ppsci.loss.MSELoss("mean"), name="EQ")
+    bc = ppsci.constraint.BoundaryConstraint({"u": lambda out: out["u"]}, {"u": lambda d: d["x"] ** 2 - d["y"] ** 2}, rect,
+                                             {**cfg, "batch_size": 128}, ppsci.loss.MSELoss("mean"), name="BC")
+    lr = ppsci.optimizer.lr_scheduler.ExponentialDecay(1, iters, 1e-3, 0.5, 4, by_epoch=False)() if sched else 1e-3
+    opt = ppsci.optimizer.Adam(lr)(model)
+    p0 = model.flat.detach().cpu().double().clone()
+    solver = ppsci.solver.Solver(model, {"EQ": pde, "BC": bc}, None, opt, lr if sched else None, epochs=1, iters_per_epoch=iters,
+                                 equation={"lap": eq}, to_static=to_static, log_freq=5)
+    solver.train()
+    return model.flat.detach().cpu().double(), p0, solver
+
+
+def test_to_static_replays_the_iteration_as_a_cuda_graph():
+    """Solver(to_static=True): two eager iterations, one capture, then one graph launch per iteration (scheduler-driven
+    learning rate and Adam bias corrections read from device memory) == the eager loop."""
+    iters = 14
+    pe, p0, _ = _train_params(False, iters)
+    pg, _, sg = _train_params(True, iters)
+    assert sg._graph_step is not None and sg._graph_step.replays == iters - 2
+    step = float((pe - p0).norm())
+    assert step > 0
+    assert float((pg - pe).norm()) / step <= 1e-4  # same kernels; float atomics order differs between runs
+    assert sg.optimizer.t == iters
+    assert np.isfinite(sg.last_loss)
+
+
+def test_to_static_copies_fresh_batches_into_the_graph():
+    """Batches that change every iteration (a shuffled epoch over a fixed point set) reach the replayed graph."""
+    iters = 4
+    pe, p0, _ = _train_params(False, iters, sched=False, dataset="NamedArrayDataset")
+    pg, _, sg = _train_params(True, iters, sched=False, dataset="NamedArrayDataset")
+    assert sg._graph_step is not None and sg._graph_step.replays == iters - 2
+    step = float((pe - p0).norm())
+    assert float((pg - pe).norm()) / step <= 1e-4

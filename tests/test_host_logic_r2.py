@@ -132,3 +132,29 @@ def test_random_weight_factorization_reparametrisation(monkeypatch):
     loss.backward()
     assert float(losses_all["laplace"]) == pytest.approx(float(loss.detach()), rel=1e-11)
     np.testing.assert_allclose(m.flat.grad.numpy(), raw.grad.numpy(), rtol=1e-8, atol=1e-12 * float(raw.grad.abs().max()))
+
+
+def test_graph_step_signature_and_adam_scalars():
+    """Host side of Solver(to_static=True) (solver/graph_step.py): the batch signature that keys a captured graph, the
+    eligibility check, and the per-step scalars FlatAdam.advance() hands to the device-side Adam."""
+    import math
+
+    from paddlescience_b200.solver.graph_step import GraphedTrainStep, _flatten
+
+    a, b = torch.zeros(8, 1), torch.zeros(8, 1, dtype=torch.float64)
+    items, sig = _flatten(({"x": a, "y": b}, None, {"u": 0.5}))
+    assert [(i, k) for i, k, _ in items] == [(0, "x"), (0, "y")]
+    assert sig == ((0, "x", (8, 1), "torch.float32"), (0, "y", (8, 1), "torch.float64"), (1, None), (2, "u", "const", 0.5))
+    assert _flatten(({"x": torch.zeros(9, 1), "y": b}, None, {"u": 0.5}))[1] != sig
+
+    m = ppsci.arch.MLP(("x",), ("u",), 2, 8, "tanh")
+    opt = ppsci.optimizer.Adam(lambda: 0.25, beta1=0.5, beta2=0.75)(m)
+    opt.grad_scale = 0.5
+    h1, h2 = opt.advance(), opt.advance()
+    assert h1 == [0.25, 0.5, 0.25, 0.5] and opt.t == 2
+    assert math.isclose(h2[1], 1 - 0.25) and math.isclose(h2[2], 1 - 0.75 ** 2)
+
+    class S:  # the attributes the eligibility check reads
+        model, world_size, update_freq, optimizer, loss_aggregator = m, 1, 1, opt, ppsci.loss.mtl.Sum()
+
+    assert "CUDA" in GraphedTrainStep(S()).unsupported_reason()  # CPU parameters: never captured, never a CPU fallback
