@@ -80,7 +80,7 @@ def test_mlp_constructor_and_state_dict_layout():
     with pytest.raises(ValueError):
         ppsci.arch.MLP(("x",), ("u",), 2, 16, activation="nope")
     with pytest.raises(NotImplementedError):
-        ppsci.arch.MLP(("x",), ("u",), 2, 16, skip_connection=True)
+        ppsci.arch.MLP(("x",), ("u",), 2, 16, skip_connection=True, weight_norm=True)
 
 
 def test_equations_and_detach_strings_match_reference_docstring():
