@@ -91,6 +91,18 @@ __host__ __device__ inline int fused_fwd_smem_bytes(int N) {
 // chunk c has retired (its A stage, its weight slot and its full barrier may be reused)
 __device__ __forceinline__ void f_wait_done(uint32_t bars, uint32_t c) { mbar_wait_warp(bars + 8 * (c % FA), (c / FA) & 1u); }
 __device__ __forceinline__ void f_wait_done_lane(uint32_t bars, uint32_t c) { mbar_wait(bars + 8 * (c % FA), (c / FA) & 1u); }
+// Workers keep a watermark `seen`: every chunk below it is known to have retired (tcgen05.commit arrives in issue
+// order, so observing chunk c covers all earlier ones).  A stage wait whose chunk lies below the watermark is skipped:
+// the two-CTA timeline of round 2 showed 350 - 900 cycles per poll even for a long-completed phase (divergent lane-0
+// poll + reconvergence), on the workers' critical path four times per layer.  Polls only ever move forward by at
+// most one phase per barrier (the chunk FA before the awaited one is always below the watermark), so the parity
+// test cannot alias.
+__device__ __forceinline__ void f_wait_done_seen(uint32_t bars, uint32_t c, uint32_t& seen) {
+  if (c >= seen) {
+    f_wait_done(bars, c);
+    seen = c + 1;
+  }
+}
 
 // Shared prologue: barriers, pair-wide TMEM allocation, zeroed A stages, cluster rendezvous.
 __device__ __forceinline__ uint32_t fused_setup(uint32_t base, unsigned char* base_ptr, uint32_t bars_off, uint32_t ncols, int full_count) {
@@ -243,7 +255,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
     const int pl0 = wg7 * 4 + psub;               // this thread's point in the first item pass (28 points per pass)
     constexpr int MAXI = (TP + 27) / 28;
     const float comp = tc_rz_comp_single(nchunks);
-    uint32_t it = 0, lay = 0;
+    uint32_t it = 0, lay = 0, seen = 0;
     // hand-off of the two chunks of a step: every warp arrives on both full barriers (see the file header)
     auto hand_off = [&](uint32_t it0, bool has1) {
       fence_proxy_async();
@@ -258,7 +270,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
     // completes in issue order): one barrier poll per step instead of two (each costs ~250 cycles even when complete)
     auto wait_stages = [&](uint32_t it0, bool has1) {
       const uint32_t last = has1 ? it0 + 1 : it0;
-      if (last >= FA) f_wait_done(bars, last - FA);
+      if (last >= FA) f_wait_done_seen(bars, last - FA, seen);
     };
     for (int tp = pair; tp < n_tile_pairs; tp += npairs) {
       const long long tile = 2LL * tp + rank;
@@ -323,7 +335,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
       for (int l = 0; l < NLf; ++l, ++lay) {
         const bool produce_next = l + 1 < NLf;
         const uint32_t acc = acc_base + (lay & 1u) * (uint32_t)N;
-        f_wait_done(bars, it - 1);  // the layer's last chunk: its accumulator is final
+        f_wait_done_seen(bars, it - 1, seen);  // the layer's last chunk: its accumulator is final
         tc_fence_after();
         const float* bias = g.bias[l];
         float* zout = g.Zout[l];
@@ -519,8 +531,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
   const int n_tile_pairs = (g.num_tiles + 1) / 2;
   const int my_tp = pair < n_tile_pairs ? (n_tile_pairs - 1 - pair) / npairs + 1 : 0;
   const uint32_t chunks_per_tile = (uint32_t)(nch32 + (NLf - 1) * nch64);
-  const bool dbg0 = g.dbg && blockIdx.x == 0;
-#define FDBG(cond, row, slot) do { if (dbg0 && (cond) && (row) < 48u) g.dbg[(row) * 16 + (slot)] = clock64(); } while (0)
+  // timeline rows: CTA 0 (leader) rows 0..47, CTA 1 (its peer) rows 48..95; each SM has its own cycle counter, the two are
+  // aligned offline on the multicast mma_done events (epi_start)
+  const bool dbg0 = g.dbg && blockIdx.x < 2;
+  const uint32_t dbg_r0 = blockIdx.x * 48u;
+#define FDBG(cond, row, slot) do { if (dbg0 && (cond) && (row) < 48u) g.dbg[(dbg_r0 + (row)) * 16 + (slot)] = clock64(); } while (0)
+#define FDBG_MAX(cond, row, slot) do { if (dbg0 && (cond) && (row) < 48u) atomicMax((unsigned long long*)&g.dbg[(dbg_r0 + (row)) * 16 + (slot)], (unsigned long long)clock64()); } while (0)
 
   if (warp == T2_TMA_WARP) {
     if (lane == 0) {  // weight streamer (see fused_stream_weights): layer 0 has nch32 chunks, the others nch64; same bytes per chunk
@@ -580,7 +596,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
           }
       } else {
         for (uint32_t it = 0; it < total_it; ++it) {
+          FDBG(true, it, 8);
           mbar_wait(bars + 64 + 8 * (it % FA), (it / FA) & 1u);
+          FDBG(true, it, 9);
           mbar_remote_arrive(bars + 64 + 8 * (it % FA), 0);
         }
       }
@@ -590,7 +608,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
     const int kq = lane & 7, psub = lane >> 3;
     const int pl0 = wg7 * 4 + psub;
     constexpr int MAXI = (TP + 27) / 28;
-    uint32_t it = 0, lay = 0;
+    uint32_t it = 0, lay = 0, seen = 0;
     // exchange / operand cells of this thread's first-pass item (constant over steps, layers and tiles)
     uint32_t coff0[CS];
 #pragma unroll
@@ -628,7 +646,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
           const int j = j0 + grp;
           {
             const uint32_t last = has1 ? it + 1 : it;
-            if (last >= FA) f_wait_done(bars, last - FA);
+            if (last >= FA) f_wait_done_seen(bars, last - FA, seen);
           }
           if (j < nch32) {
             unsigned char* stage_ptr = base_ptr + ((it + (uint32_t)grp) % FA) * (2 * A_TILE_BYTES);
@@ -664,7 +682,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
       for (int l = 0; l < NLf; ++l, ++lay) {
         const bool produce_next = l + 1 < NLf;
         const uint32_t acc = acc_base + (lay & 1u) * (uint32_t)N;
-        f_wait_done(bars, it - 1);  // the layer's last chunk: its accumulator is final
+        f_wait_done_seen(bars, it - 1, seen);  // the layer's last chunk: its accumulator is final
         tc_fence_after();
         const float* bias = g.bias[l];
         float* zout = g.Zout[l];
@@ -719,7 +737,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
           const int col = cb * 32 + 4 * kq;
           const float4 b4 = bias ? make_float4(__ldg(bias + col), __ldg(bias + col + 1), __ldg(bias + col + 2), __ldg(bias + col + 3))
                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-          if (produce_next && itc >= FA) f_wait_done(bars, itc - FA);
+          if (produce_next && itc >= FA) f_wait_done_seen(bars, itc - FA, seen);
           FDBG(tid == 0, drow, 1);
           unsigned char* stage_ptr = base_ptr + (itc % FA) * (2 * A_TILE_BYTES);
           if (wg7 < 4) {  // raw block -> the 8-byte cells its items will overwrite: (v0, v1) -> hi cell, (v2, v3) -> lo cell
@@ -780,9 +798,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
             }
           }
           FDBG(tid == 0, drow, 5);
+          FDBG_MAX(lane == 0, drow, 12);  // the slowest warp's items_done
           if (produce_next) hand_off(itc, false);
           else t2_prod_sync();  // scratch stage reuse two steps later is ordered by the next step's sync; keep groups together
           FDBG(tid == 0, drow, 6);
+          FDBG_MAX(lane == 0, drow, 7);   // the slowest warp's arrival
         }
         if (produce_next) it += (uint32_t)nsteps;
         else tc_fence_before();
@@ -790,6 +810,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
     }
   }
 #undef FDBG
+#undef FDBG_MAX
   __syncwarp();
   tc_fence_before();
   __syncthreads();
@@ -853,11 +874,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
   const int act = act_id<ACT>(g.act);
   const int n_tile_pairs = (g.num_tiles + 1) / 2;
   const int my_tp = pair < n_tile_pairs ? (n_tile_pairs - 1 - pair) / npairs + 1 : 0;
+  const bool dbg0 = g.dbg && blockIdx.x == 0;
+#define FDBG(cond, row, slot) do { if (dbg0 && (cond) && (row) < 48u) g.dbg[(row) * 16 + (slot)] = clock64(); } while (0)
 
   if (warp == T2_TMA_WARP) {
     if (lane == 0) fused_stream_weights(base, bars, b_off, g.WimgT, my_tp, NLf, nchunks, N, rank);
   } else if (warp == T2_MMA_WARP) {
-    if (lane == 0) fused_issue_mmas(base, bars, b_off, acc_base, my_tp, NLf, nchunks, N, rank, [](uint32_t, int) {});
+    if (lane == 0)
+      fused_issue_mmas(base, bars, b_off, acc_base, my_tp, NLf, nchunks, N, rank, [&](uint32_t row, int slot) { FDBG(true, row, slot); });
   } else {
     // ---- workers (see k_fused_fwd) ----
     const int grp = warp / 7, wg7 = warp - grp * 7;
@@ -869,7 +893,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
     uint32_t coff0[CS];
 #pragma unroll
     for (int c = 0; c < CS; ++c) coff0[c] = sw128_q(c * TP + (pl0 < TP ? pl0 : 0), kq);
-    uint32_t it = 0, lay = 0;
+    uint32_t it = 0, lay = 0, seen = 0;
     auto hand_off = [&](uint32_t it0, bool has1) {
       fence_proxy_async();
       tc_fence_before();
@@ -880,10 +904,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
       }
     };
     // both stages of a step are free once the LATER of the two chunks that used them has retired (tcgen05.commit
-    // completes in issue order): one barrier poll per step instead of two (each costs ~250 cycles even when complete)
+    // completes in issue order): one barrier poll per step instead of two, and none when the watermark covers it
     auto wait_stages = [&](uint32_t it0, bool has1) {
       const uint32_t last = has1 ? it0 + 1 : it0;
-      if (last >= FA) f_wait_done(bars, last - FA);
+      if (last >= FA) f_wait_done_seen(bars, last - FA, seen);
     };
     for (int tp = pair; tp < n_tile_pairs; tp += npairs) {
       const long long tile = 2LL * tp + rank;
@@ -947,14 +971,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
 #pragma unroll
         for (int c = 0; c < CS; ++c) zc0[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (grp < ncb && pl0 < vpts) load_z(zc0, pl0, grp);
-        f_wait_done(bars, it - 1);  // the layer's last chunk: Abar_{l-1} is final
+        f_wait_done_seen(bars, it - 1, seen);  // the layer's last chunk: Abar_{l-1} is final
         tc_fence_after();
+        FDBG(tid == 0, produce_next ? it : 46u, 11);
         for (int i = 0; i < nsteps; ++i) {
           const uint32_t it0 = it + 2 * (uint32_t)i;
           const bool has1 = 2 * i + 1 < ncb;
+          const uint32_t drow = produce_next ? it0 : 47u;
+          FDBG(tid == 0, drow, 0);
           // the two stages of this step (operand chunks AND exchange tiles) have been released; the last layer's
           // epilogue only borrows them as scratch (every MMA issued so far has retired, nothing to wait for)
           if (produce_next) wait_stages(it0, has1);
+          FDBG(tid == 0, drow, 1);
           const int cb = 2 * i + grp;
           unsigned char* stage_ptr = base_ptr + ((it + (uint32_t)cb) % FA) * (2 * A_TILE_BYTES);
           unsigned char* Xb = stage_ptr + A_TILE_BYTES;  // exchange tile = the A_lo region of the destination stage
@@ -974,7 +1002,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
                   make_float4(__uint_as_float(v[4 * t4]) * comp, __uint_as_float(v[4 * t4 + 1]) * comp,
                               __uint_as_float(v[4 * t4 + 2]) * comp, __uint_as_float(v[4 * t4 + 3]) * comp);
           }
+          FDBG(tid == 0, drow, 2);
           t2_prod_sync();  // exchange tiles complete
+          FDBG(tid == 0, drow, 3);
           if (cb < ncb) {
             for (int pl = pl0; pl < TP; pl += 28) {
               const bool valid = pl < vpts;
@@ -1030,7 +1060,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
               }
             }
           }
+          FDBG(tid == 0, drow, 5);
           if (produce_next) hand_off(it0, has1);
+          FDBG(tid == 0, drow, 6);
           // this thread's Z block of the next step (its block index advances by 2); requested AFTER the hand-off:
           // fence.proxy.async also waits for the thread's outstanding global loads
           if (cb + 2 < ncb && pl0 < vpts) load_z(zc0, pl0, cb + 2);
@@ -1047,6 +1079,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
       }
     }
   }
+#undef FDBG
   __syncwarp();
   tc_fence_before();
   __syncthreads();

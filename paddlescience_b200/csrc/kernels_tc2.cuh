@@ -38,12 +38,17 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster.
+// Default (.release.cta) semantics on purpose: `.release.cluster` compiles to MEMBAR.ALL.GPU and the matching
+// `.acquire.cluster` wait to CCTL.IVALL (an L1 invalidate per chunk) — the ncu source page + the two-CTA timeline of
+// round 2 showed the MMA lane starting 1.1 - 1.6 k cycles after the last operand arrival because of that membar.
+// What the MMAs read is shared memory the workers already published to the async proxy (fence.proxy.async before
+// their own arrival); the relay only observes that barrier and forwards the signal.
 __device__ __forceinline__ void mbar_remote_arrive(uint32_t local_bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(local_bar),
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(local_bar),
       "r"(rank)
       : "memory");
 }
@@ -51,7 +56,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)

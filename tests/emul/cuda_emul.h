@@ -190,6 +190,11 @@ inline unsigned atomicMax(unsigned* addr, unsigned v) {
   while (old < v && !__atomic_compare_exchange_n(addr, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
   return old;
 }
+inline unsigned long long atomicMax(unsigned long long* addr, unsigned long long v) {
+  unsigned long long old = __atomic_load_n(addr, __ATOMIC_RELAXED);
+  while (old < v && !__atomic_compare_exchange_n(addr, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+  return old;
+}
 inline double atomicAdd(double* addr, double v) {
   uint64_t* ia = reinterpret_cast<uint64_t*>(addr);
   uint64_t old = __atomic_load_n(ia, __ATOMIC_RELAXED);
