@@ -103,6 +103,25 @@ __device__ __forceinline__ void f_wait_done_seen(uint32_t bars, uint32_t c, uint
     seen = c + 1;
   }
 }
+// Layer-start wait (the accumulator of the layer is final): every worker warp is idle until then, so lane 0 probes
+// with the non-suspending test_wait instead of try_wait, whose suspended wait is woken noticeably later
+// (the timeline showed ~1.5 k cycles between the last MMA retiring and the workers resuming).
+__device__ __forceinline__ void f_spin_done_seen(uint32_t bars, uint32_t c, uint32_t& seen) {
+#ifdef PPSCI_EMUL
+  f_wait_done_seen(bars, c, seen);  // OS threads: the yielding wait
+  return;
+#endif
+  if (c >= seen) {
+    if ((threadIdx.x & 31) == 0) {
+      uint32_t spins = 0;
+      while (!mbar_test_wait(bars + 8 * (c % FA), (c / FA) & 1u)) {
+        if (++spins > (1u << 26)) __trap();
+      }
+    }
+    __syncwarp();
+    seen = c + 1;
+  }
+}
 
 // Shared prologue: barriers, pair-wide TMEM allocation, zeroed A stages, cluster rendezvous.
 __device__ __forceinline__ uint32_t fused_setup(uint32_t base, unsigned char* base_ptr, uint32_t bars_off, uint32_t ncols, int full_count) {
@@ -335,7 +354,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
       for (int l = 0; l < NLf; ++l, ++lay) {
         const bool produce_next = l + 1 < NLf;
         const uint32_t acc = acc_base + (lay & 1u) * (uint32_t)N;
-        f_wait_done_seen(bars, it - 1, seen);  // the layer's last chunk: its accumulator is final
+        f_spin_done_seen(bars, it - 1, seen);  // the layer's last chunk: its accumulator is final
         tc_fence_after();
         const float* bias = g.bias[l];
         float* zout = g.Zout[l];
@@ -606,7 +625,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
   } else {
     const int grp = warp / 7, wg7 = warp - grp * 7;
     const int kq = lane & 7, psub = lane >> 3;
-    const int pl0 = wg7 * 4 + psub;
+    // Point of this thread's item.  The fp16 operand cells are 8 bytes, so one shared-memory wavefront serves a HALF
+    // warp = two points: with consecutive points their rows (c TP + pl) mostly share bit 2 of (row & 7), the 128-byte
+    // swizzle then maps both onto the same 16 banks and every LDS.64 / STS.64 of the item loop took ~1.9x its ideal
+    // wavefronts (ncu source page, round 2).  For TP <= 25 the two points of a half warp are 4 apart instead:
+    // warp pairs cover 8 points as {0,4,1,5} | {2,6,3,7}, the seventh warp takes point 24.
+    const int pl0 = (TP <= 25) ? (8 * (wg7 >> 1) + 2 * (wg7 & 1) + (psub >> 1) + 4 * (psub & 1)) : wg7 * 4 + psub;
     constexpr int MAXI = (TP + 27) / 28;
     uint32_t it = 0, lay = 0, seen = 0;
     // exchange / operand cells of this thread's first-pass item (constant over steps, layers and tiles)
@@ -682,7 +706,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
       for (int l = 0; l < NLf; ++l, ++lay) {
         const bool produce_next = l + 1 < NLf;
         const uint32_t acc = acc_base + (lay & 1u) * (uint32_t)N;
-        f_wait_done_seen(bars, it - 1, seen);  // the layer's last chunk: its accumulator is final
+        f_spin_done_seen(bars, it - 1, seen);  // the layer's last chunk: its accumulator is final
         tc_fence_after();
         const float* bias = g.bias[l];
         float* zout = g.Zout[l];
@@ -971,7 +995,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
 #pragma unroll
         for (int c = 0; c < CS; ++c) zc0[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (grp < ncb && pl0 < vpts) load_z(zc0, pl0, grp);
-        f_wait_done_seen(bars, it - 1, seen);  // the layer's last chunk: Abar_{l-1} is final
+        f_spin_done_seen(bars, it - 1, seen);  // the layer's last chunk: Abar_{l-1} is final
         tc_fence_after();
         FDBG(tid == 0, produce_next ? it : 46u, 11);
         for (int i = 0; i < nsteps; ++i) {
