@@ -134,6 +134,12 @@ typedef struct ppsci_plan_spec {
    * when non-zero, n_in must be 1, x_cols[0] is a row-major [n_points][n_feat] matrix (n_feat up to 4096, the
    * feat_* arrays are ignored) and no input derivatives are available (n_dir must be 0). */
   int32_t dense_in;
+  /* Activation applied to the output of the FIRST linear layer when it differs from `act` (PPSCI_ACT_* id), or -1:
+   * FourierEmbedding (ppsci/arch/mlp.py:117-136, 298-315) is  [cos(x B), sin(x B)] = sin(x [B | B] + [pi/2 | 0]),
+   * i.e. one more linear layer with tied weights whose activation is sin whatever the network's own activation is.
+   * A plan with act_first != act runs on the CUDA-core kernels (the tensor-core kernels are specialised for one
+   * activation across the layers they fuse). */
+  int32_t act_first;
 } ppsci_plan_spec;
 
 typedef struct ppsci_plan ppsci_plan;

@@ -69,18 +69,28 @@ class OracleMLP:
         activation: str = "tanh",
         periods: Optional[Dict[str, Tuple[float, bool]]] = None,
         skip_connection: bool = False,
+        fourier: Optional[Dict[str, float]] = None,
     ):
         self.input_keys = tuple(input_keys)
         self.output_keys = tuple(output_keys)
         self.periods = periods or {}
         self.skip_connection = skip_connection
         n_feat = len(self.input_keys) + len(self.periods)  # mlp.py:222-226
-        self.widths = [n_feat] + list(hidden) + [len(self.output_keys)]
+        self.n_feat = n_feat
+        # FourierEmbedding (mlp.py:117-136, 228-232): kernel [cur_size, dim // 2], then cur_size = dim.
+        # Its kernel is stored BEHIND the linear layers in the flat vector: [W_1 | b_1 | ... | kernel].
+        self.fourier = dict(fourier) if fourier else None
+        first = int(self.fourier["dim"]) if self.fourier else n_feat
+        self.widths = [first] + list(hidden) + [len(self.output_keys)]
         self.act = get_activation(activation)
 
     @property
-    def n_params(self) -> int:
+    def n_linear_params(self) -> int:
         return sum(a * b + b for a, b in zip(self.widths[:-1], self.widths[1:]))
+
+    @property
+    def n_params(self) -> int:
+        return self.n_linear_params + (self.n_feat * (int(self.fourier["dim"]) // 2) if self.fourier else 0)
 
     def split_params(self, flat: torch.Tensor):
         out, off = [], 0
@@ -101,6 +111,10 @@ class OracleMLP:
             else:
                 feats.append(x[k])
         y = torch.cat(feats, dim=-1) if len(feats) > 1 else feats[0]
+        if self.fourier:  # FourierEmbedding.forward, mlp.py:128-136; applied after the concat, mlp.py:306-309
+            dh = int(self.fourier["dim"]) // 2
+            kernel = flat[self.n_linear_params : self.n_linear_params + self.n_feat * dh].view(self.n_feat, dh)
+            y = torch.cat([torch.cos(y @ kernel), torch.sin(y @ kernel)], dim=-1)
         layers = self.split_params(flat)
         skip = None
         for i, (W, b) in enumerate(layers[:-1]):  # mlp.py:281-296, statement by statement

@@ -90,8 +90,12 @@ class MLP(base.Arch):
     """Multi layer perceptron network (same arguments as the reference, mlp.py:179-193).
 
     ``weight_norm``, ``random_weight`` and ``skip_connection`` are host-side reparametrisations around the unchanged
-    engine call (effective [W | b] before it, chain rule after it).  Not yet supported by the jet kernels (raise
-    ``NotImplementedError`` at construction): ``fourier``, trainable periods.
+    engine call (effective [W | b] before it, chain rule after it).  ``fourier={"dim": D, "scale": s}``
+    (FourierEmbedding, mlp.py:117-136, applied after the period embedding, mlp.py:298-315) is one more linear layer
+    for the kernels: ``[cos(x B), sin(x B)] = sin(x [B | B] + [pi/2 | 0])`` — tied effective weights, a constant bias
+    and ``sin`` as that layer's activation (``NetSpec.act_first``); the gradient of the trainable kernel ``B`` is the
+    sum of the two halves of the effective layer's weight gradient.  Not yet supported (raise ``NotImplementedError``
+    at construction): trainable periods, ``fourier`` together with weight_norm / random_weight / skip_connection.
     """
 
     def __init__(
@@ -125,8 +129,13 @@ class MLP(base.Arch):
         else:
             raise ValueError(f"hidden_size should be list of int or int, but got {type(hidden_size)}")
         self.weight_norm = bool(weight_norm)
-        if fourier:
-            raise NotImplementedError("MLP(fourier=...) is not supported by the jet kernels yet")
+        self.fourier = dict(fourier) if fourier else None
+        if self.fourier:
+            if int(self.fourier["dim"]) % 2 != 0:  # FourierEmbedding.__init__, mlp.py:120-121
+                raise ValueError(f"out_features must be even, but got {self.fourier['dim']}.")
+            if weight_norm or random_weight or skip_connection:
+                raise NotImplementedError("MLP(fourier=...) together with weight_norm / random_weight / skip_connection "
+                                          "is not supported yet")
         # random_weight = {"mean": m, "std": s}: RandomWeightFactorization on EVERY layer incl. last_fc (mlp.py:56-92,
         # 248-256, 262-270): W = g * V (column scaling), g = exp(N(m, s)), V = glorot_normal / g
         self.random_weight = dict(random_weight) if random_weight else None
@@ -162,7 +171,13 @@ class MLP(base.Arch):
                 if k not in self.input_keys:
                     raise KeyError(f"period key {k} is not an input key")
         widths = [len(feat_src)] + hidden + [len(self.output_keys)]
-        self._net = NetSpec(self.input_keys, self.output_keys, feat_src, feat_kind, feat_omega, widths, self.activation)
+        eng_widths = widths
+        if self.fourier:  # the embedding is layer 1 of the network the kernels see; the reference's own layers start at D
+            d_f = int(self.fourier["dim"])
+            eng_widths = [len(feat_src), d_f] + hidden + [len(self.output_keys)]
+            widths = [d_f] + hidden + [len(self.output_keys)]
+        self._net = NetSpec(self.input_keys, self.output_keys, feat_src, feat_kind, feat_omega, eng_widths, self.activation,
+                            act_first="sin" if self.fourier else None)
         self._shapes = list(zip(widths[:-1], widths[1:]))
         self._w_off, self._b_off = [], []
         off = 0
@@ -171,7 +186,9 @@ class MLP(base.Arch):
             off += a * b
             self._b_off.append(off)
             off += b
-        self._n_eff = off  # length of the [W | b] buffer the kernels read
+        self._n_eff = off  # length of the [W | b] buffer of the reference's own linear layers
+        self._n_lin = off
+        self._f_n0 = 0     # fourier: length of the effective first layer [W0 | b0] in front of them in the engine buffer
         self._g_off = []   # weight_norm: per hidden layer, offset of its gain vector g_l (appended after the last bias)
         if self.weight_norm or self.random_weight:
             for a, b in (self._shapes if self.random_weight else self._shapes[:-1]):
@@ -179,6 +196,14 @@ class MLP(base.Arch):
                 off += b
             self.register_buffer("_eff", torch.zeros(self._n_eff, dtype=dtype), persistent=False)
             self.register_buffer("_eff_grad", torch.zeros(self._n_eff, dtype=dtype), persistent=False)
+        if self.fourier:  # trainable kernel B [n_feat, D/2] stored behind the linear layers
+            nf, dh = len(feat_src), int(self.fourier["dim"]) // 2
+            self._f_shape = (nf, dh)
+            self._f_off = off
+            off += nf * dh
+            self._f_n0 = nf * 2 * dh + 2 * dh
+            self.register_buffer("_eff", torch.zeros(self._f_n0 + self._n_lin, dtype=dtype), persistent=False)
+            self.register_buffer("_eff_grad", torch.zeros(self._f_n0 + self._n_lin, dtype=dtype), persistent=False)
         self.flat = nn.Parameter(torch.zeros(off, dtype=dtype))
         self.linears = [_LinearView(self, i) for i in range(len(hidden))]
         self.last_fc = _LinearView(self, len(hidden))
@@ -212,6 +237,17 @@ class MLP(base.Arch):
                     self.flat.data[self._w_off[i]: self._w_off[i] + a * b] = (v / g).reshape(-1).to(self.flat.dtype)
                     self.flat.data[self._g_off[i]: self._g_off[i] + b] = g.to(self.flat.dtype)
 
+            if self.fourier:  # FourierEmbedding: Normal(std=scale) (mlp.py:123-126)
+                nf, dh = self._f_shape
+                k = torch.randn(nf * dh, dtype=torch.float64) * float(self.fourier["scale"])
+                self.flat.data[self._f_off: self._f_off + nf * dh] = k.to(self.flat.dtype)
+
+    @property
+    def fourier_kernel(self) -> torch.Tensor:
+        """View of the FourierEmbedding kernel B [n_feat, D/2] (``fourier_emb.kernel`` in the reference)."""
+        nf, dh = self._f_shape
+        return self.flat.data[self._f_off: self._f_off + nf * dh].view(nf, dh)
+
     def net_spec(self) -> NetSpec:
         return self._net
 
@@ -225,6 +261,18 @@ class MLP(base.Arch):
 
     def engine_params(self) -> torch.Tensor:
         """The flat [W_1 | b_1 | ...] buffer passed to the native calls (effective weights under weight_norm)."""
+        if self.fourier:
+            with torch.no_grad():
+                nf, dh = self._f_shape
+                k = self.fourier_kernel
+                w0 = self._eff[: nf * 2 * dh].view(nf, 2 * dh)
+                w0[:, :dh].copy_(k)
+                w0[:, dh:].copy_(k)
+                b0 = self._eff[nf * 2 * dh: self._f_n0]
+                b0[:dh] = math.pi / 2  # cos(z) = sin(z + pi/2)
+                b0[dh:] = 0
+                self._eff[self._f_n0:].copy_(self.flat.data[: self._n_lin])
+            return self._eff
         if self._skip_layers:
             with torch.no_grad():
                 self._eff.copy_(self.flat.data[: self._n_eff])
@@ -249,11 +297,19 @@ class MLP(base.Arch):
         """Buffer the native calls accumulate the weight gradient into (same layout as ``engine_params``)."""
         if self.flat.grad is None:
             self.flat.grad = torch.zeros_like(self.flat.data)
-        return self._eff_grad if (self.weight_norm or self.random_weight or self._skip_layers) else self.flat.grad
+        return self._eff_grad if (self.weight_norm or self.random_weight or self._skip_layers or self.fourier) else self.flat.grad
 
     def finish_grads(self):
         """Chain rule of the weight normalisation: gradients w.r.t. the effective weights -> (V, g); then the
         staging buffer is cleared.  No-op for plain layers (the kernels accumulated into ``flat.grad`` directly)."""
+        if self.fourier:
+            with torch.no_grad():
+                nf, dh = self._f_shape
+                self.flat.grad[: self._n_lin] += self._eff_grad[self._f_n0:]
+                dw0 = self._eff_grad[: nf * 2 * dh].view(nf, 2 * dh)
+                self.flat.grad[self._f_off: self._f_off + nf * dh].view(nf, dh).add_(dw0[:, :dh] + dw0[:, dh:])
+                self._eff_grad.zero_()  # the constant bias [pi/2 | 0] takes no gradient
+            return
         if self._skip_layers:
             with torch.no_grad():
                 for i in self._skip_layers:
@@ -303,12 +359,21 @@ class MLP(base.Arch):
             else:
                 out[f"{name}.weight"] = v.weight.detach().clone()
             out[f"{name}.bias"] = v.bias.detach().clone()
+        if self.fourier:
+            out["fourier_emb.kernel"] = self.fourier_kernel.detach().clone()
         return out
 
     def load_state_dict(self, state_dict, strict: bool = True):
         views = self.linears + [self.last_fc]
-        missing, unexpected = [], [k for k in state_dict if k.rsplit(".", 1)[0] not in self._layer_names()]
+        missing, unexpected = [], [k for k in state_dict if k.rsplit(".", 1)[0] not in self._layer_names() + (["fourier_emb"] if self.fourier else [])]
         with torch.no_grad():
+            if self.fourier:
+                if "fourier_emb.kernel" in state_dict:
+                    src = state_dict["fourier_emb.kernel"]
+                    src = torch.as_tensor(np.asarray(src.cpu() if hasattr(src, "cpu") else src))
+                    self.fourier_kernel.copy_(src.to(self.flat.dtype).to(self.flat.device))
+                else:
+                    missing.append("fourier_emb.kernel")
             for i, (name, v) in enumerate(zip(self._layer_names(), views)):
                 for part in (("weight_v", "weight_g", "bias") if self._wn_layer(i) else ("weight", "bias")):
                     key = f"{name}.{part}"

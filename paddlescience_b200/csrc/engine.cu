@@ -179,6 +179,7 @@ extern "C" int ppsci_b200_plan_create(const ppsci_plan_spec* s, ppsci_plan** out
   for (int l = 0; l <= s->n_layers; ++l)
     if (s->widths[l] < 1 || s->widths[l] > 4096) return fail("plan_create: layer width out of range");
   if (s->act < 0 || s->act > PPSCI_ACT_GELU) return fail("plan_create: unknown activation");
+  if (s->act_first < -1 || s->act_first > PPSCI_ACT_GELU) return fail("plan_create: unknown first-layer activation");
   for (int f = 0; f < (s->dense_in ? 0 : s->n_feat); ++f) {
     if (s->feat_src[f] < 0 || s->feat_src[f] >= s->n_in) return fail("plan_create: feat_src out of range");
     if (s->feat_kind[f] < 0 || s->feat_kind[f] > PPSCI_FEAT_SIN) return fail("plan_create: bad feat_kind");
@@ -283,6 +284,7 @@ extern "C" int ppsci_b200_plan_create(const ppsci_plan_spec* s, ppsci_plan** out
   }
   P->use_tc = tc_plan_supported(P->spec, P->C, P->kmax) && s->backend != 1;
 #ifdef PPSCI_EMUL
+  if (s->act_first >= 0 && s->act_first != s->act) P->use_tc = false;  // one activation across the fused layers
   if (s->backend != 2) P->use_tc = false;  // the emulated tensor-core kernels (1,024 OS threads per CTA pair) run on request only
 #endif
   if (const char* m = getenv("PPSCI_B200_TC_MASK")) P->tc_mask = atoi(m);
@@ -432,10 +434,13 @@ static void fill_seed(const ppsci_plan* P, const void* const* x_cols, int64_t x_
   for (int i = 0; i < PPSCI_MAX_IN; ++i) S.x_cols[i] = i < s.n_in ? x_cols[i] : nullptr;
 }
 
+// activation applied to the output of linear layer `lin` (1-based)
+static inline int act_of_layer(const ppsci_plan_spec& s, int lin) { return (lin == 1 && s.act_first >= 0) ? s.act_first : s.act; }
+
 template <typename T>
-static void fill_act(const ppsci_plan* P, const T* Z, int ld, int64_t nc, int mode, AOperand<T>* A) {
+static void fill_act(const ppsci_plan* P, const T* Z, int ld, int64_t nc, int mode, AOperand<T>* A, int lin = 0) {
   A->mode = mode;
-  A->act = P->spec.act;
+  A->act = act_of_layer(P->spec, lin);
   A->Z = Z;
   A->ld = ld;
   A->plane = (long long)nc * ld;
@@ -598,7 +603,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
       if (l == L && thin_last) {
         LastArgs<T> f;
         memset(&f, 0, sizeof(f));
-        fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[L - 1]), P->ld[L - 1], nc_max, A_ACT, &f.A);
+        fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[L - 1]), P->ld[L - 1], nc_max, A_ACT, &f.A, L - 1);
         f.J = P->J;
         f.W = params + P->w_off[L];
         f.bias = params + P->b_off[L];
@@ -749,7 +754,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
       GemmArgs<T> g;
       memset(&g, 0, sizeof(g));
       if (l == 1) fill_first<T>(P, a.x_cols, c0, nc_max, &g.A);
-      else fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[l - 1]), P->ld[l - 1], nc_max, A_ACT, &g.A);
+      else fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[l - 1]), P->ld[l - 1], nc_max, A_ACT, &g.A, l - 1);
       g.J = P->J;
       g.B = params + P->w_off[l];
       g.Kdim = s.widths[l - 1];
@@ -868,7 +873,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
       if (l == L && thin_last) {  // dW_L, db_L and Zbar_{L-1} in one streaming pass
         LastArgs<T> f;
         memset(&f, 0, sizeof(f));
-        fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[L - 1]), P->ld[L - 1], nc_max, A_ACT, &f.A);
+        fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[L - 1]), P->ld[L - 1], nc_max, A_ACT, &f.A, L - 1);
         f.J = P->J;
         f.W = params + P->w_off[L];
         f.K = s.widths[L - 1];
@@ -1012,7 +1017,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         DwArgs<T> g;
         memset(&g, 0, sizeof(g));
         if (l == 1) fill_first<T>(P, a.x_cols, c0, nc_max, &g.A);
-        else fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[l - 1]), P->ld[l - 1], nc_max, A_ACT, &g.A);
+        else fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[l - 1]), P->ld[l - 1], nc_max, A_ACT, &g.A, l - 1);
         g.J = P->J;
         g.Zbar = zbar_cur;
         g.ldzb = zbar_ld;
@@ -1106,7 +1111,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         g.Zprev = reinterpret_cast<const T*>(ws + cv.z[l - 1]);
         g.ldz = P->ld[l - 1];
         g.zplane = (long long)nc_max * P->ld[l - 1];
-        g.act = s.act;
+        g.act = act_of_layer(s, l - 1);
         dim3 grid(ptiles, (unsigned)((g.Nout + TN - 1) / TN));
         ProfScope ps_(P, CLS_DX, st);
         PPSCI_LAUNCH(kx, grid, dim3(NTHREADS), smem_x, st, g);

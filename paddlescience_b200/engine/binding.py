@@ -74,6 +74,7 @@ class PlanSpec(C.Structure):
         ("chunk_points", C.c_int32),
         ("backend", C.c_int32),
         ("dense_in", C.c_int32),
+        ("act_first", C.c_int32),
     ]
 
 

@@ -55,6 +55,7 @@ class NetSpec:
     widths: List[int]  # [n_feat, hidden..., n_out]
     act: str = "tanh"
     dense_in: bool = False  # the single input key is a row-major [N, n_feat] matrix (DeepONet branch net); values only
+    act_first: Optional[str] = None  # activation of the FIRST linear layer's output when it differs (FourierEmbedding: "sin")
 
     @property
     def n_params(self) -> int:

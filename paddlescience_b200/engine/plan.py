@@ -73,6 +73,10 @@ class ResidualPlan:
         for i, w in enumerate(net.widths):
             s.widths[i] = w
         s.act = B.ACT_IDS[net.act.lower()]
+        act_first = getattr(net, "act_first", None)
+        if act_first is not None and act_first.lower() not in B.ACT_IDS:
+            raise NotImplementedError(f"activation {act_first!r} has no jet kernel (supported: {sorted(B.ACT_IDS)})")
+        s.act_first = B.ACT_IDS[act_first.lower()] if act_first is not None else -1
         s.n_dir = len(compiled.dirs)
         for d, dr in enumerate(compiled.dirs):
             s.dir_order[d] = dr.order
