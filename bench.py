@@ -345,11 +345,12 @@ def run_ours(args):
     params_init = model.engine_params().detach().clone() if plan is not None else None  # parity is checked on these too
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def make_step(lab):
+    def make_step(lab, comm=True):
         def step(inp):
             losses_all, _ = helper.train_forward((cst.output_expr,), (inp,), model, constraint, (lab,), (None,))
             if world > 1:
-                dist.all_reduce(model.flat.grad)
+                if comm:
+                    dist.all_reduce(model.flat.grad)
                 opt.grad_scale = 1.0 / world
             opt.step()
             opt.clear_grad()
@@ -503,8 +504,29 @@ def run_ours(args):
         for _ in range(3):
             s_step(s_in)
         ms_s, _ = timed(s_step, s_in, args.steps)
+        # where the strong-scaling step goes: the same step without the all-reduce (weights then differ per rank: done
+        # last, on a throw-away copy of the step), and the all-reduce of the flat gradient alone
+        nocomm_step = make_step({k: v[:ns].contiguous() for k, v in labels.items()}, comm=False)
+        ms_nc, _ = timed(nocomm_step, s_in, args.steps)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for _ in range(3):
+            dist.all_reduce(model.flat.grad)
+        sync_all()
+        ev[0].record()
+        for _ in range(20):
+            dist.all_reduce(model.flat.grad)
+        ev[1].record()
+        sync_all()
+        ar_ms = torch.tensor([ev[0].elapsed_time(ev[1]) / 20], device=dev, dtype=torch.float64)
+        dist.all_reduce(ar_ms, op=dist.ReduceOp.MAX)
+        dist.broadcast(model.flat.data, 0)  # the no-comm steps let the ranks drift apart: re-synchronise the weights
+        model.flat.grad.zero_()
         strong = {"global_points": ns * world, "points_per_gpu": ns, "ms_per_step": ms_s, "value": ns * world / (ms_s * 1e-3),
-                  "unit": UNIT, "note": "strong scaling: the N=1 global batch split over the ranks, same step, same timing rules"}
+                  "unit": UNIT, "ms_per_step_without_allreduce": ms_nc, "allreduce_ms_back_to_back": float(ar_ms),
+                  "allreduce_bytes": int(model.flat.grad.numel() * model.flat.grad.element_size()),
+                  "note": "strong scaling: the N=1 global batch split over the ranks, same step, same timing rules; "
+                          "ms_per_step_without_allreduce = the identical step with the NCCL all-reduce left out, "
+                          "allreduce_ms_back_to_back = 20 all-reduces of the flat gradient timed alone (max over ranks)"}
         log(f"strong-scaling pass done: {ms_s:.2f} ms/step")
 
     # ---------------- per-kernel-class shares (separate, untimed pass) ----------------
