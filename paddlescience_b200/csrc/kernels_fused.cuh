@@ -260,7 +260,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
   const int n_tile_pairs = (g.num_tiles + 1) / 2;
   const int my_tp = pair < n_tile_pairs ? (n_tile_pairs - 1 - pair) / npairs + 1 : 0;
   const bool dbg0 = g.dbg && blockIdx.x == 0;
+#ifdef PPSCI_B200_TIMELINE
 #define FDBG(cond, row, slot) do { if (dbg0 && (cond) && (row) < 48u) g.dbg[(row) * 16 + (slot)] = clock64(); } while (0)
+#else  // product build: no stamp code at all (even predicated off it costs issue slots in the item loops)
+#define FDBG(cond, row, slot) do { } while (0)
+#endif
 
   if (warp == T2_TMA_WARP) {
     if (lane == 0) fused_stream_weights(base, bars, b_off, g.Wimg, my_tp, NLf, nchunks, N, rank);
@@ -554,8 +558,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
   // aligned offline on the multicast mma_done events (epi_start)
   const bool dbg0 = g.dbg && blockIdx.x < 2;
   const uint32_t dbg_r0 = blockIdx.x * 48u;
+#ifdef PPSCI_B200_TIMELINE
 #define FDBG(cond, row, slot) do { if (dbg0 && (cond) && (row) < 48u) g.dbg[(dbg_r0 + (row)) * 16 + (slot)] = clock64(); } while (0)
+#else  // product build: no stamp code at all (even predicated off it costs issue slots in the item loops)
+#define FDBG(cond, row, slot) do { } while (0)
+#endif
+#ifdef PPSCI_B200_TIMELINE
 #define FDBG_MAX(cond, row, slot) do { if (dbg0 && (cond) && (row) < 48u) atomicMax((unsigned long long*)&g.dbg[(dbg_r0 + (row)) * 16 + (slot)], (unsigned long long)clock64()); } while (0)
+#else  // product build: no stamp code at all (even predicated off it costs issue slots in the item loops)
+#define FDBG_MAX(cond, row, slot) do { } while (0)
+#endif
 
   if (warp == T2_TMA_WARP) {
     if (lane == 0) {  // weight streamer (see fused_stream_weights): layer 0 has nch32 chunks, the others nch64; same bytes per chunk
@@ -899,7 +911,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_
   const int n_tile_pairs = (g.num_tiles + 1) / 2;
   const int my_tp = pair < n_tile_pairs ? (n_tile_pairs - 1 - pair) / npairs + 1 : 0;
   const bool dbg0 = g.dbg && blockIdx.x == 0;
+#ifdef PPSCI_B200_TIMELINE
 #define FDBG(cond, row, slot) do { if (dbg0 && (cond) && (row) < 48u) g.dbg[(row) * 16 + (slot)] = clock64(); } while (0)
+#else  // product build: no stamp code at all (even predicated off it costs issue slots in the item loops)
+#define FDBG(cond, row, slot) do { } while (0)
+#endif
 
   if (warp == T2_TMA_WARP) {
     if (lane == 0) fused_stream_weights(base, bars, b_off, g.WimgT, my_tp, NLf, nchunks, N, rank);

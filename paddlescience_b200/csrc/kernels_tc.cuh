@@ -495,7 +495,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
   }
   const bool dbgp = g.dbg && blockIdx.x == 0 && tid == 0;
   const bool dbgm = g.dbg && blockIdx.x == 0 && is_mma && lane == 0;
+#ifdef PPSCI_B200_TIMELINE
 #define DBG_STAMP(cond, slot) do { if ((cond) && it < 48) g.dbg[it * 16 + (slot)] = clock64(); } while (0)
+#else  // product build: no stamp code at all (even predicated off it costs issue slots in the item loops)
+#define DBG_STAMP(cond, slot) do { } while (0)
+#endif
   uint32_t it = 0;  // running chunk counter (stage = it & 1, use index = it >> 1)
   for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
     const long long p0 = (long long)tile * TP;
@@ -760,7 +764,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_dx(TcDxArgs g) {
   }
   const bool dbgp = g.dbg && blockIdx.x == 0 && tid == 0;
   const bool dbgm = g.dbg && blockIdx.x == 0 && is_mma && lane == 0;
+#ifdef PPSCI_B200_TIMELINE
 #define DBG_STAMP(cond, slot) do { if ((cond) && it < 48) g.dbg[it * 16 + (slot)] = clock64(); } while (0)
+#else  // product build: no stamp code at all (even predicated off it costs issue slots in the item loops)
+#define DBG_STAMP(cond, slot) do { } while (0)
+#endif
   uint32_t it = 0;
   for (int tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
     const long long p0 = (long long)tile * TP;
@@ -1044,7 +1052,11 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_tc_dw(TcDwArgs g) {
   };
   const bool dbgp = g.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
   const bool dbgm = g.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && is_mma && lane == 0;
+#ifdef PPSCI_B200_TIMELINE
 #define DBG_STAMP(cond, slot) do { if ((cond) && it < 48) g.dbg[it * 16 + (slot)] = clock64(); } while (0)
+#else  // product build: no stamp code at all (even predicated off it costs issue slots in the item loops)
+#define DBG_STAMP(cond, slot) do { } while (0)
+#endif
   // one reduction chunk: producers split the register-resident block of chunk `ch` into the operand stage and
   // refill the same registers with chunk ch+2; the MMA warp issues the chunk's 8 MMAs
   auto step = [&](float4 (&buf)[4], long long ch, uint32_t it) {

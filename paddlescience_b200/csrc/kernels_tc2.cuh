@@ -233,7 +233,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_fw
   const int my_tp = pair < n_tile_pairs ? (n_tile_pairs - 1 - pair) / npairs + 1 : 0;
   const uint32_t total_it = (uint32_t)my_tp * (uint32_t)nchunks;
   const bool dbg0 = g.dbg && blockIdx.x == 0;
+#ifdef PPSCI_B200_TIMELINE
 #define DBG_STAMP(cond, slot) do { if (dbg0 && (cond) && it < 48) g.dbg[it * 16 + (slot)] = clock64(); } while (0)
+#else  // product build: no stamp code at all (even predicated off it costs issue slots in the item loops)
+#define DBG_STAMP(cond, slot) do { } while (0)
+#endif
 
   if (warp == T2_TMA_WARP) {
     // ---- weight streamer: this CTA's N/2 rows of W_hi and W_lo for every chunk, up to 3 chunks ahead ----
@@ -501,7 +505,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_tc2_dx
   const int my_tp = pair < n_tile_pairs ? (n_tile_pairs - 1 - pair) / npairs + 1 : 0;
   const uint32_t total_it = (uint32_t)my_tp * (uint32_t)nchunks;
   const bool dbg0 = g.dbg && blockIdx.x == 0;
+#ifdef PPSCI_B200_TIMELINE
 #define DBG_STAMP(cond, slot) do { if (dbg0 && (cond) && it < 48) g.dbg[it * 16 + (slot)] = clock64(); } while (0)
+#else  // product build: no stamp code at all (even predicated off it costs issue slots in the item loops)
+#define DBG_STAMP(cond, slot) do { } while (0)
+#endif
 
   if (warp == T2_TMA_WARP) {
     if (lane == 0) {
@@ -763,7 +771,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DW_THREADS, 1) k_tc2
   };
   const bool is_mma = (warp == DW_MMA_WARP);
   const bool dbg0 = g.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+#ifdef PPSCI_B200_TIMELINE
 #define DBG_STAMP(cond, slot) do { if (dbg0 && (cond) && it < 48) g.dbg[it * 16 + (slot)] = clock64(); } while (0)
+#else  // product build: no stamp code at all (even predicated off it costs issue slots in the item loops)
+#define DBG_STAMP(cond, slot) do { } while (0)
+#endif
 
   if (is_mma) {
     if (lane == 0) {

@@ -28,17 +28,22 @@ def sources():
     return sorted(os.path.join(SRC, f) for f in os.listdir(SRC))
 
 
-def build_native(force: bool = False, verbose: bool = False) -> str:
+def build_native(force: bool = False, verbose: bool = False, timeline: bool = False) -> str:
+    """``timeline=True`` builds the bring-up variant ``libppsci_b200_timeline.so`` (-DPPSCI_B200_TIMELINE: clock64 stamps
+    in the tensor-core kernels, used by tests/tools/timeline*.py); the product library carries no stamp code."""
+    out = OUT.replace("libppsci_b200.so", "libppsci_b200_timeline.so") if timeline else OUT
     deps = sources() + [os.path.join(ROOT, "include", "ppsci_b200.h")]
-    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
-        return OUT
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
     cmd = [_nvcc()] + NVCC_FLAGS + ["-I" + os.path.join(ROOT, "include"), "-I" + SRC,
-                                    os.path.join(SRC, "engine.cu"), "-o", OUT]
+                                    os.path.join(SRC, "engine.cu"), "-o", out]
+    if timeline:
+        cmd.insert(1, "-DPPSCI_B200_TIMELINE")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

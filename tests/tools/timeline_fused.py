@@ -10,10 +10,13 @@ os.environ.setdefault("PPSCI_B200_DEBUG_KERNEL", "3")
 from tests.cases import make_net
 from paddlescience_b200.engine.compiler import compile_residuals
 from paddlescience_b200.engine.plan import ResidualPlan
+from paddlescience_b200.engine import binding as B
+from paddlescience_b200.engine.build import build_native
+_tl_lib = B.Library(build_native(timeline=True))  # the stamp code exists only in the -DPPSCI_B200_TIMELINE build
 from oracle import ppsci_oracle as O
 net = make_net(("x", "y"), ("u", "v", "p"), [256] * 6, "tanh")
 cr = compile_residuals(net, O.navier_stokes_expr(0.01, 1.0, 2, False))
-plan = ResidualPlan(cr, torch.float32, ["mean"] * 3, None)
+plan = ResidualPlan(cr, torch.float32, ["mean"] * 3, None, library=_tl_lib)
 params = O.xavier_uniform_params(net.widths, 1, torch.float32).to(dev)
 grads = torch.zeros_like(params)
 N = int(os.environ.get("TL_POINTS", 262144))
