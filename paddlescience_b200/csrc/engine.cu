@@ -541,7 +541,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
 
   if constexpr (sizeof(T) == 4) {
     if (P->use_tc) {
-      for (int l = 2; l < L; ++l) {
+      for (int l = 2; l <= L; ++l) {  // hidden -> hidden layers and a wide output layer
         if (!tc_layer_ok(s, l)) continue;
         const int K = s.widths[l - 1], N = s.widths[l];
         const long long tot = (long long)K * N;
@@ -719,7 +719,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           t.Kdim = s.widths[l - 1];
           t.Nout = s.widths[l];
           t.bias = reinterpret_cast<const float*>(params) + P->b_off[l];
-          t.Out = reinterpret_cast<float*>(ws + cv.z[l]);
+          t.Out = reinterpret_cast<float*>(ws + (l == L ? cv.y : cv.z[l]));  // a wide output layer writes Y
           t.ldo = P->ld[l];
           t.oplane = (long long)nc_max * P->ld[l];
           t.Np = nc;
@@ -1337,7 +1337,7 @@ extern "C" int ppsci_b200_adam_step_dev(int32_t dtype, void* params, void* grads
 // a_l is stashed by the tensor-core forward of layer l+1 and consumed by the tensor-core dW of layer l+1
 static bool tc_astash_needed(const ppsci_plan* P, int l) {
   const int lay = l + 1;
-  return P->use_tc && (P->tc_mask & 1) && (P->tc_mask & 4) && lay < P->spec.n_layers && tc_layer_ok(P->spec, lay) &&
+  return P->use_tc && (P->tc_mask & 1) && (P->tc_mask & 4) && lay <= P->spec.n_layers && tc_layer_ok(P->spec, lay) &&
          tc_dw_ok(P->spec, lay);
 }
 static size_t tc_scratch_bytes(const ppsci_plan* P, int64_t nc) {

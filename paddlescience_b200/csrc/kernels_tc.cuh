@@ -1166,9 +1166,10 @@ __global__ void k_bias_grad(const float* __restrict__ Zbar0, int ld, long long N
 
 // ---- host side ------------------------------------------------------------------------------------
 inline bool tc_layer_ok(const ppsci_plan_spec& s, int l) {
-  // hidden -> hidden layers only: the input layer has K = n_feat (2..3), the last layer N = n_out
+  // hidden -> hidden layers, and a WIDE output layer (DeepONet sub-networks end in num_features = 128 units,
+  // deeponet.py:96-119); the input layer has K = n_feat (2..3) and a PINN's output layer N = n_out (1..4): thin kernels
   if (s.dtype != PPSCI_F32) return false;
-  if (l < 2 || l >= s.n_layers) return false;
+  if (l < 2 || l > s.n_layers) return false;
   const int K = s.widths[l - 1], N = s.widths[l];
   return (K % tc::KCH == 0) && K >= 32 && K <= 1024 && (N % 32 == 0) && N >= 32 && N <= 256;
 }
@@ -1238,7 +1239,7 @@ inline int tc_pick_layout(const JetLayout& J, int act) {
 
 
 inline bool tc_plan_supported(const ppsci_plan_spec& s, int /*C*/, int /*kmax*/) {
-  for (int l = 2; l < s.n_layers; ++l)
+  for (int l = 2; l <= s.n_layers; ++l)
     if (tc_layer_ok(s, l)) return true;
   return false;
 }
@@ -1251,7 +1252,7 @@ inline size_t tc_img_offset(const ppsci_plan_spec& s, int layer) {
   return off;
 }
 inline size_t tc_imgT_offset(const ppsci_plan_spec& s, int layer) {  // transposed (dx) images follow the forward ones
-  size_t off = tc_img_offset(s, s.n_layers);
+  size_t off = tc_img_offset(s, s.n_layers + 1);
   for (int l = 2; l < layer; ++l)
     if (tc_dx_ok(s, l)) off += (size_t)s.widths[l - 1] * s.widths[l] * 8;
   return off;
