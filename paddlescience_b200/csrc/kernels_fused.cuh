@@ -880,11 +880,6 @@ struct FusedDxArgs {
   long long* dbg;
 };
 
-#ifndef PPSCI_EMUL
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-#else
-inline void prefetch_l2(const void*) {}
-#endif
 
 template <class L, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) k_fused_dx(FusedDxArgs g) {
