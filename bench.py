@@ -31,8 +31,8 @@ NU, RHO = 0.01, 1.0
 # dram__bytes_read.sum + dram__bytes_write.sum of the hidden-layer kernels of cfg3 from the committed `ncu --set full`
 # captures of this round (profiles/r02_summary.md; one 65,536-point chunk, all five hidden->hidden layers): bytes PER POINT.
 # Equal to the plane sets the design streams (no re-reads): fwd 1 read + 10 written sets, dx 6 read + 5 written, dW 10 read.
-NCU_DRAM_BYTES_PER_POINT_CFG3 = {"fwd_gemm": (368.6e6 + 3299.8e6) / 65536, "dx_gemm": (2064.9e6 + 1661.3e6) / 65536,
-                                 "dw_gemm": 5 * (671.5e6 + 3.6e6) / 65536}
+NCU_DRAM_BYTES_PER_POINT_CFG3 = {"fwd_gemm": (364.1e6 + 3294.9e6) / 65536, "dx_gemm": (2060.0e6 + 1635.9e6) / 65536,
+                                 "dw_gemm": 5 * (671.5e6 + 4.3e6) / 65536}  # profiles/r02c_ncu_*_details.txt (final build)
 
 # name, metric label, points per GPU, dtype
 CONFIGS = {

@@ -551,6 +551,15 @@ static int run(ppsci_plan* P, const CallArgs& a) {
                      reinterpret_cast<float*>(ws + cv.tc + tc_img_offset(s, l)), K, N, 0);
         P->launches++;
       }
+      if ((P->tc_mask & 1) && tc_dense_first_ok(s)) {  // dense first layer: K rounded up to the chunk width, zero rows beyond
+        const int K = s.widths[0], N = s.widths[1];
+        float* img = reinterpret_cast<float*>(ws + cv.tc + tc_dense_img_offset(s));
+        ProfScope ps_(P, CLS_MISC, st);
+        CK(cudaMemsetAsync(img, 0, (size_t)tc_dense_kpad(s) * N * 8, st));
+        PPSCI_LAUNCH(tc::k_tc_prep_w, dim3((unsigned)(((long long)K * N + 255) / 256)), dim3(256), 0, st,
+                     reinterpret_cast<const float*>(params) + P->w_off[1], img, K, N, 0);
+        P->launches++;
+      }
       if (do_bwd && (P->tc_mask & 2)) {
         for (int l = 2; l <= L; ++l) {
           if (!tc_dx_ok(s, l)) continue;
@@ -630,6 +639,38 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         continue;
       }
       if constexpr (sizeof(T) == 4) {
+        if (l == 1 && P->use_tc && (P->tc_mask & 1) && tc_dense_first_ok(s)) {
+          // dense first layer (DeepONet branch net: [N][num_loc] sensor matrix) on the tensor cores: the operand is the
+          // caller's matrix itself ("activation" = identity, values only), columns beyond K read as zero
+          tc::TcFwdArgs t;
+          memset(&t, 0, sizeof(t));
+          const int nf = s.widths[0];
+          fill_act<float>(P, reinterpret_cast<const float*>(a.x_cols[0]) + c0 * nf, nf, nc_max, A_ACT, &t.A);
+          t.A.act = PPSCI_ACT_IDENTITY;
+          t.J = P->J;
+          t.Wimg = reinterpret_cast<const float*>(ws + cv.tc + tc_dense_img_offset(s));
+          t.Kdim = tc_dense_kpad(s);
+          t.Kvalid = nf;
+          t.Nout = s.widths[1];
+          t.bias = reinterpret_cast<const float*>(params) + P->b_off[1];
+          t.Out = reinterpret_cast<float*>(ws + (L > 1 ? cv.z[1] : cv.y));
+          t.ldo = P->ld[1];
+          t.oplane = (long long)nc_max * P->ld[1];
+          t.Np = nc;
+          t.TP = TP;
+          t.num_tiles = (int)ptiles;
+          const int smem_tc = tc::tc_fwd_smem_bytes(t.Nout);
+          const unsigned gridx = ptiles < (unsigned)P->num_sms ? ptiles : (unsigned)P->num_sms;
+          void (*kd)(tc::TcFwdArgs) = tc::k_tc_fwd<tc::SLay<0, 0, 0, 0>, -1>;
+          {
+            cudaError_t e_ = cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_tc);
+            if (e_ != cudaSuccess) return fail(std::string("cudaFuncSetAttribute(k_tc_fwd dense): ") + cudaGetErrorString(e_));
+          }
+          ProfScope ps_(P, CLS_FWD, st);
+          PPSCI_KLAUNCH(kd, dim3(gridx), dim3(tc::THREADS), smem_tc, st, 1, t);
+          P->launches++;
+          continue;
+        }
         if (l == 2 && fused_fwd16_ok(P)) {  // fused forward, fp16 hi / lo operands after the first layer (accurate for wide layers)
           const int H = s.widths[1], NLf = L - 2;
           unsigned char* w16 = ws + cv.w16;
@@ -945,12 +986,19 @@ static int run(ppsci_plan* P, const CallArgs& a) {
       }
       bool dw_done = false;
       if constexpr (sizeof(T) == 4) {
-        if (tc_astash_needed(P, l - 1)) {
+        const bool dense_tc = l == 1 && P->use_tc && (P->tc_mask & 1) && (P->tc_mask & 4) && tc_dense_first_ok(s);
+        if (dense_tc || (l >= 2 && tc_astash_needed(P, l - 1))) {
           tc::TcDwArgs t;
           memset(&t, 0, sizeof(t));
-          t.Aact = reinterpret_cast<const float*>(ws + cv.a[l - 1]);
-          t.lda = P->ld[l - 1];
-          t.aplane = (long long)nc_max * P->ld[l - 1];
+          if (dense_tc) {  // the operand of dW_1 is the caller's sensor matrix itself (fan-in rows beyond K are masked)
+            t.Aact = reinterpret_cast<const float*>(a.x_cols[0]) + c0 * s.widths[0];
+            t.lda = s.widths[0];
+            t.aplane = 0;
+          } else {
+            t.Aact = reinterpret_cast<const float*>(ws + cv.a[l - 1]);
+            t.lda = P->ld[l - 1];
+            t.aplane = (long long)nc_max * P->ld[l - 1];
+          }
           t.J = P->J;
           t.Zbar = reinterpret_cast<const float*>(zbar_cur);
           t.ldzb = zbar_ld;
@@ -985,7 +1033,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
                                return fail(std::string("cudaFuncSetAttribute(k_tc2_dw): ") + cudaGetErrorString(e_)));
             P->launches++;
           } else {
-          const unsigned kt = (unsigned)(t.Kdim / 128), nb = (unsigned)(s.widths[l] / NC);
+          const unsigned kt = (unsigned)((t.Kdim + 127) / 128), nb = (unsigned)(s.widths[l] / NC);
           long long want = P->num_sms / (kt * nb);
           if (want < 1) want = 1;
           if (want > total_chunks) want = total_chunks;

@@ -378,7 +378,8 @@ struct TcFwdArgs {
   AOperand<float> A;  // A_ACT over Z_{l-1}
   JetLayout J;
   const float* Wimg;  // [K/32][2][N*32] swizzled hi / lo images
-  int Kdim;
+  int Kdim;           // contraction length of the weight image (a multiple of the chunk width)
+  int Kvalid;         // operand columns that exist (0 = Kdim): a dense first-layer operand [N][100] is read as [N][128]
   int Nout;
   const float* bias;
   float* Out;
@@ -477,11 +478,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_tc_fwd(TcFwdArgs g) {
     if constexpr (L::kStatic) {
       const long long p0r = (long long)tile_r * TP;
       const int col = jr * KCH + 4 * kq;
+      const bool col_ok = col < (g.Kvalid ? g.Kvalid : g.Kdim);  // zero columns beyond a padded contraction length
 #pragma unroll
       for (int i = 0; i < MAXI; ++i) {
         const int pl = warp * 4 + psub + i * PPR;
         const long long p = p0r + pl;
-        const bool ok = pl < TP && p < g.Np;
+        const bool ok = pl < TP && p < g.Np && col_ok;
         const float* src = g.A.Z + p * g.A.ld + col;
 #pragma unroll
         for (int c = 0; c < CS; ++c)
@@ -1028,7 +1030,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) k_tc_dw(TcDwArgs g) {
       const int rr = 4 * q + e;
       uint32_t b8 = 0xFFu;
       g_off[e] = 0;
-      if (has_task && rr < rows_used) {
+      if (has_task && rr < rows_used && (!t_isA || k0 + row0 < g.Kdim)) {  // fan-in rows beyond Kdim (100 -> 128): zeros
         const int c = rr / PT, pl = rr - c * PT;
         b8 = (uint32_t)pl;
         g_off[e] = t_isA ? (uint32_t)((long long)c * g.aplane + (long long)pl * g.lda + k0 + row0)
@@ -1243,6 +1245,7 @@ inline bool tc_plan_supported(const ppsci_plan_spec& s, int /*C*/, int /*kmax*/)
     if (tc_layer_ok(s, l)) return true;
   return false;
 }
+inline bool tc_dense_first_ok(const ppsci_plan_spec& s);
 
 // scratch = weight images (hi+lo) of every eligible layer, forward orientation
 inline size_t tc_img_offset(const ppsci_plan_spec& s, int layer) {
@@ -1257,8 +1260,18 @@ inline size_t tc_imgT_offset(const ppsci_plan_spec& s, int layer) {  // transpos
     if (tc_dx_ok(s, l)) off += (size_t)s.widths[l - 1] * s.widths[l] * 8;
   return off;
 }
+// dense first layer (DeepONet branch net, K = num_loc): tensor-core eligible when its width is, the operand columns come in
+// whole float4s and there are no input derivatives; its weight image (contraction length rounded up to the chunk width,
+// zero rows beyond K) sits behind the other images
+inline int tc_dense_kpad(const ppsci_plan_spec& s) { return (s.widths[0] + tc::KCH - 1) / tc::KCH * tc::KCH; }
+inline bool tc_dense_first_ok(const ppsci_plan_spec& s) {
+  if (s.dtype != PPSCI_F32 || !s.dense_in || s.n_dir != 0 || s.n_layers < 2) return false;
+  const int K = s.widths[0], N = s.widths[1];
+  return K % 4 == 0 && K >= 32 && tc_dense_kpad(s) <= 1024 && N % 32 == 0 && N >= 32 && N <= 256 && N % tc_dw_cols_per_cta(N) == 0;
+}
+inline size_t tc_dense_img_offset(const ppsci_plan_spec& s) { return tc_imgT_offset(s, s.n_layers + 1); }
 inline size_t tc_scratch_bytes_impl(const ppsci_plan_spec& s, int /*C*/, int64_t /*nc*/) {
-  return tc_imgT_offset(s, s.n_layers + 1) + 1024;
+  return tc_imgT_offset(s, s.n_layers + 1) + (tc_dense_first_ok(s) ? (size_t)tc_dense_kpad(s) * s.widths[1] * 8 : 0) + 1024;
 }
 
 }  // namespace ppsci

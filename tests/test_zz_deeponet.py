@@ -97,7 +97,7 @@ def test_wide_output_layer_on_the_emulated_tensor_core_kernels(monkeypatch):
     monkeypatch.setattr(B, "_default", B.Library(build()))
     monkeypatch.setenv("PPSCI_B200_BACKEND", "2")
     hidden = [128, 128]
-    model, cst, data = _setup(torch.float32, "cpu", 150, 10, 128, hidden)
+    model, cst, data = _setup(torch.float32, "cpu", 150, 100, 128, hidden)  # num_loc = 100: the dense first layer takes the tensor-core path too (K padded to 128)
     losses_all, _ = _train_forward(model, cst, "cpu", torch.float32)
     plans = model._get_plans()
     assert all(p.uses_tcgen05 for p in plans)
