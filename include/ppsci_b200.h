@@ -31,6 +31,7 @@ extern "C" {
 #define PPSCI_MAX_ORDER 4   /* highest Taylor order per direction                        */
 #define PPSCI_MAX_RES 16    /* residual (equation) outputs per call (one constraint, or a batch of them) */
 #define PPSCI_MAX_REG 256   /* register file of the residual program                     */
+#define PPSCI_MAX_PGRAD 32  /* (residual, learnable parameter) gradient terms per plan    */
 
 /* dtype */
 enum { PPSCI_F32 = 0, PPSCI_F64 = 1 };
@@ -140,6 +141,16 @@ typedef struct ppsci_plan_spec {
    * A plan with act_first != act runs on the CUDA-core kernels (the tensor-core kernels are specialised for one
    * activation across the layers they fuse). */
   int32_t act_first;
+  /* Learnable scalar parameters of the equations — replaces ParameterNode (ppsci/utils/symbolic.py:471-485) and the
+   * autograd path into PDE.learnable_parameters (ppsci/equation/pde/base.py:38, e.g. Vibration, pde/viv.py:41-60):
+   * an auxiliary column flagged in aux_bcast is ONE device scalar (of the plan's dtype) read by every point, and the
+   * n_pgrad triples (residual k, aux index, register holding d residual_k / d parameter) make the head kernel
+   * accumulate dLoss/dparameter into the fp64 device scalar registered with ppsci_b200_plan_set_aux_grad. */
+  int32_t aux_bcast[PPSCI_MAX_IN];
+  int32_t n_pgrad;
+  int32_t pgrad_res[PPSCI_MAX_PGRAD];
+  int32_t pgrad_aux[PPSCI_MAX_PGRAD];
+  int32_t pgrad_reg[PPSCI_MAX_PGRAD];
 } ppsci_plan_spec;
 
 typedef struct ppsci_plan ppsci_plan;
@@ -152,6 +163,10 @@ void ppsci_b200_plan_destroy(ppsci_plan* plan);
 /* Number of parameters in the flat buffer: for each layer l, W_l [in,out] row-major
  * (the reference's nn.Linear layout, ppsci/arch/mlp.py:246,274) followed by b_l [out]. */
 int64_t ppsci_b200_plan_param_count(const ppsci_plan* plan);
+
+/* Where the loss-and-gradient calls ACCUMULATE dLoss/d(aux parameter `aux_index`) (a device fp64 scalar owned by the
+ * caller; NULL = do not accumulate).  Only meaningful for aux columns flagged in aux_bcast. */
+int ppsci_b200_plan_set_aux_grad(ppsci_plan* plan, int32_t aux_index, double* grad_dev);
 int32_t ppsci_b200_plan_channels(const ppsci_plan* plan);
 
 /* Bytes of caller-provided device workspace needed for a call with n_points points. */

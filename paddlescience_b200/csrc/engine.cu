@@ -60,6 +60,7 @@ struct ppsci_plan {
   int* d_grad_res = nullptr;
   int* d_grad_in = nullptr;
   int* d_grad_reg = nullptr;
+  double* aux_grad[PPSCI_MAX_IN] = {};  // ppsci_b200_plan_set_aux_grad
   int64_t launches = 0;
   bool attrs_set = false;
   // optional per-kernel-class timing (bench only; adds event records, no syncs)
@@ -220,6 +221,13 @@ extern "C" int ppsci_b200_plan_create(const ppsci_plan_spec* s, ppsci_plan** out
     if (s->grad_in[g] < 0 || s->grad_in[g] >= C * n_out) return fail("plan_create: grad_in out of range");
     if (s->grad_reg[g] < 0 || s->grad_reg[g] >= s->n_reg) return fail("plan_create: grad_reg out of range");
     if (g > 0 && s->grad_in[g] < s->grad_in[g - 1]) return fail("plan_create: grad list must be sorted by grad_in");
+  }
+  if (s->n_pgrad < 0 || s->n_pgrad > PPSCI_MAX_PGRAD) return fail("plan_create: n_pgrad out of range");
+  for (int g = 0; g < s->n_pgrad; ++g) {
+    if (s->pgrad_res[g] < 0 || s->pgrad_res[g] >= s->n_res) return fail("plan_create: pgrad_res out of range");
+    if (s->pgrad_aux[g] < 0 || s->pgrad_aux[g] >= s->n_aux || !s->aux_bcast[s->pgrad_aux[g]])
+      return fail("plan_create: pgrad_aux must name a learnable (aux_bcast) parameter");
+    if (s->pgrad_reg[g] < 0 || s->pgrad_reg[g] >= s->n_reg) return fail("plan_create: pgrad_reg out of range");
   }
 
   ppsci_plan* P = new ppsci_plan();
@@ -835,6 +843,16 @@ static int run(ppsci_plan* P, const CallArgs& a) {
       h.P.grad_res = P->d_grad_res;
       h.P.grad_in = P->d_grad_in;
       h.P.grad_reg = P->d_grad_reg;
+      h.P.n_pgrad = s.n_pgrad;
+      for (int g = 0; g < PPSCI_MAX_PGRAD; ++g) {
+        h.P.pgrad_res[g] = g < s.n_pgrad ? s.pgrad_res[g] : 0;
+        h.P.pgrad_aux[g] = g < s.n_pgrad ? s.pgrad_aux[g] : -1;
+        h.P.pgrad_reg[g] = g < s.n_pgrad ? s.pgrad_reg[g] : 0;
+      }
+      for (int i = 0; i < PPSCI_MAX_IN; ++i) {
+        h.aux_bcast[i] = i < s.n_aux ? s.aux_bcast[i] : 0;
+        h.aux_grad[i] = (i < s.n_aux && s.aux_bcast[i] && do_bwd) ? P->aux_grad[i] : nullptr;
+      }
       h.C = C;
       h.n_out = n_out;
       h.n_in = s.n_in;
@@ -1200,6 +1218,14 @@ static int dispatch(ppsci_plan* P, const CallArgs& a) {
   }
   if (P->spec.dtype == PPSCI_F64) return dispatch_k<double>(P, a);
   return dispatch_k<float>(P, a);
+}
+
+extern "C" int ppsci_b200_plan_set_aux_grad(ppsci_plan* plan, int32_t aux_index, double* grad_dev) {
+  if (!plan) return fail("null plan");
+  if (aux_index < 0 || aux_index >= plan->spec.n_aux || !plan->spec.aux_bcast[aux_index])
+    return fail("plan_set_aux_grad: aux_index is not a learnable (broadcast) parameter of this plan");
+  plan->aux_grad[aux_index] = grad_dev;
+  return 0;
 }
 
 extern "C" int ppsci_b200_values_fwd_bwd(ppsci_plan* plan, const void* const* x_cols, const void* const* aux_cols,

@@ -653,6 +653,11 @@ struct HeadProgram {  // all pointers are device pointers owned by the plan
   const int* grad_res;
   const int* grad_in;
   const int* grad_reg;
+  // learnable equation parameters (ppsci_plan_spec.aux_bcast / pgrad_*): passed by value, at most PPSCI_MAX_PGRAD terms
+  int n_pgrad;
+  int pgrad_res[PPSCI_MAX_PGRAD];
+  int pgrad_aux[PPSCI_MAX_PGRAD];
+  int pgrad_reg[PPSCI_MAX_PGRAD];
 };
 
 template <typename T>
@@ -665,6 +670,8 @@ struct HeadArgs {
   T* Ybar;  // same layout, may be null
   const void* x_cols[PPSCI_MAX_IN];
   const void* aux_cols[PPSCI_MAX_IN];
+  int aux_bcast[PPSCI_MAX_IN];      // 1: aux_cols[a] is one scalar (a learnable parameter), not a column
+  double* aux_grad[PPSCI_MAX_IN];   // fp64 accumulators of dLoss/d(parameter a), or null
   long long x_off;  // chunk offset into the caller's columns
   long long Np;
   const void* label_cols[PPSCI_MAX_RES];
@@ -740,7 +747,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) k_head(HeadArgs<T> h) {
       for (int j = 0; j < h.n_out; ++j) r[c * h.n_out + j] = h.Y[(long long)c * h.yplane + p * h.ldy + j];
     for (int i = 0; i < h.n_in; ++i) r[nY + i] = reinterpret_cast<const T*>(h.x_cols[i])[h.x_off + p];
     for (int a = 0; a < h.n_aux; ++a)
-      r[nY + h.n_in + a] = reinterpret_cast<const T*>(h.aux_cols[a])[h.x_off + p];
+      r[nY + h.n_in + a] = reinterpret_cast<const T*>(h.aux_cols[a])[h.aux_bcast[a] ? 0 : h.x_off + p];
     vm_run<T>(h.P, r);
   }
   for (int k = 0; k < h.P.n_res; ++k) {
@@ -766,6 +773,24 @@ __global__ void __launch_bounds__(HEAD_THREADS) k_head(HeadArgs<T> h) {
         __syncthreads();
       }
       if (threadIdx.x == 0) atomicAdd(h.loss_acc + k, red[0]);
+      __syncthreads();
+    }
+  }
+  // dLoss/d(learnable parameter a) = sum over points and residuals of (2 coef w e) * d residual / d parameter
+  if (h.P.n_pgrad > 0 && h.Ybar) {
+    for (int a = 0; a < h.n_aux; ++a) {
+      if (!h.aux_grad[a]) continue;  // uniform across the block
+      double acc = 0.0;
+      if (valid)
+        for (int g = 0; g < h.P.n_pgrad; ++g)
+          if (h.P.pgrad_aux[g] == a) acc += (double)(rb[h.P.pgrad_res[g]] * r[h.P.pgrad_reg[g]]);
+      red[threadIdx.x] = acc;
+      __syncthreads();
+      for (int s = HEAD_THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) atomicAdd(h.aux_grad[a], red[0]);
       __syncthreads();
     }
   }

@@ -17,6 +17,7 @@ MAX_DIR = 8
 MAX_ORDER = 4
 MAX_RES = 16
 MAX_REG = 256
+MAX_PGRAD = 32
 
 F32, F64 = 0, 1
 
@@ -75,6 +76,11 @@ class PlanSpec(C.Structure):
         ("backend", C.c_int32),
         ("dense_in", C.c_int32),
         ("act_first", C.c_int32),
+        ("aux_bcast", C.c_int32 * MAX_IN),
+        ("n_pgrad", C.c_int32),
+        ("pgrad_res", C.c_int32 * MAX_PGRAD),
+        ("pgrad_aux", C.c_int32 * MAX_PGRAD),
+        ("pgrad_reg", C.c_int32 * MAX_PGRAD),
     ]
 
 
@@ -82,6 +88,7 @@ EXPORTED_SYMBOLS = (
     "ppsci_b200_plan_create",
     "ppsci_b200_plan_destroy",
     "ppsci_b200_plan_param_count",
+    "ppsci_b200_plan_set_aux_grad",
     "ppsci_b200_plan_channels",
     "ppsci_b200_plan_workspace_bytes",
     "ppsci_b200_residual_loss_fwd_bwd",
@@ -133,6 +140,8 @@ class Library:
         L.ppsci_b200_plan_destroy.restype = None
         L.ppsci_b200_plan_param_count.argtypes = [vp]
         L.ppsci_b200_plan_param_count.restype = i64
+        L.ppsci_b200_plan_set_aux_grad.argtypes = [vp, C.c_int32, vp]
+        L.ppsci_b200_plan_set_aux_grad.restype = C.c_int
         L.ppsci_b200_plan_channels.argtypes = [vp]
         L.ppsci_b200_plan_channels.restype = i32
         L.ppsci_b200_plan_workspace_bytes.argtypes = [vp, i64]

@@ -81,6 +81,12 @@ class CompiledResidual:
     grad_res: List[int]
     grad_in: List[int]
     grad_reg: List[int]
+    # learnable equation parameters (ParameterNode, ppsci/utils/symbolic.py:471-485): aux keys that are ONE scalar, and
+    # the (residual, aux index, register of d residual / d parameter) terms of their loss gradient
+    param_keys: List[str] = field(default_factory=list)
+    pgrad_res: List[int] = field(default_factory=list)
+    pgrad_aux: List[int] = field(default_factory=list)
+    pgrad_reg: List[int] = field(default_factory=list)
     # alpha (multi-index over raw inputs) -> [(dir index, coefficient)]; D^alpha u = sum c * k! * Y[dir,k]
     combos: Dict[Tuple[int, ...], List[Tuple[int, Fraction]]] = field(default_factory=dict)
 
@@ -376,6 +382,7 @@ def compile_residuals(
     exprs: Dict[str, sp.Basic],
     aux_keys: Optional[Sequence[str]] = None,
     with_grad: bool = True,
+    param_keys: Optional[Sequence[str]] = None,
 ) -> CompiledResidual:
     """Compile residual expressions for ``net``.
 
@@ -385,6 +392,8 @@ def compile_residuals(
       * ``Derivative(f(...), ...)``                   -> input derivative of a network output
       * any other ``Symbol`` / applied function       -> auxiliary data column of that name
       * ``detach(sub)``                              -> value of sub, no gradient
+    ``param_keys``: names among those auxiliary symbols that are learnable scalar parameters of the equation
+    (``PDE.learnable_parameters``): one value for all points, and the program also carries d residual / d parameter.
     """
     n_in = len(net.input_keys)
     n_out = len(net.output_keys)
@@ -512,10 +521,21 @@ def compile_residuals(
                     if g != 0:
                         grads.append((k, c * n_out + j, restore(g)))
     grads.sort(key=lambda t: (t[1], t[0]))
+    param_set = set(param_keys or [])
+    pgrads: List[Tuple[int, int, sp.Basic]] = []  # (res k, aux index, expr)
+    if with_grad:
+        for k, e in enumerate(stripped):
+            for nm, s_ in auxsym.items():
+                if nm in param_set and s_ in e.free_symbols:
+                    g = sp.diff(e, s_)
+                    if g != 0:
+                        pgrads.append((k, aux_list.index(nm), restore(g)))
+    if len(pgrads) > B.MAX_PGRAD:
+        raise NotImplementedError(f"{len(pgrads)} (residual, learnable parameter) gradient terms (max {B.MAX_PGRAD})")
 
     # ---- 4. CSE + emission -------------------------------------------------------------------
     n_fixed = C * n_out + n_in + len(aux_list)
-    all_exprs = values + [g for _, _, g in grads]
+    all_exprs = values + [g for _, _, g in grads] + [g for _, _, g in pgrads]
     repl, reduced = sp.cse(all_exprs, order="none") if all_exprs else ([], [])
     em = _Emitter(n_fixed)
     for (c, j), s in ysym.items():
@@ -563,8 +583,12 @@ def compile_residuals(
         res_reg=out_regs[:n_res],
         grad_res=[k for k, _, _ in grads],
         grad_in=[i for _, i, _ in grads],
-        grad_reg=out_regs[n_res:],
+        grad_reg=out_regs[n_res:n_res + len(grads)],
         combos=combos,
+        param_keys=[nm for nm in aux_list if nm in param_set],
+        pgrad_res=[k for k, _, _ in pgrads],
+        pgrad_aux=[a for _, a, _ in pgrads],
+        pgrad_reg=out_regs[n_res + len(grads):],
     )
     if cr.n_reg > B.MAX_REG:
         raise NotImplementedError(f"residual program needs {cr.n_reg} registers (max {B.MAX_REG})")

@@ -83,6 +83,18 @@ class ResidualPlan:
             for i, v in enumerate(dr.vec):
                 s.dir_vec[d][i] = float(v)
         s.n_aux = len(compiled.aux_keys)
+        if s.n_aux > B.MAX_IN:
+            raise NotImplementedError(f"more than {B.MAX_IN} auxiliary columns / learnable parameters")
+        # learnable equation parameters: one scalar for all points + dLoss/dparameter accumulated by the head kernel
+        self.param_keys = list(getattr(compiled, "param_keys", []) or [])
+        for i, k in enumerate(compiled.aux_keys):
+            s.aux_bcast[i] = 1 if k in self.param_keys else 0
+        s.n_pgrad = len(getattr(compiled, "pgrad_res", []) or [])
+        for g in range(s.n_pgrad):
+            s.pgrad_res[g] = compiled.pgrad_res[g]
+            s.pgrad_aux[g] = compiled.pgrad_aux[g]
+            s.pgrad_reg[g] = compiled.pgrad_reg[g]
+        self._param_grad = None  # fp64 [n_aux] device buffer the head kernel accumulates dLoss/dparameter into
         s.n_reg = compiled.n_reg
         s.n_ops = len(compiled.prog)
         flat = [x for op in compiled.prog for x in op]
@@ -166,6 +178,35 @@ class ResidualPlan:
             return torch.cuda.current_stream(device).cuda_stream
         return 0
 
+    def _aux_tensors(self, inputs, aux_keys, n: int, device):
+        """Auxiliary data columns ([n] values) and learnable parameters (ONE value of the plan's dtype on the device)."""
+        out = []
+        for k in aux_keys:
+            if k in self.param_keys:
+                t = inputs[k]
+                if t.numel() != 1:
+                    raise ValueError(f"learnable parameter '{k}' must be a scalar, got shape {tuple(t.shape)}")
+                t = t.detach().reshape(1)
+                if t.dtype != self.dtype or t.device != device:
+                    t = t.to(device=device, dtype=self.dtype)
+                out.append(t.contiguous())
+            else:
+                out.append(_col(inputs[k], n, self.dtype, device, f"aux '{k}'"))
+        return out
+
+    def param_grad_buffer(self, device) -> Optional[torch.Tensor]:
+        """fp64 [n_aux] device buffer registered with the plan: entry i ACCUMULATES dLoss/d(aux key i) for the learnable
+        parameters over every loss_fwd_bwd call until the caller zeroes it (None if the plan has none)."""
+        if not self.param_keys:
+            return None
+        if self._param_grad is None or self._param_grad.device != device:
+            self._param_grad = torch.zeros(len(self.compiled.aux_keys), dtype=torch.float64, device=device)
+            for i, k in enumerate(self.compiled.aux_keys):
+                if k in self.param_keys:
+                    rc = self.lib.lib.ppsci_b200_plan_set_aux_grad(self.handle, i, self._param_grad.data_ptr() + 8 * i)
+                    self.lib.check(rc, "plan_set_aux_grad")
+        return self._param_grad
+
     def _ptr_array(self, tensors: Sequence[Optional[torch.Tensor]], length: int):
         arr = (C.c_void_p * max(1, length))()
         for i, t in enumerate(tensors):
@@ -191,7 +232,7 @@ class ResidualPlan:
         n = first.numel()
         keep = []  # keep contiguous copies alive for the duration of the call
         xs = [_col(inputs[k], n, self.dtype, device, f"input '{k}'") for k in net.input_keys]
-        auxs = [_col(inputs[k], n, self.dtype, device, f"aux '{k}'") for k in cr.aux_keys]
+        auxs = self._aux_tensors(inputs, cr.aux_keys, n, device)
         labs: List[Optional[torch.Tensor]] = []
         wts: List[Optional[torch.Tensor]] = []
         lconst = (C.c_double * B.MAX_RES)()
@@ -216,6 +257,8 @@ class ResidualPlan:
             raise ValueError("grads must match params in dtype/size/device and be contiguous")
         if self._loss is None or self._loss.device != device:
             self._loss = torch.zeros(B.MAX_RES, dtype=self.dtype, device=device)
+        if grads is not None:
+            self.param_grad_buffer(device)
         ws = self._workspace(n, device)
         wptr, wbytes = self._aligned(ws)
         rc = self.lib.lib.ppsci_b200_residual_loss_fwd_bwd(
@@ -258,7 +301,7 @@ class ResidualPlan:
         cr = self.compiled
         device = params.device
         n, xs = self._inputs(inputs, device)
-        auxs = [_col(inputs[k], n, self.dtype, device, f"aux '{k}'") for k in cr.aux_keys]
+        auxs = self._aux_tensors(inputs, cr.aux_keys, n, device)
         if ybar.shape != (n, self.n_out) or ybar.dtype != self.dtype or ybar.device != device:
             raise ValueError(f"ybar must be [{n}, {self.n_out}] {self.dtype} on {device}")
         if grads.dtype != params.dtype or grads.numel() != params.numel() or grads.device != device or not grads.is_contiguous():
@@ -280,7 +323,7 @@ class ResidualPlan:
         At most ``chunk_points`` points (``ppsci_b200_values_fwd_keep``); follow with ``values_bwd_kept``."""
         device = params.device
         n, xs = self._inputs(inputs, device)
-        auxs = [_col(inputs[k], n, self.dtype, device, f"aux '{k}'") for k in self.compiled.aux_keys]
+        auxs = self._aux_tensors(inputs, self.compiled.aux_keys, n, device)
         y = torch.empty((n, self.n_out), dtype=self.dtype, device=device)
         ws = self._workspace(n, device)
         wptr, wbytes = self._aligned(ws)
@@ -317,7 +360,7 @@ class ResidualPlan:
         net = cr.net
         device = params.device
         n, xs = self._inputs(inputs, device)
-        auxs = [_col(inputs[k], n, self.dtype, device, f"aux '{k}'") for k in cr.aux_keys]
+        auxs = self._aux_tensors(inputs, cr.aux_keys, n, device)
         jets = torch.empty((self.channels, n, self.n_out), dtype=self.dtype, device=device) if want_jets else None
         res_t = [torch.empty((n, 1), dtype=self.dtype, device=device) for _ in range(self.n_res)] if want_residuals else []
         ws = self._workspace(n, device)

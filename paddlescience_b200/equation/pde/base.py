@@ -7,7 +7,34 @@ import sympy as sp
 import torch
 from torch import nn
 
+import itertools
+import weakref
+
 from ...engine.compiler import DETACH_FUNC_NAME, cvt_to_key
+
+# Learnable equation parameters by name.  The reference matches sympy symbols against ``param.name`` of the
+# ``extra_parameters`` the solver collects from every equation (ppsci/solver/solver.py:491-514,
+# ppsci/utils/symbolic.py:798, 849-858); torch parameters carry no name, so ``PDE.create_parameter`` gives them one
+# and records it here — the residual compiler looks the free symbols of an expression up in this table.
+_PARAMETERS: "weakref.WeakValueDictionary[str, nn.Parameter]" = weakref.WeakValueDictionary()
+_param_counter = itertools.count()
+
+
+class NamedParameter(nn.Parameter):
+    """``nn.Parameter`` with paddle's ``.name`` (torch's own ``Tensor.name`` is a read-only slot)."""
+
+    @property
+    def name(self):  # noqa: D401
+        return getattr(self, "_ppsci_name", None)
+
+    @name.setter
+    def name(self, value):
+        self._ppsci_name = value
+
+
+def lookup_parameter(name: str):
+    """The learnable parameter registered under ``name`` (None if there is none)."""
+    return _PARAMETERS.get(name)
 
 
 class PDE:
@@ -23,6 +50,18 @@ class PDE:
     @staticmethod
     def create_symbols(symbol_str: str):
         return sp.symbols(symbol_str)
+
+    def create_parameter(self, value: float, name: Optional[str] = None, dtype: Optional[torch.dtype] = None) -> nn.Parameter:
+        """A learnable scalar of this equation — the counterpart of ``paddle.create_parameter(shape=[], ...)`` +
+        ``self.learnable_parameters.append(...)`` (e.g. ppsci/equation/pde/viv.py:44-55).  The returned parameter has a
+        unique ``.name``; ``create_symbols(p.name)`` is the symbol that stands for it in the equations."""
+        p = NamedParameter(torch.tensor(float(value), dtype=dtype or torch.get_default_dtype()))
+        p.name = name or f"learnable_parameter_{next(_param_counter)}"
+        if p.name in _PARAMETERS:
+            raise ValueError(f"a learnable parameter named {p.name!r} already exists")
+        _PARAMETERS[p.name] = p
+        self.learnable_parameters.append(p)
+        return p
 
     def create_function(self, name: str, invars: Tuple[sp.Symbol, ...]) -> sp.Function:
         return sp.Function(name)(*invars)

@@ -14,8 +14,13 @@ class FlatAdam:
     """Adam over ``model.flat`` (paddle.optimizer.Adam semantics: L2 ``weight_decay`` folded into
     the gradient, bias-corrected moments, no amsgrad)."""
 
-    def __init__(self, model, learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8, weight_decay=None, decoupled=False):
+    def __init__(self, model, learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8, weight_decay=None, decoupled=False,
+                 extra_params=()):
         self.model = model
+        # learnable equation parameters (``Adam(lr)((model, equation))``, ppsci/optimizer/optimizer.py:225-248 collects the
+        # parameters of every entry of model_list): each is stepped by the same fused kernel, one tiny launch per scalar
+        self.extra_params = list(extra_params)
+        self._extra_state = {}
         self._lr = learning_rate
         self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
         self.weight_decay = float(weight_decay) if weight_decay else 0.0
@@ -57,6 +62,20 @@ class FlatAdam:
                                           self.epsilon, self.weight_decay, self.t, self.grad_scale,
                                           torch.cuda.current_stream(p.device).cuda_stream)
         lib.check(rc, "adam_step")
+        for q in self.extra_params:
+            if q.grad is None:
+                continue
+            if q.device.type != "cuda":
+                raise RuntimeError("learnable equation parameters must live on the CUDA device of the model")
+            st = self._extra_state.get(id(q))
+            if st is None or st[0].device != q.device or st[0].dtype != q.dtype:
+                st = self._extra_state[id(q)] = (torch.zeros_like(q.data), torch.zeros_like(q.data))
+            qd = B.F64 if q.dtype == torch.float64 else B.F32
+            rc = lib.lib.ppsci_b200_adam_step(qd, q.data.data_ptr(), q.grad.data_ptr(), st[0].data_ptr(), st[1].data_ptr(),
+                                              q.numel(), self.get_lr(), self.beta1, self.beta2, self.epsilon,
+                                              self.weight_decay, self.t, self.grad_scale,
+                                              torch.cuda.current_stream(q.device).cuda_stream)
+            lib.check(rc, "adam_step (equation parameter)")
 
     # -- the same step split for CUDA-graph replay (solver/graph_step.py): ``step_dev`` is the launch (recorded once,
     #    every scalar that changes per step is read from ``hyper_dev``), ``advance`` the host-side bookkeeping that
@@ -67,6 +86,8 @@ class FlatAdam:
         return [self.get_lr(), 1.0 - self.beta1 ** self.t, 1.0 - self.beta2 ** self.t, float(self.grad_scale)]
 
     def step_dev(self, hyper_dev: torch.Tensor, zero_grads: bool = True):
+        if self.extra_params:
+            raise NotImplementedError("CUDA-graph replay (to_static) with learnable equation parameters is not supported yet")
         p = self.model.flat
         if p.device.type != "cuda":
             raise RuntimeError("FlatAdam.step_dev needs parameters on a CUDA (B200) device: no CPU fallback")
@@ -84,6 +105,9 @@ class FlatAdam:
     def clear_grad(self):
         if self.model.flat.grad is not None:
             self.model.flat.grad.zero_()
+        for q in self.extra_params:
+            if q.grad is not None:
+                q.grad.zero_()
 
     zero_grad = clear_grad
 
@@ -91,6 +115,8 @@ class FlatAdam:
         # like paddle's optimizer state ("LR_Scheduler" entry): a resumed run continues the warm-up / decay where it
         # stopped instead of replaying it from step 0
         sd = {"t": self.t, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq}
+        if self.extra_params:
+            sd["extra"] = [self._extra_state.get(id(q)) for q in self.extra_params]
         if hasattr(self._lr, "state_dict"):
             sd["LR_Scheduler"] = self._lr.state_dict()
         return sd
@@ -98,6 +124,9 @@ class FlatAdam:
     def set_state_dict(self, sd):
         self.t = int(sd["t"])
         self.exp_avg, self.exp_avg_sq = sd["exp_avg"], sd["exp_avg_sq"]
+        for q, st in zip(self.extra_params, sd.get("extra", [])):
+            if st is not None:
+                self._extra_state[id(q)] = (st[0], st[1])
         if "LR_Scheduler" in sd and hasattr(self._lr, "set_state_dict"):
             self._lr.set_state_dict(sd["LR_Scheduler"])
 
@@ -115,11 +144,20 @@ class Adam:
         self.weight_decay = weight_decay
 
     def __call__(self, model_list):
+        extra = []
         if isinstance(model_list, (tuple, list)):
-            if len(model_list) != 1:
+            # (model, equation, ...): entries without a flat parameter buffer contribute their learnable scalars
+            models = [m for m in model_list if hasattr(m, "flat")]
+            for m in model_list:
+                if not hasattr(m, "flat"):
+                    if not hasattr(m, "learnable_parameters"):
+                        raise TypeError(f"{type(m).__name__} is neither a model nor an equation with learnable parameters")
+                    extra += list(m.learnable_parameters)
+            if len(models) != 1:
                 raise NotImplementedError("one optimizer over several models is not supported yet")
-            model_list = model_list[0]
-        return FlatAdam(model_list, self.learning_rate, self.beta1, self.beta2, self.epsilon, self.weight_decay)
+            model_list = models[0]
+        return FlatAdam(model_list, self.learning_rate, self.beta1, self.beta2, self.epsilon, self.weight_decay,
+                        extra_params=extra)
 
 
 class FlatLBFGS:

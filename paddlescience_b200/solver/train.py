@@ -120,6 +120,9 @@ def train_epoch_func(solver, epoch_id: int, log_freq: int):
                 import torch.distributed as dist
 
                 dist.all_reduce(model.flat.grad)  # the only collective on the path (train.py:171)
+                for q in getattr(solver.optimizer, "extra_params", ()):  # learnable equation scalars (a few bytes each)
+                    if q.grad is not None:
+                        dist.all_reduce(q.grad)
                 scale /= solver.world_size
             solver.optimizer.grad_scale = scale
             solver.optimizer.step()

@@ -20,6 +20,42 @@ from ..engine.plan import ResidualPlan
 from . import symbolic
 
 
+def _learnable_parameters(exprs: Dict[str, sp.Basic]) -> Dict[str, "torch.nn.Parameter"]:
+    """Free symbols of the expressions that name a learnable equation parameter (``PDE.create_parameter``): what the
+    reference receives as ``extra_parameters`` and turns into ParameterNodes (symbolic.py:798, 849-858)."""
+    from ..equation.pde.base import lookup_parameter
+
+    found = {}
+    for e in exprs.values():
+        for s_ in e.free_symbols:
+            p = lookup_parameter(str(s_))
+            if p is not None:
+                found[str(s_)] = p
+    return found
+
+
+def _with_parameters(inputs: Dict[str, torch.Tensor], params: Dict[str, "torch.nn.Parameter"]):
+    if not params:
+        return inputs
+    merged = dict(inputs)
+    merged.update(params)
+    return merged
+
+
+def _collect_parameter_grads(plan: ResidualPlan, params: Dict[str, "torch.nn.Parameter"], device):
+    """dLoss/dparameter from the plan's fp64 accumulators into ``param.grad`` (accumulating, like backward())."""
+    if not params:
+        return
+    buf = plan.param_grad_buffer(device)
+    for i, k in enumerate(plan.compiled.aux_keys):
+        p = params.get(k)
+        if p is None:
+            continue
+        g = buf[i].to(p.dtype).reshape(p.shape).to(p.device)
+        p.grad = g.clone() if p.grad is None else p.grad + g
+    buf.zero_()
+
+
 class CompiledConstraint:
     """Residual plan(s) of one constraint, built lazily per dtype."""
 
@@ -28,7 +64,8 @@ class CompiledConstraint:
         self.cst = cst
         self.exprs = _constraint_exprs(model, cst, extra_keys)  # the loss iterates label keys (mse.py:85); same order
         self.names = list(self.exprs)
-        self.compiled = compile_residuals(model.net_spec(), self.exprs)
+        self.parameters = _learnable_parameters(self.exprs)
+        self.compiled = compile_residuals(model.net_spec(), self.exprs, param_keys=list(self.parameters))
         self._plans: Dict[torch.dtype, ResidualPlan] = {}
         self._key_plans: Dict[tuple, ResidualPlan] = {}
 
@@ -100,7 +137,8 @@ class BatchedConstraints:
                 self.loss_weights.append(cst.loss.weight_of(key) if hasattr(cst.loss, "weight_of") else 1.0)
         if len(self.slots) > B.MAX_RES:
             raise NotImplementedError(f"{len(self.slots)} residuals in one batch (max {B.MAX_RES})")
-        self.compiled = compile_residuals(model.net_spec(), exprs)
+        self.parameters = _learnable_parameters(exprs)
+        self.compiled = compile_residuals(model.net_spec(), exprs, param_keys=list(self.parameters))
         self._plans: Dict[torch.dtype, ResidualPlan] = {}
         self._mask_cache = {}
 
@@ -121,6 +159,9 @@ class BatchedConstraints:
         ntot = offs[-1]
         cols = {}
         for k in list(cr.net.input_keys) + list(cr.aux_keys):
+            if k in self.parameters:  # a learnable scalar, not a data column
+                cols[k] = self.parameters[k]
+                continue
             buf = torch.zeros(ntot, 1, dtype=dtype, device=dev)
             for i, d in enumerate(input_dicts):
                 if k in d:
@@ -142,7 +183,10 @@ class BatchedConstraints:
             if "area" in input_dicts[i]:  # mse.py:92-93
                 rng.mul_(input_dicts[i]["area"].to(dtype).reshape(-1, 1))
             weights[slot] = w
-        return plan.loss_fwd_bwd(cols, params, grads, labels=labels, weights=weights, n_norm=ntot).clone()
+        out = plan.loss_fwd_bwd(cols, params, grads, labels=labels, weights=weights, n_norm=ntot).clone()
+        if grads is not None:
+            _collect_parameter_grads(plan, self.parameters, dev)
+        return out
 
 
 class ExpressionSolver(nn.Module):
@@ -199,6 +243,8 @@ class ExpressionSolver(nn.Module):
                 if "area" in input_dicts[i]:
                     area = input_dicts[i]["area"]
                     weights = {k: (weights[k] * area if weights and k in weights else area) for k in cc.names}
+                if cc.parameters:
+                    raise NotImplementedError("per-term gradients with learnable equation parameters are not supported yet")
                 for k, key in enumerate(cc.names):
                     g = grads_by_key.setdefault(key, torch.zeros_like(flat.data))
                     lv = cc.plan_for_key(flat.dtype, k).loss_fwd_bwd(input_dicts[i], params, g, labels=label_dicts[i],
@@ -254,8 +300,10 @@ class ExpressionSolver(nn.Module):
             if "area" in input_dicts[i]:  # mse.py:92-93 multiplies by the area column when present
                 area = input_dicts[i]["area"]
                 weights = {k: (weights[k] * area if weights and k in weights else area) for k in cc.names}
-            loss_vec = plan.loss_fwd_bwd(input_dicts[i], params, grads, labels=label_dicts[i], weights=weights)
+            loss_vec = plan.loss_fwd_bwd(_with_parameters(input_dicts[i], cc.parameters), params, grads, labels=label_dicts[i],
+                                         weights=weights)
             loss_vec = loss_vec.clone()
+            _collect_parameter_grads(plan, cc.parameters, flat.device)
             losses_constraint[cst_name] = loss_vec.sum()
             for k, key in enumerate(cc.names):
                 losses_all[key] = losses_all[key] + loss_vec[k] if key in losses_all else loss_vec[k]

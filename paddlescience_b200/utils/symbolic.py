@@ -55,14 +55,19 @@ class CompiledExpr:
         from ..engine.plan import ResidualPlan
 
         if dtype not in self._plans:
-            cr = compile_residuals(self.model.net_spec(), {self.name: self.expr}, with_grad=False)
+            from ..equation.pde.base import lookup_parameter
+
+            self._parameters = {str(s_): lookup_parameter(str(s_)) for s_ in self.expr.free_symbols
+                                if lookup_parameter(str(s_)) is not None}
+            cr = compile_residuals(self.model.net_spec(), {self.name: self.expr}, with_grad=False,
+                                   param_keys=list(self._parameters))
             self._plans[dtype] = ResidualPlan(cr, dtype, ["mean"], [1.0])
         return self._plans[dtype]
 
     def __call__(self, data_dict: Dict[str, torch.Tensor]) -> torch.Tensor:
         plan = self._plan(self.model.dtype)
         keys = list(self.model.input_keys) + list(plan.compiled.aux_keys)
-        cols = {k: data_dict[k] for k in keys}
+        cols = {k: (self._parameters[k] if k in self._parameters else data_dict[k]) for k in keys}  # ParameterNode: the parameter itself
         _, res = plan.forward(cols, self.model.engine_params(), want_jets=False, want_residuals=True)
         return res[self.name]
 
@@ -82,8 +87,15 @@ def lambdify(
     """Convert sympy expression(s) to callable(s) — same signature as the reference
     (symbolic.py:681-689).  ``create_graph`` / ``retain_graph`` / ``fuse_derivative`` are accepted
     for compatibility; they have no meaning without an autograd graph."""
+    # ``extra_parameters``: the learnable parameters are found by the NAME of the symbols (``PDE.create_parameter``
+    # registers them), exactly what the reference does with ``param.name`` (symbolic.py:798, 849-858); the argument is
+    # accepted and checked for consistency only.
     if extra_parameters:
-        raise NotImplementedError("learnable equation parameters are not compiled into residual programs yet")
+        from ..equation.pde.base import lookup_parameter
+
+        for prm in extra_parameters:
+            if lookup_parameter(getattr(prm, "name", "")) is not prm:
+                raise ValueError("extra_parameters must be created with PDE.create_parameter (they are matched by name)")
     if models is None:
         raise ValueError("lambdify needs the model whose outputs the expression refers to")
     if isinstance(models, (list, tuple)):
