@@ -23,4 +23,4 @@ for spec in "k_fused_fwd16 1" "k_fused_dx 1" "k_tc2_dw 7"; do
 done
 timeout 300 python tests/tools/timeline_fused.py > gpurun_out/timeline_fwd16.txt 2>&1
 PPSCI_B200_DEBUG_KERNEL=4 timeout 300 python tests/tools/timeline_fused.py > gpurun_out/timeline_fused_dx.txt 2>&1
-timeout 900 python examples/laplace/laplace2d.py --epochs 20000 --output_dir /tmp/out_laplace --result_json gpurun_out/laplace2d_result.json > gpurun_out/laplace2d.log 2>&1
+timeout 600 python examples/laplace/laplace2d.py --epochs 20000 --output_dir /tmp/out_laplace --result_json gpurun_out/laplace2d_result.json > gpurun_out/laplace2d.log 2>&1
