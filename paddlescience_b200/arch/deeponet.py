@@ -34,9 +34,81 @@ def _hidden(num_layers, hidden_size) -> List[int]:
     return [int(hidden_size)] * num_layers
 
 
+class _SubnetReparam:
+    """Host-side reparametrisation of one sub-network around the unchanged native calls, exactly as ``arch.MLP`` does it:
+    ``weight_norm`` (WeightNormLinear on the hidden layers, mlp.py:31-53, 234-246: W = g V / ||V||_col, stored as V in the
+    weight slot and g behind the model's other parameters) and ``skip_connection`` (mlp.py:281-296 as executed: the
+    pre-activation of every even hidden layer i >= 2 is doubled, i.e. effective 2 W_i, 2 b_i)."""
+
+    def __init__(self, widths, lo: int, weight_norm: bool, skip: bool, g_off: int):
+        self.shapes = list(zip(widths[:-1], widths[1:]))
+        self.lo = lo
+        self.weight_norm, self.skip = bool(weight_norm), bool(skip)
+        self.w_off, self.b_off, off = [], [], 0
+        for a, b in self.shapes:
+            self.w_off.append(off)
+            off += a * b
+            self.b_off.append(off)
+            off += b
+        self.n = off
+        n_hidden = len(self.shapes) - 1
+        self.g_off = []  # absolute offsets of the gain vectors of the weight-normalised hidden layers
+        for _, b in (self.shapes[:-1] if self.weight_norm else []):
+            self.g_off.append(g_off)
+            g_off += b
+        self.g_end = g_off
+        self.skip_layers = [i for i in range(n_hidden) if self.skip and i % 2 == 0 and i >= 2]
+        self.active = self.weight_norm or bool(self.skip_layers)
+        self.eff = self.eff_grad = None
+
+    def params(self, flat: torch.Tensor) -> torch.Tensor:
+        raw = flat.data[self.lo: self.lo + self.n]
+        if not self.active:
+            return raw
+        if self.eff is None or self.eff.device != raw.device or self.eff.dtype != raw.dtype:
+            self.eff, self.eff_grad = torch.empty_like(raw), torch.zeros_like(raw)
+        with torch.no_grad():
+            self.eff.copy_(raw)
+            for i, (a, b) in enumerate(self.shapes[:-1]):
+                w = self.eff[self.w_off[i]: self.w_off[i] + a * b].view(a, b)
+                if self.weight_norm:
+                    g = flat.data[self.g_off[i]: self.g_off[i] + b]
+                    w.mul_(g / w.norm(p=2, dim=0, keepdim=True))
+                if i in self.skip_layers:
+                    self.eff[self.w_off[i]: self.b_off[i] + b].mul_(2.0)
+        return self.eff
+
+    def grads(self, flat: torch.Tensor) -> torch.Tensor:
+        return self.eff_grad if self.active else flat.grad[self.lo: self.lo + self.n]
+
+    def finish(self, flat: torch.Tensor):
+        """Chain rule from the effective-weight gradients into (V, g, b); clears the staging buffer."""
+        if not self.active:
+            return
+        with torch.no_grad():
+            eg = self.eff_grad
+            for i in self.skip_layers:
+                a, b = self.shapes[i]
+                eg[self.w_off[i]: self.b_off[i] + b].mul_(2.0)
+            gr = flat.grad[self.lo: self.lo + self.n]
+            gr += eg
+            if self.weight_norm:
+                for i, (a, b) in enumerate(self.shapes[:-1]):
+                    sl = slice(self.w_off[i], self.w_off[i] + a * b)
+                    v = flat.data[self.lo: self.lo + self.n][sl].view(a, b)
+                    g = flat.data[self.g_off[i]: self.g_off[i] + b]
+                    dw = eg[sl].view(a, b)
+                    norm = v.norm(p=2, dim=0, keepdim=True)
+                    dot = (dw * v).sum(dim=0, keepdim=True)
+                    dv = (g / norm) * (dw - v * (dot / (norm * norm)))
+                    gr[sl].view(a, b).add_(dv - dw)
+                    flat.grad[self.g_off[i]: self.g_off[i] + b] += (dot / norm).view(-1)
+            eg.zero_()
+
+
 class DeepONet(base.Arch):
-    """Same arguments as the reference (deeponet.py:71-89).  ``*_skip_connection`` / ``*_weight_norm`` are not
-    supported yet and raise ``NotImplementedError``."""
+    """Same arguments as the reference (deeponet.py:71-89), including ``*_skip_connection`` / ``*_weight_norm`` (host-side
+    reparametrisations of the sub-networks, like ``arch.MLP``)."""
 
     def __init__(
         self,
@@ -59,10 +131,9 @@ class DeepONet(base.Arch):
         dtype: torch.dtype = torch.float32,
     ):
         super().__init__()
-        for flag, name in ((branch_skip_connection, "branch_skip_connection"), (trunk_skip_connection, "trunk_skip_connection"),
-                           (branch_weight_norm, "branch_weight_norm"), (trunk_weight_norm, "trunk_weight_norm")):
-            if flag:
-                raise NotImplementedError(f"DeepONet({name}=True) is not supported yet")
+        for wn, sk, name in ((branch_weight_norm, branch_skip_connection, "branch"), (trunk_weight_norm, trunk_skip_connection, "trunk")):
+            if wn and sk:  # the reference picks WeightNormLinear first and then applies the skip to it (mlp.py:238-296)
+                raise NotImplementedError(f"DeepONet({name}_weight_norm=True, {name}_skip_connection=True) is not supported yet")
         self.u_key, self.y_key = u_key, y_key
         self.input_keys = (u_key, y_key)
         self.output_keys = (G_key,)
@@ -79,7 +150,10 @@ class DeepONet(base.Arch):
         t0 = (nb + 3) // 4 * 4
         self._t_rng = (t0, t0 + nt)
         self._bias_off = (t0 + nt + 3) // 4 * 4
-        self.flat = nn.Parameter(torch.zeros(self._bias_off + (1 if self.use_bias else 0), dtype=dtype))
+        g0 = self._bias_off + (1 if self.use_bias else 0)
+        self._rb = _SubnetReparam(bw, 0, branch_weight_norm, branch_skip_connection, g0)
+        self._rt = _SubnetReparam(tw, t0, trunk_weight_norm, trunk_skip_connection, self._rb.g_end)
+        self.flat = nn.Parameter(torch.zeros(self._rt.g_end, dtype=dtype))
         self.reset_parameters()
         self._plans = None
 
@@ -101,6 +175,9 @@ class DeepONet(base.Arch):
                 for _, (a, b), w0, w1 in self._layers(which):
                     lim = math.sqrt(6.0 / (a + b))
                     self.flat.data[w0:w1] = ((torch.rand(a * b, dtype=torch.float64) * 2 - 1) * lim).to(self.flat.dtype)
+            for r in (self._rb, self._rt):  # WeightNormLinear._init_weights: g = 1
+                for i, (a, b) in enumerate(r.shapes[:-1] if r.weight_norm else []):
+                    self.flat.data[r.g_off[i]: r.g_off[i] + b] = 1
 
     @property
     def dtype(self) -> torch.dtype:
@@ -108,9 +185,13 @@ class DeepONet(base.Arch):
 
     def state_dict(self, *args, **kwargs):  # reference-style keys
         out = OrderedDict()
-        for which in ("branch_net", "trunk_net"):
-            for name, (a, b), w0, w1 in self._layers(which):
-                out[f"{name}.weight"] = self.flat.data[w0:w1].view(a, b).detach().clone()
+        for which, r in (("branch_net", self._rb), ("trunk_net", self._rt)):
+            for i, (name, (a, b), w0, w1) in enumerate(self._layers(which)):
+                if r.weight_norm and i < len(r.g_off):  # WeightNormLinear: weight_v / weight_g (mlp.py:31-53)
+                    out[f"{name}.weight_v"] = self.flat.data[w0:w1].view(a, b).detach().clone()
+                    out[f"{name}.weight_g"] = self.flat.data[r.g_off[i]: r.g_off[i] + b].detach().clone()
+                else:
+                    out[f"{name}.weight"] = self.flat.data[w0:w1].view(a, b).detach().clone()
                 out[f"{name}.bias"] = self.flat.data[w1: w1 + b].detach().clone()
         if self.use_bias:
             out["b"] = self.flat.data[self._bias_off: self._bias_off + 1].detach().clone()
@@ -119,9 +200,13 @@ class DeepONet(base.Arch):
     def load_state_dict(self, state_dict, strict: bool = True):
         missing = []
         with torch.no_grad():
-            for which in ("branch_net", "trunk_net"):
-                for name, (a, b), w0, w1 in self._layers(which):
-                    for key, lo, hi in ((f"{name}.weight", w0, w1), (f"{name}.bias", w1, w1 + b)):
+            for which, r in (("branch_net", self._rb), ("trunk_net", self._rt)):
+                for i, (name, (a, b), w0, w1) in enumerate(self._layers(which)):
+                    wn = r.weight_norm and i < len(r.g_off)
+                    slots = [(f"{name}.weight_v" if wn else f"{name}.weight", w0, w1), (f"{name}.bias", w1, w1 + b)]
+                    if wn:
+                        slots.append((f"{name}.weight_g", r.g_off[i], r.g_off[i] + b))
+                    for key, lo, hi in slots:
                         if key not in state_dict:
                             missing.append(key)
                             continue
@@ -151,8 +236,8 @@ class DeepONet(base.Arch):
         dt = self.flat.dtype
         u = x[self.u_key].to(dt)
         y = x[self.y_key].to(dt)
-        b = pb.forward({self.u_key: u}, self.flat.data[self._b_rng[0]: self._b_rng[1]], want_jets=True, want_residuals=False)[0][0]
-        t = pt.forward({self.y_key: y}, self.flat.data[self._t_rng[0]: self._t_rng[1]], want_jets=True, want_residuals=False)[0][0]
+        b = pb.forward({self.u_key: u}, self._rb.params(self.flat), want_jets=True, want_residuals=False)[0][0]
+        t = pt.forward({self.y_key: y}, self._rt.params(self.flat), want_jets=True, want_residuals=False)[0][0]
         return u, y, b, t
 
     def _combine(self, b: torch.Tensor, t: torch.Tensor, bias) -> torch.Tensor:
@@ -211,8 +296,8 @@ class DeepONet(base.Arch):
         coef = float(loss_fn.weight_of(key) if hasattr(loss_fn, "weight_of") else 1.0) * (1.0 / n if red == "mean" else 1.0)
         pb, pt = self._get_plans()
         lib = pb.lib
-        pbr, ptr_ = flat.data[self._b_rng[0]: self._b_rng[1]], flat.data[self._t_rng[0]: self._t_rng[1]]
-        gbr, gtr = flat.grad[self._b_rng[0]: self._b_rng[1]], flat.grad[self._t_rng[0]: self._t_rng[1]]
+        pbr, ptr_ = self._rb.params(flat), self._rt.params(flat)  # effective [W | b] under weight_norm / skip_connection
+        gbr, gtr = self._rb.grads(flat), self._rt.grads(flat)
         loss_acc = torch.zeros(1, dtype=torch.float64, device=dev)
         bias = flat.data[self._bias_off: self._bias_off + 1] if self.use_bias else None
         dbias = flat.grad[self._bias_off: self._bias_off + 1] if self.use_bias else None
@@ -232,4 +317,6 @@ class DeepONet(base.Arch):
             lib.check(rc, "deeponet_head")
             pb.values_bwd_kept(pbr, gbr, bf)  # bf / tf now hold dL/d(branch), dL/d(trunk)
             pt.values_bwd_kept(ptr_, gtr, tf)
+        self._rb.finish(flat)
+        self._rt.finish(flat)
         return {key: loss_acc[0].to(dt)}

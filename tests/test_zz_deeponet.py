@@ -12,9 +12,9 @@ from oracle import ppsci_oracle as O
 from paddlescience_b200.engine import binding as B
 
 
-def _setup(dtype, device, n, num_loc, feats, hidden, seed=5, weights=True):
+def _setup(dtype, device, n, num_loc, feats, hidden, seed=5, weights=True, **options):
     ppsci.utils.misc.set_random_seed(seed)
-    model = ppsci.arch.DeepONet("u", "y", "G", num_loc, feats, None, None, tuple(hidden), tuple(hidden), dtype=dtype)
+    model = ppsci.arch.DeepONet("u", "y", "G", num_loc, feats, None, None, tuple(hidden), tuple(hidden), dtype=dtype, **options)
     with torch.no_grad():
         model.flat.data += 0.05 * torch.randn_like(model.flat.data)
     model.to(device)
@@ -29,14 +29,31 @@ def _setup(dtype, device, n, num_loc, feats, hidden, seed=5, weights=True):
     return model, cst, data
 
 
+def _effective(model, raw, r):
+    """Independent restatement of the sub-network reparametrisation: W = g V / ||V||_col on weight-normalised hidden
+    layers (mlp.py:31-53), doubled pre-activation at even hidden layers >= 2 under skip_connection (mlp.py:281-296)."""
+    sub = raw[r.lo: r.lo + r.n]
+    parts = []
+    for i, (a, b) in enumerate(r.shapes):
+        w = sub[r.w_off[i]: r.w_off[i] + a * b].view(a, b)
+        bias = sub[r.b_off[i]: r.b_off[i] + b]
+        if r.weight_norm and i < len(r.shapes) - 1:
+            g = raw[r.g_off[i]: r.g_off[i] + b]
+            w = g * w / torch.sqrt((w * w).sum(dim=0, keepdim=True))
+        if i in r.skip_layers:
+            w, bias = 2 * w, 2 * bias
+        parts += [w.reshape(-1), bias]
+    return torch.cat(parts)
+
+
 def _oracle(model, cst, hidden, weights=True):
     ds = cst.data_loader.loader  # the tensors the constraint actually delivers (weights are stored in the default dtype)
     data = {"u": ds.input["u"].cpu(), "y": ds.input["y"].cpu(), "G": ds.label["G"].cpu(),
             "w": ds.weight["G"].cpu() if weights else None}
     od = O.OracleDeepONet(model.num_loc, model.num_features, hidden, hidden)
     raw = model.flat.detach().cpu().double().clone().requires_grad_(True)
-    pb = raw[model._b_rng[0]: model._b_rng[1]]
-    pt = raw[model._t_rng[0]: model._t_rng[1]]
+    pb = _effective(model, raw, model._rb)
+    pt = _effective(model, raw, model._rt)
     b = raw[model._bias_off: model._bias_off + 1]
     g = od(pb, pt, b, torch.as_tensor(data["u"]).double(), torch.as_tensor(data["y"]).double())
     sq = (g - torch.as_tensor(data["G"]).double()) ** 2
@@ -67,7 +84,7 @@ def test_constructor_layout_and_unsupported_flags():
     m2.load_state_dict(sd)
     np.testing.assert_array_equal(m2.flat.data.numpy(), m.flat.data.numpy())
     with pytest.raises(NotImplementedError):
-        ppsci.arch.DeepONet("u", "y", "G", 10, 8, 1, 1, 8, 8, branch_weight_norm=True)
+        ppsci.arch.DeepONet("u", "y", "G", 10, 8, 1, 1, 8, 8, branch_weight_norm=True, branch_skip_connection=True)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m({"u": torch.zeros(3, 100), "y": torch.zeros(3, 1)})
 
@@ -89,6 +106,33 @@ def test_fused_training_call_through_emulated_kernels_matches_oracle(monkeypatch
     np.testing.assert_allclose(model.flat.grad.numpy(), 2 * grad.numpy(), rtol=1e-9, atol=1e-13 * float(grad.abs().max()))
 
 
+@pytest.mark.parametrize("options", [dict(branch_weight_norm=True, trunk_weight_norm=True),
+                                     dict(branch_skip_connection=True, trunk_skip_connection=True),
+                                     dict(branch_weight_norm=True, trunk_skip_connection=True)])
+def test_subnet_weight_norm_and_skip_connection_through_emulated_kernels(monkeypatch, options):
+    """``*_weight_norm`` / ``*_skip_connection`` (deeponet.py:96-119 hands them to the two MLPs): host-side
+    reparametrisation around the unchanged native calls, checked against the oracle with the reparametrisation under
+    autograd; reference-style checkpoint keys."""
+    from tests.emul.build_emul import build
+
+    monkeypatch.setattr(B, "_default", B.Library(build()))
+    hidden = [12, 12, 12]
+    model, cst, data = _setup(torch.float64, "cpu", 41, 7, 9, hidden, **options)
+    with torch.no_grad():
+        model.flat.data += 0.05 * torch.randn_like(model.flat.data)  # gains off 1
+    losses_all, _ = _train_forward(model, cst, "cpu", torch.float64)
+    _, loss, grad = _oracle(model, cst, hidden)
+    assert abs(float(losses_all["G"]) - loss) <= 1e-12 * abs(loss)
+    np.testing.assert_allclose(model.flat.grad.numpy(), grad.numpy(), rtol=1e-8, atol=1e-12 * float(grad.abs().max()))
+    sd = model.state_dict()
+    if options.get("branch_weight_norm"):
+        assert "branch_net.linears.0.weight_v" in sd and "branch_net.linears.0.weight_g" in sd and "branch_net.last_fc.weight" in sd
+    m2 = ppsci.arch.DeepONet("u", "y", "G", 7, 9, None, None, tuple(hidden), tuple(hidden), dtype=torch.float64, **options)
+    m2.load_state_dict(sd)
+    sd2 = m2.state_dict()  # (the flat buffer has alignment gaps between the sub-networks that no key covers)
+    assert list(sd2) == list(sd) and all(torch.equal(sd2[k], sd[k]) for k in sd)
+
+
 def test_wide_output_layer_on_the_emulated_tensor_core_kernels(monkeypatch):
     """The sub-networks end in ``num_features`` (128) units: that output layer and its dW run on the tensor-core kernels
     (fp32, forced here with backend 2 because the emulated tcgen05 path runs on request only), like the hidden layers."""
@@ -108,9 +152,10 @@ def test_wide_output_layer_on_the_emulated_tensor_core_kernels(monkeypatch):
 
 
 @pytest.mark.gpu
-def test_cfg5_shapes_on_gpu_match_oracle():
+@pytest.mark.parametrize("options", [{}, dict(branch_weight_norm=True, trunk_skip_connection=True)])
+def test_cfg5_shapes_on_gpu_match_oracle(options):
     hidden = [128, 128, 128]
-    model, cst, data = _setup(torch.float32, "cuda", 4096, 100, 128, hidden)
+    model, cst, data = _setup(torch.float32, "cuda", 4096, 100, 128, hidden, **options)
     g = model({"u": torch.as_tensor(data["u"], dtype=torch.float32, device="cuda"),
                "y": torch.as_tensor(data["y"], dtype=torch.float32, device="cuda")})["G"]
     losses_all, _ = _train_forward(model, cst, "cuda", torch.float32)
