@@ -1,8 +1,9 @@
 from .base import LossAggregator
+from .grad_norm import GradNorm
 from .pcgrad import PCGrad
 from .sum import Sum
 
-__all__ = ["LossAggregator", "Sum", "PCGrad", "build_mtl_aggregator"]
+__all__ = ["LossAggregator", "Sum", "PCGrad", "GradNorm", "build_mtl_aggregator"]
 
 
 def build_mtl_aggregator(cfg):

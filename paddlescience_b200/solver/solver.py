@@ -114,9 +114,9 @@ class Solver:
         self.forward_helper = expression.ExpressionSolver()
         self.forward_helper.nvtx_flag = self.nvtx_flag
         self.loss_aggregator = loss_aggregator or mtl.Sum()
-        if type(self.loss_aggregator).__name__ not in ("Sum", "PCGrad"):
-            raise NotImplementedError("loss aggregators supported by the adjoint kernels: Sum (one fused call), PCGrad "
-                                      "(one call per loss term)")
+        if type(self.loss_aggregator).__name__ not in ("Sum", "PCGrad", "GradNorm"):
+            raise NotImplementedError("loss aggregators supported by the adjoint kernels: Sum (one fused call), PCGrad and "
+                                      "GradNorm (one call per loss term)")
         # compile every constraint's expressions now (solver.py:496-535 does its sympy conversion here)
         for cst in ([] if hasattr(self.model, "fused_train_forward") else self.constraint.values()):
             sample_keys = None

@@ -52,3 +52,43 @@ def test_per_key_gradients_and_projection_match_autograd(monkeypatch):
             grad = grad - torch.clamp(torch.sum(grad * g2) / torch.sum(g2 * g2), max=0.0) * g2
         tot += grad
     np.testing.assert_allclose(model.flat.grad.numpy(), tot.numpy(), rtol=1e-7, atol=1e-12 * float(tot.abs().max()))
+
+
+def test_grad_norm_weights_and_total_gradient_match_the_reference_formulas(monkeypatch):
+    """mtl.GradNorm (ppsci/loss/mtl/grad_norm.py:29-143) on the per-term gradients of the adjoint kernels: the loss and its
+    gradient use the weights from before the step's update; w~ <- m w~ + (1 - m) mean(||g||) / ||g_i|| every update_freq steps."""
+    from tests.emul.build_emul import build
+
+    monkeypatch.setattr(B, "_default", B.Library(build()))
+    ppsci.utils.misc.set_random_seed(7)
+    model = ppsci.arch.MLP(("x", "y"), ("u", "v", "p"), 2, 12, "tanh", dtype=torch.float64)
+    eq = ppsci.equation.NavierStokes(0.1, 1.0, 2, False)
+    rect = ppsci.geometry.Rectangle((0, 0), (1, 1))
+    cst = ppsci.constraint.InteriorConstraint(eq.equations, {"continuity": 0, "momentum_x": 0, "momentum_y": 0}, rect,
+                                              {"dataset": "IterableNamedArrayDataset", "iters_per_epoch": 1, "batch_size": 30},
+                                              ppsci.loss.MSELoss("mean"), name="EQ")
+    ds = cst.data_loader.loader
+    inp = {k: v.double() for k, v in ds.input.items()}
+    lab = {k: v.double() for k, v in ds.label.items()}
+    fh = ppsci.utils.ExpressionSolver()
+    la, _, gk = fh.train_forward((cst.output_expr,), [inp], model, {"EQ": cst}, [lab], [None], per_key_grads=True)
+    agg = ppsci.loss.mtl.GradNorm(model, num_losses=3, update_freq=2, momentum=0.9, init_weights=[1.0, 2.0, 0.5])
+    keys = list(la)
+    w0 = torch.tensor([1.0, 2.0, 0.5], dtype=torch.float64)
+    a = agg(la, 0)  # step 0: an update step
+    assert float(a.loss) == pytest.approx(float(sum(w0[i] * la[k] for i, k in enumerate(keys))), rel=1e-12)
+    a.set_grads(gk)
+    a.backward()
+    want = sum(w0[i] * gk[k] for i, k in enumerate(keys))
+    np.testing.assert_allclose(model.flat.grad.numpy(), want.numpy(), rtol=1e-12)
+    norms = torch.stack([gk[k].norm() for k in keys])
+    w1 = 0.9 * w0 + 0.1 * (norms.mean() / norms)
+    np.testing.assert_allclose(agg.weight.double().numpy(), w1.numpy(), rtol=1e-6)
+    model.flat.grad.zero_()
+    a = agg(la, 1)  # step 1: no update, the loss uses w1
+    a.set_grads(gk)
+    a.backward()
+    np.testing.assert_allclose(agg.weight.double().numpy(), w1.numpy(), rtol=1e-6)
+    np.testing.assert_allclose(model.flat.grad.numpy(), sum(agg.weight[i].double() * gk[k] for i, k in enumerate(keys)).numpy(), rtol=1e-6)
+    with pytest.raises(ValueError):
+        ppsci.loss.mtl.GradNorm(model, num_losses=2, init_weights=[1.0])
