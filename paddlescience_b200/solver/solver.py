@@ -94,6 +94,11 @@ class Solver:
             # the native library allocates / launches on the CURRENT device (plan_create: cudaGetDevice + cudaMalloc)
             torch.cuda.set_device(self.device)
             self.model.to(self.device)
+            for eq in (self.equation or {}).values():  # learnable equation scalars live beside the model (paddle creates them there)
+                for q in getattr(eq, "learnable_parameters", ()):
+                    q.data = q.data.to(self.device)
+                    if q.grad is not None:
+                        q.grad = q.grad.to(self.device)
         else:
             self.device = torch.device("cpu")  # construction / host logic only; train() raises
         for cst in self.constraint.values():

@@ -131,3 +131,36 @@ def test_learnable_parameters_on_gpu_match_oracle_and_train(dtype, tol):
         data[p.name] = p.detach().cpu().double()
     ref = O.eval_expr(pde.equations["f"], data).detach()
     assert float((res.cpu().double() - ref).norm() / ref.norm()) <= (1e-11 if dtype == torch.float64 else 5e-6)
+
+
+@pytest.mark.gpu
+def test_solver_trains_model_and_equation_parameters_and_checkpoints_them(tmp_path):
+    """Inverse problem through ``Solver.train``: data generated with known (k1, k2), the optimizer over (model, equation)
+    moves the equation's learnable parameters, and the checkpoint carries them (``.pdeqn``, like the reference's
+    equation state dict, ppsci/utils/save_load.py)."""
+    ppsci.utils.misc.set_random_seed(3)
+    model = ppsci.arch.MLP(("t_f",), ("eta",), 3, 32, "tanh")
+    pde = ppsci.equation.Vibration(1.0, 0.0, 0.0)
+    # the reference's VIV example feeds measured (t_f -> eta, f) pairs through a SupervisedConstraint whose output_expr holds
+    # the network output and the equation (examples/fsi/viv.py)
+    n = 512
+    t = np.random.rand(n, 1).astype(np.float32)
+    eq_cst = ppsci.constraint.SupervisedConstraint(
+        {"dataset": {"name": "IterableNamedArrayDataset", "input": {"t_f": t},
+                     "label": {"eta": np.sin(3 * t).astype(np.float32), "f": np.full((n, 1), 0.5, np.float32)}}, "batch_size": n},
+        ppsci.loss.MSELoss("mean"), {"eta": lambda out: out["eta"], **pde.equations}, name="EQ")
+    opt = ppsci.optimizer.Adam(5e-3)((model, pde))
+    solver = ppsci.solver.Solver(model, {"EQ": eq_cst}, str(tmp_path), opt, epochs=1, iters_per_epoch=40, equation={"viv": pde},
+                                 save_freq=1)
+    k_before = [float(p.detach()) for p in pde.parameters()]
+    w_before = model.flat.detach().clone()
+    solver.train()
+    k_after = [float(p.detach()) for p in pde.parameters()]
+    assert all(abs(a - b) > 1e-3 for a, b in zip(k_after, k_before)), (k_before, k_after)
+    assert float((model.flat.detach() - w_before).abs().max()) > 0
+    import os
+
+    eqn = [f for f in os.listdir(os.path.join(str(tmp_path), "checkpoints")) if f.endswith(".pdeqn")]
+    assert eqn
+    sd = torch.load(os.path.join(str(tmp_path), "checkpoints", "latest.pdeqn"))
+    assert [float(v) for v in sd["viv"].values()] == pytest.approx(k_after)
