@@ -114,3 +114,36 @@ def test_fourier_train_forward_on_gpu_matches_oracle(dtype, tol):
     om = O.OracleMLP(("x", "y"), ("u",), [16, 16], "tanh", fourier={"dim": 12, "scale": 1.5})
     ref = om(m.flat.data.detach().cpu().double(), {k: v.cpu().double() for k, v in inp.items()})["u"]
     assert float((out["u"].cpu().double() - ref).norm() / ref.norm()) <= (1e-12 if dtype == torch.float64 else 2e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("to_static", [False, True])
+def test_solver_trains_a_fourier_feature_network(to_static):
+    """Solver.train over an MLP with a FourierEmbedding: the tied kernel is part of ``model.flat`` (stepped by the fused
+    Adam), eagerly and with the iteration replayed as a CUDA graph."""
+    ppsci.utils.misc.set_random_seed(9)
+    model = ppsci.arch.MLP(("x", "y"), ("u",), 3, 32, "tanh", fourier={"dim": 32, "scale": 1.0})
+    eq = ppsci.equation.Laplace(2)
+    rect = ppsci.geometry.Rectangle((0, 0), (1, 1))
+    cfg = {"dataset": "IterableNamedArrayDataset", "iters_per_epoch": 1}
+    pde = ppsci.constraint.InteriorConstraint(eq.equations, {"laplace": 0}, rect, {**cfg, "batch_size": 1024},
+                                              ppsci.loss.MSELoss("mean"), name="EQ")
+    bc = ppsci.constraint.BoundaryConstraint({"u": lambda out: out["u"]}, {"u": lambda d: d["x"] ** 2 - d["y"] ** 2}, rect,
+                                             {**cfg, "batch_size": 256}, ppsci.loss.MSELoss("mean"), name="BC")
+    solver = ppsci.solver.Solver(model, {"EQ": pde, "BC": bc}, None, ppsci.optimizer.Adam(2e-3)(model), epochs=1,
+                                 iters_per_epoch=60, equation={"lap": eq}, to_static=to_static)
+    k0 = model.fourier_kernel.detach().clone()
+    fh = ppsci.utils.ExpressionSolver()
+
+    def total_loss():
+        out = fh.train_forward(tuple(c.output_expr for c in (pde, bc)),
+                               [{k: v for k, v in c.data_loader.loader.input.items()} for c in (pde, bc)], model,
+                               {"EQ": pde, "BC": bc}, [c.data_loader.loader.label for c in (pde, bc)], [None, None])[0]
+        model.flat.grad.zero_()
+        return float(sum(out.values()))
+
+    l0 = total_loss()
+    solver.train()
+    l1 = total_loss()
+    assert l1 < 0.5 * l0, (l0, l1)
+    assert float((model.fourier_kernel.detach() - k0).abs().max()) > 1e-4  # the kernel is trained
