@@ -115,6 +115,9 @@ class Solver:
             # Paddle's DataParallel broadcasts rank 0's parameters at wrap time (solver.py:299-310); ranks seeded
             # differently would otherwise train diverging replicas without any error
             dist.broadcast(self.model.flat.data, src=0)
+            for eq in (self.equation or {}).values():  # the equations are wrapped the same way (paddle.DataParallel around every equation with learnable parameters, like the model)
+                for q in getattr(eq, "learnable_parameters", ()):
+                    dist.broadcast(q.data, src=0)
 
         self.forward_helper = expression.ExpressionSolver()
         self.forward_helper.nvtx_flag = self.nvtx_flag
