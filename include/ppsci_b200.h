@@ -231,7 +231,9 @@ int ppsci_b200_values_fwd_bwd(ppsci_plan* plan, const void* const* x_cols, const
  * training call does (everything the adjoint reads stays in `workspace`) and writes the network outputs
  * y_out[n_points][n_out]; values_bwd_kept then runs ONLY the adjoint from that stash — the forward is not recomputed.
  * Both calls take at most plan_chunk_points points, the same inputs / params / workspace, and nothing else may use the
- * workspace in between. */
+ * workspace in between.  In-place use (no copies): y_out may be NULL — the outputs are then read at
+ * workspace + plan_stash_offset(plan, n_points, n_layers) as [n_points][ld], ld = n_out rounded up to a multiple of 4 —
+ * and ybar may be workspace + plan_stash_offset(plan, n_points, 300) (same layout), written by the caller's head kernel. */
 int32_t ppsci_b200_plan_chunk_points(const ppsci_plan* plan);
 int ppsci_b200_values_fwd_keep(ppsci_plan* plan, const void* const* x_cols, const void* const* aux_cols,
                                int64_t n_points, const void* params, void* y_out, void* workspace,

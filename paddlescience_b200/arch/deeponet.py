@@ -306,17 +306,23 @@ class DeepONet(base.Arch):
         stream = torch.cuda.current_stream(dev).cuda_stream if dev.type == "cuda" else 0
         for s0 in range(0, n, chunk):
             sl = slice(s0, min(n, s0 + chunk))
-            bf = pb.values_fwd_keep({self.u_key: u[sl]}, pbr)
-            tf = pt.values_fwd_keep({self.y_key: y[sl]}, ptr_)
+            if self.num_features % 4 == 0:
+                # in place: the head reads the features where the forward left them (workspace) and writes the adjoints
+                # where the adjoint call expects them — no copy kernels in between
+                bf, bbar = pb.values_fwd_keep_inplace({self.u_key: u[sl]}, pbr)
+                tf, tbar = pt.values_fwd_keep_inplace({self.y_key: y[sl]}, ptr_)
+            else:
+                bf = bbar = pb.values_fwd_keep({self.u_key: u[sl]}, pbr)
+                tf = tbar = pt.values_fwd_keep({self.y_key: y[sl]}, ptr_)
             m = bf.shape[0]
             rc = lib.lib.ppsci_b200_deeponet_head(
                 B.F64 if dt == torch.float64 else B.F32, act, bf.data_ptr(), tf.data_ptr(),
                 bias.data_ptr() if bias is not None else None, label[sl].data_ptr(),
                 weight[sl].data_ptr() if weight is not None else None, m, self.num_features, coef, None,
-                loss_acc.data_ptr(), bf.data_ptr(), tf.data_ptr(), dbias.data_ptr() if dbias is not None else None, stream)
+                loss_acc.data_ptr(), bbar.data_ptr(), tbar.data_ptr(), dbias.data_ptr() if dbias is not None else None, stream)
             lib.check(rc, "deeponet_head")
-            pb.values_bwd_kept(pbr, gbr, bf)  # bf / tf now hold dL/d(branch), dL/d(trunk)
-            pt.values_bwd_kept(ptr_, gtr, tf)
+            pb.values_bwd_kept(pbr, gbr, bbar)  # bbar / tbar hold dL/d(branch), dL/d(trunk)
+            pt.values_bwd_kept(ptr_, gtr, tbar)
         self._rb.finish(flat)
         self._rt.finish(flat)
         return {key: loss_acc[0].to(dt)}

@@ -377,6 +377,7 @@ extern "C" int64_t ppsci_b200_plan_stash_offset(const ppsci_plan* P, int64_t n_p
   carve(P, nc, &cv);
   if (layer > 100 && layer - 100 < P->spec.n_layers) return (int64_t)cv.zb[layer - 100];   // debug: Zbar_l (fused dx chain)
   if (layer > 200 && layer - 200 < P->spec.n_layers) return (int64_t)cv.a[layer - 200];    // debug: a-stash of layer l
+  if (layer == 300) return (int64_t)cv.ybar;  // output adjoints Ybar (values_bwd_kept accepts this address: no seeding copy)
   if (layer < 1 || layer > P->spec.n_layers) return -1;
   return (int64_t)(layer < P->spec.n_layers ? cv.z[layer] : cv.y);
 }
@@ -879,7 +880,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
       P->launches++;
     }
     if (!do_bwd || a.phase == 1) continue;
-    if (a.ybar_in) {  // output adjoints from the caller instead of the residual head
+    if (a.ybar_in && a.ybar_in != static_cast<const void*>(ws + cv.ybar)) {  // output adjoints from the caller (not already in place)
       const long long tot = (long long)nc * P->ld[L];
       auto ks = k_seed_ybar<T>;
       ProfScope ps_(P, CLS_MISC, st);
@@ -1275,7 +1276,8 @@ extern "C" int32_t ppsci_b200_plan_chunk_points(const ppsci_plan* P) { return P 
 
 extern "C" int ppsci_b200_values_fwd_keep(ppsci_plan* plan, const void* const* x_cols, const void* const* aux_cols, int64_t n_points,
                                           const void* params, void* y_out, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!y_out) return fail("values_fwd_keep: null y_out");
+  // y_out may be NULL: the caller then reads the outputs in place, [n_points][ld] at plan_stash_offset(n_layers) of the
+  // workspace (no copy; ld = n_out rounded up to a multiple of 4)
   if (plan && n_points > plan->chunk) return fail("values_fwd_keep: at most plan_chunk_points points per call");
   CallArgs a;
   memset(&a, 0, sizeof(a));

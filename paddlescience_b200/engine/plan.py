@@ -333,6 +333,31 @@ class ResidualPlan:
         self.lib.check(rc, "values_fwd_keep")
         return y
 
+    def values_fwd_keep_inplace(self, inputs: Dict[str, torch.Tensor], params: torch.Tensor):
+        """``values_fwd_keep`` without the output copy: returns (y, ybar) VIEWS [N, n_out] into this plan's workspace (the
+        network outputs, and the buffer the caller's head writes the output adjoints into before ``values_bwd_kept``).
+        Needs n_out % 4 == 0 (row pitch = n_out); otherwise use ``values_fwd_keep``."""
+        if self.n_out % 4:
+            raise ValueError("in-place outputs need n_out to be a multiple of 4")
+        device = params.device
+        n, xs = self._inputs(inputs, device)
+        auxs = self._aux_tensors(inputs, self.compiled.aux_keys, n, device)
+        ws = self._workspace(n, device)
+        wptr, wbytes = self._aligned(ws)
+        self._kept = (xs, auxs, n)
+        rc = self.lib.lib.ppsci_b200_values_fwd_keep(self.handle, self._ptr_array(xs, len(xs)), self._ptr_array(auxs, len(auxs)), n,
+                                                     params.data_ptr(), None, wptr, wbytes, self._stream(device))
+        self.lib.check(rc, "values_fwd_keep")
+        base = wptr - ws.data_ptr()
+        es = 8 if self.dtype == torch.float64 else 4
+        views = []
+        for code in (len(self.compiled.net.widths) - 1, 300):  # output jets Y, output adjoints Ybar
+            off = int(self.lib.lib.ppsci_b200_plan_stash_offset(self.handle, n, code))
+            if off < 0:
+                raise RuntimeError("plan_stash_offset failed")
+            views.append(ws[base + off: base + off + n * self.n_out * es].view(self.dtype).view(n, self.n_out))
+        return views[0], views[1]
+
     def values_bwd_kept(self, params: torch.Tensor, grads: torch.Tensor, ybar: torch.Tensor):
         """Adjoint of the most recent ``values_fwd_keep`` (its forward is NOT recomputed); accumulates into ``grads``."""
         xs, auxs, n = self._kept
