@@ -391,10 +391,16 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    don_launches0 = sum(p.two_phase_launches for p in model._get_plans()) if plan is None else 0
     t_wall0 = time.perf_counter()
     ms_per_step, losses = timed(step, dev_in, args.steps)
     t_wall = time.perf_counter() - t_wall0
-    launches_per_step = (plan.last_launches if plan else sum(p.last_launches for p in model._get_plans()) + 1) + 1  # + fused Adam
+    if plan is not None:
+        launches_per_step = plan.last_launches + 1  # + fused Adam
+    else:  # DeepONet: every two-phase call of both sub-network plans over the timed steps, + head kernels + fused Adam
+        tp = sum(p.two_phase_launches for p in model._get_plans()) - don_launches0
+        n_slices = (N + min(p.chunk_points for p in model._get_plans()) - 1) // min(p.chunk_points for p in model._get_plans())
+        launches_per_step = tp // args.steps + n_slices + 1
     value = world * N / (ms_per_step * 1e-3)
     log(f"timed region done: {ms_per_step:.2f} ms/step")
 

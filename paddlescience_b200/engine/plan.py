@@ -95,6 +95,7 @@ class ResidualPlan:
             s.pgrad_aux[g] = compiled.pgrad_aux[g]
             s.pgrad_reg[g] = compiled.pgrad_reg[g]
         self._param_grad = None  # fp64 [n_aux] device buffer the head kernel accumulates dLoss/dparameter into
+        self.two_phase_launches = 0  # kernels launched by values_fwd_keep / values_bwd_kept calls so far (bench instrumentation)
         s.n_reg = compiled.n_reg
         s.n_ops = len(compiled.prog)
         flat = [x for op in compiled.prog for x in op]
@@ -331,6 +332,7 @@ class ResidualPlan:
         rc = self.lib.lib.ppsci_b200_values_fwd_keep(self.handle, self._ptr_array(xs, len(xs)), self._ptr_array(auxs, len(auxs)), n,
                                                      params.data_ptr(), y.data_ptr(), wptr, wbytes, self._stream(device))
         self.lib.check(rc, "values_fwd_keep")
+        self.two_phase_launches += self.last_launches
         return y
 
     def values_fwd_keep_inplace(self, inputs: Dict[str, torch.Tensor], params: torch.Tensor):
@@ -348,6 +350,7 @@ class ResidualPlan:
         rc = self.lib.lib.ppsci_b200_values_fwd_keep(self.handle, self._ptr_array(xs, len(xs)), self._ptr_array(auxs, len(auxs)), n,
                                                      params.data_ptr(), None, wptr, wbytes, self._stream(device))
         self.lib.check(rc, "values_fwd_keep")
+        self.two_phase_launches += self.last_launches
         base = wptr - ws.data_ptr()
         es = 8 if self.dtype == torch.float64 else 4
         views = []
@@ -371,6 +374,7 @@ class ResidualPlan:
                                                      params.data_ptr(), grads.data_ptr(), yb.data_ptr(), wptr, wbytes,
                                                      self._stream(device))
         self.lib.check(rc, "values_bwd_kept")
+        self.two_phase_launches += self.last_launches
         self._kept = None
 
     def forward(
