@@ -1,9 +1,11 @@
 from .base import LossAggregator
 from .grad_norm import GradNorm
+from .ntk import NTK
 from .pcgrad import PCGrad
+from .relobralo import Relobralo
 from .sum import Sum
 
-__all__ = ["LossAggregator", "Sum", "PCGrad", "GradNorm", "build_mtl_aggregator"]
+__all__ = ["LossAggregator", "Sum", "PCGrad", "GradNorm", "NTK", "Relobralo", "build_mtl_aggregator"]
 
 
 def build_mtl_aggregator(cfg):

@@ -92,3 +92,46 @@ def test_grad_norm_weights_and_total_gradient_match_the_reference_formulas(monke
     np.testing.assert_allclose(model.flat.grad.numpy(), sum(agg.weight[i].double() * gk[k] for i, k in enumerate(keys)).numpy(), rtol=1e-6)
     with pytest.raises(ValueError):
         ppsci.loss.mtl.GradNorm(model, num_losses=2, init_weights=[1.0])
+
+
+def test_ntk_and_relobralo_weights_follow_the_reference_formulas():
+    """mtl.NTK (ppsci/loss/mtl/ntk.py:28-86, with its cumulative-gradient norms) and mtl.Relobralo
+    (ppsci/loss/mtl/relobralo.py:27-127) on given per-term gradients: host-side logic only."""
+    torch.manual_seed(0)
+
+    class _M:
+        flat = torch.nn.Parameter(torch.zeros(50, dtype=torch.float64))
+
+    m = _M()
+    losses = {"a": torch.tensor(2.0, dtype=torch.float64), "b": torch.tensor(0.5, dtype=torch.float64), "c": torch.tensor(1.5, dtype=torch.float64)}
+    gk = {k: torch.randn(50, dtype=torch.float64) for k in losses}
+    # ---- NTK
+    ntk = ppsci.loss.mtl.NTK(m, num_losses=3, update_freq=1)
+    a = ntk(losses, 0)
+    assert float(a.loss) == pytest.approx(4.0)
+    a.set_grads(gk)
+    a.backward()
+    np.testing.assert_allclose(m.flat.grad.numpy(), (gk["a"] + gk["b"] + gk["c"]).numpy())
+    v = torch.stack([gk["a"].norm(), (gk["a"] + gk["b"]).norm(), (gk["a"] + gk["b"] + gk["c"]).norm()])
+    np.testing.assert_allclose(ntk.weight.double().numpy(), (v.sum() / v).numpy(), rtol=1e-6)
+    m.flat.grad.zero_()
+    a = ntk(list(losses.values()), 1)  # the reference signature takes a list
+    assert float(a.loss) == pytest.approx(float(sum(ntk._used[i].double() * x for i, x in enumerate(losses.values()))))
+    # ---- Relobralo
+    rb = ppsci.loss.mtl.Relobralo(3, alpha=0.9, beta=1.0, tau=1.0, model=m)  # beta = 1: rho = 1 always (no lookback randomness)
+    r = rb(losses, 0)
+    assert float(r.loss) == pytest.approx(4.0)
+    np.testing.assert_allclose(rb.losses_init.double().numpy(), [2.0, 0.5, 1.5])
+    l2 = {"a": torch.tensor(1.0, dtype=torch.float64), "b": torch.tensor(0.6, dtype=torch.float64), "c": torch.tensor(0.3, dtype=torch.float64)}
+    r = rb(l2, 1)
+    s2 = torch.tensor([1.0, 0.6, 0.3])
+    prev = torch.tensor([2.0, 0.5, 1.5])
+    bal = 3 * torch.softmax(s2 / (prev + 1e-8), dim=0)
+    lam = 0.9 * torch.ones(3) + 0.1 * bal
+    np.testing.assert_allclose(rb.lmbda.numpy(), lam.numpy(), rtol=1e-6)
+    assert float(r.loss) == pytest.approx(float((lam.double() * s2.double()).sum()), rel=1e-6)
+    m.flat.grad.zero_()
+    r.set_grads(gk)
+    r.backward()
+    np.testing.assert_allclose(m.flat.grad.numpy(), sum(lam[i].double() * gk[k] for i, k in enumerate(l2)).numpy(), rtol=1e-6)
+    np.testing.assert_allclose(rb.losses_prev.numpy(), s2.numpy())
