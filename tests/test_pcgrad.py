@@ -135,3 +135,41 @@ def test_ntk_and_relobralo_weights_follow_the_reference_formulas():
     r.backward()
     np.testing.assert_allclose(m.flat.grad.numpy(), sum(lam[i].double() * gk[k] for i, k in enumerate(l2)).numpy(), rtol=1e-6)
     np.testing.assert_allclose(rb.losses_prev.numpy(), s2.numpy())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["PCGrad", "GradNorm", "NTK", "Relobralo"])
+def test_solver_trains_with_per_term_gradient_aggregators(name):
+    """Solver.train with the aggregators that consume per-term gradients (one fused call per loss key): the loss goes down and,
+    where the aggregator keeps weights, they move."""
+    ppsci.utils.misc.set_random_seed(4)
+    model = ppsci.arch.MLP(("x", "y"), ("u",), 3, 32, "tanh")
+    eq = ppsci.equation.Laplace(2)
+    rect = ppsci.geometry.Rectangle((0, 0), (1, 1))
+    cfg = {"dataset": "IterableNamedArrayDataset", "iters_per_epoch": 1}
+    pde = ppsci.constraint.InteriorConstraint(eq.equations, {"laplace": 0}, rect, {**cfg, "batch_size": 1024},
+                                              ppsci.loss.MSELoss("mean"), name="EQ")
+    bc = ppsci.constraint.BoundaryConstraint({"u": lambda out: out["u"]}, {"u": lambda d: d["x"] ** 2 - d["y"] ** 2}, rect,
+                                             {**cfg, "batch_size": 256}, ppsci.loss.MSELoss("mean"), name="BC")
+    mtl = ppsci.loss.mtl
+    agg = {"PCGrad": lambda: mtl.PCGrad(model), "GradNorm": lambda: mtl.GradNorm(model, 2, update_freq=5),
+           "NTK": lambda: mtl.NTK(model, 2, update_freq=5), "Relobralo": lambda: mtl.Relobralo(2)}[name]()
+    solver = ppsci.solver.Solver(model, {"EQ": pde, "BC": bc}, None, ppsci.optimizer.Adam(2e-3)(model), epochs=1,
+                                 iters_per_epoch=60, equation={"lap": eq}, loss_aggregator=agg)
+    fh = ppsci.utils.ExpressionSolver()
+
+    def total_loss():
+        out = fh.train_forward(tuple(c.output_expr for c in (pde, bc)),
+                               [dict(c.data_loader.loader.input) for c in (pde, bc)], model, {"EQ": pde, "BC": bc},
+                               [c.data_loader.loader.label for c in (pde, bc)], [None, None])[0]
+        model.flat.grad.zero_()
+        return float(sum(out.values()))
+
+    l0 = total_loss()
+    solver.train()
+    l1 = total_loss()
+    assert l1 < 0.7 * l0, (name, l0, l1)
+    if name in ("GradNorm", "NTK"):
+        assert float((agg.weight - 1).abs().max()) > 1e-3
+    if name == "Relobralo":
+        assert float((agg.lmbda - 1).abs().max()) > 1e-4
