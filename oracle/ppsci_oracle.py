@@ -48,6 +48,10 @@ def get_activation(name: str) -> Callable[[torch.Tensor], torch.Tensor]:
         "identity": lambda x: x,
         "relu": torch.relu,
         "gelu": lambda x: torch.nn.functional.gelu(x),
+        # paddle defaults (activation.py:139-145): nn.ELU(alpha=1.0), nn.SELU(), nn.LeakyReLU(negative_slope=0.01)
+        "elu": lambda x: torch.where(x > 0, x, torch.exp(x) - 1),
+        "selu": lambda x: 1.0507009873554804934193349852946 * torch.where(x > 0, x, 1.6732632423543772848170429916717 * (torch.exp(x) - 1)),
+        "leaky_relu": lambda x: torch.where(x > 0, x, 0.01 * x),
     }
     if name not in table:
         raise ValueError(f"act_name({name}) not found in act_func_dict")

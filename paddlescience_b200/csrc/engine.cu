@@ -179,8 +179,8 @@ extern "C" int ppsci_b200_plan_create(const ppsci_plan_spec* s, ppsci_plan** out
   if (s->widths[0] != s->n_feat) return fail("plan_create: widths[0] must equal n_feat");
   for (int l = 0; l <= s->n_layers; ++l)
     if (s->widths[l] < 1 || s->widths[l] > 4096) return fail("plan_create: layer width out of range");
-  if (s->act < 0 || s->act > PPSCI_ACT_GELU) return fail("plan_create: unknown activation");
-  if (s->act_first < -1 || s->act_first > PPSCI_ACT_GELU) return fail("plan_create: unknown first-layer activation");
+  if (s->act < 0 || s->act > PPSCI_ACT_LAST) return fail("plan_create: unknown activation");
+  if (s->act_first < -1 || s->act_first > PPSCI_ACT_LAST) return fail("plan_create: unknown first-layer activation");
   for (int f = 0; f < (s->dense_in ? 0 : s->n_feat); ++f) {
     if (s->feat_src[f] < 0 || s->feat_src[f] >= s->n_in) return fail("plan_create: feat_src out of range");
     if (s->feat_kind[f] < 0 || s->feat_kind[f] > PPSCI_FEAT_SIN) return fail("plan_create: bad feat_kind");
@@ -1320,7 +1320,7 @@ extern "C" int ppsci_b200_deeponet_head(int32_t dtype, int32_t act, const void* 
                                         void* g_out, double* loss_acc, void* bbar, void* tbar, void* dbias, void* stream) {
   if (!b || !t || n <= 0 || n_features <= 0) return fail("deeponet_head: bad arguments");
   if ((bbar == nullptr) != (tbar == nullptr)) return fail("deeponet_head: bbar and tbar must both be given or both be null");
-  if (act < 0 || act > PPSCI_ACT_GELU) return fail("deeponet_head: unknown activation");
+  if (act < 0 || act > PPSCI_ACT_LAST) return fail("deeponet_head: unknown activation");
   const long long warps = n < 148LL * 64 ? n : 148LL * 64;  // 8 warps per block
   const unsigned blocks = (unsigned)((warps + 7) / 8);
   if (dtype == PPSCI_F64) {

@@ -34,6 +34,9 @@ enum ActId {
   ACT_IDENTITY = 5,
   ACT_RELU = 6,
   ACT_GELU = 7,
+  ACT_ELU = 8,
+  ACT_SELU = 9,
+  ACT_LEAKY_RELU = 10,
 };
 
 template <typename T>
@@ -138,6 +141,28 @@ PPSCI_HD void act_coef(int act, T z0, T& y0, T (&s)[6]) {
       d[3] = phi * z0 * (z2 - T(4));
       d[4] = phi * (T(-4) + z2 * (T(7) - z2));
       d[5] = phi * z0 * (T(18) + z2 * (T(-11) + z2));
+      break;
+    }
+    case ACT_ELU:
+    case ACT_SELU: {  // scale * (x > 0 ? x : alpha (e^x - 1)): every derivative of the negative branch is scale alpha e^x
+      const T scale = act == ACT_SELU ? T(1.0507009873554804934193349852946) : T(1);
+      const T alpha = act == ACT_SELU ? T(1.6732632423543772848170429916717) : T(1);
+      if (z0 > T(0)) {
+        y0 = scale * z0;
+        d[1] = scale;
+        d[2] = d[3] = d[4] = d[5] = T(0);
+      } else {
+        const T e = scale * alpha * m_exp<T>(z0);
+        y0 = e - scale * alpha;
+        d[1] = d[2] = d[3] = d[4] = d[5] = e;
+      }
+      break;
+    }
+    case ACT_LEAKY_RELU: {
+      const T sl = z0 > T(0) ? T(1) : T(0.01);
+      y0 = sl * z0;
+      d[1] = sl;
+      d[2] = d[3] = d[4] = d[5] = T(0);
       break;
     }
     case ACT_IDENTITY:

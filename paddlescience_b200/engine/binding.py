@@ -31,6 +31,9 @@ ACT_IDS = {
     "identity": 5,
     "relu": 6,
     "gelu": 7,
+    "elu": 8,
+    "selu": 9,
+    "leaky_relu": 10,
 }
 
 OPS = {

@@ -54,6 +54,15 @@ def _mixed_exprs():
             "third": u.diff(x, 3) + v.diff(y) * u.diff(y)}
 
 
+def _first_order_exprs():
+    # piecewise-linear activations: every second input derivative of the network vanishes identically and the autograd
+    # oracle (like Paddle) cannot differentiate the resulting constant again — first derivatives only
+    x, y = sp.symbols("x y")
+    u = sp.Function("u")(x, y)
+    v = sp.Function("v")(x, y)
+    return {"div": u.diff(x) + v.diff(y) - u * y, "adv": u * v.diff(x) + sp.sin(x) * u.diff(y)}
+
+
 CASES = {
     # name: dict(in_keys, out_keys, hidden, act, exprs, dtype, periods, reduction, weights, labels_rand, oracle_exprs, ranges, chunk)
     "ns_f32": dict(in_keys=("x", "y"), out_keys=("u", "v", "p"), hidden=[20, 20], act="tanh",
@@ -84,6 +93,13 @@ CASES = {
                                  exprs=_mixed_exprs, dtype=torch.float64),
     "poisson_sigmoid_f64": dict(in_keys=("x", "y"), out_keys=("p",), hidden=[12, 12], act="sigmoid",
                                 exprs=lambda: O.poisson_expr(2), dtype=torch.float64),
+    # the reference's piecewise activations (activation.py:139-145: nn.ELU(), nn.SELU(), nn.LeakyReLU() with paddle's defaults)
+    "ns_elu_f64": dict(in_keys=("x", "y"), out_keys=("u", "v", "p"), hidden=[12, 12], act="elu",
+                       exprs=lambda: O.navier_stokes_expr(0.1, 1.0, 2, False), dtype=torch.float64),
+    "laplace_selu_f32": dict(in_keys=("x", "y"), out_keys=("u",), hidden=[16, 16], act="selu",
+                             exprs=lambda: O.laplace_expr(2), dtype=torch.float32),
+    "first_order_leaky_relu_f64": dict(in_keys=("x", "y"), out_keys=("u", "v"), hidden=[12, 12], act="leaky_relu",
+                                       exprs=_first_order_exprs, dtype=torch.float64),
 }
 
 # shapes served by the tcgen05 kernels (hidden widths multiple of 32/128); CPU emulation skips them
