@@ -49,7 +49,8 @@ enum {
   PPSCI_ACT_ELU = 8,        /* nn.ELU(alpha = 1):  x > 0 ? x : exp(x) - 1 */
   PPSCI_ACT_SELU = 9,       /* nn.SELU: scale * (x > 0 ? x : alpha * (exp(x) - 1)), scale = 1.0507009873554805, alpha = 1.6732632423543772 */
   PPSCI_ACT_LEAKY_RELU = 10, /* nn.LeakyReLU(negative_slope = 0.01) */
-  PPSCI_ACT_LAST = 10
+  PPSCI_ACT_SIREN = 11,     /* Siren(w0 = 30): sin(30 x)  (activation.py:89-101) */
+  PPSCI_ACT_LAST = 11
 };
 
 /* input feature kinds — identity, or PeriodEmbedding (ppsci/arch/mlp.py:95-114) */

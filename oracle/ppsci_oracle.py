@@ -52,6 +52,7 @@ def get_activation(name: str) -> Callable[[torch.Tensor], torch.Tensor]:
         "elu": lambda x: torch.where(x > 0, x, torch.exp(x) - 1),
         "selu": lambda x: 1.0507009873554804934193349852946 * torch.where(x > 0, x, 1.6732632423543772848170429916717 * (torch.exp(x) - 1)),
         "leaky_relu": lambda x: torch.where(x > 0, x, 0.01 * x),
+        "siren": lambda x: torch.sin(30.0 * x),  # Siren(w0=30).forward, activation.py:99-101
     }
     if name not in table:
         raise ValueError(f"act_name({name}) not found in act_func_dict")

@@ -22,6 +22,7 @@ _TORCH_ACT = {
     "tanh": torch.tanh, "sin": torch.sin, "cos": torch.cos, "sigmoid": torch.sigmoid, "silu": torch.nn.functional.silu,
     "swish": torch.nn.functional.silu, "gelu": torch.nn.functional.gelu, "relu": torch.relu, "identity": lambda t: t,
     "elu": torch.nn.functional.elu, "selu": torch.nn.functional.selu, "leaky_relu": torch.nn.functional.leaky_relu,
+    "siren": lambda t: torch.sin(30.0 * t),
 }
 
 

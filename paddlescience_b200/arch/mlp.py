@@ -227,6 +227,10 @@ class MLP(base.Arch):
             for i, (a, b) in enumerate(self._shapes):
                 lim = math.sqrt(6.0 / (a + b))
                 w = (torch.rand(a * b, dtype=torch.float64) * 2 - 1) * lim
+                if self.activation == "siren" and i < len(self._shapes) - 1:
+                    # Siren.init_for_first_layer / init_for_hidden_layer (activation.py:103-136, applied in mlp.py:256-260)
+                    lim = 1.0 / a if i == 0 else math.sqrt(6.0 / a) / 30.0
+                    w = (torch.rand(a * b, dtype=torch.float64) * 2 - 1) * lim
                 self.flat.data[self._w_off[i]: self._w_off[i] + a * b] = w.to(self.flat.dtype)
                 self.flat.data[self._b_off[i]: self._b_off[i] + b] = 0
                 if self._wn_layer(i) and not self.random_weight:  # WeightNormLinear._init_weights: V xavier-uniform, g = 1, bias = 0

@@ -37,6 +37,7 @@ enum ActId {
   ACT_ELU = 8,
   ACT_SELU = 9,
   ACT_LEAKY_RELU = 10,
+  ACT_SIREN = 11,
 };
 
 template <typename T>
@@ -141,6 +142,15 @@ PPSCI_HD void act_coef(int act, T z0, T& y0, T (&s)[6]) {
       d[3] = phi * z0 * (z2 - T(4));
       d[4] = phi * (T(-4) + z2 * (T(7) - z2));
       d[5] = phi * z0 * (T(18) + z2 * (T(-11) + z2));
+      break;
+    }
+    case ACT_SIREN: {  // sin(w0 z), w0 = 30: d^k/dz^k = w0^k sin^(k)(w0 z)
+      const T w0 = T(30);
+      T sn, cs;
+      m_sincos<T>(w0 * z0, &sn, &cs);
+      y0 = sn;
+      const T w2 = w0 * w0;
+      d[1] = w0 * cs; d[2] = -w2 * sn; d[3] = -w2 * w0 * cs; d[4] = w2 * w2 * sn; d[5] = w2 * w2 * w0 * cs;
       break;
     }
     case ACT_ELU:

@@ -34,6 +34,7 @@ ACT_IDS = {
     "elu": 8,
     "selu": 9,
     "leaky_relu": 10,
+    "siren": 11,
 }
 
 OPS = {

@@ -98,6 +98,8 @@ CASES = {
                        exprs=lambda: O.navier_stokes_expr(0.1, 1.0, 2, False), dtype=torch.float64),
     "laplace_selu_f32": dict(in_keys=("x", "y"), out_keys=("u",), hidden=[16, 16], act="selu",
                              exprs=lambda: O.laplace_expr(2), dtype=torch.float32),
+    "laplace_siren_f64": dict(in_keys=("x", "y"), out_keys=("u",), hidden=[12, 12], act="siren",
+                              exprs=lambda: O.laplace_expr(2), dtype=torch.float64, siren_init=True),
     "first_order_leaky_relu_f64": dict(in_keys=("x", "y"), out_keys=("u", "v"), hidden=[12, 12], act="leaky_relu",
                                        exprs=_first_order_exprs, dtype=torch.float64),
 }
@@ -207,7 +209,10 @@ def run_case(name, n: int, library=None, device="cpu", backend: int = 0, seed: i
             inputs[k] = (torch.rand(n, 1, dtype=torch.float64) * (hi - lo) + lo).to(dtype)
     om = O.OracleMLP(c["in_keys"], c["out_keys"], c["hidden"], c["act"], periods)
     params = O.xavier_uniform_params(om.widths, 1, torch.float64)
-    params = (params + 0.1 * torch.randn_like(params)).to(dtype)
+    params = (params + 0.1 * torch.randn_like(params))
+    if c.get("siren_init"):  # weights on the scale Siren's initialisers use (sqrt(6 / in) / w0, activation.py:103-136)
+        params = params / 30.0
+    params = params.to(dtype)
     labels = {k: (torch.randn(n, 1, dtype=torch.float64).to(dtype) if c.get("labels_rand") else torch.zeros(n, 1, dtype=dtype))
               for k in cr.names}
     wts = {k: torch.rand(n, 1, dtype=torch.float64).to(dtype) for k in cr.names} if c.get("weights") else None

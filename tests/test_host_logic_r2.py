@@ -158,3 +158,38 @@ def test_graph_step_signature_and_adam_scalars():
         model, world_size, update_freq, optimizer, loss_aggregator = m, 1, 1, opt, ppsci.loss.mtl.Sum()
 
     assert "CUDA" in GraphedTrainStep(S()).unsupported_reason()  # CPU parameters: never captured, never a CPU fallback
+
+
+def test_siren_activation_initialisers_and_train_forward(monkeypatch):
+    """MLP(activation="siren"): sin(30 z) in the jet kernels with Siren's own initialisers (activation.py:89-136,
+    applied per hidden layer in mlp.py:256-260: first layer U(-1/in, 1/in), later hidden layers U(+-sqrt(6/in)/30),
+    zero biases, last_fc untouched); one train_forward against the oracle through the CPU emulation of the kernels."""
+    import math
+
+    import numpy as np
+
+    from oracle import ppsci_oracle as O
+    from paddlescience_b200.engine import binding as B
+    from tests.emul.build_emul import build
+
+    monkeypatch.setattr(B, "_default", B.Library(build()))
+    ppsci.utils.misc.set_random_seed(3)
+    m = ppsci.arch.MLP(("x", "y"), ("u",), 3, 24, "siren", dtype=torch.float64)
+    bounds = [1.0 / 2, math.sqrt(6.0 / 24) / 30.0, math.sqrt(6.0 / 24) / 30.0, math.sqrt(6.0 / (24 + 1))]
+    for i, ((a, b), lim) in enumerate(zip(m._shapes, bounds)):
+        w = m.flat.data[m._w_off[i]: m._w_off[i] + a * b]
+        assert float(w.abs().max()) <= lim and float(w.abs().max()) > 0.6 * lim, (i, float(w.abs().max()), lim)
+        assert float(m.flat.data[m._b_off[i]: m._b_off[i] + b].abs().max()) == 0.0
+    eq = ppsci.equation.Laplace(2)
+    rect = ppsci.geometry.Rectangle((0, 0), (1, 1))
+    cst = ppsci.constraint.InteriorConstraint(eq.equations, {"laplace": 0}, rect,
+                                              {"dataset": "IterableNamedArrayDataset", "iters_per_epoch": 1, "batch_size": 30},
+                                              ppsci.loss.MSELoss("mean"), name="EQ")
+    ds = cst.data_loader.loader
+    inp = {k: v.double() for k, v in ds.input.items()}
+    lab = {k: v.double() for k, v in ds.label.items()}
+    losses_all, _ = ppsci.utils.ExpressionSolver().train_forward((cst.output_expr,), [inp], m, {"EQ": cst}, [lab], [None])
+    om = O.OracleMLP(("x", "y"), ("u",), [24] * 3, "siren")
+    lo, _, g = O.train_forward_backward(om, m.flat.data.clone(), O.laplace_expr(2), {k: inp[k] for k in ("x", "y")}, lab, None, "mean")
+    assert float(losses_all["laplace"]) == pytest.approx(float(lo["laplace"]), rel=1e-10)
+    np.testing.assert_allclose(m.flat.grad.numpy(), g.numpy(), rtol=1e-8, atol=1e-11 * float(g.abs().max()))
