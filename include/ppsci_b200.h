@@ -156,6 +156,12 @@ typedef struct ppsci_plan_spec {
   int32_t pgrad_res[PPSCI_MAX_PGRAD];
   int32_t pgrad_aux[PPSCI_MAX_PGRAD];
   int32_t pgrad_reg[PPSCI_MAX_PGRAD];
+  /* Gated network — ModifiedMLP.forward_tensor (ppsci/arch/mlp.py:488-506): two extra first layers
+   *   U = act(x Wu + bu),  V = act(x Wv + bv)            (embed_u / embed_v, n_feat -> widths[1])
+   * and after every hidden layer  y <- y * U + (1 - y) * V  (a truncated Taylor product per jet direction).
+   * When non-zero: n_layers >= 2, all hidden widths equal, no dense_in / act_first; the parameter buffer is
+   * [W_1 | b_1 | ... | W_L | b_L | Wu | bu | Wv | bv] and the plan runs on the CUDA-core kernels (kernels_gate.cuh). */
+  int32_t gated;
 } ppsci_plan_spec;
 
 typedef struct ppsci_plan ppsci_plan;

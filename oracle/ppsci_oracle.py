@@ -75,7 +75,19 @@ class OracleMLP:
         periods: Optional[Dict[str, Tuple[float, bool]]] = None,
         skip_connection: bool = False,
         fourier: Optional[Dict[str, float]] = None,
+        modified: bool = False,
+        pirate: bool = False,
     ):
+        # pirate=True: PirateNet (mlp.py:530-830) — ``hidden`` holds one entry per block (all equal to the input width of
+        # the blocks, i.e. fourier["dim"]); flat vector:
+        # [block_0.linear1 | linear2 | linear3 | block_1... | last_fc | Wu | bu | Wv | bv | alpha_0..alpha_{B-1} | fourier kernel]
+        self.pirate = pirate
+        if pirate:
+            self.n_blocks = len(hidden)
+            hidden = [h for h in hidden for _ in range(3)]
+        # modified=True: ModifiedMLP (mlp.py:318-506) — embed_u / embed_v (n_feat -> hidden[0]) stored BEHIND the linear
+        # layers in the flat vector: [W_1 | b_1 | ... | W_L | b_L | Wu | bu | Wv | bv]
+        self.modified = modified
         self.input_keys = tuple(input_keys)
         self.output_keys = tuple(output_keys)
         self.periods = periods or {}
@@ -95,7 +107,12 @@ class OracleMLP:
 
     @property
     def n_params(self) -> int:
-        return self.n_linear_params + (self.n_feat * (int(self.fourier["dim"]) // 2) if self.fourier else 0)
+        n = self.n_linear_params + (self.n_feat * (int(self.fourier["dim"]) // 2) if self.fourier else 0)
+        if self.modified or self.pirate:
+            n += 2 * (self.widths[0] * self.widths[1] + self.widths[1])
+        if self.pirate:
+            n += self.n_blocks
+        return n
 
     def split_params(self, flat: torch.Tensor):
         out, off = [], 0
@@ -118,9 +135,52 @@ class OracleMLP:
         y = torch.cat(feats, dim=-1) if len(feats) > 1 else feats[0]
         if self.fourier:  # FourierEmbedding.forward, mlp.py:128-136; applied after the concat, mlp.py:306-309
             dh = int(self.fourier["dim"]) // 2
-            kernel = flat[self.n_linear_params : self.n_linear_params + self.n_feat * dh].view(self.n_feat, dh)
+            koff = self.n_params - self.n_feat * dh  # the kernel is the LAST segment of the flat vector
+            kernel = flat[koff : koff + self.n_feat * dh].view(self.n_feat, dh)
             y = torch.cat([torch.cos(y @ kernel), torch.sin(y @ kernel)], dim=-1)
         layers = self.split_params(flat)
+        if self.pirate:  # PirateNet.forward_tensor (mlp.py:800-809) over PirateNetBlock.forward (mlp.py:617-624)
+            a, h = self.widths[0], self.widths[1]
+            off = self.n_linear_params
+            Wu, bu = flat[off : off + a * h].view(a, h), flat[off + a * h : off + a * h + h]
+            off += a * h + h
+            Wv, bv = flat[off : off + a * h].view(a, h), flat[off + a * h : off + a * h + h]
+            off += a * h + h
+            alpha = flat[off : off + self.n_blocks]
+            u = self.act(y @ Wu + bu)
+            v = self.act(y @ Wv + bv)
+            for k in range(self.n_blocks):
+                (W1, b1), (W2, b2), (W3, b3) = layers[3 * k : 3 * k + 3]
+                f = self.act(y @ W1 + b1)
+                z1 = f * u + (1 - f) * v
+                g = self.act(z1 @ W2 + b2)
+                z2 = g * u + (1 - g) * v
+                hh = self.act(z2 @ W3 + b3)
+                y = alpha[k] * hh + (1 - alpha[k]) * y
+            W, b = layers[-1]
+            y = y @ W + b
+            if len(self.output_keys) == 1:
+                return {self.output_keys[0]: y}
+            parts = torch.split(y, 1, dim=-1)
+            return {k: parts[i] for i, k in enumerate(self.output_keys)}
+        if self.modified:  # ModifiedMLP.forward_tensor, mlp.py:488-506 (skip_connection off)
+            a, h = self.widths[0], self.widths[1]
+            off = self.n_linear_params
+            Wu, bu = flat[off : off + a * h].view(a, h), flat[off + a * h : off + a * h + h]
+            off += a * h + h
+            Wv, bv = flat[off : off + a * h].view(a, h), flat[off + a * h : off + a * h + h]
+            u = self.act(y @ Wu + bu)  # embed_u = Sequential(Linear, act), mlp.py:397-418
+            v = self.act(y @ Wv + bv)
+            for W, b in layers[:-1]:
+                y = y @ W + b
+                y = self.act(y)
+                y = y * u + (1 - y) * v
+            W, b = layers[-1]
+            y = y @ W + b
+            if len(self.output_keys) == 1:
+                return {self.output_keys[0]: y}
+            parts = torch.split(y, 1, dim=-1)
+            return {k: parts[i] for i, k in enumerate(self.output_keys)}
         skip = None
         for i, (W, b) in enumerate(layers[:-1]):  # mlp.py:281-296, statement by statement
             y = y @ W + b

@@ -1,9 +1,9 @@
 from .base import Arch
-from .mlp import MLP
+from .mlp import MLP, ModifiedMLP, PirateNet
 from .deeponet import DeepONet
 from .activation import get_activation
 
-__all__ = ["Arch", "MLP", "DeepONet", "get_activation", "build_model"]
+__all__ = ["Arch", "MLP", "ModifiedMLP", "PirateNet", "DeepONet", "get_activation", "build_model"]
 
 
 def build_model(cfg):

@@ -98,6 +98,10 @@ class MLP(base.Arch):
     at construction): trainable periods, ``fourier`` together with weight_norm / random_weight / skip_connection.
     """
 
+    # 1: ModifiedMLP (two embedding layers + the gate after every hidden layer); 2: PirateNet (blocks of three layers,
+    # gates after the first two, adaptive residual after the third; the embeddings read the Fourier features)
+    _gated = 0
+
     def __init__(
         self,
         input_keys: Tuple[str, ...],
@@ -177,8 +181,13 @@ class MLP(base.Arch):
             eng_widths = [len(feat_src), d_f] + hidden + [len(self.output_keys)]
             widths = [d_f] + hidden + [len(self.output_keys)]
         self._net = NetSpec(self.input_keys, self.output_keys, feat_src, feat_kind, feat_omega, eng_widths, self.activation,
-                            act_first="sin" if self.fourier else None)
+                            act_first="sin" if self.fourier else None, gated=int(self._gated))
         self._shapes = list(zip(widths[:-1], widths[1:]))
+        self._n_hidden = len(hidden)
+        if self._gated:  # embed_u / embed_v (n_feat -> hidden[0]) stored behind last_fc: [... | Wu | bu | Wv | bv]
+            if len(set(hidden)) != 1:
+                raise ValueError("ModifiedMLP takes one hidden_size for all layers")
+            self._shapes += [(widths[0], hidden[0])] * 2
         self._w_off, self._b_off = [], []
         off = 0
         for a, b in self._shapes:
@@ -186,6 +195,10 @@ class MLP(base.Arch):
             off += a * b
             self._b_off.append(off)
             off += b
+        self._alpha_off, self._n_blocks = off, 0
+        if self._gated == 2:  # PirateNetBlock.alpha, one trainable scalar per block (mlp.py:592-597), behind the embeddings
+            self._n_blocks = len(hidden) // 3
+            off += self._n_blocks
         self._n_eff = off  # length of the [W | b] buffer of the reference's own linear layers
         self._n_lin = off
         self._f_n0 = 0     # fourier: length of the effective first layer [W0 | b0] in front of them in the engine buffer
@@ -207,6 +220,9 @@ class MLP(base.Arch):
         self.flat = nn.Parameter(torch.zeros(off, dtype=dtype))
         self.linears = [_LinearView(self, i) for i in range(len(hidden))]
         self.last_fc = _LinearView(self, len(hidden))
+        if self._gated:
+            self.embed_u = _LinearView(self, len(hidden) + 1)
+            self.embed_v = _LinearView(self, len(hidden) + 2)
         # Reference semantics of skip_connection (mlp.py:281-296), restated exactly: at every even hidden layer i >= 2
         # the code executes ``skip = y; y = y + skip`` — the freshly assigned skip IS y, so the pre-activation is
         # doubled (the first even layer only records skip).  A doubled pre-activation is the same linear layer with
@@ -227,7 +243,7 @@ class MLP(base.Arch):
             for i, (a, b) in enumerate(self._shapes):
                 lim = math.sqrt(6.0 / (a + b))
                 w = (torch.rand(a * b, dtype=torch.float64) * 2 - 1) * lim
-                if self.activation == "siren" and i < len(self._shapes) - 1:
+                if self.activation == "siren" and i < self._n_hidden:
                     # Siren.init_for_first_layer / init_for_hidden_layer (activation.py:103-136, applied in mlp.py:256-260)
                     lim = 1.0 / a if i == 0 else math.sqrt(6.0 / a) / 30.0
                     w = (torch.rand(a * b, dtype=torch.float64) * 2 - 1) * lim
@@ -241,6 +257,8 @@ class MLP(base.Arch):
                     self.flat.data[self._w_off[i]: self._w_off[i] + a * b] = (v / g).reshape(-1).to(self.flat.dtype)
                     self.flat.data[self._g_off[i]: self._g_off[i] + b] = g.to(self.flat.dtype)
 
+            if self._n_blocks:  # alpha = 0: every block starts as the identity (mlp.py:592-597)
+                self.flat.data[self._alpha_off: self._alpha_off + self._n_blocks] = 0
             if self.fourier:  # FourierEmbedding: Normal(std=scale) (mlp.py:123-126)
                 nf, dh = self._f_shape
                 k = torch.randn(nf * dh, dtype=torch.float64) * float(self.fourier["scale"])
@@ -261,7 +279,7 @@ class MLP(base.Arch):
         plain) or every layer under random weight factorization."""
         if self.random_weight:
             return True
-        return self.weight_norm and i < len(self._shapes) - 1
+        return self.weight_norm and i < self._n_hidden
 
     def engine_params(self) -> torch.Tensor:
         """The flat [W_1 | b_1 | ...] buffer passed to the native calls (effective weights under weight_norm)."""
@@ -350,12 +368,17 @@ class MLP(base.Arch):
         return self.flat.dtype
 
     def _layer_names(self):
-        names = [f"linears.{i}" for i in range(len(self._shapes) - 1)] + ["last_fc"]
+        names = [f"linears.{i}" for i in range(self._n_hidden)] + ["last_fc"]
+        if self._gated:  # nn.Sequential(Linear, act): the linear layer is item 0 (mlp.py:397-438)
+            names += ["embed_u.0", "embed_v.0"]
         return names
+
+    def _views(self):
+        return self.linears + [self.last_fc] + ([self.embed_u, self.embed_v] if self._gated else [])
 
     def state_dict(self, *args, **kwargs):  # reference-style keys
         out = OrderedDict()
-        views = self.linears + [self.last_fc]
+        views = self._views()
         for i, (name, v) in enumerate(zip(self._layer_names(), views)):
             if self._wn_layer(i):
                 out[f"{name}.weight_v"] = v.weight_v.detach().clone()
@@ -368,7 +391,7 @@ class MLP(base.Arch):
         return out
 
     def load_state_dict(self, state_dict, strict: bool = True):
-        views = self.linears + [self.last_fc]
+        views = self._views()
         missing, unexpected = [], [k for k in state_dict if k.rsplit(".", 1)[0] not in self._layer_names() + (["fourier_emb"] if self.fourier else [])]
         with torch.no_grad():
             if self.fourier:
@@ -423,3 +446,137 @@ class MLP(base.Arch):
         if self._output_transform is not None:
             out = self._output_transform(x, out)
         return out
+
+
+class ModifiedMLP(MLP):
+    """Modified multi layer perceptron (https://arxiv.org/pdf/2001.04536.pdf) — same arguments as the reference
+    (mlp.py:318-487).  ``forward_tensor`` of the reference (mlp.py:488-506):
+
+        u = act(embed_u(x)); v = act(embed_v(x))
+        for linear: y = act(linear(y)); y = y * u + (1 - y) * v
+        y = last_fc(y)
+
+    runs inside the engine as a gated plan (``ppsci_plan_spec.gated``): two more first layers from the same seeds and a
+    jet-product gate after every hidden layer (csrc/kernels_gate.cuh), values, input derivatives of any supported order
+    and the weight gradient included.  The flat parameter vector is ``[W_1 | b_1 | ... | last_fc | Wu | bu | Wv | bv]``;
+    checkpoints use the reference's keys (``linears.i.*``, ``last_fc.*``, ``embed_u.0.*``, ``embed_v.0.*``).
+    ``periods`` are supported; ``skip_connection`` / ``weight_norm`` / ``fourier`` / ``random_weight`` raise
+    ``NotImplementedError`` (not built)."""
+
+    _gated = 1
+
+    def __init__(
+        self,
+        input_keys: Tuple[str, ...],
+        output_keys: Tuple[str, ...],
+        num_layers: int,
+        hidden_size: int,
+        activation: str = "tanh",
+        skip_connection: bool = False,
+        weight_norm: bool = False,
+        input_dim: Optional[int] = None,
+        output_dim: Optional[int] = None,
+        periods: Optional[Dict[str, Tuple[float, bool]]] = None,
+        fourier: Optional[Dict[str, Union[float, int]]] = None,
+        random_weight: Optional[Dict[str, float]] = None,
+        dtype: torch.dtype = torch.float32,
+    ):
+        if not isinstance(hidden_size, int):  # mlp.py:381-382
+            raise ValueError(f"hidden_size should be int, but got {type(hidden_size)}")
+        if not isinstance(num_layers, int):  # mlp.py:378-379
+            raise ValueError("num_layers should be an int")
+        if num_layers < 1:
+            raise ValueError("ModifiedMLP needs at least one hidden layer (embed_u / embed_v map onto hidden_size)")
+        if skip_connection or weight_norm or fourier or random_weight:
+            raise NotImplementedError("ModifiedMLP(skip_connection / weight_norm / fourier / random_weight) is not "
+                                      "supported by the gated kernels yet")
+        super().__init__(input_keys, output_keys, num_layers, hidden_size, activation, False, False, input_dim, output_dim,
+                         periods, None, None, dtype)
+
+
+class PirateNet(MLP):
+    """PirateNet (https://arxiv.org/pdf/2402.00326.pdf) — same arguments as the reference (mlp.py:627-798).
+    ``forward_tensor`` (mlp.py:800-809) over ``PirateNetBlock.forward`` (mlp.py:617-624):
+
+        u = act(embed_u(x)); v = act(embed_v(x))                       # x = the Fourier features
+        per block:  f = act(linear1(x)); z1 = f u + (1 - f) v
+                    g = act(linear2(z1)); z2 = g u + (1 - g) v
+                    h = act(linear3(z2)); x = alpha h + (1 - alpha) x   # alpha: trainable scalar, 0 at start
+        y = last_fc(x)
+
+    runs inside the engine as a gated plan of kind 2 (``ppsci_plan_spec.gated``, csrc/kernels_gate.cuh): the Fourier
+    embedding is the engine's first layer (tied weights, ``sin`` activation, like ``MLP(fourier=...)``), the gates and the
+    adaptive residual are jet-level elementwise kernels between the linear layers, dLoss/dalpha is reduced on the device.
+    The block input must have the blocks' width: ``fourier["dim"] == hidden_size`` (the reference's own constraint:
+    ``PirateNetBlock(cur_size)`` adds its input to a ``cur_size``-wide output and multiplies it with ``hidden_size``-wide
+    embeddings).  Flat parameter vector: ``[blocks' linears | last_fc | Wu | bu | Wv | bv | alphas | fourier kernel]``;
+    checkpoints use the reference's keys (``blocks.k.linear{1,2,3}.*``, ``blocks.k.alpha``, ``embed_{u,v}.0.*``,
+    ``last_fc.*``, ``fourier_emb.kernel``).  ``weight_norm`` / ``random_weight`` and a PirateNet without ``fourier``
+    raise ``NotImplementedError`` (not built)."""
+
+    _gated = 2
+
+    def __init__(
+        self,
+        input_keys: Tuple[str, ...],
+        output_keys: Tuple[str, ...],
+        num_blocks: int,
+        hidden_size: int,
+        activation: str = "tanh",
+        weight_norm: bool = False,
+        input_dim: Optional[int] = None,
+        output_dim: Optional[int] = None,
+        periods: Optional[Dict[str, Tuple[float, bool]]] = None,
+        fourier: Optional[Dict[str, Union[float, int]]] = None,
+        random_weight: Optional[Dict[str, float]] = None,
+        dtype: torch.dtype = torch.float32,
+    ):
+        if not isinstance(hidden_size, int):  # mlp.py:700-705
+            raise ValueError(f"hidden_size should be int, but got {type(hidden_size)}")
+        if not isinstance(num_blocks, int):
+            raise ValueError("num_blocks should be an int")
+        if num_blocks < 1:
+            raise ValueError("PirateNet needs at least one block")
+        if weight_norm or random_weight:
+            raise NotImplementedError("PirateNet(weight_norm / random_weight) is not supported by the gated kernels yet")
+        if not fourier:
+            raise NotImplementedError("PirateNet without fourier features is not supported (the blocks need an input of "
+                                      "their own width)")
+        if int(fourier["dim"]) != hidden_size:
+            raise ValueError(f"PirateNet blocks keep their input width: fourier['dim'] ({fourier['dim']}) must equal "
+                             f"hidden_size ({hidden_size})")
+        super().__init__(input_keys, output_keys, None, (hidden_size,) * (3 * num_blocks), activation, False, False,
+                         input_dim, output_dim, periods, fourier, None, dtype)
+
+    @property
+    def alphas(self) -> torch.Tensor:
+        """View of the blocks' residual weights ``alpha`` [num_blocks]."""
+        return self.flat.data[self._alpha_off: self._alpha_off + self._n_blocks]
+
+    def _layer_names(self):
+        return [f"blocks.{i // 3}.linear{i % 3 + 1}" for i in range(self._n_hidden)] + ["last_fc", "embed_u.0", "embed_v.0"]
+
+    def state_dict(self, *args, **kwargs):
+        out = super().state_dict(*args, **kwargs)
+        for k in range(self._n_blocks):
+            out[f"blocks.{k}.alpha"] = self.alphas[k: k + 1].detach().clone()
+        return out
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        sd = dict(state_dict)
+        missing = []
+        with torch.no_grad():
+            for k in range(self._n_blocks):
+                key = f"blocks.{k}.alpha"
+                if key in sd:
+                    src = sd.pop(key)
+                    src = torch.as_tensor(np.asarray(src.cpu() if hasattr(src, "cpu") else src)).reshape(-1)
+                    self.alphas[k: k + 1].copy_(src.to(self.flat.dtype).to(self.flat.device))
+                else:
+                    missing.append(key)
+        if strict and missing:
+            raise KeyError(f"missing keys {missing}")
+        m2, unexpected = super().load_state_dict(sd, strict)
+        return missing + m2, unexpected
+
+    set_state_dict = load_state_dict

@@ -17,6 +17,7 @@
 #include "kernels_tc2.cuh"
 #include "kernels_fused.cuh"
 #include "kernels_thin.cuh"
+#include "kernels_gate.cuh"
 
 using namespace ppsci;
 
@@ -46,6 +47,8 @@ struct ppsci_plan {
   int64_t b_off[PPSCI_MAX_LAYERS + 1];
   int ld[PPSCI_MAX_LAYERS + 1];
   int64_t n_params = 0;
+  int64_t gate_w_off[2] = {0, 0};  // gated plans: embed_u / embed_v weights and biases behind the layers
+  int64_t gate_b_off[2] = {0, 0};
   int ld_hidden_max = 4;
   int chunk = 0;
   int num_sms = 148;
@@ -107,6 +110,9 @@ struct Carve {
   size_t loss_acc;
   size_t tc;  // scratch of the tcgen05 backend
   size_t w16;  // fp16 hi / lo weight images of the fused forward's layers 2.. (+ per-layer |W|max and scale words)
+  // gated plans (ModifiedMLP): gated jets G_l per hidden layer, pre-activations of embed_u / embed_v and their adjoints
+  size_t gt[PPSCI_MAX_LAYERS + 1];
+  size_t zu, zv, zub, zvb;
   size_t total;
 };
 
@@ -137,6 +143,12 @@ static void carve(const ppsci_plan* P, int64_t nc, Carve* cv) {
   cv->tc = take(tc_scratch_bytes(P, nc));
   cv->w16 = take(fused_fwd16_ok(P) ? (size_t)(L - 3 > 0 ? L - 3 : 0) * P->spec.widths[1] * P->spec.widths[1] * 4 + 16 * PPSCI_MAX_LAYERS : 0);
   for (int l = 1; l < L; ++l) cv->a[l] = take(tc_astash_needed(P, l) ? (size_t)P->C * nc * P->ld[l] * es : 0);
+  const bool gated = P->spec.gated != 0;
+  for (int l = 1; l < L; ++l) cv->gt[l] = take(gated ? (size_t)P->C * nc * P->ld[l] * es : 0);
+  cv->zu = take(gated ? (size_t)P->C * nc * P->ld[1] * es : 0);
+  cv->zv = take(gated ? (size_t)P->C * nc * P->ld[1] * es : 0);
+  cv->zub = take(gated ? (size_t)P->C * nc * P->ld[1] * es : 0);
+  cv->zvb = take(gated ? (size_t)P->C * nc * P->ld[1] * es : 0);
   cv->total = off;
 }
 
@@ -186,6 +198,13 @@ extern "C" int ppsci_b200_plan_create(const ppsci_plan_spec* s, ppsci_plan** out
     if (s->feat_kind[f] < 0 || s->feat_kind[f] > PPSCI_FEAT_SIN) return fail("plan_create: bad feat_kind");
   }
   if (s->n_dir < 0 || s->n_dir > PPSCI_MAX_DIR) return fail("plan_create: n_dir out of range");
+  if (s->gated) {  // ModifiedMLP: the gate multiplies every hidden layer's output with the (same-width) embeddings
+    if (s->n_layers < 2) return fail("plan_create: a gated network needs at least one hidden layer");
+    if (s->dense_in || s->act_first >= 0) return fail("plan_create: gated networks take neither dense_in nor act_first");
+    for (int l = 2; l < s->n_layers; ++l)
+      if (s->widths[l] != s->widths[1]) return fail("plan_create: a gated network needs equal hidden widths");
+    if (s->backend == 2) return fail("plan_create: gated networks run on the CUDA-core kernels (backend 0 or 1)");
+  }
   int C = 1, kmax = 1;
   for (int d = 0; d < s->n_dir; ++d) {
     if (s->dir_order[d] < 1 || s->dir_order[d] > PPSCI_MAX_ORDER) return fail("plan_create: dir_order out of range");
@@ -259,6 +278,14 @@ extern "C" int ppsci_b200_plan_create(const ppsci_plan_spec* s, ppsci_plan** out
     P->ld[l] = round4(s->widths[l]);
     if (l < s->n_layers && P->ld[l] > P->ld_hidden_max) P->ld_hidden_max = P->ld[l];
   }
+  if (s->gated) {
+    for (int e = 0; e < 2; ++e) {
+      P->gate_w_off[e] = off;
+      off += (int64_t)s->widths[0] * s->widths[1];
+      P->gate_b_off[e] = off;
+      off += s->widths[1];
+    }
+  }
   P->n_params = off;
   // default points per workspace chunk: large chunks amortise kernel prologues / tails and give the dW kernels long
   // reductions per split (measured on cfg3: 65,536 -> 77.7 ms/step, 262,144 -> 73.7 ms/step); capped below by memory
@@ -290,7 +317,7 @@ extern "C" int ppsci_b200_plan_create(const ppsci_plan_spec* s, ppsci_plan** out
     delete P;
     return fail("plan_create: no CUDA device available (the engine has no CPU fallback)");
   }
-  P->use_tc = tc_plan_supported(P->spec, P->C, P->kmax) && s->backend != 1;
+  P->use_tc = tc_plan_supported(P->spec, P->C, P->kmax) && s->backend != 1 && !s->gated;
 #ifdef PPSCI_EMUL
   if (s->act_first >= 0 && s->act_first != s->act) P->use_tc = false;  // one activation across the fused layers
   if (s->backend != 2) P->use_tc = false;  // the emulated tensor-core kernels (1,024 OS threads per CTA pair) run on request only
@@ -524,8 +551,24 @@ static int run(ppsci_plan* P, const CallArgs& a) {
   const int TP = TM / C;
   const int PT = RC / C;
   const bool thin_on = getenv("PPSCI_B200_NO_THIN") == nullptr;
-  const bool thin_first = thin_on && L >= 2 && s.widths[0] <= THIN_MAXF && !s.dense_in;
-  const bool thin_last = thin_on && L >= 2 && n_out <= THIN_MAXM && C * n_out <= THIN_MAXCM;
+  const bool gated = s.gated != 0;  // ModifiedMLP: generic tile GEMMs + the gate kernels (kernels_gate.cuh)
+  const bool thin_first = thin_on && L >= 2 && s.widths[0] <= THIN_MAXF && !s.dense_in && !gated;
+  const bool thin_last = thin_on && L >= 2 && n_out <= THIN_MAXM && C * n_out <= THIN_MAXCM && !gated;
+  if (gated && a.phase != 0) return fail("two-phase value calls are not offered for gated networks");
+  auto kgf = k_gate_fwd<T, KMAX>;
+  auto kgb = k_gate_bwd<T, KMAX>;
+  auto fill_gate = [&](int l, int64_t nc, GateArgs<T>* ga) {  // gate of hidden layer l
+    memset(ga, 0, sizeof(*ga));
+    ga->J = P->J;
+    ga->act = s.act;
+    ga->Z = reinterpret_cast<const T*>(ws + cv.z[l]);
+    ga->Zu = reinterpret_cast<const T*>(ws + cv.zu);
+    ga->Zv = reinterpret_cast<const T*>(ws + cv.zv);
+    ga->ld = P->ld[l];
+    ga->plane = (long long)nc_max * P->ld[l];
+    ga->Np = nc;
+    ga->H = s.widths[l];
+  };
   // fp32 + one of the compile-time jet layouts: vectorised thin kernels (kernels_thin.cuh)
   const int thin_lay = tc_pick_layout(P->J, PPSCI_ACT_TANH);
   const bool thin_vec = sizeof(T) == 4 && thin_lay != TC_LAY_DYN && getenv("PPSCI_B200_NO_THINV") == nullptr;
@@ -804,6 +847,16 @@ static int run(ppsci_plan* P, const CallArgs& a) {
       GemmArgs<T> g;
       memset(&g, 0, sizeof(g));
       if (l == 1) fill_first<T>(P, a.x_cols, c0, nc_max, &g.A);
+      else if (gated) {  // G_{l-1} = V + act(Z_{l-1}) (U - V), then a plain operand
+        GateArgs<T> ga;
+        fill_gate(l - 1, nc, &ga);
+        ga.G = reinterpret_cast<T*>(ws + cv.gt[l - 1]);
+        const long long tot = (long long)nc * ga.H;
+        ProfScope ps_(P, CLS_MISC, st);
+        PPSCI_LAUNCH(kgf, dim3((unsigned)((tot + 127) / 128)), dim3(128), 0, st, ga);
+        P->launches++;
+        fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.gt[l - 1]), P->ld[l - 1], nc_max, A_PLAIN, &g.A);
+      }
       else fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[l - 1]), P->ld[l - 1], nc_max, A_ACT, &g.A, l - 1);
       g.J = P->J;
       g.B = params + P->w_off[l];
@@ -817,9 +870,21 @@ static int run(ppsci_plan* P, const CallArgs& a) {
       g.Np = nc;
       g.TP = TP;
       dim3 grid(ptiles, (unsigned)((g.Nout + TN - 1) / TN));
-      ProfScope ps_(P, CLS_FWD, st);
-      PPSCI_LAUNCH(kf, grid, dim3(NTHREADS), smem_f, st, g);
-      P->launches++;
+      {
+        ProfScope ps_(P, CLS_FWD, st);
+        PPSCI_LAUNCH(kf, grid, dim3(NTHREADS), smem_f, st, g);
+        P->launches++;
+      }
+      if (gated && l == 1) {  // embed_u / embed_v: the same seeds through two more first layers
+        for (int e = 0; e < 2; ++e) {
+          g.B = params + P->gate_w_off[e];
+          g.bias = params + P->gate_b_off[e];
+          g.Out = reinterpret_cast<T*>(ws + (e == 0 ? cv.zu : cv.zv));
+          ProfScope ps_(P, CLS_FWD, st);
+          PPSCI_LAUNCH(kf, grid, dim3(NTHREADS), smem_f, st, g);
+          P->launches++;
+        }
+      }
     }
     // ---------------- residual program + loss + output adjoints ----------------
     if (a.jets_out) {
@@ -1084,6 +1149,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         DwArgs<T> g;
         memset(&g, 0, sizeof(g));
         if (l == 1) fill_first<T>(P, a.x_cols, c0, nc_max, &g.A);
+        else if (gated) fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.gt[l - 1]), P->ld[l - 1], nc_max, A_PLAIN, &g.A);
         else fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[l - 1]), P->ld[l - 1], nc_max, A_ACT, &g.A, l - 1);
         g.J = P->J;
         g.Zbar = zbar_cur;
@@ -1103,9 +1169,23 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         const long long cps = (total_chunks + want - 1) / want;
         const unsigned splits = (unsigned)((total_chunks + cps - 1) / cps);
         g.chunks_per_split = (int)cps;
-        ProfScope ps_(P, CLS_DW, st);
-        PPSCI_LAUNCH(kw, dim3(kt, nt, splits), dim3(NTHREADS), smem_w, st, g);
-        P->launches++;
+        {
+          ProfScope ps_(P, CLS_DW, st);
+          PPSCI_LAUNCH(kw, dim3(kt, nt, splits), dim3(NTHREADS), smem_w, st, g);
+          P->launches++;
+        }
+        if (gated && l == 1) {  // dWu, dbu, dWv, dbv from the adjoints the gates accumulated
+          for (int e = 0; e < 2; ++e) {
+            g.Zbar = reinterpret_cast<const T*>(ws + (e == 0 ? cv.zub : cv.zvb));
+            g.ldzb = P->ld[1];
+            g.zbplane = (long long)nc_max * P->ld[1];
+            g.dW = grads + P->gate_w_off[e];
+            g.db = grads + P->gate_b_off[e];
+            ProfScope ps_(P, CLS_DW, st);
+            PPSCI_LAUNCH(kw, dim3(kt, nt, splits), dim3(NTHREADS), smem_w, st, g);
+            P->launches++;
+          }
+        }
       }
       if (l == 1) break;
       if (fdx && l <= L - 1) {  // Zbar_{l-1} was produced by the fused chain
@@ -1178,11 +1258,25 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         g.Zprev = reinterpret_cast<const T*>(ws + cv.z[l - 1]);
         g.ldz = P->ld[l - 1];
         g.zplane = (long long)nc_max * P->ld[l - 1];
-        g.act = act_of_layer(s, l - 1);
+        g.act = gated ? (int)PPSCI_ACT_IDENTITY : act_of_layer(s, l - 1);  // gated: Gbar_{l-1}, the gate's adjoint follows
         dim3 grid(ptiles, (unsigned)((g.Nout + TN - 1) / TN));
-        ProfScope ps_(P, CLS_DX, st);
-        PPSCI_LAUNCH(kx, grid, dim3(NTHREADS), smem_x, st, g);
-        P->launches++;
+        {
+          ProfScope ps_(P, CLS_DX, st);
+          PPSCI_LAUNCH(kx, grid, dim3(NTHREADS), smem_x, st, g);
+          P->launches++;
+        }
+        if (gated) {  // Gbar_{l-1} -> Zbar_{l-1} in place; adjoints of the embeddings' pre-activations accumulate
+          GateArgs<T> ga;
+          fill_gate(l - 1, nc, &ga);
+          ga.G = outp;
+          ga.Zub = reinterpret_cast<T*>(ws + cv.zub);
+          ga.Zvb = reinterpret_cast<T*>(ws + cv.zvb);
+          ga.first = (l == L) ? 1 : 0;
+          const long long tot = (long long)nc * ga.H;
+          ProfScope ps_(P, CLS_MISC, st);
+          PPSCI_LAUNCH(kgb, dim3((unsigned)((tot + 127) / 128)), dim3(128), 0, st, ga);
+          P->launches++;
+        }
         zbar_cur = outp;
         zbar_ld = P->ld[l - 1];
         flip ^= 1;

@@ -85,6 +85,7 @@ class PlanSpec(C.Structure):
         ("pgrad_res", C.c_int32 * MAX_PGRAD),
         ("pgrad_aux", C.c_int32 * MAX_PGRAD),
         ("pgrad_reg", C.c_int32 * MAX_PGRAD),
+        ("gated", C.c_int32),
     ]
 
 

@@ -56,10 +56,19 @@ class NetSpec:
     act: str = "tanh"
     dense_in: bool = False  # the single input key is a row-major [N, n_feat] matrix (DeepONet branch net); values only
     act_first: Optional[str] = None  # activation of the FIRST linear layer's output when it differs (FourierEmbedding: "sin")
+    # 1: ModifiedMLP (mlp.py:488-506): U / V embeddings from the features + y <- y U + (1 - y) V after every hidden layer
+    # 2: PirateNet (mlp.py:617-624, 800-809): layer 1 is the Fourier embedding, U / V read its output, then blocks of three
+    #    layers (gate, gate, x <- alpha h + (1 - alpha) x)
+    gated: int = 0
 
     @property
     def n_params(self) -> int:
-        return sum(self.widths[i] * self.widths[i + 1] + self.widths[i + 1] for i in range(len(self.widths) - 1))
+        n = sum(self.widths[i] * self.widths[i + 1] + self.widths[i + 1] for i in range(len(self.widths) - 1))
+        if self.gated:  # [Wu | bu | Wv | bv] behind the layers (input: the features, or layer 1's output for kind 2)
+            n += 2 * (self.widths[1 if self.gated == 2 else 0] * self.widths[-2] + self.widths[-2])
+        if self.gated == 2:  # one alpha per block
+            n += (len(self.widths) - 3) // 3
+        return n
 
 
 @dataclass

@@ -77,6 +77,7 @@ class ResidualPlan:
         if act_first is not None and act_first.lower() not in B.ACT_IDS:
             raise NotImplementedError(f"activation {act_first!r} has no jet kernel (supported: {sorted(B.ACT_IDS)})")
         s.act_first = B.ACT_IDS[act_first.lower()] if act_first is not None else -1
+        s.gated = int(getattr(net, "gated", 0) or 0)  # 1 ModifiedMLP, 2 PirateNet (embeddings + gates [+ adaptive residuals])
         s.n_dir = len(compiled.dirs)
         for d, dr in enumerate(compiled.dirs):
             s.dir_order[d] = dr.order

@@ -13,7 +13,7 @@ from paddlescience_b200.engine.compiler import NetSpec, compile_residuals
 from paddlescience_b200.engine.plan import ResidualPlan
 
 
-def make_net(in_keys, out_keys, hidden, act, periods=None) -> NetSpec:
+def make_net(in_keys, out_keys, hidden, act, periods=None, gated=False) -> NetSpec:
     feat_src, feat_kind, feat_omega = [], [], []
     for i, k in enumerate(in_keys):
         if periods and k in periods:
@@ -26,7 +26,7 @@ def make_net(in_keys, out_keys, hidden, act, periods=None) -> NetSpec:
             feat_kind.append(0)
             feat_omega.append(0.0)
     return NetSpec(tuple(in_keys), tuple(out_keys), feat_src, feat_kind, feat_omega,
-                   [len(feat_src)] + list(hidden) + [len(out_keys)], act)
+                   [len(feat_src)] + list(hidden) + [len(out_keys)], act, gated=gated)
 
 
 def _ac_exprs():
@@ -100,6 +100,16 @@ CASES = {
                              exprs=lambda: O.laplace_expr(2), dtype=torch.float32),
     "laplace_siren_f64": dict(in_keys=("x", "y"), out_keys=("u",), hidden=[12, 12], act="siren",
                               exprs=lambda: O.laplace_expr(2), dtype=torch.float64, siren_init=True),
+    # ModifiedMLP (mlp.py:318-506): embed_u / embed_v + y <- y u + (1 - y) v after every hidden layer (kernels_gate.cuh)
+    "modified_ns_f64": dict(in_keys=("x", "y"), out_keys=("u", "v", "p"), hidden=[12, 12, 12], act="tanh", modified=True,
+                            exprs=lambda: O.navier_stokes_expr(0.1, 1.0, 2, False), dtype=torch.float64),
+    "modified_laplace_f32": dict(in_keys=("x", "y"), out_keys=("u",), hidden=[20, 20], act="tanh", modified=True,
+                                 exprs=lambda: O.laplace_expr(2), dtype=torch.float32),
+    "modified_biharmonic_silu_f64": dict(in_keys=("x", "y"), out_keys=("u",), hidden=[10, 10], act="silu", modified=True,
+                                         exprs=_biharm_exprs, dtype=torch.float64),
+    "modified_ac_period_f64": dict(in_keys=("t", "x"), out_keys=("u",), hidden=[12, 12], act="tanh", modified=True,
+                                   periods={"x": (2.0, False)}, exprs=_ac_exprs, dtype=torch.float64,
+                                   ranges={"x": (-1, 1)}),
     "first_order_leaky_relu_f64": dict(in_keys=("x", "y"), out_keys=("u", "v"), hidden=[12, 12], act="leaky_relu",
                                        exprs=_first_order_exprs, dtype=torch.float64),
 }
@@ -190,7 +200,7 @@ def run_case(name, n: int, library=None, device="cpu", backend: int = 0, seed: i
     dtype = c["dtype"]
     exprs = c["exprs"]()
     periods = c.get("periods")
-    net = make_net(c["in_keys"], c["out_keys"], c["hidden"], c["act"], periods)
+    net = make_net(c["in_keys"], c["out_keys"], c["hidden"], c["act"], periods, gated=bool(c.get("modified")))
     cr = compile_residuals(net, exprs)
     nres = len(cr.names)
     reduction = c.get("reduction", "mean")
@@ -207,8 +217,11 @@ def run_case(name, n: int, library=None, device="cpu", backend: int = 0, seed: i
         for k in c["in_keys"]:
             lo, hi = (c.get("ranges") or {}).get(k, (0, 1))
             inputs[k] = (torch.rand(n, 1, dtype=torch.float64) * (hi - lo) + lo).to(dtype)
-    om = O.OracleMLP(c["in_keys"], c["out_keys"], c["hidden"], c["act"], periods)
+    om = O.OracleMLP(c["in_keys"], c["out_keys"], c["hidden"], c["act"], periods, modified=bool(c.get("modified")))
     params = O.xavier_uniform_params(om.widths, 1, torch.float64)
+    if c.get("modified"):  # [Wu | bu | Wv | bv] behind the layers
+        params = torch.cat([params, O.xavier_uniform_params([om.widths[0], om.widths[1]], 2, torch.float64),
+                            O.xavier_uniform_params([om.widths[0], om.widths[1]], 3, torch.float64)])
     params = (params + 0.1 * torch.randn_like(params))
     if c.get("siren_init"):  # weights on the scale Siren's initialisers use (sqrt(6 / in) / w0, activation.py:103-136)
         params = params / 30.0

@@ -193,3 +193,49 @@ def test_siren_activation_initialisers_and_train_forward(monkeypatch):
     lo, _, g = O.train_forward_backward(om, m.flat.data.clone(), O.laplace_expr(2), {k: inp[k] for k in ("x", "y")}, lab, None, "mean")
     assert float(losses_all["laplace"]) == pytest.approx(float(lo["laplace"]), rel=1e-10)
     np.testing.assert_allclose(m.flat.grad.numpy(), g.numpy(), rtol=1e-8, atol=1e-11 * float(g.abs().max()))
+
+
+def test_modified_mlp_gated_plan_and_checkpoint_keys(monkeypatch):
+    """arch.ModifiedMLP (mlp.py:318-506): embed_u / embed_v + the gate after every hidden layer run inside the engine
+    (ppsci_plan_spec.gated, csrc/kernels_gate.cuh); loss and weight gradient of a Navier-Stokes constraint against the
+    oracle's restatement of forward_tensor through the CPU emulation of the kernels; reference checkpoint keys."""
+    import numpy as np
+
+    from oracle import ppsci_oracle as O
+    from paddlescience_b200.engine import binding as B
+    from tests.emul.build_emul import build
+
+    monkeypatch.setattr(B, "_default", B.Library(build()))
+    ppsci.utils.misc.set_random_seed(5)
+    m = ppsci.arch.ModifiedMLP(("x", "y"), ("u", "v", "p"), 3, 14, "tanh", dtype=torch.float64)
+    n_lin = 2 * 14 + 14 + 2 * (14 * 14 + 14) + 14 * 3 + 3
+    assert m.flat.numel() == n_lin + 2 * (2 * 14 + 14)
+    with torch.no_grad():
+        m.flat.data += 0.1 * torch.randn_like(m.flat.data)
+    sd = m.state_dict()
+    assert list(sd) == [f"linears.{i}.{p}" for i in range(3) for p in ("weight", "bias")] + [
+        "last_fc.weight", "last_fc.bias", "embed_u.0.weight", "embed_u.0.bias", "embed_v.0.weight", "embed_v.0.bias"]
+    assert tuple(sd["embed_u.0.weight"].shape) == (2, 14) and tuple(sd["embed_v.0.bias"].shape) == (14,)
+    m2 = ppsci.arch.ModifiedMLP(("x", "y"), ("u", "v", "p"), 3, 14, "tanh", dtype=torch.float64)
+    m2.set_state_dict(sd)
+    assert torch.equal(m2.flat.data, m.flat.data)
+    eq = ppsci.equation.NavierStokes(0.1, 1.0, 2, False)
+    rect = ppsci.geometry.Rectangle((0, 0), (1, 1))
+    cst = ppsci.constraint.InteriorConstraint(eq.equations, {"continuity": 0, "momentum_x": 0, "momentum_y": 0}, rect,
+                                              {"dataset": "IterableNamedArrayDataset", "iters_per_epoch": 1, "batch_size": 40},
+                                              ppsci.loss.MSELoss("mean"), name="EQ")
+    ds = cst.data_loader.loader
+    inp = {k: v.double() for k, v in ds.input.items()}
+    lab = {k: v.double() for k, v in ds.label.items()}
+    losses_all, _ = ppsci.utils.ExpressionSolver().train_forward((cst.output_expr,), [inp], m, {"EQ": cst}, [lab], [None])
+    om = O.OracleMLP(("x", "y"), ("u", "v", "p"), [14] * 3, "tanh", modified=True)
+    assert om.n_params == m.flat.numel()
+    lo, _, g = O.train_forward_backward(om, m.flat.data.clone(), O.navier_stokes_expr(0.1, 1.0, 2, False),
+                                        {k: inp[k] for k in ("x", "y")}, lab, None, "mean")
+    for k in lo:
+        assert float(losses_all[k]) == pytest.approx(float(lo[k]), rel=1e-10)
+    np.testing.assert_allclose(m.flat.grad.numpy(), g.numpy(), rtol=1e-8, atol=1e-11 * float(g.abs().max()))
+    with pytest.raises(NotImplementedError):
+        ppsci.arch.ModifiedMLP(("x",), ("u",), 2, 8, weight_norm=True)
+    with pytest.raises(ValueError):
+        ppsci.arch.ModifiedMLP(("x",), ("u",), None, (8, 8))
