@@ -163,7 +163,7 @@ class OracleMLP:
                 return {self.output_keys[0]: y}
             parts = torch.split(y, 1, dim=-1)
             return {k: parts[i] for i, k in enumerate(self.output_keys)}
-        if self.modified:  # ModifiedMLP.forward_tensor, mlp.py:488-506 (skip_connection off)
+        if self.modified:  # ModifiedMLP.forward_tensor, mlp.py:488-506
             a, h = self.widths[0], self.widths[1]
             off = self.n_linear_params
             Wu, bu = flat[off : off + a * h].view(a, h), flat[off + a * h : off + a * h + h]
@@ -171,10 +171,17 @@ class OracleMLP:
             Wv, bv = flat[off : off + a * h].view(a, h), flat[off + a * h : off + a * h + h]
             u = self.act(y @ Wu + bu)  # embed_u = Sequential(Linear, act), mlp.py:397-418
             v = self.act(y @ Wv + bv)
-            for W, b in layers[:-1]:
+            skip = None
+            for i, (W, b) in enumerate(layers[:-1]):  # mlp.py:494-504, statement by statement
                 y = y @ W + b
                 y = self.act(y)
                 y = y * u + (1 - y) * v
+                if self.skip_connection and i % 2 == 0:
+                    if skip is not None:
+                        skip = y
+                        y = y + skip
+                    else:
+                        skip = y
             W, b = layers[-1]
             y = y @ W + b
             if len(self.output_keys) == 1:

@@ -49,6 +49,7 @@ struct ppsci_plan {
   int64_t n_params = 0;
   int64_t gate_w_off[2] = {0, 0};  // gated plans: embed_u / embed_v weights and biases behind the layers
   int64_t gate_b_off[2] = {0, 0};
+  int64_t alpha_off = 0;  // gated == 2: one residual weight per block behind the embeddings
   int ld_hidden_max = 4;
   int chunk = 0;
   int num_sms = 148;
@@ -113,6 +114,7 @@ struct Carve {
   // gated plans (ModifiedMLP): gated jets G_l per hidden layer, pre-activations of embed_u / embed_v and their adjoints
   size_t gt[PPSCI_MAX_LAYERS + 1];
   size_t zu, zv, zub, zvb;
+  size_t xres, wtu, wtv;  // gated == 2: adjoint carried by the blocks' residual path; transposed embedding weights
   size_t total;
 };
 
@@ -149,6 +151,10 @@ static void carve(const ppsci_plan* P, int64_t nc, Carve* cv) {
   cv->zv = take(gated ? (size_t)P->C * nc * P->ld[1] * es : 0);
   cv->zub = take(gated ? (size_t)P->C * nc * P->ld[1] * es : 0);
   cv->zvb = take(gated ? (size_t)P->C * nc * P->ld[1] * es : 0);
+  const bool pirate = P->spec.gated == 2;
+  cv->xres = take(pirate ? (size_t)P->C * nc * P->ld[1] * es : 0);
+  cv->wtu = take(pirate ? (size_t)P->spec.widths[1] * P->spec.widths[1] * es : 0);
+  cv->wtv = take(pirate ? (size_t)P->spec.widths[1] * P->spec.widths[1] * es : 0);
   cv->total = off;
 }
 
@@ -200,7 +206,11 @@ extern "C" int ppsci_b200_plan_create(const ppsci_plan_spec* s, ppsci_plan** out
   if (s->n_dir < 0 || s->n_dir > PPSCI_MAX_DIR) return fail("plan_create: n_dir out of range");
   if (s->gated) {  // ModifiedMLP: the gate multiplies every hidden layer's output with the (same-width) embeddings
     if (s->n_layers < 2) return fail("plan_create: a gated network needs at least one hidden layer");
-    if (s->dense_in || s->act_first >= 0) return fail("plan_create: gated networks take neither dense_in nor act_first");
+    if (s->gated != 1 && s->gated != 2) return fail("plan_create: gated must be 0, 1 (ModifiedMLP) or 2 (PirateNet)");
+    if (s->dense_in) return fail("plan_create: gated networks do not take dense_in");
+    if (s->gated == 1 && s->act_first >= 0) return fail("plan_create: a gated network of kind 1 has one activation");
+    if (s->gated == 2 && (s->n_layers < 5 || (s->n_layers - 2) % 3 != 0))
+      return fail("plan_create: gated kind 2 needs 1 embedding layer + 3 layers per block + the output layer");
     for (int l = 2; l < s->n_layers; ++l)
       if (s->widths[l] != s->widths[1]) return fail("plan_create: a gated network needs equal hidden widths");
     if (s->backend == 2) return fail("plan_create: gated networks run on the CUDA-core kernels (backend 0 or 1)");
@@ -281,9 +291,13 @@ extern "C" int ppsci_b200_plan_create(const ppsci_plan_spec* s, ppsci_plan** out
   if (s->gated) {
     for (int e = 0; e < 2; ++e) {
       P->gate_w_off[e] = off;
-      off += (int64_t)s->widths[0] * s->widths[1];
+      off += (int64_t)s->widths[s->gated == 2 ? 1 : 0] * s->widths[1];  // kind 2: the embeddings read layer 1's output
       P->gate_b_off[e] = off;
       off += s->widths[1];
+    }
+    if (s->gated == 2) {
+      P->alpha_off = off;
+      off += (s->n_layers - 2) / 3;
     }
   }
   P->n_params = off;
@@ -555,8 +569,27 @@ static int run(ppsci_plan* P, const CallArgs& a) {
   const bool thin_first = thin_on && L >= 2 && s.widths[0] <= THIN_MAXF && !s.dense_in && !gated;
   const bool thin_last = thin_on && L >= 2 && n_out <= THIN_MAXM && C * n_out <= THIN_MAXCM && !gated;
   if (gated && a.phase != 0) return fail("two-phase value calls are not offered for gated networks");
+  const bool pirate = s.gated == 2;  // PirateNet: layer 1 = embedding, blocks of (gate, gate, adaptive residual)
   auto kgf = k_gate_fwd<T, KMAX>;
   auto kgb = k_gate_bwd<T, KMAX>;
+  auto kmf = k_mix_fwd<T, KMAX>;
+  auto kmb = k_mix_bwd<T, KMAX>;
+  // what follows hidden layer l in a gated plan: 0 gate, 1 adaptive residual (end of a block), 2 plain activation
+  auto post_kind = [&](int l) -> int { return !pirate ? 0 : (l == 1 ? 2 : ((l - 2) % 3 == 2 ? 1 : 0)); };
+  auto fill_mix = [&](int l, int64_t nc, MixArgs<T>* ma) {
+    memset(ma, 0, sizeof(*ma));
+    ma->J = P->J;
+    ma->act = act_of_layer(s, l);
+    ma->Z = reinterpret_cast<const T*>(ws + cv.z[l]);
+    if (post_kind(l) == 1) {
+      ma->Xprev = reinterpret_cast<const T*>(ws + cv.gt[l - 3]);
+      ma->alpha = params + P->alpha_off + (l - 2) / 3;
+    }
+    ma->ld = P->ld[l];
+    ma->plane = (long long)nc_max * P->ld[l];
+    ma->Np = nc;
+    ma->H = s.widths[l];
+  };
   auto fill_gate = [&](int l, int64_t nc, GateArgs<T>* ga) {  // gate of hidden layer l
     memset(ga, 0, sizeof(*ga));
     ga->J = P->J;
@@ -587,6 +620,15 @@ static int run(ppsci_plan* P, const CallArgs& a) {
       ProfScope ps_(P, CLS_MISC, st);
       PPSCI_LAUNCH(kt, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, params + P->w_off[l],
                    reinterpret_cast<T*>(ws + cv.wt[l]), K, N);
+      P->launches++;
+    }
+    for (int e = 0; e < (pirate ? 2 : 0); ++e) {  // the embeddings hand an adjoint back to layer 1's output
+      const int K = s.widths[1], N = s.widths[1];
+      const long long tot = (long long)K * N;
+      auto kt = k_transpose<T>;
+      ProfScope ps_(P, CLS_MISC, st);
+      PPSCI_LAUNCH(kt, dim3((unsigned)((tot + 255) / 256)), dim3(256), 0, st, params + P->gate_w_off[e],
+                   reinterpret_cast<T*>(ws + (e == 0 ? cv.wtu : cv.wtv)), K, N);
       P->launches++;
     }
   }
@@ -847,16 +889,8 @@ static int run(ppsci_plan* P, const CallArgs& a) {
       GemmArgs<T> g;
       memset(&g, 0, sizeof(g));
       if (l == 1) fill_first<T>(P, a.x_cols, c0, nc_max, &g.A);
-      else if (gated) {  // G_{l-1} = V + act(Z_{l-1}) (U - V), then a plain operand
-        GateArgs<T> ga;
-        fill_gate(l - 1, nc, &ga);
-        ga.G = reinterpret_cast<T*>(ws + cv.gt[l - 1]);
-        const long long tot = (long long)nc * ga.H;
-        ProfScope ps_(P, CLS_MISC, st);
-        PPSCI_LAUNCH(kgf, dim3((unsigned)((tot + 127) / 128)), dim3(128), 0, st, ga);
-        P->launches++;
+      else if (gated)  // the gate / residual / activation that follows layer l-1 was stored when that layer finished
         fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.gt[l - 1]), P->ld[l - 1], nc_max, A_PLAIN, &g.A);
-      }
       else fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[l - 1]), P->ld[l - 1], nc_max, A_ACT, &g.A, l - 1);
       g.J = P->J;
       g.B = params + P->w_off[l];
@@ -875,7 +909,28 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         PPSCI_LAUNCH(kf, grid, dim3(NTHREADS), smem_f, st, g);
         P->launches++;
       }
-      if (gated && l == 1) {  // embed_u / embed_v: the same seeds through two more first layers
+      auto post_fwd = [&](int lay) {  // operand of layer lay + 1
+        const long long tot = (long long)nc * s.widths[lay];
+        ProfScope ps_(P, CLS_MISC, st);
+        if (post_kind(lay) == 0) {  // G = V + act(Z) (U - V)
+          GateArgs<T> ga;
+          fill_gate(lay, nc, &ga);
+          ga.G = reinterpret_cast<T*>(ws + cv.gt[lay]);
+          PPSCI_LAUNCH(kgf, dim3((unsigned)((tot + 127) / 128)), dim3(128), 0, st, ga);
+        } else {  // X = alpha act(Z) + (1 - alpha) X_block_in, or X = act(Z)
+          MixArgs<T> ma;
+          fill_mix(lay, nc, &ma);
+          ma.X = reinterpret_cast<T*>(ws + cv.gt[lay]);
+          PPSCI_LAUNCH(kmf, dim3((unsigned)((tot + 127) / 128)), dim3(128), 0, st, ma);
+        }
+        P->launches++;
+      };
+      if (pirate && l == 1) post_fwd(1);
+      if (gated && l == 1) {  // embed_u / embed_v: two more layers from the seeds (kind 1) / from layer 1's output (kind 2)
+        if (pirate) {
+          fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.gt[1]), P->ld[1], nc_max, A_PLAIN, &g.A);
+          g.Kdim = s.widths[1];
+        }
         for (int e = 0; e < 2; ++e) {
           g.B = params + P->gate_w_off[e];
           g.bias = params + P->gate_b_off[e];
@@ -885,6 +940,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           P->launches++;
         }
       }
+      if (gated && l < L && !(pirate && l == 1)) post_fwd(l);
     }
     // ---------------- residual program + loss + output adjoints ----------------
     if (a.jets_out) {
@@ -1175,6 +1231,12 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           P->launches++;
         }
         if (gated && l == 1) {  // dWu, dbu, dWv, dbv from the adjoints the gates accumulated
+          unsigned kt_e = kt;
+          if (pirate) {
+            fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.gt[1]), P->ld[1], nc_max, A_PLAIN, &g.A);
+            g.Kdim = s.widths[1];
+            kt_e = (unsigned)((g.Kdim + TM - 1) / TM);
+          }
           for (int e = 0; e < 2; ++e) {
             g.Zbar = reinterpret_cast<const T*>(ws + (e == 0 ? cv.zub : cv.zvb));
             g.ldzb = P->ld[1];
@@ -1182,7 +1244,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
             g.dW = grads + P->gate_w_off[e];
             g.db = grads + P->gate_b_off[e];
             ProfScope ps_(P, CLS_DW, st);
-            PPSCI_LAUNCH(kw, dim3(kt, nt, splits), dim3(NTHREADS), smem_w, st, g);
+            PPSCI_LAUNCH(kw, dim3(kt_e, nt, splits), dim3(NTHREADS), smem_w, st, g);
             P->launches++;
           }
         }
@@ -1265,16 +1327,42 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           PPSCI_LAUNCH(kx, grid, dim3(NTHREADS), smem_x, st, g);
           P->launches++;
         }
-        if (gated) {  // Gbar_{l-1} -> Zbar_{l-1} in place; adjoints of the embeddings' pre-activations accumulate
-          GateArgs<T> ga;
-          fill_gate(l - 1, nc, &ga);
-          ga.G = outp;
-          ga.Zub = reinterpret_cast<T*>(ws + cv.zub);
-          ga.Zvb = reinterpret_cast<T*>(ws + cv.zvb);
-          ga.first = (l == L) ? 1 : 0;
-          const long long tot = (long long)nc * ga.H;
+        if (gated && pirate && l == 2) {  // layer 1's output also feeds the embeddings: += Zubar Wu^T + Zvbar Wv^T
+          for (int e = 0; e < 2; ++e) {
+            fill_act<T>(P, reinterpret_cast<const T*>(ws + (e == 0 ? cv.zub : cv.zvb)), P->ld[1], nc_max, A_PLAIN, &g.A);
+            g.B = reinterpret_cast<const T*>(ws + (e == 0 ? cv.wtu : cv.wtv));
+            g.accum = 1;
+            ProfScope ps_(P, CLS_DX, st);
+            PPSCI_LAUNCH(kx, grid, dim3(NTHREADS), smem_x, st, g);
+            P->launches++;
+          }
+        }
+        if (gated) {  // adjoint of what follows layer l-1, in place: operand adjoint -> Zbar_{l-1}
+          const long long tot = (long long)nc * s.widths[l - 1];
           ProfScope ps_(P, CLS_MISC, st);
-          PPSCI_LAUNCH(kgb, dim3((unsigned)((tot + 127) / 128)), dim3(128), 0, st, ga);
+          if (post_kind(l - 1) == 0) {  // gate; the adjoints of the embeddings' pre-activations accumulate
+            GateArgs<T> ga;
+            fill_gate(l - 1, nc, &ga);
+            ga.G = outp;
+            ga.Zub = reinterpret_cast<T*>(ws + cv.zub);
+            ga.Zvb = reinterpret_cast<T*>(ws + cv.zvb);
+            ga.first = (l - 1 == (pirate ? L - 2 : L - 1)) ? 1 : 0;
+            PPSCI_LAUNCH(kgb, dim3((unsigned)((tot + 127) / 128)), dim3(128), 0, st, ga);
+          } else {  // adaptive residual of a block (dLoss/dalpha reduced here), or the embedding layer's activation
+            MixArgs<T> ma;
+            fill_mix(l - 1, nc, &ma);
+            ma.X = outp;
+            ma.Xres = reinterpret_cast<T*>(ws + cv.xres);
+            if (post_kind(l - 1) == 1) {
+              ma.alpha_grad = grads + P->alpha_off + (l - 3) / 3;
+              ma.use_res = (l - 1 != L - 1) ? 1 : 0;  // the last block's output feeds the output layer only
+              ma.write_res = 1;
+            } else {
+              ma.use_res = 1;  // block 0's residual path
+            }
+            const long long want = (tot + 127) / 128, cap = 8LL * P->num_sms;
+            PPSCI_LAUNCH(kmb, dim3((unsigned)(want < cap ? want : cap)), dim3(128), 0, st, ma);
+          }
           P->launches++;
         }
         zbar_cur = outp;

@@ -161,4 +161,73 @@ __global__ void __launch_bounds__(128) k_gate_bwd(GateArgs<T> g) {
   gate_act_adj<T, KMAX>(g.J, sv, zv, gb, g.Zvb + e, g.plane, !g.first);
 }
 
+// ---- PirateNet: adaptive residual of a block (mlp.py:617-624)  x <- alpha act(z3) + (1 - alpha) x ---------------------
+// alpha == nullptr: plain activation, X = act(Z) (the Fourier embedding's output as a stored operand).
+template <typename T>
+struct MixArgs {
+  JetLayout J;
+  int act;
+  const T* Z;      // [C][Np][ld] pre-activations (third layer of the block, or layer 1)
+  const T* Xprev;  // block input jets (may be null: no residual path)
+  const T* alpha;  // device scalar of the plan's dtype (may be null: alpha = 1)
+  T* X;            // fwd: out.  bwd: Xbar in -> Zbar out (in place)
+  T* Xres;         // bwd: adjoint carried by the residual path (read if use_res, written if write_res)
+  T* alpha_grad;   // bwd: dLoss/dalpha (atomicAdd of one partial sum per CTA)
+  int ld;
+  long long plane;
+  long long Np;
+  int H;
+  int use_res;
+  int write_res;
+};
+
+template <typename T, int KMAX>
+__global__ void __launch_bounds__(128) k_mix_fwd(MixArgs<T> g) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= g.Np * g.H) return;
+  const long long p = idx / g.H;
+  const int h = (int)(idx % g.H);
+  const long long e = p * g.ld + h;
+  T zj[GATE_MAXC], y[GATE_MAXC], s[6];
+  gate_act_jet<T, KMAX>(g.act, g.J, g.Z + e, g.plane, zj, y, s);
+  const T a = g.alpha ? g.alpha[0] : T(1);
+  for (int c = 0; c < g.J.C; ++c) {
+    T v = a * y[c];
+    if (g.Xprev) v += (T(1) - a) * g.Xprev[e + (long long)c * g.plane];
+    g.X[e + (long long)c * g.plane] = v;
+  }
+}
+
+template <typename T, int KMAX>
+__global__ void __launch_bounds__(128) k_mix_bwd(MixArgs<T> g) {
+  __shared__ double red[128];
+  const long long total = g.Np * g.H;
+  const T a = g.alpha ? g.alpha[0] : T(1);
+  double part = 0.0;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long p = idx / g.H;
+    const int h = (int)(idx % g.H);
+    const long long e = p * g.ld + h;
+    T zj[GATE_MAXC], y[GATE_MAXC], xb[GATE_MAXC], s[6];
+    gate_act_jet<T, KMAX>(g.act, g.J, g.Z + e, g.plane, zj, y, s);
+    for (int c = 0; c < g.J.C; ++c) {
+      T v = g.X[e + (long long)c * g.plane];
+      if (g.use_res) v += g.Xres[e + (long long)c * g.plane];
+      if (g.alpha_grad) part += (double)(v * (y[c] - (g.Xprev ? g.Xprev[e + (long long)c * g.plane] : T(0))));
+      if (g.write_res) g.Xres[e + (long long)c * g.plane] = (T(1) - a) * v;
+      xb[c] = a * v;
+    }
+    gate_act_adj<T, KMAX>(g.J, s, zj, xb, g.X + e, g.plane, false);
+  }
+  if (g.alpha_grad) {  // uniform across the grid
+    red[threadIdx.x] = part;
+    __syncthreads();
+    for (int st = 64; st > 0; st >>= 1) {
+      if ((int)threadIdx.x < st) red[threadIdx.x] += red[threadIdx.x + st];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(g.alpha_grad, (T)red[0]);
+  }
+}
+
 }  // namespace ppsci

@@ -180,6 +180,7 @@ struct GemmArgs {
   int ldz;
   long long zplane;
   int act;
+  int accum;  // dx: add to Out instead of storing (a second consumer of the same operand)
 };
 
 template <int TN>
@@ -316,9 +317,13 @@ __global__ void __launch_bounds__(NTHREADS) k_gemm_dx(GemmArgs<T> g) {
       jet_adj_dir<T, KMAX>(s, zz, yb, zb, sb);
 #pragma unroll
       for (int q = 0; q < KMAX; ++q)
-        if (q < K) zb_out[(long long)(base + q) * g.oplane] = zb[q];
+        if (q < K) {
+          T* o = zb_out + (long long)(base + q) * g.oplane;
+          *o = g.accum ? *o + zb[q] : zb[q];
+        }
     }
-    zb_out[0] = jet_adj_z0<T, KMAX>(s, y0b, sb);
+    const T z0b = jet_adj_z0<T, KMAX>(s, y0b, sb);
+    zb_out[0] = g.accum ? zb_out[0] + z0b : z0b;
   }
 }
 
