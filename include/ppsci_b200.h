@@ -156,11 +156,17 @@ typedef struct ppsci_plan_spec {
   int32_t pgrad_res[PPSCI_MAX_PGRAD];
   int32_t pgrad_aux[PPSCI_MAX_PGRAD];
   int32_t pgrad_reg[PPSCI_MAX_PGRAD];
-  /* Gated network — ModifiedMLP.forward_tensor (ppsci/arch/mlp.py:488-506): two extra first layers
-   *   U = act(x Wu + bu),  V = act(x Wv + bv)            (embed_u / embed_v, n_feat -> widths[1])
-   * and after every hidden layer  y <- y * U + (1 - y) * V  (a truncated Taylor product per jet direction).
-   * When non-zero: n_layers >= 2, all hidden widths equal, no dense_in / act_first; the parameter buffer is
-   * [W_1 | b_1 | ... | W_L | b_L | Wu | bu | Wv | bv] and the plan runs on the CUDA-core kernels (kernels_gate.cuh). */
+  /* Gated networks.  0: plain MLP.
+   * 1 — ModifiedMLP.forward_tensor (ppsci/arch/mlp.py:488-506): two extra layers
+   *       U = act(x Wu + bu),  V = act(x Wv + bv)            (embed_u / embed_v)
+   *     and after every hidden layer  y <- y * U + (1 - y) * V  (a truncated Taylor product per jet direction).
+   *     With act_first >= 0 (a Fourier embedding as layer 1) x is layer 1's stored output, otherwise the features.
+   * 2 — PirateNet.forward_tensor over PirateNetBlock.forward (mlp.py:617-624, 800-809): layer 1 is the embedding
+   *     (width = the blocks' width), then blocks of three layers: gate, gate, x <- alpha act(z3) + (1 - alpha) x
+   *     with one trainable alpha per block; n_layers = 1 + 3 * blocks + 1.
+   * Needs n_layers >= 2 (+1 with an embedding layer), equal widths of the gated layers, no dense_in.  Parameter /
+   * gradient buffers: [W_1 | b_1 | ... | W_L | b_L | Wu | bu | Wv | bv | alpha_0 ... alpha_{B-1}].  Gated plans run on
+   * the CUDA-core kernels (csrc/kernels_gate.cuh + the generic tile GEMMs); two-phase value calls are not offered. */
   int32_t gated;
 } ppsci_plan_spec;
 

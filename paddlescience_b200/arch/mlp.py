@@ -95,7 +95,8 @@ class MLP(base.Arch):
     for the kernels: ``[cos(x B), sin(x B)] = sin(x [B | B] + [pi/2 | 0])`` — tied effective weights, a constant bias
     and ``sin`` as that layer's activation (``NetSpec.act_first``); the gradient of the trainable kernel ``B`` is the
     sum of the two halves of the effective layer's weight gradient.  Not yet supported (raise ``NotImplementedError``
-    at construction): trainable periods, ``fourier`` together with weight_norm / random_weight / skip_connection.
+    at construction): trainable periods.  ``fourier`` composes with weight_norm / random_weight / skip_connection (one
+    staging buffer: the tied first layer in front of the reparametrised linear layers).
     """
 
     # 1: ModifiedMLP (two embedding layers + the gate after every hidden layer); 2: PirateNet (blocks of three layers,
@@ -137,9 +138,6 @@ class MLP(base.Arch):
         if self.fourier:
             if int(self.fourier["dim"]) % 2 != 0:  # FourierEmbedding.__init__, mlp.py:120-121
                 raise ValueError(f"out_features must be even, but got {self.fourier['dim']}.")
-            if weight_norm or random_weight or skip_connection:
-                raise NotImplementedError("MLP(fourier=...) together with weight_norm / random_weight / skip_connection "
-                                          "is not supported yet")
         # random_weight = {"mean": m, "std": s}: RandomWeightFactorization on EVERY layer incl. last_fc (mlp.py:56-92,
         # 248-256, 262-270): W = g * V (column scaling), g = exp(N(m, s)), V = glorot_normal / g
         self.random_weight = dict(random_weight) if random_weight else None
@@ -202,21 +200,18 @@ class MLP(base.Arch):
         self._n_eff = off  # length of the [W | b] buffer of the reference's own linear layers
         self._n_lin = off
         self._f_n0 = 0     # fourier: length of the effective first layer [W0 | b0] in front of them in the engine buffer
-        self._g_off = []   # weight_norm: per hidden layer, offset of its gain vector g_l (appended after the last bias)
+        self._g_off = {}   # weight_norm / random_weight: layer index -> offset of its gain vector g (behind the last bias)
         if self.weight_norm or self.random_weight:
-            for a, b in (self._shapes if self.random_weight else self._shapes[:-1]):
-                self._g_off.append(off)
-                off += b
-            self.register_buffer("_eff", torch.zeros(self._n_eff, dtype=dtype), persistent=False)
-            self.register_buffer("_eff_grad", torch.zeros(self._n_eff, dtype=dtype), persistent=False)
+            for i, (a, b) in enumerate(self._shapes):
+                if self._wn_layer(i):
+                    self._g_off[i] = off
+                    off += b
         if self.fourier:  # trainable kernel B [n_feat, D/2] stored behind the linear layers
             nf, dh = len(feat_src), int(self.fourier["dim"]) // 2
             self._f_shape = (nf, dh)
             self._f_off = off
             off += nf * dh
             self._f_n0 = nf * 2 * dh + 2 * dh
-            self.register_buffer("_eff", torch.zeros(self._f_n0 + self._n_lin, dtype=dtype), persistent=False)
-            self.register_buffer("_eff_grad", torch.zeros(self._f_n0 + self._n_lin, dtype=dtype), persistent=False)
         self.flat = nn.Parameter(torch.zeros(off, dtype=dtype))
         self.linears = [_LinearView(self, i) for i in range(len(hidden))]
         self.last_fc = _LinearView(self, len(hidden))
@@ -228,11 +223,15 @@ class MLP(base.Arch):
         # doubled (the first even layer only records skip).  A doubled pre-activation is the same linear layer with
         # W and b scaled by 2: the kernels read effective weights 2 W_i, 2 b_i for those layers and the chain rule
         # returns 2 x their gradients (host-side reparametrisation, like weight_norm).
+        # ModifiedMLP (mlp.py:495-504) doubles the GATED output of those layers instead (``y = y + skip`` behind the
+        # gate): the next linear layer sees 2 y, i.e. its weight (not its bias) is doubled.
         self.skip_connection = bool(skip_connection)
         self._skip_layers = [i for i in range(len(hidden)) if self.skip_connection and i % 2 == 0 and i >= 2]
-        if self._skip_layers:
-            self.register_buffer("_eff", torch.zeros(self._n_eff, dtype=dtype), persistent=False)
-            self.register_buffer("_eff_grad", torch.zeros(self._n_eff, dtype=dtype), persistent=False)
+        # the engine reads effective weights from a staging buffer [W0 | b0 (fourier) | reparametrised linear layers]
+        self._has_eff = bool(self.weight_norm or self.random_weight or self.fourier or self._skip_layers)
+        if self._has_eff:
+            self.register_buffer("_eff", torch.zeros(self._f_n0 + self._n_eff, dtype=dtype), persistent=False)
+            self.register_buffer("_eff_grad", torch.zeros(self._f_n0 + self._n_eff, dtype=dtype), persistent=False)
         self.reset_parameters()
         self._value_plan = None
 
@@ -279,12 +278,38 @@ class MLP(base.Arch):
         plain) or every layer under random weight factorization."""
         if self.random_weight:
             return True
-        return self.weight_norm and i < self._n_hidden
+        return self.weight_norm and i != self._n_hidden  # hidden layers (and the gated networks' embed_u / embed_v)
+
+    def _skip_slices(self):
+        """(start, stop) ranges of the staging buffer that the reference's skip connection doubles."""
+        out = []
+        for i in self._skip_layers:
+            if self._gated:  # the layer BEHIND hidden layer i reads 2 y: its weight
+                a, b = self._shapes[i + 1]
+                out.append((self._w_off[i + 1], self._w_off[i + 1] + a * b))
+            else:  # the pre-activation of hidden layer i is doubled: W_i and b_i (contiguous)
+                a, b = self._shapes[i]
+                out.append((self._w_off[i], self._b_off[i] + b))
+        return out
 
     def engine_params(self) -> torch.Tensor:
-        """The flat [W_1 | b_1 | ...] buffer passed to the native calls (effective weights under weight_norm)."""
-        if self.fourier:
-            with torch.no_grad():
+        """The flat [W_1 | b_1 | ...] buffer passed to the native calls (effective weights under weight_norm /
+        random_weight / skip_connection, the tied first layer of the Fourier embedding in front)."""
+        if not self._has_eff:
+            return self.flat.data
+        with torch.no_grad():
+            lin = self._eff[self._f_n0: self._f_n0 + self._n_eff]
+            lin.copy_(self.flat.data[: self._n_eff])
+            for i, (a, b) in enumerate(self._shapes):
+                if not self._wn_layer(i):
+                    continue
+                v = self.flat.data[self._w_off[i]: self._w_off[i] + a * b].view(a, b)
+                g = self.flat.data[self._g_off[i]: self._g_off[i] + b]
+                scale = g if self.random_weight else g / v.norm(p=2, dim=0, keepdim=True)
+                lin[self._w_off[i]: self._w_off[i] + a * b].view(a, b).copy_(v * scale)
+            for lo, hi in self._skip_slices():
+                lin[lo:hi].mul_(2.0)
+            if self.fourier:
                 nf, dh = self._f_shape
                 k = self.fourier_kernel
                 w0 = self._eff[: nf * 2 * dh].view(nf, 2 * dh)
@@ -293,65 +318,33 @@ class MLP(base.Arch):
                 b0 = self._eff[nf * 2 * dh: self._f_n0]
                 b0[:dh] = math.pi / 2  # cos(z) = sin(z + pi/2)
                 b0[dh:] = 0
-                self._eff[self._f_n0:].copy_(self.flat.data[: self._n_lin])
-            return self._eff
-        if self._skip_layers:
-            with torch.no_grad():
-                self._eff.copy_(self.flat.data[: self._n_eff])
-                for i in self._skip_layers:
-                    a, b = self._shapes[i]
-                    self._eff[self._w_off[i]: self._b_off[i] + b].mul_(2.0)  # W_i and b_i are contiguous
-            return self._eff
-        if not (self.weight_norm or self.random_weight):
-            return self.flat.data
-        with torch.no_grad():
-            self._eff.copy_(self.flat.data[: self._n_eff])
-            for i, (a, b) in enumerate(self._shapes):
-                if not self._wn_layer(i):
-                    continue
-                v = self.flat.data[self._w_off[i]: self._w_off[i] + a * b].view(a, b)
-                g = self.flat.data[self._g_off[i]: self._g_off[i] + b]
-                scale = g if self.random_weight else g / v.norm(p=2, dim=0, keepdim=True)
-                self._eff[self._w_off[i]: self._w_off[i] + a * b].view(a, b).copy_(v * scale)
         return self._eff
 
     def engine_grads(self) -> torch.Tensor:
         """Buffer the native calls accumulate the weight gradient into (same layout as ``engine_params``)."""
         if self.flat.grad is None:
             self.flat.grad = torch.zeros_like(self.flat.data)
-        return self._eff_grad if (self.weight_norm or self.random_weight or self._skip_layers or self.fourier) else self.flat.grad
+        return self._eff_grad if self._has_eff else self.flat.grad
 
     def finish_grads(self):
-        """Chain rule of the weight normalisation: gradients w.r.t. the effective weights -> (V, g); then the
-        staging buffer is cleared.  No-op for plain layers (the kernels accumulated into ``flat.grad`` directly)."""
-        if self.fourier:
-            with torch.no_grad():
-                nf, dh = self._f_shape
-                self.flat.grad[: self._n_lin] += self._eff_grad[self._f_n0:]
-                dw0 = self._eff_grad[: nf * 2 * dh].view(nf, 2 * dh)
-                self.flat.grad[self._f_off: self._f_off + nf * dh].view(nf, dh).add_(dw0[:, :dh] + dw0[:, dh:])
-                self._eff_grad.zero_()  # the constant bias [pi/2 | 0] takes no gradient
-            return
-        if self._skip_layers:
-            with torch.no_grad():
-                for i in self._skip_layers:
-                    a, b = self._shapes[i]
-                    self._eff_grad[self._w_off[i]: self._b_off[i] + b].mul_(2.0)  # d/dW = 2 d/dW_eff
-                self.flat.grad[: self._n_eff] += self._eff_grad
-                self._eff_grad.zero_()
-            return
-        if not (self.weight_norm or self.random_weight):
+        """Chain rule of the reparametrisations: gradients w.r.t. the effective weights -> the stored parameters
+        ((V, g), the tied Fourier kernel, the doubled layers); then the staging buffer is cleared.  No-op for plain
+        layers (the kernels accumulated into ``flat.grad`` directly)."""
+        if not self._has_eff:
             return
         with torch.no_grad():
             gr = self.flat.grad
-            gr[: self._n_eff] += self._eff_grad  # biases and the plain last layer pass through; V parts are fixed below
+            lin_g = self._eff_grad[self._f_n0: self._f_n0 + self._n_eff]
+            for lo, hi in self._skip_slices():
+                lin_g[lo:hi].mul_(2.0)  # d/dW = 2 d/dW_eff
+            gr[: self._n_eff] += lin_g  # biases and plain layers pass through; the V parts are fixed below
             for i, (a, b) in enumerate(self._shapes):
                 if not self._wn_layer(i):
                     continue
                 sl = slice(self._w_off[i], self._w_off[i] + a * b)
                 v = self.flat.data[sl].view(a, b)
                 g = self.flat.data[self._g_off[i]: self._g_off[i] + b]
-                dw = self._eff_grad[sl].view(a, b)
+                dw = lin_g[sl].view(a, b)
                 if self.random_weight:  # W = g * V  ->  dV = g * dW,  dg = sum_in V * dW
                     gr[sl].view(a, b).add_(g * dw - dw)
                     gr[self._g_off[i]: self._g_off[i] + b] += (v * dw).sum(dim=0)
@@ -361,6 +354,10 @@ class MLP(base.Arch):
                 dv = (g / norm) * (dw - v * (dot / (norm * norm)))
                 gr[sl].view(a, b).add_(dv - dw)  # replace the pass-through dW by dV
                 gr[self._g_off[i]: self._g_off[i] + b] += (dot / norm).view(-1)
+            if self.fourier:  # the tied kernel takes the sum of both halves; the constant bias [pi/2 | 0] takes none
+                nf, dh = self._f_shape
+                dw0 = self._eff_grad[: nf * 2 * dh].view(nf, 2 * dh)
+                gr[self._f_off: self._f_off + nf * dh].view(nf, dh).add_(dw0[:, :dh] + dw0[:, dh:])
             self._eff_grad.zero_()
 
     @property
@@ -460,8 +457,11 @@ class ModifiedMLP(MLP):
     jet-product gate after every hidden layer (csrc/kernels_gate.cuh), values, input derivatives of any supported order
     and the weight gradient included.  The flat parameter vector is ``[W_1 | b_1 | ... | last_fc | Wu | bu | Wv | bv]``;
     checkpoints use the reference's keys (``linears.i.*``, ``last_fc.*``, ``embed_u.0.*``, ``embed_v.0.*``).
-    ``periods`` are supported; ``skip_connection`` / ``weight_norm`` / ``fourier`` / ``random_weight`` raise
-    ``NotImplementedError`` (not built)."""
+    With ``fourier`` the embedding is the engine's first layer and ``embed_u`` / ``embed_v`` read its stored output
+    (any ``fourier["dim"]``).  ``periods``, ``fourier``, ``weight_norm`` (hidden layers and both embeddings),
+    ``random_weight`` (every layer) and ``skip_connection`` (the reference's ``y = y + skip`` behind the gate, i.e. a
+    doubled input of the next layer) are host-side reparametrisations as in ``MLP``; ``skip_connection`` together with
+    weight_norm / random_weight raises ``NotImplementedError``."""
 
     _gated = 1
 
@@ -487,11 +487,11 @@ class ModifiedMLP(MLP):
             raise ValueError("num_layers should be an int")
         if num_layers < 1:
             raise ValueError("ModifiedMLP needs at least one hidden layer (embed_u / embed_v map onto hidden_size)")
-        if skip_connection or weight_norm or fourier or random_weight:
-            raise NotImplementedError("ModifiedMLP(skip_connection / weight_norm / fourier / random_weight) is not "
-                                      "supported by the gated kernels yet")
-        super().__init__(input_keys, output_keys, num_layers, hidden_size, activation, False, False, input_dim, output_dim,
-                         periods, None, None, dtype)
+        if skip_connection and (weight_norm or random_weight):
+            raise NotImplementedError("ModifiedMLP(skip_connection=True) together with weight_norm / random_weight is not "
+                                      "supported yet")
+        super().__init__(input_keys, output_keys, num_layers, hidden_size, activation, skip_connection, weight_norm,
+                         input_dim, output_dim, periods, fourier, random_weight, dtype)
 
 
 class PirateNet(MLP):
@@ -511,8 +511,9 @@ class PirateNet(MLP):
     ``PirateNetBlock(cur_size)`` adds its input to a ``cur_size``-wide output and multiplies it with ``hidden_size``-wide
     embeddings).  Flat parameter vector: ``[blocks' linears | last_fc | Wu | bu | Wv | bv | alphas | fourier kernel]``;
     checkpoints use the reference's keys (``blocks.k.linear{1,2,3}.*``, ``blocks.k.alpha``, ``embed_{u,v}.0.*``,
-    ``last_fc.*``, ``fourier_emb.kernel``).  ``weight_norm`` / ``random_weight`` and a PirateNet without ``fourier``
-    raise ``NotImplementedError`` (not built)."""
+    ``last_fc.*``, ``fourier_emb.kernel``).  ``random_weight`` (every layer: the configuration of the reference's
+    examples) and ``weight_norm`` (the two embeddings) are host-side reparametrisations as in ``MLP``; a PirateNet
+    without ``fourier`` raises ``NotImplementedError``."""
 
     _gated = 2
 
@@ -537,16 +538,21 @@ class PirateNet(MLP):
             raise ValueError("num_blocks should be an int")
         if num_blocks < 1:
             raise ValueError("PirateNet needs at least one block")
-        if weight_norm or random_weight:
-            raise NotImplementedError("PirateNet(weight_norm / random_weight) is not supported by the gated kernels yet")
         if not fourier:
             raise NotImplementedError("PirateNet without fourier features is not supported (the blocks need an input of "
                                       "their own width)")
         if int(fourier["dim"]) != hidden_size:
             raise ValueError(f"PirateNet blocks keep their input width: fourier['dim'] ({fourier['dim']}) must equal "
                              f"hidden_size ({hidden_size})")
-        super().__init__(input_keys, output_keys, None, (hidden_size,) * (3 * num_blocks), activation, False, False,
-                         input_dim, output_dim, periods, fourier, None, dtype)
+        super().__init__(input_keys, output_keys, None, (hidden_size,) * (3 * num_blocks), activation, False, weight_norm,
+                         input_dim, output_dim, periods, fourier, random_weight, dtype)
+
+    def _wn_layer(self, i: int) -> bool:
+        """random_weight factorises every layer (blocks, embeddings, last_fc); weight_norm only the two embeddings
+        (mlp.py:722-759 — PirateNetBlock takes no weight_norm, last_fc is plain)."""
+        if self.random_weight:
+            return True
+        return self.weight_norm and i > self._n_hidden
 
     @property
     def alphas(self) -> torch.Tensor:

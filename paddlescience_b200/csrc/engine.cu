@@ -124,6 +124,10 @@ static bool fused_fwd_ok(const ppsci_plan* P);
 static bool fused_dx_ok(const ppsci_plan* P);
 static bool fused_fwd16_ok(const ppsci_plan* P);
 
+// gated plans: 1 when layer 1 is an embedding layer whose stored output feeds the embed_u / embed_v layers and the
+// first gated layer (PirateNet always; ModifiedMLP with a Fourier embedding, act_first >= 0), 0 when they read the seeds
+static inline int gate_emb(const ppsci_plan_spec& s) { return (s.gated == 2 || (s.gated == 1 && s.act_first >= 0)) ? 1 : 0; }
+
 static void carve(const ppsci_plan* P, int64_t nc, Carve* cv) {
   const size_t es = P->spec.dtype == PPSCI_F64 ? 8 : 4;
   const int L = P->spec.n_layers;
@@ -147,14 +151,16 @@ static void carve(const ppsci_plan* P, int64_t nc, Carve* cv) {
   for (int l = 1; l < L; ++l) cv->a[l] = take(tc_astash_needed(P, l) ? (size_t)P->C * nc * P->ld[l] * es : 0);
   const bool gated = P->spec.gated != 0;
   for (int l = 1; l < L; ++l) cv->gt[l] = take(gated ? (size_t)P->C * nc * P->ld[l] * es : 0);
-  cv->zu = take(gated ? (size_t)P->C * nc * P->ld[1] * es : 0);
-  cv->zv = take(gated ? (size_t)P->C * nc * P->ld[1] * es : 0);
-  cv->zub = take(gated ? (size_t)P->C * nc * P->ld[1] * es : 0);
-  cv->zvb = take(gated ? (size_t)P->C * nc * P->ld[1] * es : 0);
+  const int emb = gate_emb(P->spec);
+  const int lg = (gated && emb + 1 <= L) ? emb + 1 : 1;  // first gated layer
+  cv->zu = take(gated ? (size_t)P->C * nc * P->ld[lg] * es : 0);
+  cv->zv = take(gated ? (size_t)P->C * nc * P->ld[lg] * es : 0);
+  cv->zub = take(gated ? (size_t)P->C * nc * P->ld[lg] * es : 0);
+  cv->zvb = take(gated ? (size_t)P->C * nc * P->ld[lg] * es : 0);
   const bool pirate = P->spec.gated == 2;
   cv->xres = take(pirate ? (size_t)P->C * nc * P->ld[1] * es : 0);
-  cv->wtu = take(pirate ? (size_t)P->spec.widths[1] * P->spec.widths[1] * es : 0);
-  cv->wtv = take(pirate ? (size_t)P->spec.widths[1] * P->spec.widths[1] * es : 0);
+  cv->wtu = take(gated && emb ? (size_t)P->spec.widths[1] * P->spec.widths[lg] * es : 0);
+  cv->wtv = take(gated && emb ? (size_t)P->spec.widths[1] * P->spec.widths[lg] * es : 0);
   cv->total = off;
 }
 
@@ -208,11 +214,14 @@ extern "C" int ppsci_b200_plan_create(const ppsci_plan_spec* s, ppsci_plan** out
     if (s->n_layers < 2) return fail("plan_create: a gated network needs at least one hidden layer");
     if (s->gated != 1 && s->gated != 2) return fail("plan_create: gated must be 0, 1 (ModifiedMLP) or 2 (PirateNet)");
     if (s->dense_in) return fail("plan_create: gated networks do not take dense_in");
-    if (s->gated == 1 && s->act_first >= 0) return fail("plan_create: a gated network of kind 1 has one activation");
     if (s->gated == 2 && (s->n_layers < 5 || (s->n_layers - 2) % 3 != 0))
       return fail("plan_create: gated kind 2 needs 1 embedding layer + 3 layers per block + the output layer");
-    for (int l = 2; l < s->n_layers; ++l)
-      if (s->widths[l] != s->widths[1]) return fail("plan_create: a gated network needs equal hidden widths");
+    const int emb = gate_emb(*s);
+    if (s->n_layers < emb + 2) return fail("plan_create: a gated network needs a hidden layer behind its embedding layer");
+    for (int l = emb + 2; l < s->n_layers; ++l)
+      if (s->widths[l] != s->widths[emb + 1]) return fail("plan_create: a gated network needs equal hidden widths");
+    if (s->gated == 2 && s->widths[1] != s->widths[2])
+      return fail("plan_create: gated kind 2 adds a block's input to its output: the embedding layer needs the blocks' width");
     if (s->backend == 2) return fail("plan_create: gated networks run on the CUDA-core kernels (backend 0 or 1)");
   }
   int C = 1, kmax = 1;
@@ -291,9 +300,10 @@ extern "C" int ppsci_b200_plan_create(const ppsci_plan_spec* s, ppsci_plan** out
   if (s->gated) {
     for (int e = 0; e < 2; ++e) {
       P->gate_w_off[e] = off;
-      off += (int64_t)s->widths[s->gated == 2 ? 1 : 0] * s->widths[1];  // kind 2: the embeddings read layer 1's output
+      const int emb = gate_emb(*s);  // 1: the embeddings read layer 1's output
+      off += (int64_t)s->widths[emb] * s->widths[emb + 1];
       P->gate_b_off[e] = off;
-      off += s->widths[1];
+      off += s->widths[emb + 1];
     }
     if (s->gated == 2) {
       P->alpha_off = off;
@@ -575,7 +585,8 @@ static int run(ppsci_plan* P, const CallArgs& a) {
   auto kmf = k_mix_fwd<T, KMAX>;
   auto kmb = k_mix_bwd<T, KMAX>;
   // what follows hidden layer l in a gated plan: 0 gate, 1 adaptive residual (end of a block), 2 plain activation
-  auto post_kind = [&](int l) -> int { return !pirate ? 0 : (l == 1 ? 2 : ((l - 2) % 3 == 2 ? 1 : 0)); };
+  const int emb = gated ? gate_emb(s) : 0;  // layer 1 is an embedding layer (its stored output feeds embed_u / embed_v)
+  auto post_kind = [&](int l) -> int { return (emb && l == 1) ? 2 : ((pirate && (l - 2) % 3 == 2) ? 1 : 0); };
   auto fill_mix = [&](int l, int64_t nc, MixArgs<T>* ma) {
     memset(ma, 0, sizeof(*ma));
     ma->J = P->J;
@@ -622,8 +633,8 @@ static int run(ppsci_plan* P, const CallArgs& a) {
                    reinterpret_cast<T*>(ws + cv.wt[l]), K, N);
       P->launches++;
     }
-    for (int e = 0; e < (pirate ? 2 : 0); ++e) {  // the embeddings hand an adjoint back to layer 1's output
-      const int K = s.widths[1], N = s.widths[1];
+    for (int e = 0; e < (emb ? 2 : 0); ++e) {  // the embeddings hand an adjoint back to layer 1's output
+      const int K = s.widths[1], N = s.widths[2];
       const long long tot = (long long)K * N;
       auto kt = k_transpose<T>;
       ProfScope ps_(P, CLS_MISC, st);
@@ -925,22 +936,28 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         }
         P->launches++;
       };
-      if (pirate && l == 1) post_fwd(1);
-      if (gated && l == 1) {  // embed_u / embed_v: two more layers from the seeds (kind 1) / from layer 1's output (kind 2)
-        if (pirate) {
+      if (emb && l == 1) post_fwd(1);
+      if (gated && l == 1) {  // embed_u / embed_v: two more layers from the seeds, or from the embedding layer's output
+        dim3 grid_e = grid;
+        if (emb) {
           fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.gt[1]), P->ld[1], nc_max, A_PLAIN, &g.A);
           g.Kdim = s.widths[1];
+          g.Nout = s.widths[2];
+          g.ldb = s.widths[2];
+          g.ldo = P->ld[2];
+          g.oplane = (long long)nc_max * P->ld[2];
+          grid_e = dim3(ptiles, (unsigned)((g.Nout + TN - 1) / TN));
         }
         for (int e = 0; e < 2; ++e) {
           g.B = params + P->gate_w_off[e];
           g.bias = params + P->gate_b_off[e];
           g.Out = reinterpret_cast<T*>(ws + (e == 0 ? cv.zu : cv.zv));
           ProfScope ps_(P, CLS_FWD, st);
-          PPSCI_LAUNCH(kf, grid, dim3(NTHREADS), smem_f, st, g);
+          PPSCI_LAUNCH(kf, grid_e, dim3(NTHREADS), smem_f, st, g);
           P->launches++;
         }
       }
-      if (gated && l < L && !(pirate && l == 1)) post_fwd(l);
+      if (gated && l < L && !(emb && l == 1)) post_fwd(l);
     }
     // ---------------- residual program + loss + output adjoints ----------------
     if (a.jets_out) {
@@ -1231,20 +1248,22 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           P->launches++;
         }
         if (gated && l == 1) {  // dWu, dbu, dWv, dbv from the adjoints the gates accumulated
-          unsigned kt_e = kt;
-          if (pirate) {
+          unsigned kt_e = kt, nt_e = nt;
+          if (emb) {
             fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.gt[1]), P->ld[1], nc_max, A_PLAIN, &g.A);
             g.Kdim = s.widths[1];
+            g.Nout = s.widths[2];
             kt_e = (unsigned)((g.Kdim + TM - 1) / TM);
+            nt_e = (unsigned)((g.Nout + TN - 1) / TN);
           }
           for (int e = 0; e < 2; ++e) {
             g.Zbar = reinterpret_cast<const T*>(ws + (e == 0 ? cv.zub : cv.zvb));
-            g.ldzb = P->ld[1];
-            g.zbplane = (long long)nc_max * P->ld[1];
+            g.ldzb = P->ld[emb + 1];
+            g.zbplane = (long long)nc_max * P->ld[emb + 1];
             g.dW = grads + P->gate_w_off[e];
             g.db = grads + P->gate_b_off[e];
             ProfScope ps_(P, CLS_DW, st);
-            PPSCI_LAUNCH(kw, dim3(kt_e, nt, splits), dim3(NTHREADS), smem_w, st, g);
+            PPSCI_LAUNCH(kw, dim3(kt_e, nt_e, splits), dim3(NTHREADS), smem_w, st, g);
             P->launches++;
           }
         }
@@ -1327,9 +1346,9 @@ static int run(ppsci_plan* P, const CallArgs& a) {
           PPSCI_LAUNCH(kx, grid, dim3(NTHREADS), smem_x, st, g);
           P->launches++;
         }
-        if (gated && pirate && l == 2) {  // layer 1's output also feeds the embeddings: += Zubar Wu^T + Zvbar Wv^T
+        if (gated && emb && l == 2) {  // layer 1's output also feeds the embeddings: += Zubar Wu^T + Zvbar Wv^T
           for (int e = 0; e < 2; ++e) {
-            fill_act<T>(P, reinterpret_cast<const T*>(ws + (e == 0 ? cv.zub : cv.zvb)), P->ld[1], nc_max, A_PLAIN, &g.A);
+            fill_act<T>(P, reinterpret_cast<const T*>(ws + (e == 0 ? cv.zub : cv.zvb)), P->ld[2], nc_max, A_PLAIN, &g.A);
             g.B = reinterpret_cast<const T*>(ws + (e == 0 ? cv.wtu : cv.wtv));
             g.accum = 1;
             ProfScope ps_(P, CLS_DX, st);
@@ -1358,7 +1377,7 @@ static int run(ppsci_plan* P, const CallArgs& a) {
               ma.use_res = (l - 1 != L - 1) ? 1 : 0;  // the last block's output feeds the output layer only
               ma.write_res = 1;
             } else {
-              ma.use_res = 1;  // block 0's residual path
+              ma.use_res = pirate ? 1 : 0;  // block 0's residual path
             }
             const long long want = (tot + 127) / 128, cap = 8LL * P->num_sms;
             PPSCI_LAUNCH(kmb, dim3((unsigned)(want < cap ? want : cap)), dim3(128), 0, st, ma);

@@ -65,7 +65,8 @@ class NetSpec:
     def n_params(self) -> int:
         n = sum(self.widths[i] * self.widths[i + 1] + self.widths[i + 1] for i in range(len(self.widths) - 1))
         if self.gated:  # [Wu | bu | Wv | bv] behind the layers (input: the features, or layer 1's output for kind 2)
-            n += 2 * (self.widths[1 if self.gated == 2 else 0] * self.widths[-2] + self.widths[-2])
+            emb = 1 if (self.gated == 2 or self.act_first is not None) else 0  # the embeddings read layer 1's output
+            n += 2 * (self.widths[emb] * self.widths[-2] + self.widths[-2])
         if self.gated == 2:  # one alpha per block
             n += (len(self.widths) - 3) // 3
         return n

@@ -1,3 +1,4 @@
+from .agda import AGDA
 from .base import LossAggregator
 from .grad_norm import GradNorm
 from .ntk import NTK
@@ -5,7 +6,7 @@ from .pcgrad import PCGrad
 from .relobralo import Relobralo
 from .sum import Sum
 
-__all__ = ["LossAggregator", "Sum", "PCGrad", "GradNorm", "NTK", "Relobralo", "build_mtl_aggregator"]
+__all__ = ["LossAggregator", "Sum", "AGDA", "PCGrad", "GradNorm", "NTK", "Relobralo", "build_mtl_aggregator"]
 
 
 def build_mtl_aggregator(cfg):

@@ -44,8 +44,7 @@ def test_constructor_layout_and_state_dict():
     np.testing.assert_array_equal(eff[36:].numpy(), m.flat.data[: m._n_lin].numpy())
     with pytest.raises(ValueError):
         ppsci.arch.MLP(("x",), ("u",), 2, 16, fourier={"dim": 5, "scale": 1.0})
-    with pytest.raises(NotImplementedError):
-        ppsci.arch.MLP(("x",), ("u",), 2, 16, fourier={"dim": 4, "scale": 1.0}, weight_norm=True)
+
 
 
 def test_kernel_gradient_is_the_sum_of_both_halves():
@@ -147,3 +146,30 @@ def test_solver_trains_a_fourier_feature_network(to_static):
     l1 = total_loss()
     assert l1 < 0.5 * l0, (l0, l1)
     assert float((model.fourier_kernel.detach() - k0).abs().max()) > 1e-4  # the kernel is trained
+
+
+@pytest.mark.parametrize("opts", [dict(weight_norm=True), dict(random_weight={"mean": 1.0, "std": 0.1}), dict(skip_connection=True)])
+def test_fourier_with_reparametrised_layers_matches_oracle(monkeypatch, opts):
+    """fourier together with weight_norm / random_weight / skip_connection: the staging buffer carries the tied first
+    layer in front of the reparametrised linear layers; gradients chain back to (V, g) and the kernel."""
+    from tests.emul.build_emul import build
+    from tests.reparam_ref import oracle_loss_and_grad
+
+    monkeypatch.setattr(B, "_default", B.Library(build()))
+    ppsci.utils.misc.set_random_seed(7)
+    nl = 4 if opts.get("skip_connection") else 2
+    m = ppsci.arch.MLP(("x", "y"), ("u",), nl, 16, "tanh", fourier={"dim": 12, "scale": 1.5}, dtype=torch.float64, **opts)
+    with torch.no_grad():
+        m.flat.data[: m._n_eff] += 0.1 * torch.randn(m._n_eff, dtype=torch.float64)
+    rect = ppsci.geometry.Rectangle((0, 0), (1, 1))
+    cst = ppsci.constraint.InteriorConstraint(ppsci.equation.Laplace(2).equations, {"laplace": 0}, rect,
+                                              {"dataset": "IterableNamedArrayDataset", "iters_per_epoch": 1, "batch_size": 40},
+                                              ppsci.loss.MSELoss("mean"), name="EQ")
+    ds = cst.data_loader.loader
+    inp = {k: v.double() for k, v in ds.input.items()}
+    lab = {k: v.double() for k, v in ds.label.items()}
+    losses_all, _ = ppsci.utils.ExpressionSolver().train_forward((cst.output_expr,), [inp], m, {"EQ": cst}, [lab], [None])
+    om = O.OracleMLP(("x", "y"), ("u",), [16] * nl, "tanh", None, bool(opts.get("skip_connection")), {"dim": 12, "scale": 1.5})
+    lo, g = oracle_loss_and_grad(m, om, O.laplace_expr(2), inp, lab)
+    assert float(losses_all["laplace"]) == pytest.approx(float(lo["laplace"]), rel=1e-10)
+    np.testing.assert_allclose(m.flat.grad.numpy(), g.numpy(), rtol=1e-7, atol=1e-10 * float(g.abs().max()))

@@ -236,6 +236,6 @@ def test_modified_mlp_gated_plan_and_checkpoint_keys(monkeypatch):
         assert float(losses_all[k]) == pytest.approx(float(lo[k]), rel=1e-10)
     np.testing.assert_allclose(m.flat.grad.numpy(), g.numpy(), rtol=1e-8, atol=1e-11 * float(g.abs().max()))
     with pytest.raises(NotImplementedError):
-        ppsci.arch.ModifiedMLP(("x",), ("u",), 2, 8, weight_norm=True)
+        ppsci.arch.ModifiedMLP(("x",), ("u",), 2, 8, weight_norm=True, skip_connection=True)
     with pytest.raises(ValueError):
         ppsci.arch.ModifiedMLP(("x",), ("u",), None, (8, 8))

@@ -138,7 +138,7 @@ def test_ntk_and_relobralo_weights_follow_the_reference_formulas():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["PCGrad", "GradNorm", "NTK", "Relobralo"])
+@pytest.mark.parametrize("name", ["PCGrad", "GradNorm", "NTK", "Relobralo", "AGDA"])
 def test_solver_trains_with_per_term_gradient_aggregators(name):
     """Solver.train with the aggregators that consume per-term gradients (one fused call per loss key): the loss goes down and,
     where the aggregator keeps weights, they move."""
@@ -153,7 +153,8 @@ def test_solver_trains_with_per_term_gradient_aggregators(name):
                                              {**cfg, "batch_size": 256}, ppsci.loss.MSELoss("mean"), name="BC")
     mtl = ppsci.loss.mtl
     agg = {"PCGrad": lambda: mtl.PCGrad(model), "GradNorm": lambda: mtl.GradNorm(model, 2, update_freq=5),
-           "NTK": lambda: mtl.NTK(model, 2, update_freq=5), "Relobralo": lambda: mtl.Relobralo(2)}[name]()
+           "NTK": lambda: mtl.NTK(model, 2, update_freq=5), "Relobralo": lambda: mtl.Relobralo(2),
+           "AGDA": lambda: mtl.AGDA(model, M=10)}[name]()
     solver = ppsci.solver.Solver(model, {"EQ": pde, "BC": bc}, None, ppsci.optimizer.Adam(2e-3)(model), epochs=1,
                                  iters_per_epoch=60, equation={"lap": eq}, loss_aggregator=agg)
     fh = ppsci.utils.ExpressionSolver()
@@ -173,3 +174,46 @@ def test_solver_trains_with_per_term_gradient_aggregators(name):
         assert float((agg.weight - 1).abs().max()) > 1e-3
     if name == "Relobralo":
         assert float((agg.lmbda - 1).abs().max()) > 1e-4
+
+
+def test_agda_follows_the_reference_formulas():
+    """mtl.AGDA (ppsci/loss/mtl/agda.py:27-161) on given per-term gradients: smoothed losses (eq. 16-18), magnitude
+    re-weighting and the projection of the data-loss gradient; L^smooth(kM) persists between calls (the reference keeps it
+    in locals and raises off the multiples of M)."""
+    torch.manual_seed(1)
+
+    class _M:
+        flat = torch.nn.Parameter(torch.zeros(40, dtype=torch.float64))
+
+    m = _M()
+    agda = ppsci.loss.mtl.AGDA(m, M=2, gamma=0.9)
+    with pytest.raises(ValueError):
+        agda({"a": torch.tensor(1.0)}, 0)
+    Lf = Lu = 0.0
+    accf = accu = 0.0
+    kM = None
+    for step, (lf, lu) in enumerate([(2.0, 0.5), (1.5, 0.6), (1.0, 0.2)]):
+        gf = torch.randn(40, dtype=torch.float64)
+        gu = torch.randn(40, dtype=torch.float64) - (0.8 * gf if step == 1 else 0)  # step 1: conflicting gradients
+        a = agda({"pde": torch.tensor(lf, dtype=torch.float64), "bc": torch.tensor(lu, dtype=torch.float64)}, step)
+        assert float(a.loss) == pytest.approx(lf + lu)
+        a.set_grads({"pde": gf, "bc": gu})
+        a.backward()
+        Lf = 0.9 * Lf + 0.1 * lf
+        Lu = 0.9 * Lu + 0.1 * lu
+        if step % 2 == 0:
+            kM = (Lf, Lu)
+        tf, tu = Lf / kM[0], Lu / kM[1]
+        accf += tf
+        accu += tu
+        rf, ru = tf / accf, tu / accu
+        nf, nu = gf.norm(), gu.norm()
+        Eg = (nf + nu) / 2
+        gfb = (rf * (Eg - nf) + nf) / nf * gf
+        gub = (ru * (Eg - nu) + nu) / nu * gu
+        d = (gfb * gub).sum()
+        if step == 1:
+            assert float(d) < 0
+        if d < 0:
+            gub = gub - d / (gfb * gfb).sum() * gfb
+        np.testing.assert_allclose(m.flat.grad.numpy(), (gfb + gub).numpy(), rtol=1e-12)

@@ -130,3 +130,59 @@ def test_solver_trains_a_piratenet():
     l1 = total_loss()
     assert l1 < 0.7 * l0, (l0, l1)
     assert float(model.alphas.abs().max()) > 1e-4  # the residual weights leave their zero start
+
+
+@pytest.mark.parametrize("opts", [
+    dict(random_weight={"mean": 1.0, "std": 0.1}, periods={"x": (2.0, False)}),  # examples/allen_cahn/conf/allen_cahn_piratenet.yaml in miniature
+    dict(weight_norm=True),
+])
+def test_piratenet_with_factorised_weights_matches_oracle(monkeypatch, opts):
+    """PirateNet(random_weight=...) — RandomWeightFactorization on the blocks' linears, both embeddings and last_fc
+    (mlp.py:553-590, 722-797), the configuration of the reference's examples — and weight_norm on the embeddings
+    (mlp.py:722-759; the blocks' linears and last_fc stay plain): host-side reparametrisation around the gated plan."""
+    from tests.emul.build_emul import build
+    from tests.reparam_ref import oracle_loss_and_grad
+
+    monkeypatch.setattr(B, "_default", B.Library(build()))
+    ppsci.utils.misc.set_random_seed(3)
+    m = ppsci.arch.PirateNet(("x", "y"), ("u", "v"), 2, 16, "tanh", fourier=FOURIER, dtype=torch.float64, **opts)
+    with torch.no_grad():
+        m.flat.data[: m._alpha_off] += 0.1 * torch.randn(m._alpha_off, dtype=torch.float64)
+        m.alphas.copy_(torch.tensor([0.3, -0.2], dtype=torch.float64))
+    inp, lab, losses_all = _train_forward(m, 36, "cpu", torch.float64)
+    om = O.OracleMLP(("x", "y"), ("u", "v"), [16] * 2, "tanh", opts.get("periods"), fourier=FOURIER, pirate=True)
+    lo, g = oracle_loss_and_grad(m, om, _exprs(), inp, lab)
+    for k in lo:
+        assert float(losses_all[k]) == pytest.approx(float(lo[k]), rel=1e-10)
+    np.testing.assert_allclose(m.flat.grad.numpy(), g.numpy(), rtol=1e-7, atol=1e-10 * float(g.abs().max()))
+    sd = m.state_dict()
+    assert "embed_u.0.weight_v" in sd and "embed_v.0.weight_g" in sd
+    assert ("blocks.0.linear1.weight_v" in sd) == bool(opts.get("random_weight"))  # weight_norm leaves the blocks plain
+    assert ("last_fc.weight_g" in sd) == bool(opts.get("random_weight"))
+    m2 = ppsci.arch.PirateNet(("x", "y"), ("u", "v"), 2, 16, "tanh", fourier=FOURIER, dtype=torch.float64, **opts)
+    m2.set_state_dict(sd)
+    assert torch.equal(m2.flat.data, m.flat.data)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float64, 1e-10), (torch.float32, 2e-5)])
+def test_piratenet_example_configuration_on_gpu_matches_oracle(dtype, tol):
+    """examples/allen_cahn/conf/allen_cahn_piratenet.yaml in miniature: 3 blocks x 64, fourier + random_weight + periods."""
+    from tests.reparam_ref import oracle_loss_and_grad
+
+    ppsci.utils.misc.set_random_seed(3)
+    opts = dict(fourier={"dim": 64, "scale": 2.0}, random_weight={"mean": 1.0, "std": 0.1}, periods={"x": (2.0, False)})
+    m = ppsci.arch.PirateNet(("x", "y"), ("u", "v"), 3, 64, "tanh", dtype=dtype, **opts)
+    with torch.no_grad():
+        m.alphas.copy_(torch.tensor([0.3, -0.2, 0.5], dtype=dtype))
+    mc = m
+    m = ppsci.arch.PirateNet(("x", "y"), ("u", "v"), 3, 64, "tanh", dtype=dtype, **opts)
+    m.flat.data.copy_(mc.flat.data)
+    m = m.to("cuda")
+    inp, lab, losses_all = _train_forward(m, 2048, "cuda", dtype)
+    om = O.OracleMLP(("x", "y"), ("u", "v"), [64] * 3, "tanh", opts["periods"], fourier=opts["fourier"], pirate=True)
+    lo, g = oracle_loss_and_grad(mc, om, _exprs(), inp, lab)
+    for k in lo:
+        assert abs(float(losses_all[k]) - float(lo[k])) <= tol * abs(float(lo[k])), k
+    err = float((m.flat.grad.detach().cpu().double() - g).norm() / g.norm())
+    assert err <= 5 * tol, err
