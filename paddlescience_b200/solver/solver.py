@@ -122,9 +122,9 @@ class Solver:
         self.forward_helper = expression.ExpressionSolver()
         self.forward_helper.nvtx_flag = self.nvtx_flag
         self.loss_aggregator = loss_aggregator or mtl.Sum()
-        if type(self.loss_aggregator).__name__ not in ("Sum", "PCGrad", "GradNorm", "NTK", "Relobralo"):
+        if type(self.loss_aggregator).__name__ not in ("Sum", "PCGrad", "GradNorm", "NTK", "Relobralo", "AGDA"):
             raise NotImplementedError("loss aggregators supported by the adjoint kernels: Sum (one fused call); PCGrad, "
-                                      "GradNorm, NTK, Relobralo (one call per loss term)")
+                                      "GradNorm, NTK, Relobralo, AGDA (one call per loss term)")
         if getattr(self.loss_aggregator, "needs_per_key_grads", False) and getattr(self.loss_aggregator, "model", None) is None:
             self.loss_aggregator.model = self.model  # Relobralo(num_losses) has no model argument in the reference
         # compile every constraint's expressions now (solver.py:496-535 does its sympy conversion here)

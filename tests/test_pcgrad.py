@@ -217,3 +217,23 @@ def test_agda_follows_the_reference_formulas():
         if d < 0:
             gub = gub - d / (gfb * gfb).sum() * gfb
         np.testing.assert_allclose(m.flat.grad.numpy(), (gfb + gub).numpy(), rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["Sum", "PCGrad", "GradNorm", "NTK", "Relobralo", "AGDA"])
+def test_solver_accepts_every_reference_aggregator(name):
+    """ppsci/loss/mtl/__init__.py:15-33 lists them; Solver wires the per-term-gradient ones to the one-call-per-loss-key path."""
+    model = ppsci.arch.MLP(("x", "y"), ("u",), 2, 8, "tanh")
+    eq = ppsci.equation.Laplace(2)
+    rect = ppsci.geometry.Rectangle((0, 0), (1, 1))
+    cfg = {"dataset": "IterableNamedArrayDataset", "iters_per_epoch": 1}
+    pde = ppsci.constraint.InteriorConstraint(eq.equations, {"laplace": 0}, rect, {**cfg, "batch_size": 16},
+                                              ppsci.loss.MSELoss("mean"), name="EQ")
+    bc = ppsci.constraint.BoundaryConstraint({"u": lambda out: out["u"]}, {"u": lambda d: d["x"] ** 2 - d["y"] ** 2}, rect,
+                                             {**cfg, "batch_size": 8}, ppsci.loss.MSELoss("mean"), name="BC")
+    mtl = ppsci.loss.mtl
+    agg = {"Sum": lambda: mtl.Sum(), "PCGrad": lambda: mtl.PCGrad(model), "GradNorm": lambda: mtl.GradNorm(model, 2),
+           "NTK": lambda: mtl.NTK(model, 2), "Relobralo": lambda: mtl.Relobralo(2), "AGDA": lambda: mtl.AGDA(model)}[name]()
+    solver = ppsci.solver.Solver(model, {"EQ": pde, "BC": bc}, None, ppsci.optimizer.Adam(2e-3)(model), epochs=1,
+                                 iters_per_epoch=2, equation={"lap": eq}, loss_aggregator=agg)
+    assert solver.loss_aggregator is agg
+    assert bool(getattr(agg, "needs_per_key_grads", False)) == (name != "Sum")
