@@ -9,6 +9,9 @@ REFERENCE_ACTS = ("elu", "relu", "selu", "gelu", "leaky_relu", "sigmoid", "silu"
                   "tanh", "identity", "siren", "stan")
 
 
+_WARNED = {"swish": False}
+
+
 def get_activation(act_name: str) -> str:
     """Validate ``act_name`` and return its canonical lower-case name.
 
@@ -21,4 +24,13 @@ def get_activation(act_name: str) -> str:
         raise NotImplementedError(
             f"activation '{act_name}' has no Taylor-jet kernel in this engine yet "
             f"(supported: {sorted(ACT_IDS)})")
+    if name == "swish" and not _WARNED["swish"]:
+        # activation.py:45-55, 149, 169-171: the reference instantiates one Swish per layer, each with a TRAINABLE scalar
+        # beta (x * sigmoid(beta x), beta = 1 at start).  The jet kernels have no per-layer activation parameter: beta
+        # stays 1, i.e. "swish" trains like "silu".  Said once, loudly, instead of silently.
+        _WARNED["swish"] = True
+        import warnings
+
+        warnings.warn("activation 'swish': the reference trains one scalar beta per layer (Swish, beta = 1 at start); this "
+                      "engine keeps beta fixed at 1 (identical to 'silu')", stacklevel=2)
     return name

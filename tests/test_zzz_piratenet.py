@@ -186,3 +186,33 @@ def test_piratenet_example_configuration_on_gpu_matches_oracle(dtype, tol):
         assert abs(float(losses_all[k]) - float(lo[k])) <= tol * abs(float(lo[k])), k
     err = float((m.flat.grad.detach().cpu().double() - g).norm() / g.norm())
     assert err <= 5 * tol, err
+
+
+@pytest.mark.parametrize("kind", ["pirate", "modified_fourier"])
+def test_gated_plans_are_chunk_invariant(kind):
+    """Several workspace chunks per call: the gates' first-use flags, the carried residual adjoint and the embeddings'
+    accumulators are per chunk; loss and gradient equal the single-chunk call (emulated kernels)."""
+    from paddlescience_b200.engine.compiler import compile_residuals
+    from paddlescience_b200.engine.plan import ResidualPlan
+    from tests.emul.build_emul import build
+
+    lib = B.Library(build())
+    if kind == "pirate":
+        m = _model(torch.float64, blocks=2)
+    else:
+        ppsci.utils.misc.set_random_seed(1)
+        m = ppsci.arch.ModifiedMLP(("x", "y"), ("u", "v"), 3, 16, "tanh", fourier={"dim": 12, "scale": 1.5}, dtype=torch.float64)
+        with torch.no_grad():
+            m.flat.data[: m._n_eff] += 0.1 * torch.randn(m._n_eff, dtype=torch.float64)
+    cr = compile_residuals(m.net_spec(), _exprs())
+    torch.manual_seed(0)
+    inp = {k: torch.rand(50, 1, dtype=torch.float64) for k in ("x", "y")}
+    lab = {k: torch.zeros(50, 1, dtype=torch.float64) for k in cr.names}
+    out = []
+    for chunk in (0, 16):  # 50 points: one chunk, then 16 + 16 + 16 + 2
+        plan = ResidualPlan(cr, torch.float64, ["mean"] * 2, [1.0, 1.0], chunk_points=chunk, library=lib)
+        g = torch.zeros_like(m.engine_params())
+        loss = plan.loss_fwd_bwd(inp, m.engine_params().clone(), g, labels=lab)
+        out.append((loss.clone(), g.clone()))
+    assert float((out[0][0] - out[1][0]).abs().max()) <= 1e-14
+    assert float((out[0][1] - out[1][1]).norm() / out[0][1].norm()) <= 1e-14
