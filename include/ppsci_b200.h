@@ -50,7 +50,11 @@ enum {
   PPSCI_ACT_SELU = 9,       /* nn.SELU: scale * (x > 0 ? x : alpha * (exp(x) - 1)), scale = 1.0507009873554805, alpha = 1.6732632423543772 */
   PPSCI_ACT_LEAKY_RELU = 10, /* nn.LeakyReLU(negative_slope = 0.01) */
   PPSCI_ACT_SIREN = 11,     /* Siren(w0 = 30): sin(30 x)  (activation.py:89-101) */
-  PPSCI_ACT_LAST = 11
+  /* Activations with a TRAINABLE parameter (plain MLP plans, CUDA-core kernels).  Their parameters sit behind every
+   * other entry of the parameter / gradient buffers, hidden layer by hidden layer: */
+  PPSCI_ACT_STAN = 12,      /* Stan (activation.py:28-46): tanh(x) (1 + beta x), one beta per unit (widths[l] values per layer), 1 at start */
+  PPSCI_ACT_SWISH_B = 13,   /* Swish (activation.py:49-58): x sigmoid(beta x), one beta per layer, 1 at start */
+  PPSCI_ACT_LAST = 13
 };
 
 /* input feature kinds — identity, or PeriodEmbedding (ppsci/arch/mlp.py:95-114) */

@@ -77,7 +77,15 @@ class OracleMLP:
         fourier: Optional[Dict[str, float]] = None,
         modified: bool = False,
         pirate: bool = False,
+        trainable_act: bool = False,
     ):
+        # trainable_act=True with activation "stan" / "swish": the reference's activation LAYERS carry parameters —
+        # Stan.beta [hidden_i] (activation.py:28-46: tanh(x) (1 + beta x)) and Swish.beta [] (activation.py:49-58:
+        # x sigmoid(beta x)), one layer instance per hidden layer (mlp.py:249-253, activation.py:169-171).  They are stored
+        # behind the linear layers (and embeddings / alphas), hidden layer by hidden layer, in front of the fourier kernel.
+        self.trainable_act = activation if (trainable_act and activation in ("stan", "swish")) else None
+        if activation == "stan" and not trainable_act:
+            raise ValueError("stan needs trainable_act=True (its beta is a parameter)")
         # pirate=True: PirateNet (mlp.py:530-830) — ``hidden`` holds one entry per block (all equal to the input width of
         # the blocks, i.e. fourier["dim"]); flat vector:
         # [block_0.linear1 | linear2 | linear3 | block_1... | last_fc | Wu | bu | Wv | bv | alpha_0..alpha_{B-1} | fourier kernel]
@@ -99,7 +107,8 @@ class OracleMLP:
         self.fourier = dict(fourier) if fourier else None
         first = int(self.fourier["dim"]) if self.fourier else n_feat
         self.widths = [first] + list(hidden) + [len(self.output_keys)]
-        self.act = get_activation(activation)
+        self.act = get_activation(activation) if activation != "stan" else None
+        self.beta_len = ([int(h) for h in hidden] if self.trainable_act == "stan" else [1] * len(hidden)) if self.trainable_act else []
 
     @property
     def n_linear_params(self) -> int:
@@ -112,6 +121,7 @@ class OracleMLP:
             n += 2 * (self.widths[0] * self.widths[1] + self.widths[1])
         if self.pirate:
             n += self.n_blocks
+        n += sum(self.beta_len)
         return n
 
     def split_params(self, flat: torch.Tensor):
@@ -189,6 +199,7 @@ class OracleMLP:
             parts = torch.split(y, 1, dim=-1)
             return {k: parts[i] for i, k in enumerate(self.output_keys)}
         skip = None
+        boff = self.n_params - sum(self.beta_len) - (self.n_feat * (int(self.fourier["dim"]) // 2) if self.fourier else 0)
         for i, (W, b) in enumerate(layers[:-1]):  # mlp.py:281-296, statement by statement
             y = y @ W + b
             if self.skip_connection and i % 2 == 0:
@@ -197,7 +208,16 @@ class OracleMLP:
                     y = y + skip
                 else:
                     skip = y
-            y = self.act(y)
+            if self.trainable_act == "stan":  # Stan.forward, activation.py:43-46
+                beta = flat[boff : boff + self.beta_len[i]]
+                boff += self.beta_len[i]
+                y = torch.tanh(y) * (1 + beta * y)
+            elif self.trainable_act == "swish":  # Swish.forward, activation.py:57-58
+                beta = flat[boff]
+                boff += 1
+                y = y * torch.sigmoid(beta * y)
+            else:
+                y = self.act(y)
         W, b = layers[-1]
         y = y @ W + b
         if len(self.output_keys) == 1:

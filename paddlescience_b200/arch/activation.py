@@ -24,13 +24,16 @@ def get_activation(act_name: str) -> str:
         raise NotImplementedError(
             f"activation '{act_name}' has no Taylor-jet kernel in this engine yet "
             f"(supported: {sorted(ACT_IDS)})")
-    if name == "swish" and not _WARNED["swish"]:
-        # activation.py:45-55, 149, 169-171: the reference instantiates one Swish per layer, each with a TRAINABLE scalar
-        # beta (x * sigmoid(beta x), beta = 1 at start).  The jet kernels have no per-layer activation parameter: beta
-        # stays 1, i.e. "swish" trains like "silu".  Said once, loudly, instead of silently.
+    return name
+
+
+def warn_fixed_swish():
+    """activation.py:49-58, 149, 169-171: the reference instantiates one Swish per layer, each with a TRAINABLE scalar
+    beta (x * sigmoid(beta x), beta = 1 at start).  ``arch.MLP`` trains it (PPSCI_ACT_SWISH_B); callers that cannot
+    (the DeepONet sub-networks) keep beta fixed at 1 — identical to 'silu' — and say so once."""
+    if not _WARNED["swish"]:
         _WARNED["swish"] = True
         import warnings
 
-        warnings.warn("activation 'swish': the reference trains one scalar beta per layer (Swish, beta = 1 at start); this "
-                      "engine keeps beta fixed at 1 (identical to 'silu')", stacklevel=2)
-    return name
+        warnings.warn("activation 'swish': the reference trains one scalar beta per layer (Swish, beta = 1 at start); "
+                      "here beta stays fixed at 1 (identical to 'silu')", stacklevel=3)

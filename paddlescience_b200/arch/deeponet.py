@@ -142,6 +142,12 @@ class DeepONet(base.Arch):
         self.num_loc, self.num_features, self.use_bias = int(num_loc), int(num_features), bool(use_bias)
         self.branch_activation = act_mod.get_activation(branch_activation)
         self.trunk_activation = act_mod.get_activation(trunk_activation)
+        for a in (self.branch_activation, self.trunk_activation):
+            if a == "stan":
+                raise NotImplementedError("DeepONet(*_activation='stan'): activations with a trainable parameter are "
+                                          "supported by arch.MLP only")
+            if a == "swish":
+                act_mod.warn_fixed_swish()
         bw = [self.num_loc] + _hidden(branch_num_layers, branch_hidden_size) + [self.num_features]
         tw = [1] + _hidden(trunk_num_layers, trunk_hidden_size) + [self.num_features]
         feats = tuple(f"f{i}" for i in range(self.num_features))

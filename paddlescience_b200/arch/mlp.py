@@ -178,7 +178,13 @@ class MLP(base.Arch):
             d_f = int(self.fourier["dim"])
             eng_widths = [len(feat_src), d_f] + hidden + [len(self.output_keys)]
             widths = [d_f] + hidden + [len(self.output_keys)]
-        self._net = NetSpec(self.input_keys, self.output_keys, feat_src, feat_kind, feat_omega, eng_widths, self.activation,
+        # trainable activation parameters: Stan's beta per unit (activation.py:28-46), Swish's beta per layer (:49-58)
+        self._beta_len = {"stan": list(hidden), "swish": [1] * len(hidden)}.get(self.activation, [])
+        if self._beta_len and self._gated:
+            raise NotImplementedError(f"{type(self).__name__}(activation={self.activation!r}): activations with a trainable "
+                                      "parameter are supported by the plain MLP plans only")
+        self._net = NetSpec(self.input_keys, self.output_keys, feat_src, feat_kind, feat_omega, eng_widths,
+                            {"swish": "swish_b"}.get(self.activation, self.activation),
                             act_first="sin" if self.fourier else None, gated=int(self._gated))
         self._shapes = list(zip(widths[:-1], widths[1:]))
         self._n_hidden = len(hidden)
@@ -197,6 +203,10 @@ class MLP(base.Arch):
         if self._gated == 2:  # PirateNetBlock.alpha, one trainable scalar per block (mlp.py:592-597), behind the embeddings
             self._n_blocks = len(hidden) // 3
             off += self._n_blocks
+        self._beta_off = []
+        for n_b in self._beta_len:  # acts.i.beta, behind the alphas (the engine's order: hidden layer by hidden layer)
+            self._beta_off.append(off)
+            off += n_b
         self._n_eff = off  # length of the [W | b] buffer of the reference's own linear layers
         self._n_lin = off
         self._f_n0 = 0     # fourier: length of the effective first layer [W0 | b0] in front of them in the engine buffer
@@ -256,6 +266,8 @@ class MLP(base.Arch):
                     self.flat.data[self._w_off[i]: self._w_off[i] + a * b] = (v / g).reshape(-1).to(self.flat.dtype)
                     self.flat.data[self._g_off[i]: self._g_off[i] + b] = g.to(self.flat.dtype)
 
+            for o, n_b in zip(self._beta_off, self._beta_len):  # Constant(1) (activation.py:38-41), Swish(beta=1.0)
+                self.flat.data[o: o + n_b] = 1
             if self._n_blocks:  # alpha = 0: every block starts as the identity (mlp.py:592-597)
                 self.flat.data[self._alpha_off: self._alpha_off + self._n_blocks] = 0
             if self.fourier:  # FourierEmbedding: Normal(std=scale) (mlp.py:123-126)
@@ -383,14 +395,26 @@ class MLP(base.Arch):
             else:
                 out[f"{name}.weight"] = v.weight.detach().clone()
             out[f"{name}.bias"] = v.bias.detach().clone()
+        for i, (o, n_b) in enumerate(zip(self._beta_off, self._beta_len)):  # acts is a LayerList of Stan / Swish layers
+            b = self.flat.data[o: o + n_b].detach().clone()
+            out[f"acts.{i}.beta"] = b if self.activation == "stan" else b.reshape(())
         if self.fourier:
             out["fourier_emb.kernel"] = self.fourier_kernel.detach().clone()
         return out
 
     def load_state_dict(self, state_dict, strict: bool = True):
         views = self._views()
-        missing, unexpected = [], [k for k in state_dict if k.rsplit(".", 1)[0] not in self._layer_names() + (["fourier_emb"] if self.fourier else [])]
+        known = self._layer_names() + (["fourier_emb"] if self.fourier else []) + [f"acts.{i}" for i in range(len(self._beta_off))]
+        missing, unexpected = [], [k for k in state_dict if k.rsplit(".", 1)[0] not in known]
         with torch.no_grad():
+            for i, (o, n_b) in enumerate(zip(self._beta_off, self._beta_len)):
+                key = f"acts.{i}.beta"
+                if key not in state_dict:
+                    missing.append(key)
+                    continue
+                src = state_dict[key]
+                src = torch.as_tensor(np.asarray(src.cpu() if hasattr(src, "cpu") else src)).reshape(-1)
+                self.flat.data[o: o + n_b].copy_(src.to(self.flat.dtype).to(self.flat.device))
             if self.fourier:
                 if "fourier_emb.kernel" in state_dict:
                     src = state_dict["fourier_emb.kernel"]

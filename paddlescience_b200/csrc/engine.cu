@@ -50,6 +50,10 @@ struct ppsci_plan {
   int64_t gate_w_off[2] = {0, 0};  // gated plans: embed_u / embed_v weights and biases behind the layers
   int64_t gate_b_off[2] = {0, 0};
   int64_t alpha_off = 0;  // gated == 2: one residual weight per block behind the embeddings
+  // trainable activation parameters (PPSCI_ACT_STAN: one beta per unit; PPSCI_ACT_SWISH_B: one per layer) of hidden
+  // layer l, behind everything else; actp_stride 1 / 0, actp_off[l] < 0: layer l's activation has none
+  int64_t actp_off[PPSCI_MAX_LAYERS + 1];
+  int actp_stride = 0;
   int ld_hidden_max = 4;
   int chunk = 0;
   int num_sms = 148;
@@ -210,6 +214,10 @@ extern "C" int ppsci_b200_plan_create(const ppsci_plan_spec* s, ppsci_plan** out
     if (s->feat_kind[f] < 0 || s->feat_kind[f] > PPSCI_FEAT_SIN) return fail("plan_create: bad feat_kind");
   }
   if (s->n_dir < 0 || s->n_dir > PPSCI_MAX_DIR) return fail("plan_create: n_dir out of range");
+  if (s->act_first == PPSCI_ACT_STAN || s->act_first == PPSCI_ACT_SWISH_B)
+    return fail("plan_create: act_first cannot be an activation with a trainable parameter");
+  if ((s->act == PPSCI_ACT_STAN || s->act == PPSCI_ACT_SWISH_B) && (s->gated || s->backend == 2))
+    return fail("plan_create: activations with a trainable parameter (stan, swish) run on plain MLP plans, CUDA-core kernels");
   if (s->gated) {  // ModifiedMLP: the gate multiplies every hidden layer's output with the (same-width) embeddings
     if (s->n_layers < 2) return fail("plan_create: a gated network needs at least one hidden layer");
     if (s->gated != 1 && s->gated != 2) return fail("plan_create: gated must be 0, 1 (ModifiedMLP) or 2 (PirateNet)");
@@ -310,6 +318,14 @@ extern "C" int ppsci_b200_plan_create(const ppsci_plan_spec* s, ppsci_plan** out
       off += (s->n_layers - 2) / 3;
     }
   }
+  P->actp_stride = s->act == PPSCI_ACT_STAN ? 1 : 0;
+  for (int l = 0; l <= PPSCI_MAX_LAYERS; ++l) P->actp_off[l] = -1;
+  for (int l = 1; l < s->n_layers; ++l) {
+    const int a_l = (l == 1 && s->act_first >= 0) ? s->act_first : s->act;
+    if (a_l != PPSCI_ACT_STAN && a_l != PPSCI_ACT_SWISH_B) continue;
+    P->actp_off[l] = off;
+    off += a_l == PPSCI_ACT_STAN ? s->widths[l] : 1;
+  }
   P->n_params = off;
   // default points per workspace chunk: large chunks amortise kernel prologues / tails and give the dW kernels long
   // reductions per split (measured on cfg3: 65,536 -> 77.7 ms/step, 262,144 -> 73.7 ms/step); capped below by memory
@@ -341,7 +357,8 @@ extern "C" int ppsci_b200_plan_create(const ppsci_plan_spec* s, ppsci_plan** out
     delete P;
     return fail("plan_create: no CUDA device available (the engine has no CPU fallback)");
   }
-  P->use_tc = tc_plan_supported(P->spec, P->C, P->kmax) && s->backend != 1 && !s->gated;
+  P->use_tc = tc_plan_supported(P->spec, P->C, P->kmax) && s->backend != 1 && !s->gated &&
+              s->act != PPSCI_ACT_STAN && s->act != PPSCI_ACT_SWISH_B;
 #ifdef PPSCI_EMUL
   if (s->act_first >= 0 && s->act_first != s->act) P->use_tc = false;  // one activation across the fused layers
   if (s->backend != 2) P->use_tc = false;  // the emulated tensor-core kernels (1,024 OS threads per CTA pair) run on request only
@@ -496,6 +513,7 @@ static void fill_seed(const ppsci_plan* P, const void* const* x_cols, int64_t x_
 
 // activation applied to the output of linear layer `lin` (1-based)
 static inline int act_of_layer(const ppsci_plan_spec& s, int lin) { return (lin == 1 && s.act_first >= 0) ? s.act_first : s.act; }
+static inline bool act_has_param(int act) { return act == PPSCI_ACT_STAN || act == PPSCI_ACT_SWISH_B; }
 
 template <typename T>
 static void fill_act(const ppsci_plan* P, const T* Z, int ld, int64_t nc, int mode, AOperand<T>* A, int lin = 0) {
@@ -577,7 +595,14 @@ static int run(ppsci_plan* P, const CallArgs& a) {
   const bool thin_on = getenv("PPSCI_B200_NO_THIN") == nullptr;
   const bool gated = s.gated != 0;  // ModifiedMLP: generic tile GEMMs + the gate kernels (kernels_gate.cuh)
   const bool thin_first = thin_on && L >= 2 && s.widths[0] <= THIN_MAXF && !s.dense_in && !gated;
-  const bool thin_last = thin_on && L >= 2 && n_out <= THIN_MAXM && C * n_out <= THIN_MAXCM && !gated;
+  const bool thin_last = thin_on && L >= 2 && n_out <= THIN_MAXM && C * n_out <= THIN_MAXCM && !gated && !act_has_param(s.act);
+  // A_ACT operand of layer lin + 1: beta(s) of layer lin's activation
+  auto set_actp = [&](AOperand<T>* A, int lin) {
+    if (lin >= 1 && lin < L && P->actp_off[lin] >= 0) {
+      A->act_param = params + P->actp_off[lin];
+      A->act_pstride = P->actp_stride;
+    }
+  };
   if (gated && a.phase != 0) return fail("two-phase value calls are not offered for gated networks");
   const bool pirate = s.gated == 2;  // PirateNet: layer 1 = embedding, blocks of (gate, gate, adaptive residual)
   auto kgf = k_gate_fwd<T, KMAX>;
@@ -902,7 +927,10 @@ static int run(ppsci_plan* P, const CallArgs& a) {
       if (l == 1) fill_first<T>(P, a.x_cols, c0, nc_max, &g.A);
       else if (gated)  // the gate / residual / activation that follows layer l-1 was stored when that layer finished
         fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.gt[l - 1]), P->ld[l - 1], nc_max, A_PLAIN, &g.A);
-      else fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[l - 1]), P->ld[l - 1], nc_max, A_ACT, &g.A, l - 1);
+      else {
+        fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[l - 1]), P->ld[l - 1], nc_max, A_ACT, &g.A, l - 1);
+        set_actp(&g.A, l - 1);
+      }
       g.J = P->J;
       g.B = params + P->w_off[l];
       g.Kdim = s.widths[l - 1];
@@ -1223,7 +1251,10 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         memset(&g, 0, sizeof(g));
         if (l == 1) fill_first<T>(P, a.x_cols, c0, nc_max, &g.A);
         else if (gated) fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.gt[l - 1]), P->ld[l - 1], nc_max, A_PLAIN, &g.A);
-        else fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[l - 1]), P->ld[l - 1], nc_max, A_ACT, &g.A, l - 1);
+        else {
+          fill_act<T>(P, reinterpret_cast<const T*>(ws + cv.z[l - 1]), P->ld[l - 1], nc_max, A_ACT, &g.A, l - 1);
+          set_actp(&g.A, l - 1);
+        }
         g.J = P->J;
         g.Zbar = zbar_cur;
         g.ldzb = zbar_ld;
@@ -1340,6 +1371,11 @@ static int run(ppsci_plan* P, const CallArgs& a) {
         g.ldz = P->ld[l - 1];
         g.zplane = (long long)nc_max * P->ld[l - 1];
         g.act = gated ? (int)PPSCI_ACT_IDENTITY : act_of_layer(s, l - 1);  // gated: Gbar_{l-1}, the gate's adjoint follows
+        if (!gated && P->actp_off[l - 1] >= 0) {  // trainable activation parameter: dLoss/dbeta comes out of this epilogue
+          g.act_param = params + P->actp_off[l - 1];
+          g.act_param_grad = grads + P->actp_off[l - 1];
+          g.act_pstride = P->actp_stride;
+        }
         dim3 grid(ptiles, (unsigned)((g.Nout + TN - 1) / TN));
         {
           ProfScope ps_(P, CLS_DX, st);
@@ -1522,6 +1558,7 @@ extern "C" int ppsci_b200_deeponet_head(int32_t dtype, int32_t act, const void* 
   if (!b || !t || n <= 0 || n_features <= 0) return fail("deeponet_head: bad arguments");
   if ((bbar == nullptr) != (tbar == nullptr)) return fail("deeponet_head: bbar and tbar must both be given or both be null");
   if (act < 0 || act > PPSCI_ACT_LAST) return fail("deeponet_head: unknown activation");
+  if (act_has_param(act)) return fail("deeponet_head: activations with a trainable parameter are not offered here");
   const long long warps = n < 148LL * 64 ? n : 148LL * 64;  // 8 warps per block
   const unsigned blocks = (unsigned)((warps + 7) / 8);
   if (dtype == PPSCI_F64) {

@@ -38,6 +38,9 @@ enum ActId {
   ACT_SELU = 9,
   ACT_LEAKY_RELU = 10,
   ACT_SIREN = 11,
+  // activations with ONE trainable parameter per layer (scalar) or per unit (vector), handed in beside z0:
+  ACT_STAN = 12,     // Stan (activation.py:28-46): tanh(z) (1 + beta z), beta per unit, 1 at start
+  ACT_SWISH_B = 13,  // Swish (activation.py:49-58): z sigmoid(beta z), beta per layer, 1 at start
 };
 
 template <typename T>
@@ -188,6 +191,83 @@ PPSCI_HD void act_coef(int act, T z0, T& y0, T (&s)[6]) {
 #pragma unroll
 #endif
   for (int k = 1; k <= NS; ++k) s[k] = d[k] * inv_fact[k];
+}
+
+// Activations with a trainable parameter beta: same contract as act_coef (y0, s[1..NS] normalised), NS <= 5.
+//   Stan     y = tanh(z) (1 + beta z):   s_k = t_k (1 + beta z0) + beta t_{k-1}
+//   Swish    y = z f(z), f = sigmoid(beta z), f_k = beta^k sig_k(beta z0):   s_k = z0 f_k + f_{k-1}
+template <typename T, int NS>
+PPSCI_HD void act_coef_p(int act, T z0, T beta, T& y0, T (&s)[6]) {
+  if (act == ACT_STAN) {
+    T t[6], t0;
+    act_coef<T, NS>(ACT_TANH, z0, t0, t);
+    t[0] = t0;
+    const T a = T(1) + beta * z0;
+    y0 = t0 * a;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int k = 1; k <= NS; ++k) s[k] = t[k] * a + beta * t[k - 1];
+    return;
+  }
+  if (act == ACT_SWISH_B) {
+    T g[6], g0;
+    act_coef<T, NS>(ACT_SIGMOID, beta * z0, g0, g);
+    g[0] = g0;
+    T bp = T(1);
+    y0 = z0 * g0;
+    T fprev = g0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int k = 1; k <= NS; ++k) {
+      bp *= beta;
+      const T fk = bp * g[k];
+      s[k] = z0 * fk + fprev;
+      fprev = fk;
+    }
+    return;
+  }
+  act_coef<T, NS>(act, z0, y0, s);
+}
+
+// q[0..KMAX]: normalised Taylor coefficients (in z, at z0) of  d y / d beta  for the two activations above
+//   Stan     z tanh(z):                 q_k = z0 t_k + t_{k-1}
+//   Swish    z^2 sigmoid'(beta z):      r_k = beta^k (k+1) sig_{k+1}(beta z0),  q_k = z0^2 r_k + 2 z0 r_{k-1} + r_{k-2}
+// The jets of dy/dbeta along a direction are jet_fwd_dir(q, z) (order >= 1) and q[0] (value).  KMAX <= 4.
+template <typename T, int KMAX>
+PPSCI_HD void act_dbeta_coef(int act, T z0, T beta, T (&q)[6]) {
+  if (act == ACT_STAN) {
+    T t[6], t0;
+    act_coef<T, KMAX>(ACT_TANH, z0, t0, t);
+    t[0] = t0;
+    q[0] = z0 * t0;
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+    for (int k = 1; k <= KMAX; ++k) q[k] = z0 * t[k] + t[k - 1];
+    return;
+  }
+  T g[6], g0;
+  act_coef<T, KMAX + 1>(ACT_SIGMOID, beta * z0, g0, g);
+  T r[6];
+  T bp = T(1);
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int k = 0; k <= KMAX; ++k) {
+    r[k] = bp * T(k + 1) * g[k + 1];
+    bp *= beta;
+  }
+#if defined(__CUDACC__)
+#pragma unroll
+#endif
+  for (int k = 0; k <= KMAX; ++k) {
+    T v = z0 * z0 * r[k];
+    if (k >= 1) v += T(2) * z0 * r[k - 1];
+    if (k >= 2) v += r[k - 2];
+    q[k] = v;
+  }
 }
 
 // Forward for one direction: z[k-1], y[k-1] hold order k (k = 1..KMAX); entries of z past

@@ -65,6 +65,9 @@ struct AOperand {
   long long plane;  // Np * ld
   SeedSpec seed;  // by value (kernel parameter space), used by A_SEED
   long long x_off;       // first point of this chunk inside the x columns
+  // A_ACT with a trainable activation parameter (ACT_STAN: one beta per unit, stride 1; ACT_SWISH_B: one per layer, stride 0)
+  const T* act_param;
+  int act_pstride;
 };
 
 // Produce all C channel values of A[(c, p), k] and hand them to st(c, value).
@@ -84,7 +87,8 @@ __device__ __forceinline__ void produce_a(const AOperand<T>& A, const JetLayout&
     const T* z = A.Z + p * A.ld + k;
     T s[6];
     T y0;
-    act_coef<T, KMAX>(A.act, z[0], y0, s);
+    if (A.act_param) act_coef_p<T, KMAX>(A.act, z[0], A.act_param[(long long)k * A.act_pstride], y0, s);
+    else act_coef<T, KMAX>(A.act, z[0], y0, s);
     st(0, y0);
     for (int d = 0; d < J.n_dir; ++d) {
       const int K = J.dir_order[d];
@@ -181,6 +185,11 @@ struct GemmArgs {
   long long zplane;
   int act;
   int accum;  // dx: add to Out instead of storing (a second consumer of the same operand)
+  // dx epilogue of an activation with a trainable parameter: beta (stride 1 per unit / 0 per layer) and where
+  // dLoss/dbeta accumulates (same stride)
+  const T* act_param;
+  T* act_param_grad;
+  int act_pstride;
 };
 
 template <int TN>
@@ -291,6 +300,8 @@ __global__ void __launch_bounds__(NTHREADS) k_gemm_dx(GemmArgs<T> g) {
   }
   __syncthreads();
   const int TP = g.TP;
+  static_assert(NTHREADS % TN == 0, "a thread keeps one output column across its items (dLoss/dbeta partial sums)");
+  T bsum = T(0);  // this thread's share of dLoss/dbeta of column n0 + threadIdx.x % TN
   for (int item = threadIdx.x; item < TP * TN; item += NTHREADS) {
     const int nn = item % TN, pl = item / TN;
     const long long p = p0 + pl;
@@ -300,8 +311,17 @@ __global__ void __launch_bounds__(NTHREADS) k_gemm_dx(GemmArgs<T> g) {
     T* zb_out = g.Out + p * g.ldo + n;
     T s[6];
     T y0;
-    act_coef<T, KMAX + 1>(g.act, z[0], y0, s);
+    T qb[6];
+    T bacc = T(0);
+    const T beta = g.act_param ? g.act_param[(long long)n * g.act_pstride] : T(0);
+    if (g.act_param) {
+      act_coef_p<T, KMAX + 1>(g.act, z[0], beta, y0, s);
+      act_dbeta_coef<T, KMAX>(g.act, z[0], beta, qb);
+    } else {
+      act_coef<T, KMAX + 1>(g.act, z[0], y0, s);
+    }
     const T y0b = Cs[pl * TN + nn];
+    if (g.act_param) bacc = y0b * qb[0];
     T sb[5] = {T(0), T(0), T(0), T(0), T(0)};
     for (int d = 0; d < g.J.n_dir; ++d) {
       const int K = g.J.dir_order[d];
@@ -315,6 +335,12 @@ __global__ void __launch_bounds__(NTHREADS) k_gemm_dx(GemmArgs<T> g) {
         zb[q] = T(0);
       }
       jet_adj_dir<T, KMAX>(s, zz, yb, zb, sb);
+      if (g.act_param) {  // dLoss/dbeta += <adjoint of the activation's output jets, jets of dy/dbeta>
+        T wq[4] = {T(0), T(0), T(0), T(0)};
+        jet_fwd_dir<T, KMAX>(qb, zz, wq);
+#pragma unroll
+        for (int qq = 0; qq < KMAX; ++qq) bacc += yb[qq] * wq[qq];
+      }
 #pragma unroll
       for (int q = 0; q < KMAX; ++q)
         if (q < K) {
@@ -324,6 +350,11 @@ __global__ void __launch_bounds__(NTHREADS) k_gemm_dx(GemmArgs<T> g) {
     }
     const T z0b = jet_adj_z0<T, KMAX>(s, y0b, sb);
     zb_out[0] = g.accum ? zb_out[0] + z0b : z0b;
+    bsum += bacc;
+  }
+  if (g.act_param_grad) {
+    const int n = n0 + (int)(threadIdx.x % TN);
+    if (n < g.Nout && bsum != T(0)) atomicAdd(g.act_param_grad + (long long)n * g.act_pstride, bsum);
   }
 }
 

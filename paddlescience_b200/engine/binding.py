@@ -35,6 +35,10 @@ ACT_IDS = {
     "selu": 9,
     "leaky_relu": 10,
     "siren": 11,
+    # activations with a trainable parameter (plain MLP plans; their betas sit behind the other parameters)
+    "stan": 12,     # tanh(x) (1 + beta x), one beta per unit
+    "swish_b": 13,  # x sigmoid(beta x), one beta per layer: what arch.MLP(activation="swish") runs (the reference's Swish);
+                    # plain "swish" above is the fixed-beta form (DeepONet sub-networks)
 }
 
 OPS = {

@@ -69,6 +69,11 @@ class NetSpec:
             n += 2 * (self.widths[emb] * self.widths[-2] + self.widths[-2])
         if self.gated == 2:  # one alpha per block
             n += (len(self.widths) - 3) // 3
+        hidden = self.widths[(2 if self.act_first is not None else 1):-1]  # layers whose activation is ``act``
+        if self.act == "stan":  # one beta per unit
+            n += sum(hidden)
+        elif self.act == "swish_b":  # one beta per layer
+            n += len(hidden)
         return n
 
 

@@ -110,6 +110,14 @@ CASES = {
     "modified_ac_period_f64": dict(in_keys=("t", "x"), out_keys=("u",), hidden=[12, 12], act="tanh", modified=True,
                                    periods={"x": (2.0, False)}, exprs=_ac_exprs, dtype=torch.float64,
                                    ranges={"x": (-1, 1)}),
+    # activations with a trainable parameter (activation.py:28-58): Stan's beta per unit, Swish's beta per layer — the dx
+    # epilogue also reduces dLoss/dbeta
+    "ns_stan_f64": dict(in_keys=("x", "y"), out_keys=("u", "v", "p"), hidden=[12, 12, 12], act="stan", trainable_act=True,
+                        exprs=lambda: O.navier_stokes_expr(0.1, 1.0, 2, False), dtype=torch.float64),
+    "biharmonic_swish_b_f64": dict(in_keys=("x", "y"), out_keys=("u",), hidden=[10, 10], act="swish", trainable_act=True,
+                                   exprs=_biharm_exprs, dtype=torch.float64),
+    "laplace_stan_f32": dict(in_keys=("x", "y"), out_keys=("u",), hidden=[20, 20], act="stan", trainable_act=True,
+                             exprs=lambda: O.laplace_expr(2), dtype=torch.float32),
     "first_order_leaky_relu_f64": dict(in_keys=("x", "y"), out_keys=("u", "v"), hidden=[12, 12], act="leaky_relu",
                                        exprs=_first_order_exprs, dtype=torch.float64),
 }
@@ -200,7 +208,8 @@ def run_case(name, n: int, library=None, device="cpu", backend: int = 0, seed: i
     dtype = c["dtype"]
     exprs = c["exprs"]()
     periods = c.get("periods")
-    net = make_net(c["in_keys"], c["out_keys"], c["hidden"], c["act"], periods, gated=bool(c.get("modified")))
+    net = make_net(c["in_keys"], c["out_keys"], c["hidden"], {"swish": "swish_b"}.get(c["act"], c["act"]) if c.get("trainable_act") else c["act"],
+                   periods, gated=bool(c.get("modified")))
     cr = compile_residuals(net, exprs)
     nres = len(cr.names)
     reduction = c.get("reduction", "mean")
@@ -217,12 +226,15 @@ def run_case(name, n: int, library=None, device="cpu", backend: int = 0, seed: i
         for k in c["in_keys"]:
             lo, hi = (c.get("ranges") or {}).get(k, (0, 1))
             inputs[k] = (torch.rand(n, 1, dtype=torch.float64) * (hi - lo) + lo).to(dtype)
-    om = O.OracleMLP(c["in_keys"], c["out_keys"], c["hidden"], c["act"], periods, modified=bool(c.get("modified")))
+    om = O.OracleMLP(c["in_keys"], c["out_keys"], c["hidden"], c["act"], periods, modified=bool(c.get("modified")),
+                     trainable_act=bool(c.get("trainable_act")))
     params = O.xavier_uniform_params(om.widths, 1, torch.float64)
     if c.get("modified"):  # [Wu | bu | Wv | bv] behind the layers
         params = torch.cat([params, O.xavier_uniform_params([om.widths[0], om.widths[1]], 2, torch.float64),
                             O.xavier_uniform_params([om.widths[0], om.widths[1]], 3, torch.float64)])
     params = (params + 0.1 * torch.randn_like(params))
+    if c.get("trainable_act"):  # Stan.beta per unit / Swish.beta per layer, behind the layers (1 at start in the reference)
+        params = torch.cat([params, 1.0 + 0.2 * torch.randn(sum(om.beta_len), dtype=torch.float64)])
     if c.get("siren_init"):  # weights on the scale Siren's initialisers use (sqrt(6 / in) / w0, activation.py:103-136)
         params = params / 30.0
     params = params.to(dtype)

@@ -16,6 +16,8 @@ def oracle_flat(m, flat: torch.Tensor) -> torch.Tensor:
         parts += [W.reshape(-1), flat[m._b_off[i]: m._b_off[i] + b]]
     if m._n_blocks:
         parts.append(flat[m._alpha_off: m._alpha_off + m._n_blocks])
+    for o, n_b in zip(m._beta_off, m._beta_len):
+        parts.append(flat[o: o + n_b])
     if m.fourier:
         nf, dh = m._f_shape
         parts.append(flat[m._f_off: m._f_off + nf * dh])
