@@ -104,7 +104,9 @@ def _constraint_exprs(model, cst, extra_keys) -> Dict[str, sp.Basic]:
         else:
             raise TypeError(f"output_expr['{name}'] must be a sympy expression or a callable, got {type(e)}")
     names = [k for k in cst.output_keys if k in exprs] if hasattr(cst, "output_keys") else list(exprs)
-    return {k: exprs[k] for k in names}
+    # a registered output transform is part of the function being trained (mlp.py:313-314): rewrite the residuals in
+    # terms of the bare network the kernels differentiate
+    return {k: symbolic.apply_output_transform(model, exprs[k]) for k in names}
 
 
 class BatchedConstraints:
@@ -265,12 +267,14 @@ class ExpressionSolver(nn.Module):
                 for key, v in losses.items():
                     losses_all[key] = losses_all[key] + v if key in losses_all else v
             return losses_all, losses_constraint
-        if getattr(model, "_input_transform", None) is not None or getattr(model, "_output_transform", None) is not None:
+        if getattr(model, "_input_transform", None) is not None:
             # MLP.forward (eval / predict / validators) applies the registered transforms; the fused residual kernels
-            # differentiate the bare network.  Training a different function than the one evaluated must not be silent.
-            raise NotImplementedError(f"{type(model).__name__}: registered input / output transforms are not traced into "
-                                      "the fused residual kernels; express the transform inside the constraint's "
-                                      "output_expr (or the equation) instead")
+            # differentiate the bare network.  Output transforms are traced into the residual program
+            # (symbolic.apply_output_transform); an input transform would change the jet seeds.  Training a different
+            # function than the one evaluated must not be silent.
+            raise NotImplementedError(f"{type(model).__name__}: a registered input transform is not traced into the fused "
+                                      "residual kernels; express it inside the constraint's output_expr (or the "
+                                      "equation) instead")
         flat = model.flat
         params, grads = model.engine_params(), model.engine_grads()  # effective weights / staging grads under weight_norm
         if self.batch_constraints and len(constraint) > 1:

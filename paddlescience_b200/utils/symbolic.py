@@ -42,6 +42,55 @@ def trace_to_sympy(fn: Callable, input_keys: Sequence[str], output_keys: Sequenc
         "receives with python / torch / sympy arithmetic so that it can be traced into a residual program")
 
 
+def trace_output_transform(model) -> Optional[Dict[str, sp.Basic]]:
+    """The model's registered output transform (``Arch.register_output_transform``, base.py:232-252; applied as
+    ``y = self._output_transform(x, y)`` at the end of ``forward``, mlp.py:313-314) as sympy expressions
+    ``{output key: T_key(inputs, network outputs)}``, traced once with symbolic proxies.  None without a transform."""
+    fn = getattr(model, "_output_transform", None)
+    if fn is None:
+        return None
+    in_syms = [sp.Symbol(k) for k in model.input_keys]
+    x = {k: SymTensor(s) for k, s in zip(model.input_keys, in_syms)}
+    y = {k: SymTensor(sp.Function(k)(*in_syms)) for k in model.output_keys}
+    out = fn(x, y)
+    if not isinstance(out, dict):
+        raise TypeError(f"output transform returned {type(out).__name__}; it must return a dict of outputs")
+    res = {}
+    for k, v in out.items():
+        if isinstance(v, SymTensor):
+            res[k] = v.expr
+        elif isinstance(v, (int, float, sp.Basic)):
+            res[k] = sp.sympify(v)
+        else:
+            raise TypeError(f"output transform produced {type(v).__name__} for '{k}'; it must combine its arguments with "
+                            "python / torch / sympy arithmetic so that it can be traced into the residual program")
+    return res
+
+
+def apply_output_transform(model, expr: sp.Basic) -> sp.Basic:
+    """Rewrite ``expr`` (written in terms of the model's OUTPUTS as the user sees them, i.e. after the registered output
+    transform) in terms of the bare network: every ``u(x, y)`` becomes ``T_u(x, y, u_net(x, y), ...)`` and the
+    derivatives are expanded by the product / chain rule, so that the fused kernels — which differentiate the bare
+    network — train exactly the function ``model.forward`` evaluates.  Identity without a transform."""
+    tr = trace_output_transform(model)
+    if tr is None or not isinstance(expr, sp.Basic):
+        return expr
+    in_syms = [sp.Symbol(k) for k in model.input_keys]
+    used = {f.func.__name__ for f in expr.atoms(sp.core.function.AppliedUndef)}
+    gone = [k for k in used if k in model.output_keys and k not in tr]
+    if gone:
+        raise KeyError(f"the output transform does not return {gone}, which the expression uses")
+    # two steps through placeholder names: T_u itself contains u(x, y)
+    hold = {k: sp.Function(f"__net_{k}")(*in_syms) for k in model.output_keys}
+    back = {hold[k]: sp.Function(k)(*in_syms) for k in model.output_keys}
+    to_hold = {sp.Function(k)(*in_syms): hold[k] for k in model.output_keys}
+    sub = {sp.Function(k)(*in_syms): t.xreplace(to_hold) for k, t in tr.items()}
+    out = expr.subs(sub, simultaneous=True).doit()
+    for h, b in back.items():
+        out = out.replace(h.func, b.func)
+    return out
+
+
 class CompiledExpr:
     """Callable ``data_dict -> Tensor[N,1]`` bound to a model (stands in for ``ComposedNode``)."""
 
@@ -59,7 +108,7 @@ class CompiledExpr:
 
             self._parameters = {str(s_): lookup_parameter(str(s_)) for s_ in self.expr.free_symbols
                                 if lookup_parameter(str(s_)) is not None}
-            cr = compile_residuals(self.model.net_spec(), {self.name: self.expr}, with_grad=False,
+            cr = compile_residuals(self.model.net_spec(), {self.name: apply_output_transform(self.model, self.expr)}, with_grad=False,
                                    param_keys=list(self._parameters))
             self._plans[dtype] = ResidualPlan(cr, dtype, ["mean"], [1.0])
         return self._plans[dtype]

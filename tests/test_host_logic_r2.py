@@ -28,9 +28,9 @@ def test_jacobian_of_composite_expression_expands_to_output_derivatives():
     assert cr.channels == 3  # value + x to order 2
 
 
-def test_train_forward_refuses_models_with_registered_transforms():
+def test_train_forward_refuses_models_with_registered_input_transforms():
     m = ppsci.arch.MLP(("x", "y"), ("u",), 2, 8, "tanh")
-    m.register_output_transform(lambda inp, out: {"u": out["u"] * inp["x"]})
+    m.register_input_transform(lambda inp: {"x": inp["x"] * 2, "y": inp["y"]})
     eq = ppsci.equation.Laplace(2)
     rect = ppsci.geometry.Rectangle((0, 0), (1, 1))
     cst = ppsci.constraint.InteriorConstraint(eq.equations, {"laplace": 0}, rect,
@@ -40,6 +40,53 @@ def test_train_forward_refuses_models_with_registered_transforms():
     fh = ppsci.utils.ExpressionSolver()
     with pytest.raises(NotImplementedError, match="transform"):
         fh.train_forward((cst.output_expr,), [ds.input], m, {"EQ": cst}, [ds.label], [None])
+
+
+def test_output_transform_is_traced_into_the_residual_program(monkeypatch):
+    """Arch.register_output_transform (base.py:232-252; ``y = self._output_transform(x, y)``, mlp.py:313-314): the
+    residuals are rewritten in terms of the bare network (product / chain rule by sympy), so the fused kernels train the
+    function ``forward`` evaluates.  Hard-constraint style transform, Navier-Stokes residuals (second derivatives of a
+    product), loss and weight gradient against the oracle with the same transform applied in torch."""
+    import numpy as np
+
+    from oracle import ppsci_oracle as O
+    from paddlescience_b200.engine import binding as B
+    from tests.emul.build_emul import build
+
+    monkeypatch.setattr(B, "_default", B.Library(build()))
+    ppsci.utils.misc.set_random_seed(6)
+    m = ppsci.arch.MLP(("x", "y"), ("u", "v", "p"), 2, 12, "tanh", dtype=torch.float64)
+    with torch.no_grad():
+        m.flat.data += 0.1 * torch.randn_like(m.flat.data)
+
+    def transform(inp, out):  # u vanishes on x = 0 / x = 1, v is shifted by a known field, p passes through
+        x, y = inp["x"], inp["y"]
+        return {"u": x * (1 - x) * out["u"] + y, "v": out["v"] * torch.sin(x) - 0.5 * y ** 2, "p": out["p"]}
+
+    m.register_output_transform(transform)
+    eq = ppsci.equation.NavierStokes(0.1, 1.0, 2, False)
+    rect = ppsci.geometry.Rectangle((0, 0), (1, 1))
+    cst = ppsci.constraint.InteriorConstraint(eq.equations, {"continuity": 0, "momentum_x": 0, "momentum_y": 0}, rect,
+                                              {"dataset": "IterableNamedArrayDataset", "iters_per_epoch": 1, "batch_size": 40},
+                                              ppsci.loss.MSELoss("mean"), name="EQ")
+    ds = cst.data_loader.loader
+    inp = {k: v.double() for k, v in ds.input.items()}
+    lab = {k: v.double() for k, v in ds.label.items()}
+    losses_all, _ = ppsci.utils.ExpressionSolver().train_forward((cst.output_expr,), [inp], m, {"EQ": cst}, [lab], [None])
+
+    class _Transformed(O.OracleMLP):  # the reference applies the transform at the end of forward
+        def __call__(self, flat, x):
+            return transform(x, super().__call__(flat, x))
+
+    om = _Transformed(("x", "y"), ("u", "v", "p"), [12, 12], "tanh")
+    lo, _, g = O.train_forward_backward(om, m.flat.data.clone(), O.navier_stokes_expr(0.1, 1.0, 2, False),
+                                        {k: inp[k] for k in ("x", "y")}, lab, None, "mean")
+    for k in lo:
+        assert float(losses_all[k]) == pytest.approx(float(lo[k]), rel=1e-10)
+    np.testing.assert_allclose(m.flat.grad.numpy(), g.numpy(), rtol=1e-8, atol=1e-11 * float(g.abs().max()))
+    # the evaluation path compiles expressions the same way
+    res = ppsci.lambdify(eq.equations["momentum_x"], m)
+    assert isinstance(res, ppsci.utils.symbolic.CompiledExpr)
 
 
 def test_optimizer_checkpoint_carries_the_lr_schedule_position():
