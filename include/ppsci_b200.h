@@ -297,7 +297,10 @@ int32_t ppsci_b200_plan_uses_tcgen05(const ppsci_plan* plan);
 
 /* Fused Adam on flat buffers — replaces paddle.optimizer.Adam.step for this path
  * (ppsci/optimizer/optimizer.py:225-248, ppsci/solver/train.py:175).
- * grad_scale multiplies grads first (1/world for DP averaging). */
+ * grad_scale multiplies grads first (1/world for DP averaging).
+ * weight_decay > 0: L2 regularisation folded into the gradient (paddle.optimizer.Adam(weight_decay=...));
+ * weight_decay < 0: DECOUPLED decay with coefficient -weight_decay — paddle.optimizer.AdamW
+ * (ppsci/optimizer/optimizer.py:386-496): params <- params (1 - lr coeff) before the Adam update. */
 int ppsci_b200_adam_step(int32_t dtype, void* params, const void* grads, void* exp_avg,
                          void* exp_avg_sq, int64_t n, double lr, double beta1, double beta2,
                          double eps, double weight_decay, int64_t step, double grad_scale,

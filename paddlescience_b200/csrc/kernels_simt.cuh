@@ -956,7 +956,8 @@ __global__ void k_adam(T* p, const T* g, T* m, T* v, long long n, double lr, dou
   if (i >= n) return;
   double gi = (double)g[i] * gscale;
   double pi = (double)p[i];
-  if (wd != 0.0) gi += wd * pi;
+  if (wd > 0.0) gi += wd * pi;                 // Adam: L2 regularisation folded into the gradient
+  else if (wd < 0.0) pi *= 1.0 + lr * wd;      // AdamW: decoupled decay, coefficient -wd (p <- p (1 - lr coeff) first)
   const double mi = b1 * (double)m[i] + (1.0 - b1) * gi;
   const double vi = b2 * (double)v[i] + (1.0 - b2) * gi * gi;
   m[i] = T(mi);
@@ -976,7 +977,8 @@ __global__ void k_adam_dev(T* p, T* g, T* m, T* v, long long n, const double* __
   const double lr = hyper[0], bc1 = hyper[1], bc2 = hyper[2], gscale = hyper[3];
   double gi = (double)g[i] * gscale;
   double pi = (double)p[i];
-  if (wd != 0.0) gi += wd * pi;
+  if (wd > 0.0) gi += wd * pi;                 // Adam: L2 regularisation folded into the gradient
+  else if (wd < 0.0) pi *= 1.0 + lr * wd;      // AdamW: decoupled decay, coefficient -wd (p <- p (1 - lr coeff) first)
   const double mi = b1 * (double)m[i] + (1.0 - b1) * gi;
   const double vi = b2 * (double)v[i] + (1.0 - b2) * gi * gi;
   m[i] = T(mi);

@@ -24,8 +24,11 @@ class FlatAdam:
         self._lr = learning_rate
         self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
         self.weight_decay = float(weight_decay) if weight_decay else 0.0
-        if decoupled:
-            raise NotImplementedError("AdamW (decoupled weight decay) is not implemented yet")
+        if self.weight_decay < 0:
+            raise ValueError("weight_decay must be non-negative")
+        self.decoupled = bool(decoupled)
+        if self.decoupled:  # the native step reads a negative coefficient as "decoupled" (include/ppsci_b200.h)
+            self.weight_decay = -self.weight_decay
         self.t = 0
         self.exp_avg: Optional[torch.Tensor] = None
         self.exp_avg_sq: Optional[torch.Tensor] = None
@@ -157,7 +160,21 @@ class Adam:
                 raise NotImplementedError("one optimizer over several models is not supported yet")
             model_list = models[0]
         return FlatAdam(model_list, self.learning_rate, self.beta1, self.beta2, self.epsilon, self.weight_decay,
-                        extra_params=extra)
+                        decoupled=getattr(self, "_decoupled", False), extra_params=extra)
+
+
+class AdamW(Adam):
+    """``ppsci.optimizer.AdamW`` factory (optimizer.py:386-496): Adam with DECOUPLED weight decay —
+    ``p <- p (1 - lr * weight_decay)`` before the Adam update, in the same fused kernel.  The per-parameter exclusions
+    (``no_weight_decay_name``, ``one_dim_param_no_weight_decay``) have no counterpart on the flat parameter buffer."""
+
+    def __init__(self, learning_rate=1e-3, beta1: float = 0.9, beta2: float = 0.999, epsilon: float = 1e-8,
+                 weight_decay: float = 0.001, grad_clip=None, no_weight_decay_name=None,
+                 one_dim_param_no_weight_decay: bool = False, amsgrad: bool = False):
+        if no_weight_decay_name or one_dim_param_no_weight_decay:
+            raise NotImplementedError("AdamW: per-parameter weight-decay exclusions are not supported on the flat buffer")
+        super().__init__(learning_rate, beta1, beta2, epsilon, weight_decay, grad_clip, False, amsgrad)
+        self._decoupled = True
 
 
 class FlatLBFGS:

@@ -286,3 +286,32 @@ def test_modified_mlp_gated_plan_and_checkpoint_keys(monkeypatch):
         ppsci.arch.ModifiedMLP(("x",), ("u",), 2, 8, weight_norm=True, skip_connection=True)
     with pytest.raises(ValueError):
         ppsci.arch.ModifiedMLP(("x",), ("u",), None, (8, 8))
+
+
+@pytest.mark.parametrize("decoupled", [False, True])
+def test_fused_adam_kernel_matches_torch_adam_and_adamw(decoupled):
+    """ppsci_b200_adam_step through the CPU emulation of the kernel source: weight_decay > 0 is paddle / torch Adam's L2
+    term, weight_decay < 0 the decoupled decay of AdamW (ppsci/optimizer/optimizer.py:386-496) — ``ppsci.optimizer.AdamW``
+    hands the coefficient over negated."""
+    from paddlescience_b200.engine import binding as B
+    from tests.emul.build_emul import build
+
+    lib = B.Library(build())
+    torch.manual_seed(0)
+    p = torch.randn(257, dtype=torch.float64)
+    ref = p.clone().requires_grad_(True)
+    opt = (torch.optim.AdamW if decoupled else torch.optim.Adam)([ref], lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for t in range(1, 5):
+        g = torch.randn(257, dtype=torch.float64)
+        ref.grad = g.clone()
+        opt.step()
+        rc = lib.lib.ppsci_b200_adam_step(B.F64, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 3e-3, 0.9,
+                                          0.999, 1e-8, -0.05 if decoupled else 0.05, t, 1.0, None)
+        assert rc == 0
+    assert float((p - ref.detach()).abs().max()) <= 1e-14
+    mdl = ppsci.arch.MLP(("x",), ("u",), 1, 4, "tanh")
+    o = (ppsci.optimizer.AdamW(1e-3, weight_decay=0.05) if decoupled else ppsci.optimizer.Adam(1e-3, weight_decay=0.05))(mdl)
+    assert o.weight_decay == (-0.05 if decoupled else 0.05) and o.decoupled is decoupled
+    with pytest.raises(NotImplementedError):
+        ppsci.optimizer.AdamW(one_dim_param_no_weight_decay=True)
