@@ -206,13 +206,13 @@ def test_gated_plans_are_chunk_invariant(kind):
             m.flat.data[: m._n_eff] += 0.1 * torch.randn(m._n_eff, dtype=torch.float64)
     cr = compile_residuals(m.net_spec(), _exprs())
     torch.manual_seed(0)
-    inp = {k: torch.rand(50, 1, dtype=torch.float64) for k in ("x", "y")}
-    lab = {k: torch.zeros(50, 1, dtype=torch.float64) for k in cr.names}
+    inp = {k: torch.rand(20, 1, dtype=torch.float64) for k in ("x", "y")}
+    lab = {k: torch.zeros(20, 1, dtype=torch.float64) for k in cr.names}
     out = []
-    for chunk in (0, 16):  # 50 points: one chunk, then 16 + 16 + 16 + 2
+    for chunk in (0, 8):  # 20 points: one chunk, then 8 + 8 + 4
         plan = ResidualPlan(cr, torch.float64, ["mean"] * 2, [1.0, 1.0], chunk_points=chunk, library=lib)
         g = torch.zeros_like(m.engine_params())
         loss = plan.loss_fwd_bwd(inp, m.engine_params().clone(), g, labels=lab)
         out.append((loss.clone(), g.clone()))
-    assert float((out[0][0] - out[1][0]).abs().max()) <= 1e-14
-    assert float((out[0][1] - out[1][1]).norm() / out[0][1].norm()) <= 1e-14
+    assert float(((out[0][0] - out[1][0]).abs() / out[0][0].abs()).max()) <= 1e-12  # summation order only
+    assert float((out[0][1] - out[1][1]).norm() / out[0][1].norm()) <= 1e-12
