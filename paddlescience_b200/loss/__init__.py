@@ -1,8 +1,8 @@
 from . import mtl
 from .base import Loss
-from .mse import MSELoss
+from .mse import CausalMSELoss, MSELoss
 
-__all__ = ["Loss", "MSELoss", "mtl", "build_loss"]
+__all__ = ["Loss", "MSELoss", "CausalMSELoss", "mtl", "build_loss"]
 
 
 def build_loss(cfg):

@@ -44,3 +44,44 @@ class MSELoss(base.Loss):
                 loss = loss * self.weight[key]
             losses[key] = loss
         return losses
+
+
+class CausalMSELoss(MSELoss):
+    r"""Causal-training MSE (reference: ppsci/loss/mse.py:109-190; Wang et al., "Respecting causality is all you need
+    for training physics-informed neural networks").  The points of a batch are ordered in time and split into
+    ``n_chunks`` equal chunks; chunk i is weighted by ``exp(-tol * sum_{j<i} mean(loss_j))`` — a weight that takes no
+    gradient (``weight_t.detach()``, mse.py:172-176).
+
+    In ``Solver.train`` the squared error, the reduction and the weight gradient still come from the fused head and
+    adjoint kernels: one forward-only native call produces the residuals the causal weights are formed from (a few
+    vector operations on the device), then the usual fused call runs with those weights as its per-point weight column
+    (``utils/expression.py``) — the constraint costs one extra forward pass."""
+
+    def __init__(self, n_chunks: int, reduction: str = "mean", weight: Optional[Union[float, Dict[str, float]]] = None,
+                 tol: float = 1.0):
+        if n_chunks <= 0:  # mse.py:141-142
+            raise ValueError(f"n_chunks should be positive, but got {n_chunks}")
+        super().__init__(reduction, weight)
+        self.n_chunks = int(n_chunks)
+        self.tol = float(tol)
+
+    def causal_weights(self, loss_pointwise: torch.Tensor) -> torch.Tensor:
+        """``[N, 1]`` per-point squared errors (already times weight / area) -> ``[N, 1]`` causal weights (no gradient)."""
+        with torch.no_grad():
+            loss_t = loss_pointwise.reshape(self.n_chunks, -1)  # [nt, nx], mse.py:171
+            acc = torch.tril(torch.ones(self.n_chunks, self.n_chunks, dtype=loss_t.dtype, device=loss_t.device), -1)
+            weight_t = torch.exp(-self.tol * (acc @ loss_t.mean(-1, keepdim=True)))  # [nt, 1], mse.py:172-174
+            return weight_t.expand(-1, loss_t.shape[1]).reshape(-1, 1).contiguous()
+
+    def forward(self, output_dict, label_dict, weight_dict=None) -> Dict[str, torch.Tensor]:
+        losses = {}
+        for key in label_dict:
+            loss = (output_dict[key] - label_dict[key]) ** 2
+            if weight_dict and key in weight_dict:
+                loss = loss * weight_dict[key]
+            if "area" in output_dict:
+                loss = loss * output_dict["area"]
+            loss = loss * self.causal_weights(loss.detach())
+            loss = loss.sum() if self.reduction == "sum" else loss.mean()
+            losses[key] = loss * self.weight_of(key)
+        return losses

@@ -84,8 +84,9 @@ class CompiledConstraint:
             loss = self.cst.loss
             red = getattr(loss, "reduction", "mean")
             lw = [loss.weight_of(k) if hasattr(loss, "weight_of") else 1.0 for k in self.names]
-            if type(loss).__name__ != "MSELoss":
-                raise NotImplementedError(f"{type(loss).__name__} has no fused head kernel; only MSELoss is on the hot path")
+            if type(loss).__name__ not in ("MSELoss", "CausalMSELoss"):
+                raise NotImplementedError(f"{type(loss).__name__} has no fused head kernel; only MSELoss / CausalMSELoss "
+                                          "are on the hot path")
             self._plans[dtype] = ResidualPlan(self.compiled, dtype, [red] * len(self.names), lw)
         return self._plans[dtype]
 
@@ -233,10 +234,21 @@ class ExpressionSolver(nn.Module):
         losses_all: Dict[str, torch.Tensor] = {}
         losses_constraint: Dict[str, torch.Tensor] = {}
         if per_key_grads:
-            if hasattr(model, "fused_train_forward") or getattr(model, "weight_norm", False) or getattr(model, "_skip_layers", None):
-                raise NotImplementedError("per-term gradients are implemented for plain MLP models")
+            if hasattr(model, "fused_train_forward"):
+                raise NotImplementedError("per-term gradients are implemented for the MLP family of models")
+            if getattr(model, "_input_transform", None) is not None:
+                raise NotImplementedError(f"{type(model).__name__}: a registered input transform is not traced into the fused "
+                                          "residual kernels")
             flat = model.flat
             params = model.engine_params()
+            # reparametrised models (weight_norm / random_weight / fourier / skip_connection): the kernels fill the
+            # staging buffer, finish_grads() chains it into flat.grad — borrowed per term and restored afterwards
+            staged = bool(getattr(model, "_has_eff", False))
+            saved = None
+            if staged:
+                if flat.grad is None:
+                    flat.grad = torch.zeros_like(flat.data)
+                saved = flat.grad.clone()
             grads_by_key: Dict[str, torch.Tensor] = {}
             for i, cst_name in enumerate(constraint):
                 cst = constraint[cst_name]
@@ -247,12 +259,23 @@ class ExpressionSolver(nn.Module):
                     weights = {k: (weights[k] * area if weights and k in weights else area) for k in cc.names}
                 if cc.parameters:
                     raise NotImplementedError("per-term gradients with learnable equation parameters are not supported yet")
+                if type(cst.loss).__name__ == "CausalMSELoss":
+                    weights = self._causal_weights(cst, cc, cc.plan(flat.dtype), input_dicts[i], label_dicts[i], weights, params)
                 for k, key in enumerate(cc.names):
                     g = grads_by_key.setdefault(key, torch.zeros_like(flat.data))
-                    lv = cc.plan_for_key(flat.dtype, k).loss_fwd_bwd(input_dicts[i], params, g, labels=label_dicts[i],
-                                                                     weights=weights)[k].clone()
+                    if staged:
+                        flat.grad.zero_()
+                        lv = cc.plan_for_key(flat.dtype, k).loss_fwd_bwd(input_dicts[i], params, model.engine_grads(),
+                                                                         labels=label_dicts[i], weights=weights)[k].clone()
+                        model.finish_grads()
+                        g.add_(flat.grad)
+                    else:
+                        lv = cc.plan_for_key(flat.dtype, k).loss_fwd_bwd(input_dicts[i], params, g, labels=label_dicts[i],
+                                                                         weights=weights)[k].clone()
                     losses_all[key] = losses_all[key] + lv if key in losses_all else lv
                     losses_constraint[cst_name] = losses_constraint[cst_name] + lv if cst_name in losses_constraint else lv
+            if staged:
+                flat.grad.copy_(saved)
             return losses_all, losses_constraint, grads_by_key
         if hasattr(model, "fused_train_forward"):  # models that combine several native networks (DeepONet)
             for i, cst_name in enumerate(constraint):
@@ -304,6 +327,8 @@ class ExpressionSolver(nn.Module):
             if "area" in input_dicts[i]:  # mse.py:92-93 multiplies by the area column when present
                 area = input_dicts[i]["area"]
                 weights = {k: (weights[k] * area if weights and k in weights else area) for k in cc.names}
+            if type(cst.loss).__name__ == "CausalMSELoss":
+                weights = self._causal_weights(cst, cc, plan, input_dicts[i], label_dicts[i], weights, params)
             loss_vec = plan.loss_fwd_bwd(_with_parameters(input_dicts[i], cc.parameters), params, grads, labels=label_dicts[i],
                                          weights=weights)
             loss_vec = loss_vec.clone()
@@ -315,6 +340,21 @@ class ExpressionSolver(nn.Module):
                 torch.cuda.nvtx.range_pop()
         model.finish_grads()  # weight_norm chain rule into model.flat.grad (no-op otherwise)
         return losses_all, losses_constraint
+
+    @staticmethod
+    def _causal_weights(cst, cc, plan, input_dict, label_dict, weights, params):
+        """CausalMSELoss (mse.py:157-190): chunk weights exp(-tol * sum of the earlier chunks' mean losses), without
+        gradient.  One forward-only native call gives the residuals they are formed from; the fused call then takes them
+        as (part of) its per-point weight column."""
+        _, res = plan.forward(_with_parameters(input_dict, cc.parameters), params, want_jets=False)
+        out = {}
+        for key in cc.names:
+            e2 = (res[key] - label_dict[key].to(res[key].dtype)) ** 2
+            if weights and key in weights:
+                e2 = e2 * weights[key]
+            cw = cst.loss.causal_weights(e2)
+            out[key] = weights[key] * cw if weights and key in weights else cw
+        return out
 
     def eval_forward(self, expr_dict, input_dict, model, validator, label_dict, weight_dict):
         """Forward for evaluation (expression.py:133-180): outputs + expressions + validator loss."""

@@ -237,3 +237,63 @@ def test_solver_accepts_every_reference_aggregator(name):
                                  iters_per_epoch=2, equation={"lap": eq}, loss_aggregator=agg)
     assert solver.loss_aggregator is agg
     assert bool(getattr(agg, "needs_per_key_grads", False)) == (name != "Sum")
+
+
+def test_per_term_gradients_of_reparametrised_models_and_causal_loss(monkeypatch):
+    """The configuration of the reference's PirateNet examples: fourier + random_weight model, CausalMSELoss on the PDE
+    constraint (ppsci/loss/mse.py:109-190), per-term gradients for an aggregator.  The per-term gradients (staged through
+    the reparametrisation's chain rule) add up to the gradient of the ordinary fused call, model.flat.grad is left as it
+    was, and the causal loss equals the reference formula evaluated on the oracle's residuals."""
+    from oracle import ppsci_oracle as O
+    from paddlescience_b200.engine import binding as B
+    from tests.emul.build_emul import build
+    from tests.reparam_ref import oracle_flat
+
+    monkeypatch.setattr(B, "_default", B.Library(build()))
+    ppsci.utils.misc.set_random_seed(8)
+    model = ppsci.arch.PirateNet(("t", "x"), ("u",), 1, 12, "tanh", periods={"x": (2.0, False)},
+                                 fourier={"dim": 12, "scale": 1.0}, random_weight={"mean": 1.0, "std": 0.1}, dtype=torch.float64)
+    with torch.no_grad():
+        model.alphas.fill_(0.4)
+    eq = ppsci.equation.AllenCahn(0.01)
+    n, n_chunks = 32, 4
+    tt = torch.sort(torch.rand(n, 1, dtype=torch.float64), dim=0).values
+    pde_in = {"t": tt, "x": torch.rand(n, 1, dtype=torch.float64) * 2 - 1}
+    pde = ppsci.constraint.SupervisedConstraint(
+        {"dataset": {"name": "IterableNamedArrayDataset", "input": {k: v.numpy() for k, v in pde_in.items()},
+                     "label": {"allen_cahn": np.zeros((n, 1))}}},
+        ppsci.loss.CausalMSELoss(n_chunks, "mean", tol=1.5), output_expr=eq.equations, name="PDE")
+    ic_in = {"t": torch.zeros(10, 1, dtype=torch.float64), "x": torch.linspace(-1, 1, 10, dtype=torch.float64).reshape(-1, 1)}
+    ic = ppsci.constraint.SupervisedConstraint(
+        {"dataset": {"name": "IterableNamedArrayDataset", "input": {k: v.numpy() for k, v in ic_in.items()},
+                     "label": {"u": (ic_in["x"] ** 2 * torch.cos(np.pi * ic_in["x"])).numpy()}}},
+        ppsci.loss.MSELoss("mean"), output_expr={"u": lambda out: out["u"]}, name="IC")
+    csts = {"PDE": pde, "IC": ic}
+    ins = [{k: v.double() for k, v in c.data_loader.loader.input.items()} for c in (pde, ic)]
+    labs = [{k: v.double() for k, v in c.data_loader.loader.label.items()} for c in (pde, ic)]
+    fh = ppsci.utils.ExpressionSolver()
+    exprs = tuple(c.output_expr for c in (pde, ic))
+    losses, _ = fh.train_forward(exprs, ins, model, csts, labs, [None, None])
+    total_grad = model.flat.grad.clone()
+    marker = torch.full_like(model.flat.grad, 0.25)
+    model.flat.grad.copy_(marker)
+    l2, _, gk = fh.train_forward(exprs, ins, model, csts, labs, [None, None], per_key_grads=True)
+    assert torch.equal(model.flat.grad, marker)  # borrowed and restored
+    assert set(gk) == {"allen_cahn", "u"}
+    np.testing.assert_allclose((gk["allen_cahn"] + gk["u"]).numpy(), total_grad.numpy(), rtol=1e-9, atol=1e-14)
+    for k in losses:
+        assert float(l2[k]) == pytest.approx(float(losses[k]), rel=1e-12)
+    # the causal loss against the formula of mse.py:157-190 on the oracle's residuals
+    om = O.OracleMLP(("t", "x"), ("u",), [12], "tanh", {"x": (2.0, False)}, fourier={"dim": 12, "scale": 1.0}, pirate=True)
+    of = oracle_flat(model, model.flat.data.clone())
+    import sympy as sp
+
+    t_, x_ = sp.symbols("t x")
+    u_ = sp.Function("u")(t_, x_)
+    ac = {"allen_cahn": u_.diff(t_) - 0.01 ** 2 * u_.diff(x_, 2) + 5 * u_ ** 3 - 5 * u_}  # equation/pde/allen_cahn.py
+    _, res, _ = O.train_forward_backward(om, of, ac, ins[0], labs[0], None, "mean", want_grad=False)
+    e2 = res["allen_cahn"] ** 2
+    lt = e2.reshape(n_chunks, -1)
+    w = torch.exp(-1.5 * (torch.tril(torch.ones(n_chunks, n_chunks, dtype=torch.float64), -1) @ lt.mean(-1, keepdim=True)))
+    assert float(losses["allen_cahn"]) == pytest.approx(float((lt * w).mean()), rel=1e-10)
+    assert float(w.min()) < 0.999  # the weighting is active
