@@ -8,7 +8,7 @@ from typing import Dict, Sequence, Tuple
 import numpy as np
 import torch
 
-__all__ = ["AverageMeter", "convert_to_dict", "convert_to_array", "set_random_seed", "typename"]
+__all__ = ["AverageMeter", "cartesian_product", "convert_to_dict", "convert_to_array", "set_random_seed", "typename"]
 
 
 class AverageMeter:
@@ -73,3 +73,10 @@ def set_random_seed(seed: int):
 
 def typename(obj) -> str:
     return obj.__class__.__name__
+
+
+def cartesian_product(*arrays: np.ndarray) -> np.ndarray:
+    """All combinations of the entries of the given 1-D arrays, first array slowest: shapes (N_1,), ..., (N_M,) ->
+    (N_1 x ... x N_M, M)  (ppsci/utils/misc.py:473-511; e.g. the (t, x) evaluation grid of the Allen-Cahn examples)."""
+    grids = np.meshgrid(*[np.asarray(a) for a in arrays], indexing="ij")
+    return np.stack([g.reshape(-1) for g in grids], axis=-1).astype(np.result_type(*arrays))
