@@ -1,7 +1,7 @@
 from . import lr_scheduler
-from .optimizer import LBFGS, Adam, AdamW, FlatAdam, FlatLBFGS
+from .optimizer import LBFGS, Adam, AdamW, ClipGradByGlobalNorm, ClipGradByNorm, ClipGradByValue, FlatAdam, FlatLBFGS
 
-__all__ = ["Adam", "AdamW", "FlatAdam", "LBFGS", "FlatLBFGS", "lr_scheduler", "build_optimizer", "build_lr_scheduler"]
+__all__ = ["Adam", "AdamW", "ClipGradByGlobalNorm", "ClipGradByNorm", "ClipGradByValue", "FlatAdam", "LBFGS", "FlatLBFGS", "lr_scheduler", "build_optimizer", "build_lr_scheduler"]
 
 
 def build_lr_scheduler(cfg, epochs, iters_per_epoch):

@@ -10,13 +10,67 @@ import torch
 from ..engine import binding as B
 
 
+class ClipGradByGlobalNorm:
+    """paddle.nn.ClipGradByGlobalNorm: every gradient of the optimizer is scaled by ``clip_norm / max(global_norm, clip_norm)``."""
+
+    def __init__(self, clip_norm: float):
+        self.clip_norm = float(clip_norm)
+
+
+class ClipGradByNorm:
+    """paddle.nn.ClipGradByNorm: each parameter TENSOR's gradient is scaled by ``clip_norm / max(its norm, clip_norm)``."""
+
+    def __init__(self, clip_norm: float):
+        self.clip_norm = float(clip_norm)
+
+
+class ClipGradByValue:
+    """paddle.nn.ClipGradByValue: gradients are clamped to ``[min, max]`` (``min`` defaults to ``-max``)."""
+
+    def __init__(self, max: float, min: Optional[float] = None):  # noqa: A002 (paddle's argument names)
+        self.max = float(max)
+        self.min = -float(max) if min is None else float(min)
+
+
+def clip_gradients(grad_clip, flat_grad: torch.Tensor, segments, extra_grads=(), grad_scale: float = 1.0) -> None:
+    """Apply a paddle-style gradient clipping object (matched by class name, so ``paddle.nn.ClipGradBy*`` instances work
+    too) in place, on the device, without a host synchronisation.  ``grad_scale`` is the factor the fused Adam kernel
+    applies to the raw gradient first (1 / world size, 1 / update_freq): the clipping thresholds refer to the scaled
+    gradient, like paddle's, which clips what the optimizer consumes.  ``segments``: (start, stop) of every parameter
+    tensor inside the flat buffer (ClipGradByNorm is per tensor)."""
+    if grad_clip is None:
+        return
+    kind = type(grad_clip).__name__
+    gs = float(grad_scale)
+    grads = [flat_grad] + [g for g in extra_grads if g is not None]
+    if kind == "ClipGradByGlobalNorm":
+        clip = float(grad_clip.clip_norm)
+        total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)) * abs(gs)
+        scale = clip / torch.clamp(total, min=clip)
+        for g in grads:
+            g.mul_(scale.to(g.dtype))
+    elif kind == "ClipGradByNorm":
+        clip = float(grad_clip.clip_norm)
+        views = [flat_grad[a:b] for a, b in segments] + grads[1:]
+        for v in views:
+            n = v.double().norm() * abs(gs)
+            v.mul_((clip / torch.clamp(n, min=clip)).to(v.dtype))
+    elif kind == "ClipGradByValue":
+        lo, hi = float(grad_clip.min), float(grad_clip.max)
+        for g in grads:
+            g.clamp_(min=lo / gs, max=hi / gs) if gs > 0 else g.clamp_(min=hi / gs, max=lo / gs)
+    else:
+        raise NotImplementedError(f"grad_clip of type {kind} is not supported (ClipGradByGlobalNorm / ByNorm / ByValue)")
+
+
 class FlatAdam:
     """Adam over ``model.flat`` (paddle.optimizer.Adam semantics: L2 ``weight_decay`` folded into
     the gradient, bias-corrected moments, no amsgrad)."""
 
     def __init__(self, model, learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8, weight_decay=None, decoupled=False,
-                 extra_params=()):
+                 extra_params=(), grad_clip=None):
         self.model = model
+        self.grad_clip = grad_clip  # paddle-style clipping object, applied to the gradients right before the fused step
         # learnable equation parameters (``Adam(lr)((model, equation))``, ppsci/optimizer/optimizer.py:225-248 collects the
         # parameters of every entry of model_list): each is stepped by the same fused kernel, one tiny launch per scalar
         self.extra_params = list(extra_params)
@@ -58,6 +112,7 @@ class FlatAdam:
             raise RuntimeError("FlatAdam.step needs parameters on a CUDA (B200) device: no CPU fallback")
         self._ensure_state()
         self.t += 1
+        self._clip()
         lib = B.get_library()
         dtype = B.F64 if p.dtype == torch.float64 else B.F32
         rc = lib.lib.ppsci_b200_adam_step(dtype, p.data.data_ptr(), p.grad.data_ptr(), self.exp_avg.data_ptr(),
@@ -83,6 +138,24 @@ class FlatAdam:
     # -- the same step split for CUDA-graph replay (solver/graph_step.py): ``step_dev`` is the launch (recorded once,
     #    every scalar that changes per step is read from ``hyper_dev``), ``advance`` the host-side bookkeeping that
     #    produces those scalars for the coming step.
+    def _param_segments(self):
+        """(start, stop) of every parameter tensor inside ``model.flat`` (weights, biases, gains, ... each on its own)."""
+        m = self.model
+        segs = []
+        if hasattr(m, "_shapes"):
+            for i, (a, b) in enumerate(m._shapes):
+                segs.append((m._w_off[i], m._w_off[i] + a * b))
+                segs.append((m._b_off[i], m._b_off[i] + b))
+        covered = max((hi for _, hi in segs), default=0)
+        if covered < m.flat.numel():
+            segs.append((covered, m.flat.numel()))  # gains / alphas / betas / fourier kernel: one segment
+        return segs
+
+    def _clip(self):
+        if self.grad_clip is not None and self.model.flat.grad is not None:
+            clip_gradients(self.grad_clip, self.model.flat.grad, self._param_segments(),
+                           [q.grad for q in self.extra_params], self.grad_scale)
+
     def advance(self):
         """t += 1; returns [lr, 1 - beta1^t, 1 - beta2^t, grad_scale] of this step."""
         self.t += 1
@@ -97,6 +170,7 @@ class FlatAdam:
         if hyper_dev.dtype != torch.float64 or hyper_dev.numel() < 4 or hyper_dev.device != p.device:
             raise ValueError("hyper_dev must be a float64 tensor of 4 values on the parameters' device")
         self._ensure_state()
+        self._clip()  # device-side vector operations: recorded into the graph with the step
         lib = B.get_library()
         dtype = B.F64 if p.dtype == torch.float64 else B.F32
         rc = lib.lib.ppsci_b200_adam_step_dev(dtype, p.data.data_ptr(), p.grad.data_ptr(), self.exp_avg.data_ptr(),
@@ -139,8 +213,7 @@ class Adam:
 
     def __init__(self, learning_rate=1e-3, beta1: float = 0.9, beta2: float = 0.999, epsilon: float = 1e-8,
                  weight_decay=None, grad_clip=None, lazy_mode: bool = False, amsgrad: bool = False):
-        if grad_clip is not None:
-            raise NotImplementedError("grad_clip is not supported yet")
+        self.grad_clip = grad_clip
         if amsgrad:
             raise NotImplementedError("amsgrad is not supported yet")
         self.learning_rate, self.beta1, self.beta2, self.epsilon = learning_rate, beta1, beta2, epsilon
@@ -160,7 +233,7 @@ class Adam:
                 raise NotImplementedError("one optimizer over several models is not supported yet")
             model_list = models[0]
         return FlatAdam(model_list, self.learning_rate, self.beta1, self.beta2, self.epsilon, self.weight_decay,
-                        decoupled=getattr(self, "_decoupled", False), extra_params=extra)
+                        decoupled=getattr(self, "_decoupled", False), extra_params=extra, grad_clip=self.grad_clip)
 
 
 class AdamW(Adam):

@@ -315,3 +315,49 @@ def test_fused_adam_kernel_matches_torch_adam_and_adamw(decoupled):
     assert o.weight_decay == (-0.05 if decoupled else 0.05) and o.decoupled is decoupled
     with pytest.raises(NotImplementedError):
         ppsci.optimizer.AdamW(one_dim_param_no_weight_decay=True)
+
+
+def test_gradient_clipping_objects_follow_paddle_semantics():
+    """Adam(grad_clip=...) (ppsci/optimizer/optimizer.py:179-248 hands paddle.nn.ClipGradBy* to the optimizer): global
+    norm, per-tensor norm and value clipping on the flat gradient, thresholds referring to the gradient the fused step
+    consumes (after grad_scale), matched by class name."""
+    from paddlescience_b200.optimizer.optimizer import clip_gradients
+
+    torch.manual_seed(0)
+    m = ppsci.arch.MLP(("x", "y"), ("u",), 2, 6, "tanh", dtype=torch.float64)
+    opt = ppsci.optimizer.Adam(1e-3, grad_clip=ppsci.optimizer.ClipGradByGlobalNorm(0.5))(m)
+    assert type(opt.grad_clip).__name__ == "ClipGradByGlobalNorm"
+    segs = opt._param_segments()
+    assert segs[0] == (0, 12) and segs[1] == (12, 18) and segs[-1][1] == m.flat.numel() and len(segs) == 6
+    g0 = torch.randn(m.flat.numel(), dtype=torch.float64) * 3
+    extra = torch.randn(1, dtype=torch.float64)
+    # global norm (with an equation scalar in the same optimizer), gradient pre-scaled by 0.5 in the step
+    g, e = g0.clone(), extra.clone()
+    clip_gradients(ppsci.optimizer.ClipGradByGlobalNorm(0.5), g, segs, [e], grad_scale=0.5)
+    tot = 0.5 * torch.sqrt((g0 ** 2).sum() + (extra ** 2).sum())
+    assert float(tot) > 0.5
+    assert torch.allclose(g, g0 * 0.5 / tot) and torch.allclose(e, extra * 0.5 / tot)
+    assert float(0.5 * torch.sqrt((g ** 2).sum() + (e ** 2).sum())) == pytest.approx(0.5)
+    small = g0 * 1e-3
+    s2 = small.clone()
+    clip_gradients(ppsci.optimizer.ClipGradByGlobalNorm(0.5), s2, segs)
+    assert torch.equal(s2, small)  # below the threshold: untouched
+    # per-tensor norm
+    g = g0.clone()
+    clip_gradients(ppsci.optimizer.ClipGradByNorm(1.0), g, segs)
+    for a, b in segs:
+        n0 = g0[a:b].norm()
+        assert torch.allclose(g[a:b], g0[a:b] * (1.0 / max(float(n0), 1.0)))
+    # value
+    g = g0.clone()
+    clip_gradients(ppsci.optimizer.ClipGradByValue(0.7), g, segs, grad_scale=0.5)
+    assert torch.allclose(g * 0.5, (g0 * 0.5).clamp(-0.7, 0.7))
+
+    class ClipGradByGlobalNorm:  # a foreign object with paddle's class name and attribute
+        clip_norm = 0.25
+
+    g = g0.clone()
+    clip_gradients(ClipGradByGlobalNorm(), g, segs)
+    assert float(g.norm()) == pytest.approx(0.25)
+    with pytest.raises(NotImplementedError):
+        clip_gradients(object(), g, segs)
