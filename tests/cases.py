@@ -110,6 +110,14 @@ CASES = {
     "modified_ac_period_f64": dict(in_keys=("t", "x"), out_keys=("u",), hidden=[12, 12], act="tanh", modified=True,
                                    periods={"x": (2.0, False)}, exprs=_ac_exprs, dtype=torch.float64,
                                    ranges={"x": (-1, 1)}),
+    "first_order_leaky_relu_f64": dict(in_keys=("x", "y"), out_keys=("u", "v"), hidden=[12, 12], act="leaky_relu",
+                                       exprs=_first_order_exprs, dtype=torch.float64),
+}
+
+# Cases added after the round's last GPU minutes were spent (never run on hardware): kept out of CASES so that the early
+# test_gpu_parity.py cannot stop a ``pytest -x`` run on them; the emulated CPU test runs them beside CASES and
+# tests/test_zzz_trainable_activations.py runs them on the GPU at the very end of the suite.
+LATE_CASES = {
     # activations with a trainable parameter (activation.py:28-58): Stan's beta per unit, Swish's beta per layer — the dx
     # epilogue also reduces dLoss/dbeta
     "ns_stan_f64": dict(in_keys=("x", "y"), out_keys=("u", "v", "p"), hidden=[12, 12, 12], act="stan", trainable_act=True,
@@ -118,8 +126,6 @@ CASES = {
                                    exprs=_biharm_exprs, dtype=torch.float64),
     "laplace_stan_f32": dict(in_keys=("x", "y"), out_keys=("u",), hidden=[20, 20], act="stan", trainable_act=True,
                              exprs=lambda: O.laplace_expr(2), dtype=torch.float32),
-    "first_order_leaky_relu_f64": dict(in_keys=("x", "y"), out_keys=("u", "v"), hidden=[12, 12], act="leaky_relu",
-                                       exprs=_first_order_exprs, dtype=torch.float64),
 }
 
 # shapes served by the tcgen05 kernels (hidden widths multiple of 32/128); CPU emulation skips them
@@ -203,7 +209,7 @@ def run_case(name, n: int, library=None, device="cpu", backend: int = 0, seed: i
     """``name``: key of CASES / TC_CASES / NAMED_CASES, or a case dict.  ``oracle_subset`` > 0: the engine runs all
     ``n`` points, the oracle only ``oracle_subset`` evenly strided points; residuals are compared on that subset and
     the engine's loss against the mean / sum of its own residuals (loss / grad errors are then not oracle errors)."""
-    c = name if isinstance(name, dict) else (CASES.get(name) or TC_CASES.get(name) or NAMED_CASES[name])
+    c = name if isinstance(name, dict) else (CASES.get(name) or LATE_CASES.get(name) or TC_CASES.get(name) or NAMED_CASES[name])
     torch.manual_seed(seed)
     dtype = c["dtype"]
     exprs = c["exprs"]()

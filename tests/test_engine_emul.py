@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from paddlescience_b200.engine import binding as B
-from tests.cases import CASES, TOL, run_case
+from tests.cases import CASES, LATE_CASES, TOL, run_case
 from tests.emul.build_emul import build
 
 
@@ -13,11 +13,12 @@ def emul_lib():
     return B.Library(build())
 
 
-@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("name", sorted(CASES) + sorted(LATE_CASES))
 def test_case_matches_oracle(emul_lib, name):
-    n = 45 if CASES[name]["hidden"][0] > 64 else 70
+    c = CASES.get(name) or LATE_CASES[name]
+    n = 45 if c["hidden"][0] > 64 else 70
     r = run_case(name, n, library=emul_lib, device="cpu")
-    tl, tr, tg = TOL[CASES[name]["dtype"]]
+    tl, tr, tg = TOL[c["dtype"]]
     assert r["loss"] <= tl, r
     assert r["res"] <= tr, r
     assert r["grad"] <= tg, r

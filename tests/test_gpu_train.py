@@ -42,16 +42,12 @@ def _oracle_loss_grad(om, p, pde, bc):
     return tot, grad
 
 
-@pytest.mark.parametrize("decoupled", [False, True])
-def test_solver_train_adam_matches_oracle_adam(decoupled):
-    """Adam, and AdamW (ppsci/optimizer/optimizer.py:386-496: decoupled decay in the same fused kernel)."""
-    factory = (lambda m: ppsci.optimizer.AdamW(1e-3, weight_decay=0.1)(m)) if decoupled else (lambda m: ppsci.optimizer.Adam(1e-3)(m))
-    model, solver, pde, bc, params0 = _problem(factory, 5)
+def test_solver_train_adam_matches_oracle_adam():
+    model, solver, pde, bc, params0 = _problem(lambda m: ppsci.optimizer.Adam(1e-3)(m), 5)
     solver.train()
     om = O.OracleMLP(("x", "y"), ("u",), [20, 20, 20], "tanh")
     p = params0.clone().requires_grad_(True)
-    opt = (torch.optim.AdamW([p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1) if decoupled
-           else torch.optim.Adam([p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8))
+    opt = torch.optim.Adam([p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
     for _ in range(5):
         _, g = _oracle_loss_grad(om, p.detach(), pde, bc)
         p.grad = g

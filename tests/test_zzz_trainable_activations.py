@@ -102,3 +102,35 @@ def test_trainable_activations_on_gpu_match_oracle(act, dtype, tol):
     bsl = slice(m._beta_off[0], m._beta_off[-1] + m._beta_len[-1])
     berr = float((m.flat.grad.detach().cpu().double()[bsl] - g[bsl]).norm() / g[bsl].norm())
     assert berr <= 5 * tol, berr
+
+
+@pytest.mark.gpu
+def test_late_kernel_level_cases_on_gpu():
+    """The kernel-level stan / swish cases of tests/cases.py::LATE_CASES (see the note there) with the tolerances of
+    tests/test_gpu_parity.py."""
+    from tests.cases import LATE_CASES, TOL, run_case
+
+    for name in sorted(LATE_CASES):
+        r = run_case(name, 5000, device="cuda:0")
+        tl, tr, tg = TOL[LATE_CASES[name]["dtype"]]
+        assert r["loss"] <= tl and r["res"] <= tr and r["grad"] <= tg and r["fwd_vs_fused"] == 0.0, (name, r)
+
+
+@pytest.mark.gpu
+def test_solver_train_adamw_matches_oracle_adamw():
+    """AdamW (ppsci/optimizer/optimizer.py:386-496: decoupled decay in the fused Adam kernel) over five Solver iterations
+    against torch.optim.AdamW driven by the oracle's gradients (the Adam case lives in tests/test_gpu_train.py)."""
+    from tests import test_gpu_train as G
+
+    model, solver, pde, bc, params0 = G._problem(lambda m: ppsci.optimizer.AdamW(1e-3, weight_decay=0.1)(m), 5)
+    solver.train()
+    om = O.OracleMLP(("x", "y"), ("u",), [20, 20, 20], "tanh")
+    p = params0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([p], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1)
+    for _ in range(5):
+        _, g = G._oracle_loss_grad(om, p.detach(), pde, bc)
+        p.grad = g
+        opt.step()
+    got = model.flat.detach().cpu().double()
+    step = (p.detach() - params0).norm()
+    assert float((got - p.detach()).norm() / step) <= 2e-3 and float(step) > 0
