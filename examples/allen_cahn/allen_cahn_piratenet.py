@@ -8,7 +8,11 @@ shipped (no network here).  The benchmark's initial condition is analytic — u(
 so it is evaluated directly on the reference's 512-point grid; pass ``--data allen_cahn.mat`` (needs scipy) to add the
 reference's L2Rel validator against ``usol``.
 
-    python examples/allen_cahn/allen_cahn_piratenet.py [--epochs 300] [--small] [--output_dir ./output_allen_cahn_piratenet]
+``--arch modifiedmlp`` runs the sibling example examples/allen_cahn/allen_cahn_sota.py (conf/allen_cahn_sota.yaml): the
+same script with ``ppsci.arch.ModifiedMLP`` (4 x 256, the same fourier / random_weight / periods options).
+
+    python examples/allen_cahn/allen_cahn_piratenet.py [--arch piratenet|modifiedmlp] [--epochs 300] [--small]
+                                                       [--output_dir ./output_allen_cahn_piratenet]
 """
 import argparse
 import json
@@ -32,6 +36,9 @@ CFG = {
               "causal": {"n_chunks": 32, "tol": 1.0}, "grad_norm": {"update_freq": 1000, "momentum": 0.9}},
     "GRID": {"nt": 201, "nx": 512, "t0": 0.0, "t1": 1.0, "x0": -1.0, "x1": 1.0},
 }
+MODEL_SOTA = {"input_keys": ("t", "x"), "output_keys": ("u",), "num_layers": 4, "hidden_size": 256, "activation": "tanh",
+              "periods": {"x": (2.0, False)}, "fourier": {"dim": 256, "scale": 2.0},
+              "random_weight": {"mean": 1.0, "std": 0.1}}  # conf/allen_cahn_sota.yaml:36-49
 SMALL = {  # wiring / smoke configuration (tests/test_examples.py builds it on the CPU)
     "MODEL": {"num_blocks": 1, "hidden_size": 16, "fourier": {"dim": 16, "scale": 2.0}},
     "TRAIN": {"epochs": 1, "iters_per_epoch": 2, "batch_size": 32, "causal": {"n_chunks": 4, "tol": 1.0},
@@ -47,11 +54,17 @@ def merged(base, over):
     return out
 
 
-def build(cfg, data_path=None):
+def build(cfg, data_path=None, arch="piratenet"):
     """Model, equation, constraints, optimizer, validators and the Solver — everything up to ``solver.train()``."""
     ppsci.utils.misc.set_random_seed(cfg["seed"])
     dtype = "float32"
-    model = ppsci.arch.PirateNet(**cfg["MODEL"])
+    if arch == "modifiedmlp":  # allen_cahn_sota.py:64
+        mcfg = dict(MODEL_SOTA)
+        if cfg["MODEL"]["hidden_size"] != CFG["MODEL"]["hidden_size"]:  # the small configuration
+            mcfg.update(num_layers=2, hidden_size=cfg["MODEL"]["hidden_size"], fourier=cfg["MODEL"]["fourier"])
+        model = ppsci.arch.ModifiedMLP(**mcfg)
+    else:
+        model = ppsci.arch.PirateNet(**cfg["MODEL"])
     equation = {"AllenCahn": ppsci.equation.AllenCahn(eps=0.01)}
     g = cfg["GRID"]
     x_star = np.linspace(g["x0"], g["x1"], g["nx"], endpoint=False).astype(dtype)  # the benchmark's periodic grid
@@ -109,6 +122,7 @@ def build(cfg, data_path=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--epochs", type=int, default=None)
+    ap.add_argument("--arch", choices=("piratenet", "modifiedmlp"), default="piratenet")
     ap.add_argument("--small", action="store_true", help="tiny configuration (wiring check)")
     ap.add_argument("--data", default=None, help="allen_cahn.mat of the reference (optional: adds the L2Rel validator)")
     ap.add_argument("--output_dir", default="./output_allen_cahn_piratenet")
@@ -116,7 +130,7 @@ def main():
     cfg = merged(CFG, SMALL) if args.small else CFG
     if args.epochs is not None:
         cfg = merged(cfg, {"TRAIN": {"epochs": args.epochs}})
-    solver, model, equation, constraint, eval_data = build(cfg, args.data)
+    solver, model, equation, constraint, eval_data = build(cfg, args.data, args.arch)
     tic = time.perf_counter()
     solver.train()
     train_s = time.perf_counter() - tic

@@ -7,6 +7,7 @@ import importlib.util
 import os
 
 import numpy as np
+import pytest
 import torch
 
 import ppsci
@@ -29,7 +30,8 @@ def test_cartesian_product_known_answer():
                             [2, 20, 100], [2, 20, 200]]
 
 
-def test_allen_cahn_piratenet_example_trains_two_iterations(monkeypatch):
+@pytest.mark.parametrize("arch", ["piratenet", "modifiedmlp"])
+def test_allen_cahn_piratenet_example_trains_two_iterations(monkeypatch, arch):
     from tests.emul.build_emul import build
 
     lib = B.Library(build())
@@ -47,8 +49,9 @@ def test_allen_cahn_piratenet_example_trains_two_iterations(monkeypatch):
     monkeypatch.setattr(opt_mod.FlatAdam, "step", cpu_step)
     ex = _load("examples/allen_cahn/allen_cahn_piratenet.py")
     cfg = ex.merged(ex.CFG, ex.SMALL)
-    solver, model, equation, constraint, eval_data = ex.build(cfg)
-    assert isinstance(model, ppsci.arch.PirateNet) and model.random_weight and model.fourier
+    solver, model, equation, constraint, eval_data = ex.build(cfg, arch=arch)
+    assert isinstance(model, ppsci.arch.PirateNet if arch == "piratenet" else ppsci.arch.ModifiedMLP)
+    assert model.random_weight and model.fourier
     assert type(constraint["PDE"].loss).__name__ == "CausalMSELoss" and type(solver.loss_aggregator).__name__ == "GradNorm"
     p0 = model.flat.data.clone()
     from paddlescience_b200.solver import train as train_mod
@@ -56,4 +59,5 @@ def test_allen_cahn_piratenet_example_trains_two_iterations(monkeypatch):
     train_mod.train_epoch_func(solver, 1, solver.log_freq)  # Solver.train's epoch body (Solver.train itself insists on CUDA)
     assert solver.global_step == 2
     assert torch.isfinite(model.flat.data).all() and float((model.flat.data - p0).abs().max()) > 0
-    assert float(model.alphas.abs().max()) > 0  # the residual weights take gradient from the first step on
+    if arch == "piratenet":
+        assert float(model.alphas.abs().max()) > 0  # the residual weights take gradient from the first step on
