@@ -64,6 +64,11 @@ class GraphedTrainStep:
             return f"loss aggregator {type(s.loss_aggregator).__name__}"
         if getattr(s.loss_aggregator, "needs_per_key_grads", False):
             return "per-term gradients"
+        for c in s.constraint.values():  # not validated under capture: stay eager
+            if type(getattr(c, "loss", None)).__name__ == "CausalMSELoss":
+                return "CausalMSELoss (two native calls with device-side weight arithmetic between them)"
+        if getattr(s.optimizer, "grad_clip", None) is not None:
+            return "gradient clipping"
         return None
 
     # -- the iteration body (runs eagerly during warm-up, once under capture) ------------------------------------------
