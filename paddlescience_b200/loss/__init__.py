@@ -1,8 +1,8 @@
 from . import mtl
 from .base import Loss
-from .mse import CausalMSELoss, MSELoss
+from .mse import CausalMSELoss, MSELoss, MSELossWithL2Decay
 
-__all__ = ["Loss", "MSELoss", "CausalMSELoss", "mtl", "build_loss"]
+__all__ = ["Loss", "MSELoss", "CausalMSELoss", "MSELossWithL2Decay", "mtl", "build_loss"]
 
 
 def build_loss(cfg):

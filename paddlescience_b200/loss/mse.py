@@ -46,6 +46,26 @@ class MSELoss(base.Loss):
         return losses
 
 
+class MSELossWithL2Decay(MSELoss):
+    r"""MSELoss plus an L2 penalty on named outputs (reference: ppsci/loss/mse.py:192-266): for every
+    ``reg_key, reg_weight`` of ``regularization_dict`` the entry ``losses[reg_key] = reg_weight * sum(output[reg_key]^2)``
+    is set AFTER the MSE terms — it replaces an MSE entry of the same key, and takes neither the loss ``weight`` nor the
+    reduction (mse.py:259-266).  On the fused path a penalty is one more residual slot of the constraint's program:
+    label 0, reduction "sum", loss weight ``reg_weight`` (``utils/expression.py``)."""
+
+    def __init__(self, reduction: str = "mean", regularization_dict: Optional[Dict[str, float]] = None,
+                 weight: Optional[Union[float, Dict[str, float]]] = None):
+        super().__init__(reduction, weight)
+        self.regularization_dict = dict(regularization_dict) if regularization_dict else None
+
+    def forward(self, output_dict, label_dict, weight_dict=None) -> Dict[str, torch.Tensor]:
+        losses = super().forward(output_dict, label_dict, weight_dict)
+        if self.regularization_dict is not None:
+            for reg_key, reg_weight in self.regularization_dict.items():
+                losses[reg_key] = (output_dict[reg_key] ** 2).sum() * reg_weight
+        return losses
+
+
 class CausalMSELoss(MSELoss):
     r"""Causal-training MSE (reference: ppsci/loss/mse.py:109-190; Wang et al., "Respecting causality is all you need
     for training physics-informed neural networks").  The points of a batch are ordered in time and split into

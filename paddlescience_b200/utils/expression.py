@@ -64,6 +64,8 @@ class CompiledConstraint:
         self.cst = cst
         self.exprs = _constraint_exprs(model, cst, extra_keys)  # the loss iterates label keys (mse.py:85); same order
         self.names = list(self.exprs)
+        # MSELossWithL2Decay: penalty slots (mse.py:259-266) — reduction "sum", their own weight, no per-point weights
+        self.reg = dict(getattr(cst.loss, "regularization_dict", None) or {})
         self.parameters = _learnable_parameters(self.exprs)
         self.compiled = compile_residuals(model.net_spec(), self.exprs, param_keys=list(self.parameters))
         self._plans: Dict[torch.dtype, ResidualPlan] = {}
@@ -73,21 +75,36 @@ class CompiledConstraint:
         """The same residual program with a one-hot loss weight: the adjoint yields d(loss of residual k)/d(params) alone
         (per-equation gradients for mtl.PCGrad and friends; the reference calls losses[key].backward() per key)."""
         if (dtype, k) not in self._key_plans:
-            loss = self.cst.loss
-            red = getattr(loss, "reduction", "mean")
-            lw = [(loss.weight_of(key) if hasattr(loss, "weight_of") else 1.0) if j == k else 0.0 for j, key in enumerate(self.names)]
-            self._key_plans[(dtype, k)] = ResidualPlan(self.compiled, dtype, [red] * len(self.names), lw)
+            reds, lw = self._loss_spec()
+            lw = [w if j == k else 0.0 for j, w in enumerate(lw)]
+            self._key_plans[(dtype, k)] = ResidualPlan(self.compiled, dtype, reds, lw)
         return self._key_plans[(dtype, k)]
+
+    def strip_penalty_slots(self, labels, weights):
+        """MSELossWithL2Decay: a penalty slot is ``sum(out^2)`` — no label, no per-point weight / area (mse.py:262-264)."""
+        if not self.reg:
+            return labels, weights
+        labels = {k: v for k, v in (labels or {}).items() if k not in self.reg}
+        weights = {k: v for k, v in weights.items() if k not in self.reg} if weights else weights
+        return labels, weights
+
+    def _loss_spec(self):
+        """Per residual slot: (reduction, loss weight)."""
+        loss = self.cst.loss
+        red = getattr(loss, "reduction", "mean")
+        reds = ["sum" if key in self.reg else red for key in self.names]
+        lw = [float(self.reg[key]) if key in self.reg else (loss.weight_of(key) if hasattr(loss, "weight_of") else 1.0)
+              for key in self.names]
+        return reds, lw
 
     def plan(self, dtype) -> ResidualPlan:
         if dtype not in self._plans:
             loss = self.cst.loss
-            red = getattr(loss, "reduction", "mean")
-            lw = [loss.weight_of(k) if hasattr(loss, "weight_of") else 1.0 for k in self.names]
-            if type(loss).__name__ not in ("MSELoss", "CausalMSELoss"):
-                raise NotImplementedError(f"{type(loss).__name__} has no fused head kernel; only MSELoss / CausalMSELoss "
-                                          "are on the hot path")
-            self._plans[dtype] = ResidualPlan(self.compiled, dtype, [red] * len(self.names), lw)
+            if type(loss).__name__ not in ("MSELoss", "CausalMSELoss", "MSELossWithL2Decay"):
+                raise NotImplementedError(f"{type(loss).__name__} has no fused head kernel; only MSELoss / CausalMSELoss / "
+                                          "MSELossWithL2Decay are on the hot path")
+            reds, lw = self._loss_spec()
+            self._plans[dtype] = ResidualPlan(self.compiled, dtype, reds, lw)
         return self._plans[dtype]
 
 
@@ -105,6 +122,13 @@ def _constraint_exprs(model, cst, extra_keys) -> Dict[str, sp.Basic]:
         else:
             raise TypeError(f"output_expr['{name}'] must be a sympy expression or a callable, got {type(e)}")
     names = [k for k in cst.output_keys if k in exprs] if hasattr(cst, "output_keys") else list(exprs)
+    for reg_key in (getattr(cst.loss, "regularization_dict", None) or {}):  # MSELossWithL2Decay: output_dict[reg_key]
+        if reg_key not in exprs:
+            if reg_key not in out_keys:
+                raise KeyError(f"regularization key '{reg_key}' is neither an output expression nor a model output")
+            exprs[reg_key] = sp.Function(reg_key)(*[sp.Symbol(k) for k in model.input_keys])
+        if reg_key not in names:
+            names.append(reg_key)
     # a registered output transform is part of the function being trained (mlp.py:313-314): rewrite the residuals in
     # terms of the bare network the kernels differentiate
     return {k: symbolic.apply_output_transform(model, exprs[k]) for k in names}
@@ -257,20 +281,21 @@ class ExpressionSolver(nn.Module):
                 if "area" in input_dicts[i]:
                     area = input_dicts[i]["area"]
                     weights = {k: (weights[k] * area if weights and k in weights else area) for k in cc.names}
+                labels_i, weights = cc.strip_penalty_slots(label_dicts[i], weights)
                 if cc.parameters:
                     raise NotImplementedError("per-term gradients with learnable equation parameters are not supported yet")
                 if type(cst.loss).__name__ == "CausalMSELoss":
-                    weights = self._causal_weights(cst, cc, cc.plan(flat.dtype), input_dicts[i], label_dicts[i], weights, params)
+                    weights = self._causal_weights(cst, cc, cc.plan(flat.dtype), input_dicts[i], labels_i, weights, params)
                 for k, key in enumerate(cc.names):
                     g = grads_by_key.setdefault(key, torch.zeros_like(flat.data))
                     if staged:
                         flat.grad.zero_()
                         lv = cc.plan_for_key(flat.dtype, k).loss_fwd_bwd(input_dicts[i], params, model.engine_grads(),
-                                                                         labels=label_dicts[i], weights=weights)[k].clone()
+                                                                         labels=labels_i, weights=weights)[k].clone()
                         model.finish_grads()
                         g.add_(flat.grad)
                     else:
-                        lv = cc.plan_for_key(flat.dtype, k).loss_fwd_bwd(input_dicts[i], params, g, labels=label_dicts[i],
+                        lv = cc.plan_for_key(flat.dtype, k).loss_fwd_bwd(input_dicts[i], params, g, labels=labels_i,
                                                                          weights=weights)[k].clone()
                     losses_all[key] = losses_all[key] + lv if key in losses_all else lv
                     losses_constraint[cst_name] = losses_constraint[cst_name] + lv if cst_name in losses_constraint else lv
@@ -327,9 +352,10 @@ class ExpressionSolver(nn.Module):
             if "area" in input_dicts[i]:  # mse.py:92-93 multiplies by the area column when present
                 area = input_dicts[i]["area"]
                 weights = {k: (weights[k] * area if weights and k in weights else area) for k in cc.names}
+            labels_i, weights = cc.strip_penalty_slots(label_dicts[i], weights)
             if type(cst.loss).__name__ == "CausalMSELoss":
-                weights = self._causal_weights(cst, cc, plan, input_dicts[i], label_dicts[i], weights, params)
-            loss_vec = plan.loss_fwd_bwd(_with_parameters(input_dicts[i], cc.parameters), params, grads, labels=label_dicts[i],
+                weights = self._causal_weights(cst, cc, plan, input_dicts[i], labels_i, weights, params)
+            loss_vec = plan.loss_fwd_bwd(_with_parameters(input_dicts[i], cc.parameters), params, grads, labels=labels_i,
                                          weights=weights)
             loss_vec = loss_vec.clone()
             _collect_parameter_grads(plan, cc.parameters, flat.device)

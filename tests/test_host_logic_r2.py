@@ -361,3 +361,52 @@ def test_gradient_clipping_objects_follow_paddle_semantics():
     assert float(g.norm()) == pytest.approx(0.25)
     with pytest.raises(NotImplementedError):
         clip_gradients(object(), g, segs)
+
+
+def test_mse_loss_with_l2_decay_known_answer_and_fused_path(monkeypatch):
+    """MSELossWithL2Decay (ppsci/loss/mse.py:192-266): the docstring's known answer, and on the fused path — a penalty is
+    one more residual slot (label 0, "sum", its own weight) — loss terms and weight gradient against the oracle."""
+    import numpy as np
+
+    from oracle import ppsci_oracle as O
+    from paddlescience_b200.engine import binding as B
+    from tests.emul.build_emul import build
+
+    out = {"u": torch.tensor([[0.5, 0.9], [1.1, -1.3]]), "v": torch.tensor([[0.5, 0.9], [1.1, -1.3]])}
+    lab = {"u": torch.tensor([[-1.8, 1.0], [-0.2, 2.5]]), "v": torch.tensor([[0.1, 0.1], [0.1, 0.1]])}
+    res = ppsci.loss.MSELossWithL2Decay(regularization_dict={"u": 2.0}, weight={"u": 0.8, "v": 0.2})(out, lab)
+    assert float(res["u"]) == pytest.approx(7.92, rel=1e-6) and float(res["v"]) == pytest.approx(0.188, rel=1e-6)  # mse.py:228-232
+
+    monkeypatch.setattr(B, "_default", B.Library(build()))
+    ppsci.utils.misc.set_random_seed(4)
+    m = ppsci.arch.MLP(("x", "y"), ("u", "v"), 2, 10, "tanh", dtype=torch.float64)
+    with torch.no_grad():
+        m.flat.data += 0.1 * torch.randn_like(m.flat.data)
+    n = 24
+    inp = {k: torch.rand(n, 1, dtype=torch.float64) for k in ("x", "y")}
+    labels = {"u": torch.randn(n, 1, dtype=torch.float64), "v": torch.randn(n, 1, dtype=torch.float64)}
+    cst = ppsci.constraint.SupervisedConstraint(
+        {"dataset": {"name": "IterableNamedArrayDataset", "input": {k: v.numpy() for k, v in inp.items()},
+                     "label": {k: v.numpy() for k, v in labels.items()}}},
+        ppsci.loss.MSELossWithL2Decay("mean", {"v": 0.3, "lap_u": 0.05}, weight={"u": 2.0}),
+        output_expr={"u": lambda o: o["u"], "v": lambda o: o["v"],
+                     "lap_u": lambda o: ppsci.autodiff.hessian(o["u"], o["x"]) + ppsci.autodiff.hessian(o["u"], o["y"])},
+        name="SUP")
+    ds = cst.data_loader.loader
+    ins = {k: v.double() for k, v in ds.input.items()}
+    labs = {k: v.double() for k, v in ds.label.items()}
+    losses, _ = ppsci.utils.ExpressionSolver().train_forward((cst.output_expr,), [ins], m, {"SUP": cst}, [labs], [None])
+    # oracle: u -> weighted MSE; v -> the penalty REPLACES its MSE entry (mse.py:262-264); lap_u -> penalty on an expression
+    flat = m.flat.data.clone().requires_grad_(True)
+    om = O.OracleMLP(("x", "y"), ("u", "v"), [10, 10], "tanh")
+    x = {k: ins[k].clone().requires_grad_(True) for k in ("x", "y")}
+    o = om(flat, x)
+    ux = torch.autograd.grad(o["u"].sum(), x["x"], create_graph=True)[0]
+    uy = torch.autograd.grad(o["u"].sum(), x["y"], create_graph=True)[0]
+    lap = torch.autograd.grad(ux.sum(), x["x"], create_graph=True)[0] + torch.autograd.grad(uy.sum(), x["y"], create_graph=True)[0]
+    ref = {"u": 2.0 * ((o["u"] - labs["u"]) ** 2).mean(), "v": 0.3 * (o["v"] ** 2).sum(), "lap_u": 0.05 * (lap ** 2).sum()}
+    (g,) = torch.autograd.grad(sum(ref.values()), flat)
+    assert set(losses) == {"u", "v", "lap_u"}
+    for k in ref:
+        assert float(losses[k]) == pytest.approx(float(ref[k].detach()), rel=1e-10)
+    np.testing.assert_allclose(m.flat.grad.numpy(), g.numpy(), rtol=1e-8, atol=1e-11 * float(g.abs().max()))
